@@ -1,0 +1,246 @@
+#!/usr/bin/env python
+"""bench.py -- DG matrix-free vmult DoF/s (3D Q4 fp64), BASELINE.json's metric.
+
+One "step" = one application of the SIPG pressure operator (NS.cc:1398-1421, NS_stage 2) to a
+device-resident vector on the C2 workload of SURVEY.md 8d: unit cube, refine_global(7) = 128^3 cells,
+FE_DGQ(4), periodic, fp64 (262,144,000 DoFs, 2.1 GB per vector => inputs exceed the 126 MB L2).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--refine R] [--degree P] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `value` = DoFs processed per second with src/dst resident in HBM;
+`e2e` = the same through dgx_op_vmult_host (pinned host buffers, H2D + vmult + D2H timed);
+`roofline` = algorithmic bytes (16 B/DoF) / kernel time vs MEASURED_PEAKS.json;
+`cpu_baseline` = the oracle's C port timed on the host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "code-gallery_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np
+
+METRIC = "DG matrix-free vmult DoF/s (3D Q4 fp64)"
+UNIT = "DoF/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--refine", type=int, default=7, help="refine_global level per GPU-count 1 (128^3 cells)")
+    ap.add_argument("--degree", type=int, default=4)
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--impl", default="dgx", choices=["dgx", "reference"])
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-refine", type=int, default=5)
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.samples, self.stop_flag = device, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.device)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def cpu_baseline(degree, refine, dtype, steps=3):
+    """Oracle C port (oracle/cpu_vmult.c) on all host cores; falls back to the numpy oracle."""
+    from oracle import cpu_port
+    return cpu_port.time_vmult(degree, refine, dtype, steps)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.time()
+    res = cpu_baseline(args.degree, args.cpu_refine, args.dtype, steps=max(1, args.steps))
+    ndofs = res["n_dofs"]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["dofs_per_s"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": f"3D SIPG pressure vmult Q{args.degree}, {2**args.cpu_refine}^3 cells periodic "
+                               f"(bounded sample of the 128^3 workload), {ndofs} DoFs", "timing": "inputs exceed host caches"},
+        "cpu_baseline": {"value": res["dofs_per_s"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
+        "e2e": {"value": res["dofs_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.time() - t0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    import dgx
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        idt = torch.zeros(dgx.NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(dgx.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().numpy().tobytes())
+    ctx = dgx.Context(local_rank, rank, world, nccl_id)
+
+    # weak scaling: per-GPU work fixed at (2^refine)^3 cells; N GPUs => N times the cells along x
+    cells0 = [world, 1, 1]
+    mesh = dgx.Mesh(3, cells0, args.refine, [0, 0, 0], [float(world), 1, 1], [True, True, True])
+    dt = dgx.F64 if args.dtype == "f64" else dgx.F32
+    mf = dgx.MatrixFree(ctx, mesh, -1, dt)
+    op = dgx.NavierStokesProjectionOperator(mf, dgx.OP_PRESSURE, args.degree, 100.0, 5e-3)
+    op.set_variant(args.variant)
+    src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+    n_local = src.locally_owned_size()
+    n_global = src.size()
+    npdt = np.float64 if dt == dgx.F64 else np.float32
+    # synthetic input: smooth field + noise, seed 1234, generated in chunks
+    rng = np.random.default_rng(1234 + rank)
+    host = torch.empty(n_local, dtype=torch.float64 if dt == dgx.F64 else torch.float32, pin_memory=True)
+    hnp = host.numpy()
+    chunk = 1 << 24
+    for o in range(0, n_local, chunk):
+        m = min(chunk, n_local - o)
+        hnp[o:o + m] = np.sin(np.arange(o, o + m) * 1e-3) + 1e-3 * rng.uniform(-1, 1, m)
+    src.from_host(hnp)
+
+    def barrier():
+        ctx.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        op.vmult(dst, src)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = dgx.kernel_launch_count()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        op.vmult(dst, src)
+    ms = ctx.timer_stop()
+    barrier()
+    launches = dgx.kernel_launch_count() - launches0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = n_global / (ms_per_step * 1e-3)
+
+    # end to end through the host-buffer entry point (pinned host memory)
+    e2e = None
+    if not args.no_e2e:
+        hout = torch.empty_like(host, pin_memory=True)
+        houtnp = hout.numpy()
+        op.vmult_host(houtnp, hnp)
+        barrier()
+        ksteps = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        ctx.timer_start()
+        for _ in range(ksteps):
+            op.vmult_host(houtnp, hnp)
+        ems = ctx.timer_stop()
+        barrier()
+        if world > 1:
+            t = torch.tensor([ems], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        bytes_each = n_local * host.element_size()
+        e2e = {"value": n_global / (ems / ksteps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": bytes_each,
+               "d2h_bytes_per_step": bytes_each, "ms_per_step": ems / ksteps, "steps": ksteps,
+               "checksum": float(np.abs(houtnp[:: max(1, n_local // 4096)]).sum())}
+
+    peaks, which = measured_peaks()
+    bytes_per_dof = 2 * host.element_size()
+    achieved = (n_local * bytes_per_dof) / (ms_per_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                "traffic": None, "peak_source": which, "algorithmic_bytes_per_dof": bytes_per_dof,
+                "kernel": "pressure vmult (1 launch per step)"}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            res = cpu_baseline(args.degree, args.cpu_refine, args.dtype)
+            cpu = {"value": res["dofs_per_s"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]}
+        except Exception as exc:  # noqa: BLE001
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"3D DG SIPG pressure-operator vmult, Q{args.degree}, {world}x{2**args.refine}^3 cells periodic Cartesian, "
+                                   f"{n_global} DoFs {args.dtype}", "l2": "inputs (2 vectors) exceed the 126 MB L2; no flush needed",
+                       "partition": f"{world} contiguous Morton chunks" if world > 1 else "single GPU"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,231 @@
+// extern "C" layer: context, operator handles (see include/dgx.h for the reference members replaced).
+#include <cmath>
+#include <cstring>
+
+#include "dgx_internal.h"
+
+#define DGX_STR2(x) #x
+#define DGX_STR(x) DGX_STR2(x)
+
+namespace dgx {
+static thread_local std::string g_error;
+long long g_launch_count = 0;
+void set_error(const std::string &msg) { g_error = msg; }
+}  // namespace dgx
+
+using namespace dgx;
+
+extern "C" {
+
+const char *dgx_last_error(void) { return g_error.c_str(); }
+const char *dgx_version(void) { return "dgx 0.1 (sm_100a, CUDA " DGX_STR(CUDART_VERSION) ")"; }
+long long dgx_kernel_launch_count(void) { return g_launch_count; }
+
+int dgx_nccl_unique_id(void *out_id) {
+  DGX_REQUIRE(out_id, "null argument");
+  return comm_unique_id(out_id);
+}
+
+int dgx_ctx_create(int device, int rank, int nranks, const void *nccl_id, dgx_ctx **out) {
+  DGX_REQUIRE(out, "null argument");
+  DGX_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "rank / nranks");
+  auto *ctx = new dgx_ctx();
+  ctx->device = device; ctx->rank = rank; ctx->nranks = nranks;
+  int ndev = 0;
+  const bool have_gpu = (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0);
+  if (!have_gpu) {
+    // host-only context: mesh / MatrixFree table queries work, every compute call fails loudly
+    cudaGetLastError();
+    ctx->device = -1;
+    if (nranks > 1 && nccl_id) { delete ctx; set_error("no CUDA device: cannot create a multi-rank context"); return DGX_ERR_CUDA; }
+    *out = ctx;
+    return DGX_OK;
+  }
+  if (device < 0 || device >= ndev) { delete ctx; set_error("device index out of range"); return DGX_ERR_INVALID; }
+  DGX_CUDA_CHECK(cudaSetDevice(device));
+  DGX_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  ctx->stream = ctx->own_stream;
+  DGX_CUDA_CHECK(cudaEventCreate(&ctx->ev0));
+  DGX_CUDA_CHECK(cudaEventCreate(&ctx->ev1));
+  ctx->scratch_doubles = 8 + 148 * 8;
+  DGX_CUDA_CHECK(cudaMalloc(&ctx->d_scratch, ctx->scratch_doubles * sizeof(double)));
+  DGX_CUDA_CHECK(cudaMemset(ctx->d_scratch, 0, ctx->scratch_doubles * sizeof(double)));
+  DGX_CUDA_CHECK(cudaMallocHost(&ctx->h_scratch, 64 * sizeof(double)));
+  int rc = comm_init(ctx, nccl_id);
+  if (rc) { delete ctx; return rc; }
+  *out = ctx;
+  return DGX_OK;
+}
+
+int dgx_ctx_destroy(dgx_ctx *ctx) {
+  if (!ctx) return DGX_OK;
+  comm_destroy(ctx);
+  if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return DGX_OK;
+}
+
+int dgx_ctx_set_stream(dgx_ctx *ctx, void *cuda_stream) {
+  DGX_REQUIRE(ctx, "null argument");
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return DGX_OK;
+}
+
+void *dgx_ctx_get_stream(dgx_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int dgx_ctx_synchronize(dgx_ctx *ctx) {
+  DGX_REQUIRE(ctx && ctx->device >= 0, "context has no device");
+  DGX_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  return DGX_OK;
+}
+
+int dgx_ctx_timer_start(dgx_ctx *ctx) {
+  DGX_REQUIRE(ctx && ctx->device >= 0, "context has no device");
+  DGX_CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
+  return DGX_OK;
+}
+
+int dgx_ctx_timer_stop(dgx_ctx *ctx, double *ms) {
+  DGX_REQUIRE(ctx && ms && ctx->device >= 0, "context has no device");
+  DGX_CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
+  DGX_CUDA_CHECK(cudaEventSynchronize(ctx->ev1));
+  float f = 0;
+  DGX_CUDA_CHECK(cudaEventElapsedTime(&f, ctx->ev0, ctx->ev1));
+  *ms = f;
+  return DGX_OK;
+}
+
+// ---- operator ---------------------------------------------------------------------------------
+int dgx_op_create(dgx_mf *mf, int kind, int degree, double Re, double dt, dgx_op **out) {
+  DGX_REQUIRE(mf && out, "null argument");
+  DGX_REQUIRE(kind >= DGX_OP_VELOCITY && kind <= DGX_OP_MASS, "kind must be an NS_stage in 1..3");
+  DGX_REQUIRE(degree >= 1 && degree <= 8, "degree must be in 1..8");
+  DGX_REQUIRE(mf->ctx->device >= 0, "no CUDA device: the operator has no CPU fallback");
+  auto *op = new dgx_op();
+  op->mf = mf; op->kind = kind; op->degree = degree; op->Re = Re; op->dt = dt;
+  op->ncomp = (kind == DGX_OP_PRESSURE) ? 1 : mf->dim;
+  *out = op;
+  return DGX_OK;
+}
+
+int dgx_op_destroy(dgx_op *op) {
+  if (!op) return DGX_OK;
+  for (dgx_vec *v : {op->u_extr, op->inv_diag, op->h_src, op->h_dst})
+    if (v) { v->borrowed = false; dgx_vec_destroy(v); }
+  delete op;
+  return DGX_OK;
+}
+
+int dgx_op_set_dt(dgx_op *op, double dt) { DGX_REQUIRE(op, "null argument"); op->dt = dt; return DGX_OK; }
+
+int dgx_op_set_TR_BDF2_stage(dgx_op *op, int stage) {
+  DGX_REQUIRE(op, "null argument");
+  DGX_REQUIRE(stage == 1 || stage == 2, "TR_BDF2_stage must be 1 or 2");   // AssertIndexRange(stage, 3), NS.cc:426-427
+  op->stage = stage;
+  return DGX_OK;
+}
+
+int dgx_op_set_variant(dgx_op *op, int variant) {
+  DGX_REQUIRE(op && variant >= 0 && variant <= 2, "variant");
+  op->variant = variant;
+  return DGX_OK;
+}
+
+int dgx_op_set_u_extr(dgx_op *op, const dgx_vec *src) {
+  DGX_REQUIRE(op && src, "null argument");
+  DGX_REQUIRE(op->kind == DGX_OP_VELOCITY, "u_extr belongs to the velocity operator");
+  if (!op->u_extr) {
+    int rc = dgx_vec_create(op->mf, op->degree, op->ncomp, &op->u_extr);
+    if (rc) return rc;
+    op->u_extr->borrowed = true;
+  }
+  int rc = dgx_vec_copy(op->u_extr, src);
+  if (rc) return rc;
+  return dgx_vec_update_ghost_values(op->u_extr);
+}
+
+long long dgx_op_m(const dgx_op *op) {
+  if (!op) return 0;
+  long long dpc = op->ncomp;
+  for (int d = 0; d < op->mf->dim; ++d) dpc *= op->degree + 1;
+  return op->mf->n_global * dpc;
+}
+
+static int check_vecs(const dgx_op *op, const dgx_vec *dst, const dgx_vec *src) {
+  DGX_REQUIRE(op && dst && src, "null argument");
+  DGX_REQUIRE(dst != src && dst->d != src->d, "dst and src must differ");
+  DGX_REQUIRE(dst->mf == op->mf && src->mf == op->mf, "vector was initialised for a different MatrixFree");
+  DGX_REQUIRE(dst->degree == op->degree && src->degree == op->degree && dst->ncomp == op->ncomp && src->ncomp == op->ncomp,
+              "vector space does not match the operator (degree / components)");
+  return DGX_OK;
+}
+
+static int apply(dgx_op *op, dgx_vec *dst, dgx_vec *src, bool add) {
+  int rc = check_vecs(op, dst, src);
+  if (rc) return rc;
+  // MatrixFree::loop: import the ghosts of src first; dst needs no compress
+  if (op->kind != DGX_OP_MASS) { rc = ghost_exchange(src); if (rc) return rc; }
+  switch (op->kind) {
+    case DGX_OP_PRESSURE: return pressure_apply(op, dst, src, add);
+    case DGX_OP_MASS: return mass_apply(op, dst, src, add);
+    default: return velocity_apply(op, dst, src, add);
+  }
+}
+
+int dgx_op_vmult(dgx_op *op, dgx_vec *dst, dgx_vec *src) { return apply(op, dst, src, false); }
+int dgx_op_vmult_add(dgx_op *op, dgx_vec *dst, dgx_vec *src) { return apply(op, dst, src, true); }
+// Base::Tvmult calls apply_add as well: no Tapply_add override in the reference (NS.cc:281)
+int dgx_op_Tvmult(dgx_op *op, dgx_vec *dst, dgx_vec *src) { return apply(op, dst, src, false); }
+int dgx_op_Tvmult_add(dgx_op *op, dgx_vec *dst, dgx_vec *src) { return apply(op, dst, src, true); }
+
+int dgx_op_compute_diagonal(dgx_op *op) {
+  DGX_REQUIRE(op, "null argument");
+  DGX_REQUIRE(op->kind == DGX_OP_VELOCITY || op->kind == DGX_OP_PRESSURE, "compute_diagonal needs NS_stage 1 or 2");  // NS.cc:2019
+  if (!op->inv_diag) {
+    int rc = dgx_vec_create(op->mf, op->degree, op->ncomp, &op->inv_diag);
+    if (rc) return rc;
+    op->inv_diag->borrowed = true;
+  }
+  return op->kind == DGX_OP_PRESSURE ? pressure_diagonal(op, op->inv_diag) : velocity_diagonal(op, op->inv_diag);
+}
+
+int dgx_op_get_matrix_diagonal_inverse(dgx_op *op, dgx_vec **out) {
+  DGX_REQUIRE(op && out, "null argument");
+  DGX_REQUIRE(op->inv_diag, "compute_diagonal() has not been called");
+  *out = op->inv_diag;
+  return DGX_OK;
+}
+
+int dgx_op_precondition_Jacobi(dgx_op *op, dgx_vec *dst, const dgx_vec *src, double omega) {
+  DGX_REQUIRE(op && dst && src, "null argument");
+  DGX_REQUIRE(op->inv_diag, "compute_diagonal() has not been called");
+  int rc = dgx_vec_equ(dst, omega, src);
+  if (rc) return rc;
+  return dgx_vec_scale_by(dst, op->inv_diag);
+}
+
+int dgx_op_vmult_host(dgx_op *op, void *dst_host, const void *src_host, long long n) {
+  DGX_REQUIRE(op && dst_host && src_host, "null argument");
+  if (!op->h_src) {
+    int rc = dgx_vec_create(op->mf, op->degree, op->ncomp, &op->h_src);
+    if (rc) return rc;
+    rc = dgx_vec_create(op->mf, op->degree, op->ncomp, &op->h_dst);
+    if (rc) return rc;
+    op->h_src->borrowed = op->h_dst->borrowed = true;
+  }
+  DGX_REQUIRE(n == op->h_src->n_owned, "host buffer size must equal the locally owned size");
+  cudaStream_t st = op->mf->ctx->stream;
+  const size_t bytes = (size_t)n * op->h_src->elem();
+  DGX_CUDA_CHECK(cudaMemcpyAsync(op->h_src->d, src_host, bytes, cudaMemcpyHostToDevice, st));
+  int rc = apply(op, op->h_dst, op->h_src, false);
+  if (rc) return rc;
+  DGX_CUDA_CHECK(cudaMemcpyAsync(dst_host, op->h_dst->d, bytes, cudaMemcpyDeviceToHost, st));
+  DGX_CUDA_CHECK(cudaStreamSynchronize(st));
+  return DGX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+// NCCL plumbing, resolved at run time with dlopen so that libdgx.so loads on machines / processes
+// without NCCL and shares the copy torch has already loaded.  Replaces the MPI calls deal.II makes
+// for the reference: Partitioner Isend/Irecv ghost import -> grouped
+// ncclSend/ncclRecv; MPI_Allreduce of dot products / norms -> ncclAllReduce of a few doubles.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+#include <mutex>
+
+#include "dgx_internal.h"
+
+namespace dgx {
+namespace {
+struct NcclApi {
+  void *handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+
+NcclApi &api() {
+  static NcclApi a;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+      a.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (a.handle) break;
+    }
+    if (!a.handle) return;
+#define LOAD(field, sym) a.field = reinterpret_cast<decltype(a.field)>(dlsym(a.handle, sym))
+    LOAD(GetUniqueId, "ncclGetUniqueId");
+    LOAD(CommInitRank, "ncclCommInitRank");
+    LOAD(CommDestroy, "ncclCommDestroy");
+    LOAD(Send, "ncclSend");
+    LOAD(Recv, "ncclRecv");
+    LOAD(AllReduce, "ncclAllReduce");
+    LOAD(GroupStart, "ncclGroupStart");
+    LOAD(GroupEnd, "ncclGroupEnd");
+    LOAD(GetErrorString, "ncclGetErrorString");
+#undef LOAD
+    a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.Send && a.Recv && a.AllReduce && a.GroupStart && a.GroupEnd;
+  });
+  return a;
+}
+
+#define DGX_NCCL_CHECK(expr)                                                                  \
+  do {                                                                                        \
+    ncclResult_t r__ = (expr);                                                                \
+    if (r__ != ncclSuccess) {                                                                 \
+      set_error(std::string(#expr) + ": " + (api().GetErrorString ? api().GetErrorString(r__) : "nccl error")); \
+      return DGX_ERR_NCCL;                                                                    \
+    }                                                                                         \
+  } while (0)
+}  // namespace
+
+int comm_unique_id(void *out) {
+  if (!api().ok) { set_error("NCCL library not found (dlopen libnccl.so.2)"); return DGX_ERR_NCCL; }
+  static_assert(sizeof(ncclUniqueId) <= DGX_NCCL_ID_BYTES, "id size");
+  ncclUniqueId id;
+  DGX_NCCL_CHECK(api().GetUniqueId(&id));
+  std::memset(out, 0, DGX_NCCL_ID_BYTES);
+  std::memcpy(out, &id, sizeof(id));
+  return DGX_OK;
+}
+
+int comm_init(dgx_ctx *ctx, const void *idbytes) {
+  if (ctx->nranks == 1) return DGX_OK;
+  if (!api().ok) { set_error("NCCL library not found (dlopen libnccl.so.2)"); return DGX_ERR_NCCL; }
+  DGX_REQUIRE(idbytes, "nccl_id required for nranks > 1");
+  ncclUniqueId id;
+  std::memcpy(&id, idbytes, sizeof(id));
+  ncclComm_t comm;
+  DGX_NCCL_CHECK(api().CommInitRank(&comm, ctx->nranks, id, ctx->rank));
+  ctx->nccl_comm = comm;
+  return DGX_OK;
+}
+
+int comm_destroy(dgx_ctx *ctx) {
+  if (ctx->nccl_comm) api().CommDestroy((ncclComm_t)ctx->nccl_comm);
+  ctx->nccl_comm = nullptr;
+  return DGX_OK;
+}
+
+int allreduce_sum(dgx_ctx *ctx, double *dvals, int n) {
+  if (ctx->nranks == 1) return DGX_OK;
+  DGX_NCCL_CHECK(api().AllReduce(dvals, dvals, n, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+  return DGX_OK;
+}
+
+int allreduce_max(dgx_ctx *ctx, double *dvals, int n) {
+  if (ctx->nranks == 1) return DGX_OK;
+  DGX_NCCL_CHECK(api().AllReduce(dvals, dvals, n, ncclFloat64, ncclMax, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+  return DGX_OK;
+}
+
+// grouped point-to-point: send[i] -> peers, recv[i] <- peers (bytes)
+int comm_exchange(dgx_ctx *ctx, int npeers, const int *ranks, const void *const *sendbuf, const size_t *sendbytes,
+                  void *const *recvbuf, const size_t *recvbytes) {
+  if (ctx->nranks == 1 || npeers == 0) return DGX_OK;
+  ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+  DGX_NCCL_CHECK(api().GroupStart());
+  for (int i = 0; i < npeers; ++i) {
+    if (sendbytes[i]) DGX_NCCL_CHECK(api().Send(sendbuf[i], sendbytes[i], ncclChar, ranks[i], comm, ctx->stream));
+    if (recvbytes[i]) DGX_NCCL_CHECK(api().Recv(recvbuf[i], recvbytes[i], ncclChar, ranks[i], comm, ctx->stream));
+  }
+  DGX_NCCL_CHECK(api().GroupEnd());
+  return DGX_OK;
+}
+
+}  // namespace dgx

@@ -1,0 +1,147 @@
+// Internal declarations of libdgx (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/dgx.h"
+
+namespace dgx {
+
+void set_error(const std::string &msg);
+extern long long g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count += n; }
+
+#define DGX_CUDA_CHECK(expr)                                                                  \
+  do {                                                                                        \
+    cudaError_t err__ = (expr);                                                               \
+    if (err__ != cudaSuccess) {                                                               \
+      ::dgx::set_error(std::string(#expr) + ": " + cudaGetErrorString(err__));                \
+      return DGX_ERR_CUDA;                                                                    \
+    }                                                                                         \
+  } while (0)
+
+#define DGX_REQUIRE(cond, msg)                                                                \
+  do {                                                                                        \
+    if (!(cond)) {                                                                            \
+      ::dgx::set_error(std::string(msg) + " (" #cond ")");                                    \
+      return DGX_ERR_INVALID;                                                                 \
+    }                                                                                         \
+  } while (0)
+
+constexpr int MAX_DIM = 3;
+constexpr int MAX_N = 9;  // degree <= 8
+
+// ---- 1-D tables (host, long double -> double) -------------------------------------------------
+struct Shape1D {
+  int n = 0, nq = 0;
+  std::vector<double> nodes, xq, wq;
+  std::vector<double> S, D;         // [nq][n]
+  std::vector<double> f[2], g[2];   // l_i(s), l_i'(s)
+  std::vector<double> M, K;         // [n][n] sum_q w S S, sum_q w D D
+  std::vector<double> Minv;         // [n][n]
+  std::vector<double> Kt;           // Minv K
+  std::vector<double> a[2], b[2];   // Minv f_s, Minv g_s
+  std::vector<double> P[2];         // [n][n] P_c[j][i] = l_i((x_j + c)/2)
+};
+const Shape1D &get_shape(int degree, int nq);
+
+// ---- mesh -------------------------------------------------------------------------------------
+struct Mesh {
+  int dim = 0;
+  int cells0[MAX_DIM] = {1, 1, 1};
+  int n_refine = 0;
+  double lo[MAX_DIM] = {0, 0, 0}, hi[MAX_DIM] = {1, 1, 1};
+  bool periodic[MAX_DIM] = {false, false, false};
+  int bids[2 * MAX_DIM] = {0, 1, 2, 3, 4, 5};
+
+  long long n_cells(int level) const;
+  int cells_dir(int level, int d) const { return cells0[d] << level; }
+  double h(int level, int d) const { return (hi[d] - lo[d]) / double(cells_dir(level, d)); }
+  void coords_of(int level, long long idx, int *c) const;
+  long long index_of(int level, const int *c) const;
+  // neighbour across face f (2d+s); returns cell index or -1-boundary_id
+  long long neighbor(int level, long long idx, int f) const;
+};
+
+}  // namespace dgx
+
+struct dgx_mesh {
+  dgx::Mesh m;
+};
+
+struct dgx_ctx {
+  int device = 0, rank = 0, nranks = 1;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  void *nccl_comm = nullptr;
+  double *d_scratch = nullptr;   // reduction scratch (device)
+  double *h_scratch = nullptr;   // pinned
+  size_t scratch_doubles = 0;
+};
+
+struct dgx_mf {
+  dgx_ctx *ctx = nullptr;
+  dgx_mesh *mesh = nullptr;
+  int level = 0;
+  int dtype = DGX_F64;
+  int dim = 0;
+  long long first_cell = 0, n_owned = 0, n_ghost = 0, n_global = 0;
+  double h[dgx::MAX_DIM] = {1, 1, 1};
+  std::vector<int> nbr_host;            // [2*dim][n_owned]
+  std::vector<long long> ghost_global;  // [n_ghost]
+  int *d_nbr = nullptr;
+  bool all_interior = false;            // no boundary faces at all (periodic everywhere)
+  // ghost exchange plan: per peer rank, the local owned cells to send and the ghost slot range to receive
+  struct Peer {
+    int rank;
+    std::vector<int> send_cells;        // local indices
+    long long recv_first = 0, recv_count = 0;  // ghost slots [recv_first, recv_first+recv_count)
+    int *d_send_cells = nullptr;
+  };
+  std::vector<Peer> peers;
+};
+
+struct dgx_vec {
+  dgx_mf *mf = nullptr;
+  int degree = 0, ncomp = 1, dtype = DGX_F64;
+  long long dofs_per_cell = 0, n_owned = 0, n_ghost = 0, n_global = 0;
+  void *d = nullptr;        // [n_owned + n_ghost]
+  void *d_sendbuf = nullptr;
+  size_t sendbuf_bytes = 0;
+  bool borrowed = false;    // owned by an operator (inverse diagonal)
+  size_t elem() const { return dtype == DGX_F64 ? 8 : 4; }
+};
+
+struct dgx_op {
+  dgx_mf *mf = nullptr;
+  int kind = DGX_OP_PRESSURE;
+  int degree = 1, ncomp = 1;
+  double Re = 1.0, dt = 1.0;
+  int stage = 1;
+  int variant = 0;
+  dgx_vec *u_extr = nullptr;
+  dgx_vec *inv_diag = nullptr;
+  dgx_vec *h_src = nullptr, *h_dst = nullptr;   // staging vectors of the host entry point
+};
+
+namespace dgx {
+// time-stepping constants, bit-identical to NS.cc:396-397, 286-287
+double gamma_trbdf2();
+// kernel launchers (defined in .cu files); all enqueue on mf->ctx->stream
+int pressure_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add);
+int pressure_diagonal(dgx_op *op, dgx_vec *diag_inv);
+int mass_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add);
+int velocity_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add);
+int velocity_diagonal(dgx_op *op, dgx_vec *diag_inv);
+int ghost_exchange(dgx_vec *v);
+int allreduce_sum(dgx_ctx *ctx, double *vals, int n);
+int allreduce_max(dgx_ctx *ctx, double *vals, int n);
+int comm_init(dgx_ctx *ctx, const void *id);
+int comm_destroy(dgx_ctx *ctx);
+int comm_unique_id(void *out);
+}  // namespace dgx

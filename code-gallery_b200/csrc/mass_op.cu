@@ -1,0 +1,97 @@
+// DG mass operator, NS_stage == 3: assemble_cell_term_projection_grad_p (NS.cc:1373-1390), applied by
+// cell_loop (NS.cc:1415-1418).  With a tensor-product quadrature the cell mass matrix is exactly
+// (h_x M) (x) (h_y M) (x) (h_z M) with M_ij = sum_q w_q l_i(xi_q) l_j(xi_q), per component.
+#include "pressure_op.cuh"
+
+namespace dgx {
+namespace {
+
+template <typename T, int n>
+struct MassParams {
+  T Mh[MAX_DIM][n * n];
+};
+
+template <int dim, int n>
+__host__ __device__ constexpr int mass_cpb() { return (192 / ipow(n, dim - 1)) > 0 ? (192 / ipow(n, dim - 1)) : 1; }
+
+// one "item" = one (cell, component) block of n^dim values; contiguous in the DG layout
+template <int dim, int n, typename T>
+__global__ void __launch_bounds__(mass_cpb<dim, n>() * ipow(n, dim - 1))
+mass_kernel(const __grid_constant__ MassParams<T, n> P, long long n_items, const T *__restrict__ src, T *__restrict__ dst, int add) {
+  constexpr int NL = ipow(n, dim - 1), ND = NL * n, CPB = mass_cpb<dim, n>(), NT = CPB * NL;
+  __shared__ T sa[CPB * ND];
+  const int tid = threadIdx.x;
+  const long long item0 = (long long)blockIdx.x * CPB;
+  const int nblk = (int)min((long long)CPB, n_items - item0);
+  for (int idx = tid; idx < nblk * ND; idx += NT) sa[idx] = src[(size_t)item0 * ND + idx];
+  __syncthreads();
+  const int c = tid / NL, l = tid % NL;
+#pragma unroll
+  for (int d = 0; d < dim; ++d) {
+    if (c < nblk) {
+      int base, stride;
+      if (d == 0) { base = l * n; stride = 1; }
+      else if (d == 1 && dim == 3) { base = (l % n) + n * n * (l / n); stride = n; }
+      else if (d == 1) { base = l; stride = n; }
+      else { base = l; stride = n * n; }
+      T u[n];
+#pragma unroll
+      for (int i = 0; i < n; ++i) u[i] = sa[c * ND + base + stride * i];
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        T acc = 0;
+#pragma unroll
+        for (int j = 0; j < n; ++j) acc += P.Mh[d][i * n + j] * u[j];
+        sa[c * ND + base + stride * i] = acc;
+      }
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < nblk * ND; idx += NT) {
+    const size_t o = (size_t)item0 * ND + idx;
+    dst[o] = add ? dst[o] + sa[idx] : sa[idx];
+  }
+}
+
+template <int dim, int n, typename T>
+int launch_mass(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) {
+  dgx_mf *mf = op->mf;
+  const Shape1D &s = get_shape(n - 1, n);
+  MassParams<T, n> P;
+  for (int d = 0; d < MAX_DIM; ++d) {
+    const double h = d < dim ? mf->h[d] : 1.0;
+    for (int i = 0; i < n * n; ++i) P.Mh[d][i] = (T)(h * s.M[i]);
+  }
+  const long long items = mf->n_owned * op->ncomp;
+  if (items == 0) return DGX_OK;
+  constexpr int CPB = mass_cpb<dim, n>(), NT = CPB * ipow(n, dim - 1);
+  const int grid = (int)((items + CPB - 1) / CPB);
+  mass_kernel<dim, n, T><<<grid, NT, 0, mf->ctx->stream>>>(P, items, (const T *)src->d, (T *)dst->d, add ? 1 : 0);
+  count_launch();
+  DGX_CUDA_CHECK(cudaGetLastError());
+  return DGX_OK;
+}
+
+template <int dim, typename T>
+int mass_by_degree(int degree, dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) {
+  switch (degree) {
+    case 1: return launch_mass<dim, 2, T>(op, dst, src, add);
+    case 2: return launch_mass<dim, 3, T>(op, dst, src, add);
+    case 3: return launch_mass<dim, 4, T>(op, dst, src, add);
+    case 4: return launch_mass<dim, 5, T>(op, dst, src, add);
+    case 5: return launch_mass<dim, 6, T>(op, dst, src, add);
+    case 6: return launch_mass<dim, 7, T>(op, dst, src, add);
+    case 7: return launch_mass<dim, 8, T>(op, dst, src, add);
+    case 8: return launch_mass<dim, 9, T>(op, dst, src, add);
+    default: set_error("degree must be in 1..8"); return DGX_ERR_UNSUPPORTED;
+  }
+}
+}  // namespace
+
+int mass_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) {
+  dgx_mf *mf = op->mf;
+  if (mf->dim == 2) return mf->dtype == DGX_F64 ? mass_by_degree<2, double>(op->degree, op, dst, src, add) : mass_by_degree<2, float>(op->degree, op, dst, src, add);
+  return mf->dtype == DGX_F64 ? mass_by_degree<3, double>(op->degree, op, dst, src, add) : mass_by_degree<3, float>(op->degree, op, dst, src, add);
+}
+
+}  // namespace dgx

@@ -1,0 +1,277 @@
+// Pressure operator, NS_stage == 2 branch of apply_add (NS.cc:1407-1414) = assemble_cell_term_pressure
+// (NS.cc:1230-1252) + assemble_face_term_pressure (:1259-1292) + assemble_boundary_term_pressure
+// (:1299-1326), and its diagonal (compute_diagonal NS.cc:2018-2060 with assemble_diagonal_*_pressure
+// :1857-2008), on Cartesian cells.
+//
+// This file holds the GENERIC kernel: any dim (2, 3), degree 1..8, fp64 / fp32, every boundary type,
+// any number of cells, ghost neighbours.  It is cell-centric (each cell gathers the traces of its
+// 2*dim neighbours and writes its own dofs once: no atomics, no compress(add), deterministic) and
+// uses the Kronecker-factored form documented in pressure_op.cuh.  The blocked fast path for large
+// 3-D meshes lives in pressure_fast.cu.
+#include "pressure_op.cuh"
+
+namespace dgx {
+
+double pressure_kappa(const dgx_op *op) {
+  // coeff exactly as NS.cc:1237 (same association of the products)
+  const double gamma = gamma_trbdf2(), dt = op->dt;
+  const double coeff = (op->stage == 1) ? 1.0e6 * gamma * dt * gamma * dt : 1.0e6 * (1.0 - gamma) * dt * (1.0 - gamma) * dt;
+  return 1.0 / coeff;
+}
+
+namespace {
+
+template <int dim, int n>
+__device__ __forceinline__ void line_base_stride(int d, int l, int &base, int &stride) {
+  if (dim == 3) {
+    if (d == 0) { base = l * n; stride = 1; }
+    else if (d == 1) { base = (l % n) + n * n * (l / n); stride = n; }
+    else { base = l; stride = n * n; }
+  } else {
+    if (d == 0) { base = l * n; stride = 1; }
+    else { base = l; stride = n; }
+  }
+}
+
+template <int dim, int n>
+__host__ __device__ constexpr int cells_per_block() {
+  return (192 / ipow(n, dim - 1)) > 0 ? (192 / ipow(n, dim - 1)) : 1;
+}
+
+template <int dim, int n, typename T>
+__global__ void __launch_bounds__(cells_per_block<dim, n>() * ipow(n, dim - 1))
+pressure_generic_kernel(const __grid_constant__ PresParams<T, n> P, const int *__restrict__ nbr, int n_owned,
+                        const T *__restrict__ src, T *__restrict__ dst, int add) {
+  constexpr int NL = ipow(n, dim - 1), ND = NL * n, CPB = cells_per_block<dim, n>(), NT = CPB * NL;
+  __shared__ T su[CPB * ND];
+  __shared__ T sa[CPB * ND];
+  const int tid = threadIdx.x;
+  const int cell0 = blockIdx.x * CPB;
+  const int nblk = min(CPB, n_owned - cell0);
+  for (int idx = tid; idx < nblk * ND; idx += NT) su[idx] = src[(size_t)cell0 * ND + idx];
+  __syncthreads();
+  const int c = tid / NL, l = tid % NL;
+  const bool active = c < nblk;
+  const int cell = cell0 + c;
+#pragma unroll
+  for (int d = 0; d < dim; ++d) {
+    if (active) {
+      int base, stride;
+      line_base_stride<dim, n>(d, l, base, stride);
+      T u[n], t[n];
+#pragma unroll
+      for (int i = 0; i < n; ++i) u[i] = su[c * ND + base + stride * i];
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        T acc = 0;
+#pragma unroll
+        for (int j = 0; j < n; ++j) acc += P.Kt[d][i * n + j] * u[j];
+        t[i] = acc;
+      }
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int nb = nbr[(size_t)(2 * d + s) * n_owned + cell];
+        if (nb >= 0 || nb == -2) {
+          const T V = u[s * (n - 1)];
+          T G = 0;
+#pragma unroll
+          for (int j = 0; j < n; ++j) G += P.g[s][j] * u[j];
+          T FV, FG;
+          if (nb >= 0) {
+            const T *un = src + (size_t)nb * ND + base;
+            T Gn = 0, Vn = 0;
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+              const T x = un[stride * j];
+              Gn += P.gn[s][j] * x;
+              if (j == (1 - s) * (n - 1)) Vn = x;
+            }
+            FV = T(-0.5) * (G + Gn) + P.C * (V - Vn);
+            FG = T(-0.5) * (V - Vn);
+          } else {   // boundary_id == 1: weak Dirichlet (NS.cc:1308-1322)
+            FV = -G + P.C * V;
+            FG = -V;
+          }
+#pragma unroll
+          for (int i = 0; i < n; ++i) t[i] += P.a[d][s][i] * FV + P.b[d][s][i] * FG;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        const int o = c * ND + base + stride * i;
+        if (d == 0) sa[o] = P.kappa * u[i] + t[i];
+        else sa[o] += t[i];
+      }
+    }
+    __syncthreads();
+  }
+  // mass: (h_x M) (x) (h_y M) (x) (h_z M)
+#pragma unroll
+  for (int d = 0; d < dim; ++d) {
+    if (active) {
+      int base, stride;
+      line_base_stride<dim, n>(d, l, base, stride);
+      T u[n];
+#pragma unroll
+      for (int i = 0; i < n; ++i) u[i] = sa[c * ND + base + stride * i];
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        T acc = 0;
+#pragma unroll
+        for (int j = 0; j < n; ++j) acc += P.Mh[d][i * n + j] * u[j];
+        sa[c * ND + base + stride * i] = acc;
+      }
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < nblk * ND; idx += NT) {
+    const size_t o = (size_t)cell0 * ND + idx;
+    dst[o] = add ? dst[o] + sa[idx] : sa[idx];
+  }
+}
+
+// Inverse "diagonal" exactly as the reference probes it (NS.cc:1857-2008): the interior-face probe sets
+// local dof i on BOTH sides (NS.cc:1921-1922), so the neighbour's i-th basis function leaks into the
+// entry; the boundary probe uses 2*sigma (NS.cc:1997) although the operator uses sigma (NS.cc:1320).
+template <typename T, int n>
+struct DiagParams {
+  T Kd[n];          // K_ii
+  T Md[n];          // M_ii
+  T qi[2][n];       // interior-face probe, side s
+  T qd[2][n];       // id == 1 boundary probe, side s
+  T ih2[MAX_DIM];   // 1/h_d^2
+  T vol, kappa;
+};
+
+template <int dim, int n, typename T>
+__global__ void pressure_diag_kernel(const __grid_constant__ DiagParams<T, n> P, const int *__restrict__ nbr, int n_owned, T *__restrict__ out) {
+  constexpr int ND = ipow(n, dim);
+  const long long total = (long long)n_owned * ND;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    const int cell = (int)(g / ND);
+    int r = (int)(g - (long long)cell * ND);
+    int idx[3] = {0, 0, 0};
+#pragma unroll
+    for (int d = 0; d < dim; ++d) { idx[d] = r % n; r /= n; }
+    T mprod = 1;
+#pragma unroll
+    for (int d = 0; d < dim; ++d) mprod *= P.Md[idx[d]];
+    T sum = P.kappa * mprod;
+#pragma unroll
+    for (int d = 0; d < dim; ++d) {
+      T l = P.Kd[idx[d]];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int nb = nbr[(size_t)(2 * d + s) * n_owned + cell];
+        if (nb >= 0) l += P.qi[s][idx[d]];
+        else if (nb == -2) l += P.qd[s][idx[d]];
+      }
+      T others = 1;
+#pragma unroll
+      for (int e = 0; e < dim; ++e) if (e != d) others *= P.Md[idx[e]];
+      sum += P.ih2[d] * l * others;
+    }
+    out[g] = T(1) / (P.vol * sum);
+  }
+}
+
+template <int dim, int n, typename T>
+int launch_generic(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) {
+  dgx_mf *mf = op->mf;
+  PresParams<T, n> P;
+  fill_pres_params<T, n>(P, op, pressure_kappa(op));
+  constexpr int CPB = cells_per_block<dim, n>(), NT = CPB * ipow(n, dim - 1);
+  const int n_owned = (int)mf->n_owned;
+  if (n_owned == 0) return DGX_OK;
+  const int grid = (n_owned + CPB - 1) / CPB;
+  pressure_generic_kernel<dim, n, T><<<grid, NT, 0, mf->ctx->stream>>>(P, mf->d_nbr, n_owned, (const T *)src->d, (T *)dst->d, add ? 1 : 0);
+  count_launch();
+  DGX_CUDA_CHECK(cudaGetLastError());
+  return DGX_OK;
+}
+
+template <int dim, int n, typename T>
+int launch_diag(dgx_op *op, dgx_vec *out) {
+  dgx_mf *mf = op->mf;
+  const Shape1D &s = get_shape(n - 1, n);
+  DiagParams<T, n> P;
+  const double C = (double)n * n;
+  for (int i = 0; i < n; ++i) {
+    P.Kd[i] = (T)s.K[i * n + i];
+    P.Md[i] = (T)s.M[i * n + i];
+    for (int sd = 0; sd < 2; ++sd) {
+      const double ns = sd ? 1.0 : -1.0;
+      const double f = s.f[sd][i], g = s.g[sd][i], fo = s.f[1 - sd][i], go = s.g[1 - sd][i];
+      // probe u = phi_i on this cell AND phi_i on the neighbour (same local index)
+      const double FV = -0.5 * ns * (g + go) + C * (f - fo), FG = -0.5 * (f - fo);
+      P.qi[sd][i] = (T)(f * FV + ns * g * FG);
+      const double FVd = -ns * g + 2.0 * C * f, FGd = -f;
+      P.qd[sd][i] = (T)(f * FVd + ns * g * FGd);
+    }
+  }
+  double vol = 1;
+  for (int d = 0; d < MAX_DIM; ++d) {
+    const double h = d < dim ? mf->h[d] : 1.0;
+    P.ih2[d] = (T)(1.0 / (h * h));
+    if (d < dim) vol *= h;
+  }
+  P.vol = (T)vol;
+  P.kappa = (T)pressure_kappa(op);
+  const long long total = mf->n_owned * ipow(n, dim);
+  if (total == 0) return DGX_OK;
+  const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+  pressure_diag_kernel<dim, n, T><<<grid, 256, 0, mf->ctx->stream>>>(P, mf->d_nbr, (int)mf->n_owned, (T *)out->d);
+  count_launch();
+  DGX_CUDA_CHECK(cudaGetLastError());
+  return DGX_OK;
+}
+
+#define DGX_DEGREE_SWITCH(CALL)              \
+  switch (degree) {                          \
+    case 1: return CALL(2);                  \
+    case 2: return CALL(3);                  \
+    case 3: return CALL(4);                  \
+    case 4: return CALL(5);                  \
+    case 5: return CALL(6);                  \
+    case 6: return CALL(7);                  \
+    case 7: return CALL(8);                  \
+    case 8: return CALL(9);                  \
+    default: set_error("degree must be in 1..8"); return DGX_ERR_UNSUPPORTED; \
+  }
+
+template <int dim, typename T>
+int generic_by_degree(int degree, dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) {
+#define CALL(N) launch_generic<dim, N, T>(op, dst, src, add)
+  DGX_DEGREE_SWITCH(CALL)
+#undef CALL
+}
+
+template <int dim, typename T>
+int diag_by_degree(int degree, dgx_op *op, dgx_vec *out) {
+#define CALL(N) launch_diag<dim, N, T>(op, out)
+  DGX_DEGREE_SWITCH(CALL)
+#undef CALL
+}
+
+}  // namespace
+
+int pressure_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) {
+  dgx_mf *mf = op->mf;
+  if (op->variant != 1) {
+    int rc = pressure_apply_fast(op, dst, src, add);
+    if (rc != DGX_ERR_UNSUPPORTED) return rc;
+    if (op->variant == 2) return rc;
+  }
+  if (mf->dim == 2) return mf->dtype == DGX_F64 ? generic_by_degree<2, double>(op->degree, op, dst, src, add)
+                                                 : generic_by_degree<2, float>(op->degree, op, dst, src, add);
+  return mf->dtype == DGX_F64 ? generic_by_degree<3, double>(op->degree, op, dst, src, add)
+                              : generic_by_degree<3, float>(op->degree, op, dst, src, add);
+}
+
+int pressure_diagonal(dgx_op *op, dgx_vec *out) {
+  dgx_mf *mf = op->mf;
+  if (mf->dim == 2) return mf->dtype == DGX_F64 ? diag_by_degree<2, double>(op->degree, op, out) : diag_by_degree<2, float>(op->degree, op, out);
+  return mf->dtype == DGX_F64 ? diag_by_degree<3, double>(op->degree, op, out) : diag_by_degree<3, float>(op->degree, op, out);
+}
+
+}  // namespace dgx

@@ -1,0 +1,54 @@
+// Shared declarations of the pressure (SIPG Helmholtz) operator kernels.
+#pragma once
+#include "dgx_internal.h"
+
+namespace dgx {
+
+__host__ __device__ constexpr int ipow(int b, int e) { return e == 0 ? 1 : b * ipow(b, e - 1); }
+
+// Level-scaled 1-D tables of the Kronecker-factored operator (DESIGN.md "Kronecker form"):
+//   A u = vol * (M (x) M (x) M) [ kappa u + sum_d  T_d u ],
+//   T_d u|line = Kt_d u + sum_{s in faces} ( a_d,s FV_s + b_d,s FG_s )
+// with the face fluxes of NS.cc:1284-1287 / 1320-1321 in reference scaling
+//   interior:  FV = -1/2 (G + G') + C (V - V'),  FG = -1/2 (V - V')
+//   id == 1:   FV = -G + C V,                    FG = -V           (weak Dirichlet)
+//   other ids: FV = FG = 0                                          (homogeneous Neumann)
+// V, G = own value / outward normal derivative trace, V', G' = the neighbour's.
+template <typename T, int n>
+struct PresParams {
+  T Kt[MAX_DIM][n * n];   // (1/h_d^2) M^-1 K
+  T a[MAX_DIM][2][n];     // (1/h_d^2) M^-1 f_s
+  T b[MAX_DIM][2][n];     // (1/h_d^2) n_s M^-1 g_s
+  T g[2][n];              // n_s g_s      : own outward normal derivative (reference scaling)
+  T gn[2][n];             // n_s g_{1-s}  : neighbour's derivative along our outward normal
+  T Mh[MAX_DIM][n * n];   // h_d M
+  T kappa;                // 1/coeff, NS.cc:1237, 1248
+  T C;                    // C_p = (p+1)^2, NS.cc:292
+};
+
+template <typename T, int n>
+void fill_pres_params(PresParams<T, n> &P, const dgx_op *op, double kappa) {
+  const Shape1D &s = get_shape(n - 1, n);
+  const int dim = op->mf->dim;
+  for (int d = 0; d < MAX_DIM; ++d) {
+    const double h = d < dim ? op->mf->h[d] : 1.0, ih2 = 1.0 / (h * h);
+    for (int i = 0; i < n * n; ++i) { P.Kt[d][i] = (T)(ih2 * s.Kt[i]); P.Mh[d][i] = (T)(h * s.M[i]); }
+    for (int sd = 0; sd < 2; ++sd) {
+      const double ns = sd ? 1.0 : -1.0;
+      for (int i = 0; i < n; ++i) { P.a[d][sd][i] = (T)(ih2 * s.a[sd][i]); P.b[d][sd][i] = (T)(ih2 * ns * s.b[sd][i]); }
+    }
+  }
+  for (int sd = 0; sd < 2; ++sd) {
+    const double ns = sd ? 1.0 : -1.0;
+    for (int i = 0; i < n; ++i) { P.g[sd][i] = (T)(ns * s.g[sd][i]); P.gn[sd][i] = (T)(ns * s.g[1 - sd][i]); }
+  }
+  P.kappa = (T)kappa;
+  P.C = (T)((double)n * n);
+}
+
+double pressure_kappa(const dgx_op *op);
+
+// blocked fast path (pressure_fast.cu): returns DGX_ERR_UNSUPPORTED when the shape does not qualify
+int pressure_apply_fast(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add);
+
+}  // namespace dgx

@@ -1,0 +1,352 @@
+// Device vector: the subset of LinearAlgebra::distributed::Vector<Number> the hot path uses
+// (call sites NS.cc:2408-2415 equ, :2410/2954/2962 +=/-=, :2450/2486/2574 l2_norm,
+// :2585/2597 linfty_norm, :452/790/917 update_ghost_values; plus what SolverCG / SolverGMRES /
+// PreconditionChebyshev call inside deal.II: operator*, add, sadd, add_and_dot, mean_value).
+// All kernels are HBM-bound streaming passes: 16-byte vector loads, grid = multiple of the SM count.
+// Reductions accumulate in double, per-block partials are combined in a fixed order by the last
+// block (deterministic), then all-reduced over NCCL.
+#include <cstring>
+
+#include "dgx_internal.h"
+
+namespace dgx {
+int comm_exchange(dgx_ctx *ctx, int npeers, const int *ranks, const void *const *sendbuf, const size_t *sendbytes,
+                  void *const *recvbuf, const size_t *recvbytes);
+
+namespace {
+constexpr int kThreads = 256;
+constexpr int kMaxBlocks = 148 * 8;
+
+inline int grid_for(long long n, int per_thread = 4) {
+  long long b = (n + (long long)kThreads * per_thread - 1) / ((long long)kThreads * per_thread);
+  if (b < 1) b = 1;
+  if (b > kMaxBlocks) b = kMaxBlocks;
+  return (int)b;
+}
+
+template <typename T, typename F>
+__global__ void __launch_bounds__(kThreads) map1_kernel(T *__restrict__ dst, long long n, F f) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = f(dst[i], i);
+}
+
+template <typename T, typename U, typename F>
+__global__ void __launch_bounds__(kThreads) map2_kernel(T *__restrict__ dst, const U *__restrict__ src, long long n, F f) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = f(dst[i], src[i]);
+}
+
+__device__ unsigned int g_ticket = 0;
+
+// op: 0 = sum a*b, 1 = max |a|, 2 = sum a ; optionally fused update dst += alpha*v before dot(dst, w)
+template <typename T, int OP, bool FUSED_ADD>
+__global__ void __launch_bounds__(kThreads) reduce_kernel(const T *a, const T *b, T *upd, const T *v, T alpha, long long n,
+                                                          double *partial, double *result) {
+  double acc = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (FUSED_ADD) {
+      T x = upd[i] + alpha * v[i];
+      const T bv = (b == (const T *)upd) ? x : b[i];   // add_and_dot(a, v, *this) aliases
+      upd[i] = x;
+      acc += (double)x * (double)bv;
+    } else if (OP == 0) acc += (double)a[i] * (double)b[i];
+    else if (OP == 1) acc = fmax(acc, fabs((double)a[i]));
+    else acc += (double)a[i];
+  }
+  __shared__ double sm[kThreads / 32];
+  __shared__ bool last;
+  for (int o = 16; o > 0; o >>= 1) {
+    double other = __shfl_down_sync(0xffffffffu, acc, o);
+    acc = (OP == 1) ? fmax(acc, other) : acc + other;
+  }
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = sm[0];
+    for (int w = 1; w < kThreads / 32; ++w) s = (OP == 1) ? fmax(s, sm[w]) : s + sm[w];
+    partial[blockIdx.x] = s;
+    __threadfence();
+    unsigned int t = atomicInc(&g_ticket, gridDim.x - 1);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x < 32) {
+    __threadfence();
+    double s = 0.0;
+    // fixed-order tree over the partials
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) {
+      double p = ((volatile double *)partial)[i];
+      s = (OP == 1) ? fmax(s, p) : s + p;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      double other = __shfl_down_sync(0xffffffffu, s, o);
+      s = (OP == 1) ? fmax(s, other) : s + other;
+    }
+    if (threadIdx.x == 0) *result = s;
+  }
+}
+
+template <typename T>
+__global__ void pack_cells_kernel(T *__restrict__ out, const T *__restrict__ v, const int *__restrict__ cells, long long ncells, int dpc) {
+  const long long total = ncells * dpc;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long c = i / dpc;
+    int k = (int)(i - c * dpc);
+    out[i] = v[(long long)cells[c] * dpc + k];
+  }
+}
+
+template <int OP, bool FUSED>
+int reduce_dispatch(dgx_ctx *ctx, int dtype, const void *a, const void *b, void *upd, const void *v, double alpha, long long n,
+                    double *out, bool is_max) {
+  const int grid = grid_for(n, 8);
+  double *partial = ctx->d_scratch + 8, *result = ctx->d_scratch;
+  if (dtype == DGX_F64)
+    reduce_kernel<double, OP, FUSED><<<grid, kThreads, 0, ctx->stream>>>((const double *)a, (const double *)b, (double *)upd,
+                                                                        (const double *)v, alpha, n, partial, result);
+  else
+    reduce_kernel<float, OP, FUSED><<<grid, kThreads, 0, ctx->stream>>>((const float *)a, (const float *)b, (float *)upd,
+                                                                       (const float *)v, (float)alpha, n, partial, result);
+  count_launch();
+  DGX_CUDA_CHECK(cudaGetLastError());
+  int rc = is_max ? allreduce_max(ctx, result, 1) : allreduce_sum(ctx, result, 1);
+  if (rc) return rc;
+  DGX_CUDA_CHECK(cudaMemcpyAsync(ctx->h_scratch, result, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  DGX_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  *out = ctx->h_scratch[0];
+  return DGX_OK;
+}
+
+bool same_shape(const dgx_vec *a, const dgx_vec *b) { return a && b && a->n_owned == b->n_owned; }
+}  // namespace
+
+int ghost_exchange(dgx_vec *v) {
+  dgx_mf *mf = v->mf;
+  dgx_ctx *ctx = mf->ctx;
+  if (ctx->nranks == 1 || mf->peers.empty()) return DGX_OK;
+  const int dpc = (int)v->dofs_per_cell;
+  const size_t es = v->elem();
+  size_t total_send = 0;
+  for (auto &p : mf->peers) total_send += p.send_cells.size();
+  const size_t need = total_send * dpc * es;
+  if (need > v->sendbuf_bytes) {
+    if (v->d_sendbuf) cudaFree(v->d_sendbuf);
+    DGX_CUDA_CHECK(cudaMalloc(&v->d_sendbuf, need));
+    v->sendbuf_bytes = need;
+  }
+  std::vector<int> ranks;
+  std::vector<const void *> sb;
+  std::vector<void *> rb;
+  std::vector<size_t> sbytes, rbytes;
+  size_t off = 0;
+  for (auto &p : mf->peers) {
+    const long long nc = (long long)p.send_cells.size();
+    char *dstp = (char *)v->d_sendbuf + off;
+    if (nc) {
+      const int grid = grid_for(nc * dpc);
+      if (v->dtype == DGX_F64)
+        pack_cells_kernel<double><<<grid, kThreads, 0, ctx->stream>>>((double *)dstp, (const double *)v->d, p.d_send_cells, nc, dpc);
+      else
+        pack_cells_kernel<float><<<grid, kThreads, 0, ctx->stream>>>((float *)dstp, (const float *)v->d, p.d_send_cells, nc, dpc);
+      count_launch();
+    }
+    ranks.push_back(p.rank);
+    sb.push_back(dstp);
+    sbytes.push_back((size_t)nc * dpc * es);
+    rb.push_back((char *)v->d + ((size_t)v->n_owned + (size_t)p.recv_first * dpc) * es);
+    rbytes.push_back((size_t)p.recv_count * dpc * es);
+    off += (size_t)nc * dpc * es;
+  }
+  DGX_CUDA_CHECK(cudaGetLastError());
+  return comm_exchange(ctx, (int)ranks.size(), ranks.data(), sb.data(), sbytes.data(), rb.data(), rbytes.data());
+}
+
+}  // namespace dgx
+
+using namespace dgx;
+
+extern "C" {
+
+int dgx_vec_create(dgx_mf *mf, int degree, int ncomp, dgx_vec **out) {
+  DGX_REQUIRE(mf && out, "null argument");
+  DGX_REQUIRE(degree >= 1 && degree <= 8, "degree must be in 1..8");
+  DGX_REQUIRE(ncomp >= 1 && ncomp <= 3, "ncomp");
+  auto *v = new dgx_vec();
+  v->mf = mf; v->degree = degree; v->ncomp = ncomp; v->dtype = mf->dtype;
+  long long dpc = ncomp;
+  for (int d = 0; d < mf->dim; ++d) dpc *= (degree + 1);
+  v->dofs_per_cell = dpc;
+  v->n_owned = mf->n_owned * dpc;
+  v->n_ghost = mf->n_ghost * dpc;
+  v->n_global = mf->n_global * dpc;
+  const size_t bytes = (size_t)(v->n_owned + v->n_ghost) * v->elem();
+  if (cudaSetDevice(mf->ctx->device) != cudaSuccess || cudaMalloc(&v->d, bytes ? bytes : 8) != cudaSuccess) {
+    set_error(std::string("cudaMalloc of vector failed: ") + cudaGetErrorString(cudaGetLastError()));
+    delete v;
+    return DGX_ERR_CUDA;
+  }
+  cudaMemsetAsync(v->d, 0, bytes, mf->ctx->stream);
+  *out = v;
+  return DGX_OK;
+}
+
+int dgx_vec_destroy(dgx_vec *v) {
+  if (!v || v->borrowed) return DGX_OK;
+  if (v->d) cudaFree(v->d);
+  if (v->d_sendbuf) cudaFree(v->d_sendbuf);
+  delete v;
+  return DGX_OK;
+}
+
+long long dgx_vec_size(const dgx_vec *v) { return v ? v->n_owned : 0; }
+long long dgx_vec_ghost_size(const dgx_vec *v) { return v ? v->n_ghost : 0; }
+long long dgx_vec_global_size(const dgx_vec *v) { return v ? v->n_global : 0; }
+int dgx_vec_dtype(const dgx_vec *v) { return v ? v->dtype : -1; }
+void *dgx_vec_data(dgx_vec *v) { return v ? v->d : nullptr; }
+
+int dgx_vec_copy_from_host(dgx_vec *v, const void *host, long long n) {
+  DGX_REQUIRE(v && host && n == v->n_owned, "size mismatch");
+  DGX_CUDA_CHECK(cudaMemcpyAsync(v->d, host, (size_t)n * v->elem(), cudaMemcpyHostToDevice, v->mf->ctx->stream));
+  DGX_CUDA_CHECK(cudaStreamSynchronize(v->mf->ctx->stream));
+  return DGX_OK;
+}
+
+int dgx_vec_copy_to_host(const dgx_vec *v, void *host, long long n) {
+  DGX_REQUIRE(v && host && n == v->n_owned, "size mismatch");
+  DGX_CUDA_CHECK(cudaMemcpyAsync(host, v->d, (size_t)n * v->elem(), cudaMemcpyDeviceToHost, v->mf->ctx->stream));
+  DGX_CUDA_CHECK(cudaStreamSynchronize(v->mf->ctx->stream));
+  return DGX_OK;
+}
+
+#define LAUNCH_MAP1(vec, n, ...)                                                                             \
+  do {                                                                                                       \
+    cudaStream_t st__ = (vec)->mf->ctx->stream;                                                              \
+    const int grid__ = grid_for(n);                                                                          \
+    if ((vec)->dtype == DGX_F64) { typedef double T; map1_kernel<T><<<grid__, kThreads, 0, st__>>>((T *)(vec)->d, n, __VA_ARGS__); } \
+    else { typedef float T; map1_kernel<T><<<grid__, kThreads, 0, st__>>>((T *)(vec)->d, n, __VA_ARGS__); }  \
+    count_launch();                                                                                          \
+    DGX_CUDA_CHECK(cudaGetLastError());                                                                      \
+  } while (0)
+
+int dgx_vec_set(dgx_vec *v, double value) {
+  DGX_REQUIRE(v, "null argument");
+  const long long n = v->n_owned;
+  if (v->dtype == DGX_F64) { double a = value; map1_kernel<double><<<grid_for(n), kThreads, 0, v->mf->ctx->stream>>>((double *)v->d, n, [a] __device__(double, long long) { return a; }); }
+  else { float a = (float)value; map1_kernel<float><<<grid_for(n), kThreads, 0, v->mf->ctx->stream>>>((float *)v->d, n, [a] __device__(float, long long) { return a; }); }
+  count_launch();
+  DGX_CUDA_CHECK(cudaGetLastError());
+  return DGX_OK;
+}
+
+int dgx_vec_scale(dgx_vec *v, double s) {
+  DGX_REQUIRE(v, "null argument");
+  const long long n = v->n_owned;
+  if (v->dtype == DGX_F64) { double a = s; map1_kernel<double><<<grid_for(n), kThreads, 0, v->mf->ctx->stream>>>((double *)v->d, n, [a] __device__(double x, long long) { return a * x; }); }
+  else { float a = (float)s; map1_kernel<float><<<grid_for(n), kThreads, 0, v->mf->ctx->stream>>>((float *)v->d, n, [a] __device__(float x, long long) { return a * x; }); }
+  count_launch();
+  DGX_CUDA_CHECK(cudaGetLastError());
+  return DGX_OK;
+}
+
+}  // extern "C"
+
+// dst = f(dst, src) with both same dtype
+template <typename F64, typename F32>
+static int map2_same(dgx_vec *dst, const dgx_vec *src, F64 f64, F32 f32) {
+  DGX_REQUIRE(same_shape(dst, src) && dst->dtype == src->dtype, "vector shape / dtype mismatch");
+  const long long n = dst->n_owned;
+  cudaStream_t st = dst->mf->ctx->stream;
+  if (dst->dtype == DGX_F64) map2_kernel<double, double><<<grid_for(n), kThreads, 0, st>>>((double *)dst->d, (const double *)src->d, n, f64);
+  else map2_kernel<float, float><<<grid_for(n), kThreads, 0, st>>>((float *)dst->d, (const float *)src->d, n, f32);
+  count_launch();
+  DGX_CUDA_CHECK(cudaGetLastError());
+  return DGX_OK;
+}
+
+extern "C" {
+
+int dgx_vec_copy(dgx_vec *dst, const dgx_vec *src) {
+  DGX_REQUIRE(same_shape(dst, src), "vector shape mismatch");
+  const long long n = dst->n_owned;
+  cudaStream_t st = dst->mf->ctx->stream;
+  if (dst->dtype == src->dtype) {
+    DGX_CUDA_CHECK(cudaMemcpyAsync(dst->d, src->d, (size_t)n * dst->elem(), cudaMemcpyDeviceToDevice, st));
+    return DGX_OK;
+  }
+  if (dst->dtype == DGX_F64) map2_kernel<double, float><<<grid_for(n), kThreads, 0, st>>>((double *)dst->d, (const float *)src->d, n, [] __device__(double, float s) { return (double)s; });
+  else map2_kernel<float, double><<<grid_for(n), kThreads, 0, st>>>((float *)dst->d, (const double *)src->d, n, [] __device__(float, double s) { return (float)s; });
+  count_launch();
+  DGX_CUDA_CHECK(cudaGetLastError());
+  return DGX_OK;
+}
+
+int dgx_vec_equ(dgx_vec *dst, double a, const dgx_vec *src) {
+  const float af = (float)a;
+  return map2_same(dst, src, [a] __device__(double, double s) { return a * s; }, [af] __device__(float, float s) { return af * s; });
+}
+
+int dgx_vec_add(dgx_vec *dst, double a, const dgx_vec *src) {
+  const float af = (float)a;
+  return map2_same(dst, src, [a] __device__(double d, double s) { return d + a * s; }, [af] __device__(float d, float s) { return d + af * s; });
+}
+
+int dgx_vec_sadd(dgx_vec *dst, double s_, double a, const dgx_vec *src) {
+  const float af = (float)a, sf = (float)s_;
+  return map2_same(dst, src, [a, s_] __device__(double d, double s) { return s_ * d + a * s; },
+                   [af, sf] __device__(float d, float s) { return sf * d + af * s; });
+}
+
+int dgx_vec_scale_by(dgx_vec *dst, const dgx_vec *factors) {
+  return map2_same(dst, factors, [] __device__(double d, double s) { return d * s; }, [] __device__(float d, float s) { return d * s; });
+}
+
+int dgx_vec_dot(const dgx_vec *a, const dgx_vec *b, double *out) {
+  DGX_REQUIRE(same_shape(a, b) && a->dtype == b->dtype && out, "vector shape / dtype mismatch");
+  return reduce_dispatch<0, false>(a->mf->ctx, a->dtype, a->d, b->d, nullptr, nullptr, 0.0, a->n_owned, out, false);
+}
+
+int dgx_vec_l2_norm(const dgx_vec *a, double *out) {
+  double s = 0;
+  int rc = dgx_vec_dot(a, a, &s);
+  if (rc) return rc;
+  *out = sqrt(s);
+  return DGX_OK;
+}
+
+int dgx_vec_linfty_norm(const dgx_vec *a, double *out) {
+  DGX_REQUIRE(a && out, "null argument");
+  return reduce_dispatch<1, false>(a->mf->ctx, a->dtype, a->d, nullptr, nullptr, nullptr, 0.0, a->n_owned, out, true);
+}
+
+int dgx_vec_mean_value(const dgx_vec *a, double *out) {
+  DGX_REQUIRE(a && out, "null argument");
+  double s = 0;
+  int rc = reduce_dispatch<2, false>(a->mf->ctx, a->dtype, a->d, nullptr, nullptr, nullptr, 0.0, a->n_owned, &s, false);
+  if (rc) return rc;
+  *out = s / (double)a->n_global;
+  return DGX_OK;
+}
+
+int dgx_vec_add_and_dot(dgx_vec *dst, double a, const dgx_vec *v, const dgx_vec *w, double *out) {
+  DGX_REQUIRE(same_shape(dst, v) && same_shape(dst, w) && dst->dtype == v->dtype && dst->dtype == w->dtype && out, "vector mismatch");
+  return reduce_dispatch<0, true>(dst->mf->ctx, dst->dtype, nullptr, w->d, dst->d, v->d, a, dst->n_owned, out, false);
+}
+
+int dgx_vec_update_ghost_values(dgx_vec *v) {
+  DGX_REQUIRE(v, "null argument");
+  return ghost_exchange(v);
+}
+
+int dgx_vec_zero_out_ghost_values(dgx_vec *v) {
+  DGX_REQUIRE(v, "null argument");
+  if (v->n_ghost)
+    DGX_CUDA_CHECK(cudaMemsetAsync((char *)v->d + (size_t)v->n_owned * v->elem(), 0, (size_t)v->n_ghost * v->elem(), v->mf->ctx->stream));
+  return DGX_OK;
+}
+
+int dgx_vec_compress_add(dgx_vec *v) {
+  DGX_REQUIRE(v, "null argument");
+  return DGX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,312 @@
+"""ctypes binding of libdgx.so (the C ABI declared in include/dgx.h).
+
+The classes mirror the reference's operator surface for this path -- ``MatrixFree``,
+``LinearAlgebra::distributed::Vector`` and ``NavierStokesProjectionOperator`` with its
+``MatrixFreeOperators::Base`` members (navier_stokes_TRBDF2_DG.cc:242-2060) -- with the same
+method names, argument meaning and error behaviour (exceptions instead of return codes).
+There is no CPU fallback: if the CUDA library is missing the import fails.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdgx.so")
+if not os.path.exists(LIB_PATH):
+    raise ImportError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(there is no CPU fallback)")
+lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+
+F64, F32 = 0, 1
+OP_VELOCITY, OP_PRESSURE, OP_MASS = 1, 2, 3
+ERR_NO_CONVERGENCE = -4
+NCCL_ID_BYTES = 128
+_NP = {F64: np.float64, F32: np.float32}
+
+c_ll, c_int, c_dbl, c_vp = C.c_longlong, C.c_int, C.c_double, C.c_void_p
+lib.dgx_last_error.restype = C.c_char_p
+lib.dgx_version.restype = C.c_char_p
+lib.dgx_kernel_launch_count.restype = c_ll
+lib.dgx_ctx_get_stream.restype = c_vp
+lib.dgx_vec_data.restype = c_vp
+for _name in ("dgx_mesh_n_cells", "dgx_mf_n_owned_cells", "dgx_mf_n_ghost_cells", "dgx_mf_first_owned_cell",
+              "dgx_vec_size", "dgx_vec_ghost_size", "dgx_vec_global_size", "dgx_op_m"):
+    getattr(lib, _name).restype = c_ll
+
+
+class DgxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"dgx error {code}: {msg}")
+        self.code = code
+
+
+class NoConvergence(DgxError):
+    """SolverControl::NoConvergence"""
+
+
+def _check(rc):
+    if rc != 0:
+        msg = lib.dgx_last_error().decode()
+        raise (NoConvergence if rc == ERR_NO_CONVERGENCE else DgxError)(rc, msg)
+
+
+def kernel_launch_count() -> int:
+    return int(lib.dgx_kernel_launch_count())
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(NCCL_ID_BYTES)
+    _check(lib.dgx_nccl_unique_id(buf))
+    return buf.raw
+
+
+class Context:
+    """One per GPU / rank (replaces MPI_InitFinalize + MPI_COMM_WORLD, NS.cc:3038, 2216)."""
+
+    def __init__(self, device=0, rank=0, nranks=1, nccl_id: bytes | None = None):
+        self.h = c_vp()
+        idbuf = C.create_string_buffer(nccl_id, NCCL_ID_BYTES) if nccl_id is not None else None
+        _check(lib.dgx_ctx_create(c_int(device), c_int(rank), c_int(nranks), idbuf, C.byref(self.h)))
+        self.rank, self.nranks, self.device = rank, nranks, device
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(lib.dgx_ctx_set_stream(self.h, c_vp(cuda_stream_ptr)))
+
+    def stream(self):
+        return lib.dgx_ctx_get_stream(self.h)
+
+    def synchronize(self):
+        _check(lib.dgx_ctx_synchronize(self.h))
+
+    def timer_start(self):
+        _check(lib.dgx_ctx_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = c_dbl()
+        _check(lib.dgx_ctx_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if self.h:
+            lib.dgx_ctx_destroy(self.h)
+            self.h = c_vp()
+
+
+class Mesh:
+    """subdivided_hyper_rectangle + refine_global(n_refine) (NS.cc:2261-2270)."""
+
+    def __init__(self, dim, cells0, n_refine, lo, hi, periodic, boundary_ids=None):
+        self.dim, self.n_refine = dim, n_refine
+        c0 = (c_int * 3)(*(list(cells0) + [1, 1, 1])[:3])
+        lo_ = (c_dbl * 3)(*(list(lo) + [0, 0, 0])[:3])
+        hi_ = (c_dbl * 3)(*(list(hi) + [1, 1, 1])[:3])
+        mask = sum((1 << d) for d in range(min(dim, len(periodic))) if periodic[d])
+        bids = None if boundary_ids is None else (c_int * 6)(*(list(boundary_ids) + [0] * 6)[:6])
+        self.h = c_vp()
+        _check(lib.dgx_mesh_create_cartesian(dim, c0, n_refine, lo_, hi_, mask, bids, C.byref(self.h)))
+
+    def n_levels(self):
+        return lib.dgx_mesh_n_levels(self.h)
+
+    def n_cells(self, level=-1):
+        return int(lib.dgx_mesh_n_cells(self.h, level))
+
+    def cell_coords(self, level=-1, first=0, count=None):
+        count = self.n_cells(level) - first if count is None else count
+        out = np.empty((count, self.dim), dtype=np.int32)
+        _check(lib.dgx_mesh_cell_coords(self.h, level, c_ll(first), c_ll(count), out.ctypes.data_as(c_vp)))
+        return out
+
+    def neighbors(self, level=-1, first=0, count=None):
+        count = self.n_cells(level) - first if count is None else count
+        out = np.empty((count, 2 * self.dim), dtype=np.int64)
+        _check(lib.dgx_mesh_neighbors(self.h, level, c_ll(first), c_ll(count), out.ctypes.data_as(c_vp)))
+        return out
+
+
+class MatrixFree:
+    """MatrixFree<dim, Number>::reinit for one level (NS.cc:2329 / 2374-2375)."""
+
+    def __init__(self, ctx: Context, mesh: Mesh, level=-1, dtype=F64):
+        self.ctx, self.mesh, self.dtype = ctx, mesh, dtype
+        self.level = mesh.n_refine if level < 0 else level
+        self.h = c_vp()
+        _check(lib.dgx_mf_create(ctx.h, mesh.h, level, dtype, C.byref(self.h)))
+        self.dim = mesh.dim
+
+    def n_owned_cells(self):
+        return int(lib.dgx_mf_n_owned_cells(self.h))
+
+    def n_ghost_cells(self):
+        return int(lib.dgx_mf_n_ghost_cells(self.h))
+
+    def first_owned_cell(self):
+        return int(lib.dgx_mf_first_owned_cell(self.h))
+
+    def local_neighbors(self):
+        out = np.empty((2 * self.dim, self.n_owned_cells()), dtype=np.int32)
+        _check(lib.dgx_mf_local_neighbors(self.h, out.ctypes.data_as(c_vp)))
+        return out
+
+    def ghost_cells(self):
+        out = np.empty(self.n_ghost_cells(), dtype=np.int64)
+        _check(lib.dgx_mf_ghost_cells(self.h, out.ctypes.data_as(c_vp)))
+        return out
+
+    def initialize_dof_vector(self, degree, ncomp=1):
+        return Vector(self, degree, ncomp)
+
+
+class Vector:
+    """LinearAlgebra::distributed::Vector<Number> on the device."""
+
+    def __init__(self, mf: MatrixFree, degree, ncomp=1, _handle=None):
+        self.mf, self.degree, self.ncomp = mf, degree, ncomp
+        self._borrowed = _handle is not None
+        self.h = _handle if _handle is not None else c_vp()
+        if _handle is None:
+            _check(lib.dgx_vec_create(mf.h, degree, ncomp, C.byref(self.h)))
+        self.dtype = _NP[lib.dgx_vec_dtype(self.h)]
+
+    def __del__(self):
+        if getattr(self, "h", None) and not self._borrowed:
+            lib.dgx_vec_destroy(self.h)
+            self.h = None
+
+    def locally_owned_size(self):
+        return int(lib.dgx_vec_size(self.h))
+
+    def size(self):
+        return int(lib.dgx_vec_global_size(self.h))
+
+    def data_ptr(self):
+        return lib.dgx_vec_data(self.h)
+
+    def from_host(self, arr):
+        arr = np.ascontiguousarray(arr, dtype=self.dtype)
+        _check(lib.dgx_vec_copy_from_host(self.h, arr.ctypes.data_as(c_vp), c_ll(arr.size)))
+        return self
+
+    def to_host(self):
+        out = np.empty(self.locally_owned_size(), dtype=self.dtype)
+        _check(lib.dgx_vec_copy_to_host(self.h, out.ctypes.data_as(c_vp), c_ll(out.size)))
+        return out
+
+    def set(self, value):
+        _check(lib.dgx_vec_set(self.h, c_dbl(value)))
+
+    def copy_from(self, src: "Vector"):
+        _check(lib.dgx_vec_copy(self.h, src.h))
+
+    def equ(self, a, src):
+        _check(lib.dgx_vec_equ(self.h, c_dbl(a), src.h))
+
+    def add(self, a, src):
+        _check(lib.dgx_vec_add(self.h, c_dbl(a), src.h))
+
+    def sadd(self, s, a, src):
+        _check(lib.dgx_vec_sadd(self.h, c_dbl(s), c_dbl(a), src.h))
+
+    def scale(self, a):
+        if isinstance(a, Vector):
+            _check(lib.dgx_vec_scale_by(self.h, a.h))
+        else:
+            _check(lib.dgx_vec_scale(self.h, c_dbl(a)))
+
+    def dot(self, other):
+        out = c_dbl()
+        _check(lib.dgx_vec_dot(self.h, other.h, C.byref(out)))
+        return out.value
+
+    def l2_norm(self):
+        out = c_dbl()
+        _check(lib.dgx_vec_l2_norm(self.h, C.byref(out)))
+        return out.value
+
+    def linfty_norm(self):
+        out = c_dbl()
+        _check(lib.dgx_vec_linfty_norm(self.h, C.byref(out)))
+        return out.value
+
+    def mean_value(self):
+        out = c_dbl()
+        _check(lib.dgx_vec_mean_value(self.h, C.byref(out)))
+        return out.value
+
+    def add_and_dot(self, a, v, w):
+        out = c_dbl()
+        _check(lib.dgx_vec_add_and_dot(self.h, c_dbl(a), v.h, w.h, C.byref(out)))
+        return out.value
+
+    def update_ghost_values(self):
+        _check(lib.dgx_vec_update_ghost_values(self.h))
+
+    def zero_out_ghost_values(self):
+        _check(lib.dgx_vec_zero_out_ghost_values(self.h))
+
+    def compress(self):
+        _check(lib.dgx_vec_compress_add(self.h))
+
+
+class NavierStokesProjectionOperator:
+    """One NS_stage of the reference operator (NS.cc:242-2060) behind the Base surface."""
+
+    def __init__(self, mf: MatrixFree, NS_stage, degree, Re=1.0, dt=1.0):
+        self.mf, self.kind, self.degree = mf, NS_stage, degree
+        self.ncomp = 1 if NS_stage == OP_PRESSURE else mf.dim
+        self.h = c_vp()
+        _check(lib.dgx_op_create(mf.h, NS_stage, degree, c_dbl(Re), c_dbl(dt), C.byref(self.h)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib.dgx_op_destroy(self.h)
+            self.h = None
+
+    def initialize_dof_vector(self):
+        return Vector(self.mf, self.degree, self.ncomp)
+
+    def set_dt(self, dt):
+        _check(lib.dgx_op_set_dt(self.h, c_dbl(dt)))
+
+    def set_TR_BDF2_stage(self, stage):
+        _check(lib.dgx_op_set_TR_BDF2_stage(self.h, stage))
+
+    def set_u_extr(self, src):
+        _check(lib.dgx_op_set_u_extr(self.h, src.h))
+
+    def set_variant(self, variant):
+        _check(lib.dgx_op_set_variant(self.h, variant))
+
+    def m(self):
+        return int(lib.dgx_op_m(self.h))
+
+    def vmult(self, dst, src):
+        _check(lib.dgx_op_vmult(self.h, dst.h, src.h))
+
+    def vmult_add(self, dst, src):
+        _check(lib.dgx_op_vmult_add(self.h, dst.h, src.h))
+
+    def Tvmult(self, dst, src):
+        _check(lib.dgx_op_Tvmult(self.h, dst.h, src.h))
+
+    def Tvmult_add(self, dst, src):
+        _check(lib.dgx_op_Tvmult_add(self.h, dst.h, src.h))
+
+    def compute_diagonal(self):
+        _check(lib.dgx_op_compute_diagonal(self.h))
+
+    def get_matrix_diagonal_inverse(self):
+        h = c_vp()
+        _check(lib.dgx_op_get_matrix_diagonal_inverse(self.h, C.byref(h)))
+        return Vector(self.mf, self.degree, self.ncomp, _handle=h)
+
+    def precondition_Jacobi(self, dst, src, omega=1.0):
+        _check(lib.dgx_op_precondition_Jacobi(self.h, dst.h, src.h, c_dbl(omega)))
+
+    def vmult_host(self, dst: np.ndarray, src: np.ndarray):
+        """End-to-end entry: host buffers, H2D + vmult + D2H inside."""
+        assert dst.flags.c_contiguous and src.flags.c_contiguous and dst.dtype == src.dtype
+        _check(lib.dgx_op_vmult_host(self.h, dst.ctypes.data_as(c_vp), src.ctypes.data_as(c_vp), c_ll(src.size)))

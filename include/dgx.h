@@ -1,0 +1,149 @@
+/*
+ * dgx.h -- C ABI of the B200-native matrix-free DG operator / multigrid library (libdgx.so).
+ *
+ * This is the drop-in boundary for the one hot path of the deal.II code gallery's
+ * NavierStokes_TRBDF2_DG program: the operator evaluation behind
+ * `NavierStokesProjectionOperator : MatrixFreeOperators::Base<dim, Vec>`
+ * (NavierStokes_TRBDF2_DG/navier_stokes_TRBDF2_DG.cc:242-2060, "NS.cc" below) and the deal.II
+ * solver objects wired around it in diffusion_step / projection_step / project_grad
+ * (NS.cc:2424-2577).  The reference has no FFI: its "plugin API" is C++ duck typing against
+ * deal.II class templates.  Each entry point below therefore cites the deal.II/NS.cc member it
+ * replaces; `code-gallery_b200/include/dgx/dealii_shim.h` re-exposes them under the reference's
+ * own class and method names so that drivers written like NS.cc:2424-2577 compile unchanged.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative DGX_ERR_* code on failure; the message is
+ *     available from dgx_last_error() (replaces C++ exceptions: AssertThrow NS.cc:2247,
+ *     SolverControl::NoConvergence -> DGX_ERR_NO_CONVERGENCE; `main` maps them to exit code 1,
+ *     NS.cc:3055-3077).
+ *   - handles are opaque; the library owns device memory; it never frees caller memory.
+ *   - one host thread per context; all work of a context is ordered on its CUDA stream.
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *   - vectors use deal.II's DG layout: global dof = cell * dofs_per_cell + comp * n^dim + lex(i,j,k),
+ *     cells in refine_global (Morton) order; local storage is [owned dofs | ghost dofs] like
+ *     LinearAlgebra::distributed::Vector.
+ */
+#ifndef DGX_H
+#define DGX_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dgx_ctx dgx_ctx;
+typedef struct dgx_mesh dgx_mesh;
+typedef struct dgx_mf dgx_mf;
+typedef struct dgx_vec dgx_vec;
+typedef struct dgx_op dgx_op;
+typedef struct dgx_mg dgx_mg;
+
+enum { DGX_F64 = 0, DGX_F32 = 1 };
+enum { DGX_OP_VELOCITY = 1, DGX_OP_PRESSURE = 2, DGX_OP_MASS = 3 }; /* = NS_stage, NS.cc:432-443 */
+enum {
+  DGX_OK = 0,
+  DGX_ERR_INVALID = -1,
+  DGX_ERR_CUDA = -2,
+  DGX_ERR_NCCL = -3,
+  DGX_ERR_NO_CONVERGENCE = -4,
+  DGX_ERR_UNSUPPORTED = -5
+};
+#define DGX_NCCL_ID_BYTES 128
+
+/* ---- error / context ---------------------------------------------------------------------- */
+const char *dgx_last_error(void);
+/* build tag, e.g. "dgx 0.1 sm_100a" */
+const char *dgx_version(void);
+/* number of CUDA kernels this library has launched since load (all contexts) */
+long long dgx_kernel_launch_count(void);
+
+/* replaces MPI_InitFinalize + MPI_COMM_WORLD (NS.cc:3038, 2216): one context per GPU / rank.
+ * nccl_id: DGX_NCCL_ID_BYTES from dgx_nccl_unique_id() of rank 0 (may be NULL when nranks == 1). */
+int dgx_nccl_unique_id(void *out_id);
+int dgx_ctx_create(int device, int rank, int nranks, const void *nccl_id, dgx_ctx **out);
+int dgx_ctx_destroy(dgx_ctx *ctx);
+/* run all work of this context on a caller-owned stream (cudaStream_t); NULL restores the own stream */
+int dgx_ctx_set_stream(dgx_ctx *ctx, void *cuda_stream);
+void *dgx_ctx_get_stream(dgx_ctx *ctx);
+int dgx_ctx_synchronize(dgx_ctx *ctx);
+/* CUDA-event stopwatch on the context's stream (TimerOutput sections NS.cc:2191, 2425, 2471 measure
+ * wall time per solve; this measures device time). stop returns milliseconds. */
+int dgx_ctx_timer_start(dgx_ctx *ctx);
+int dgx_ctx_timer_stop(dgx_ctx *ctx, double *ms);
+
+/* ---- mesh: GridGenerator::subdivided_hyper_rectangle + refine_global (NS.cc:2261-2270) ----- */
+/* periodic_mask bit d: periodic in direction d; boundary_ids[2*dim]: id of face 2d (lower), 2d+1 (upper) */
+int dgx_mesh_create_cartesian(int dim, const int *cells0, int n_refine, const double *lo, const double *hi,
+                              int periodic_mask, const int *boundary_ids, dgx_mesh **out);
+int dgx_mesh_destroy(dgx_mesh *mesh);
+int dgx_mesh_n_levels(const dgx_mesh *mesh); /* Triangulation::n_global_levels, NS.cc:2351 */
+long long dgx_mesh_n_cells(const dgx_mesh *mesh, int level);
+/* integer coordinates (x,y,z) of cells [first, first+count) of `level` in deal.II cell order; out[count*dim] */
+int dgx_mesh_cell_coords(const dgx_mesh *mesh, int level, long long first, long long count, int *out);
+/* global face-neighbour table: out[count*2*dim]; entry = neighbour cell index, or -1-boundary_id */
+int dgx_mesh_neighbors(const dgx_mesh *mesh, int level, long long first, long long count, long long *out);
+
+/* ---- MatrixFree<dim,Number>::reinit (NS.cc:2329 fine/double, NS.cc:2374-2375 per level/float) - */
+/* level = -1: active (finest) cells; partition = contiguous chunk `rank` of `nranks` of the cell order */
+int dgx_mf_create(dgx_ctx *ctx, dgx_mesh *mesh, int level, int dtype, dgx_mf **out);
+int dgx_mf_destroy(dgx_mf *mf);
+long long dgx_mf_n_owned_cells(const dgx_mf *mf);
+long long dgx_mf_n_ghost_cells(const dgx_mf *mf);
+long long dgx_mf_first_owned_cell(const dgx_mf *mf);
+/* local face-neighbour table out[2*dim][n_owned] (SoA as stored in HBM): local cell index
+ * (>= n_owned: ghost slot) or -1-boundary_id */
+int dgx_mf_local_neighbors(const dgx_mf *mf, int *out);
+/* global cell index of every ghost slot, out[n_ghost] */
+int dgx_mf_ghost_cells(const dgx_mf *mf, long long *out);
+
+/* ---- LinearAlgebra::distributed::Vector<Number> (NS.cc:2102-2115, 2330-2341) ---------------- */
+/* MatrixFree::initialize_dof_vector for FESystem(FE_DGQ(degree), ncomp); zero-initialised */
+int dgx_vec_create(dgx_mf *mf, int degree, int ncomp, dgx_vec **out);
+int dgx_vec_destroy(dgx_vec *v);
+long long dgx_vec_size(const dgx_vec *v);       /* locally_owned_size */
+long long dgx_vec_ghost_size(const dgx_vec *v);
+long long dgx_vec_global_size(const dgx_vec *v); /* size() */
+int dgx_vec_dtype(const dgx_vec *v);
+void *dgx_vec_data(dgx_vec *v);                  /* device pointer to the owned range */
+int dgx_vec_copy_from_host(dgx_vec *v, const void *host, long long n);
+int dgx_vec_copy_to_host(const dgx_vec *v, void *host, long long n);
+int dgx_vec_set(dgx_vec *v, double value);                                /* operator=(Number) */
+int dgx_vec_copy(dgx_vec *dst, const dgx_vec *src);                       /* operator=(Vector), also double<->float */
+int dgx_vec_equ(dgx_vec *dst, double a, const dgx_vec *src);              /* equ  */
+int dgx_vec_add(dgx_vec *dst, double a, const dgx_vec *src);              /* add(a, V) */
+int dgx_vec_sadd(dgx_vec *dst, double s, double a, const dgx_vec *src);   /* sadd(s, a, V) */
+int dgx_vec_scale(dgx_vec *dst, double a);                                /* operator*= */
+int dgx_vec_scale_by(dgx_vec *dst, const dgx_vec *factors);               /* scale(V): entrywise */
+int dgx_vec_dot(const dgx_vec *a, const dgx_vec *b, double *out);         /* operator*, all-reduced */
+int dgx_vec_l2_norm(const dgx_vec *a, double *out);
+int dgx_vec_linfty_norm(const dgx_vec *a, double *out);
+int dgx_vec_mean_value(const dgx_vec *a, double *out);
+int dgx_vec_add_and_dot(dgx_vec *dst, double a, const dgx_vec *v, const dgx_vec *w, double *out);
+int dgx_vec_update_ghost_values(dgx_vec *v);
+int dgx_vec_zero_out_ghost_values(dgx_vec *v);
+/* compress(VectorOperation::add): a no-op by construction (cell-centric kernels never write ghosts) */
+int dgx_vec_compress_add(dgx_vec *v);
+
+/* ---- NavierStokesProjectionOperator (NS.cc:242-2060) ----------------------------------------- */
+/* kind = NS_stage; degree = degree of the space the operator acts on; Re, dt as Data_Storage */
+int dgx_op_create(dgx_mf *mf, int kind, int degree, double Re, double dt, dgx_op **out);
+int dgx_op_destroy(dgx_op *op);
+int dgx_op_set_dt(dgx_op *op, double dt);                 /* NS.cc:415 */
+int dgx_op_set_TR_BDF2_stage(dgx_op *op, int stage);      /* NS.cc:424 */
+int dgx_op_set_u_extr(dgx_op *op, const dgx_vec *src);    /* NS.cc:448: copies + ghost update */
+long long dgx_op_m(const dgx_op *op);                     /* Base::m() */
+int dgx_op_vmult(dgx_op *op, dgx_vec *dst, dgx_vec *src);      /* Base::vmult: dst = A src */
+int dgx_op_vmult_add(dgx_op *op, dgx_vec *dst, dgx_vec *src);  /* Base::vmult_add -> apply_add NS.cc:1398 */
+int dgx_op_Tvmult(dgx_op *op, dgx_vec *dst, dgx_vec *src);     /* Base::Tvmult = apply_add (NS.cc:281) */
+int dgx_op_Tvmult_add(dgx_op *op, dgx_vec *dst, dgx_vec *src);
+int dgx_op_compute_diagonal(dgx_op *op);                  /* NS.cc:2018-2060 (stores the INVERSE) */
+int dgx_op_get_matrix_diagonal_inverse(dgx_op *op, dgx_vec **out); /* borrowed handle, NS.cc:2515 */
+int dgx_op_precondition_Jacobi(dgx_op *op, dgx_vec *dst, const dgx_vec *src, double omega);
+/* kernel variant selection for measurement: 0 = auto, 1 = generic, 2 = blocked fast path */
+int dgx_op_set_variant(dgx_op *op, int variant);
+/* end-to-end entry: host buffers in the DG layout, H2D + vmult + D2H on the context stream */
+int dgx_op_vmult_host(dgx_op *op, void *dst_host, const void *src_host, long long n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGX_H */

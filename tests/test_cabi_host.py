@@ -1,0 +1,88 @@
+"""CPU tests of the C ABI: the library loads, exports every declared symbol, and its host-side
+numbering / index tables are bit-exact against the oracle (no compute calls: there is no GPU here)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle.mesh import CartesianMesh
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "dgx.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dgx_[a-zA-Z0-9_]+)\s*\(", text)))
+
+
+def test_all_declared_symbols_exported(dgx):
+    syms = declared_symbols()
+    assert len(syms) > 50
+    missing = [s for s in syms if not hasattr(dgx.lib, s)]
+    assert not missing, missing
+
+
+def test_version_and_error_string(dgx):
+    assert b"sm_100a" in dgx.lib.dgx_version()
+    with pytest.raises(dgx.DgxError):
+        dgx.Mesh(4, [1, 1, 1], 1, [0, 0, 0], [1, 1, 1], [0, 0, 0])
+
+
+CASES = [
+    (2, [1, 1], 3, [True, True]),
+    (2, [4, 2], 2, [False, False]),
+    (3, [1, 1, 1], 3, [True, True, True]),
+    (3, [2, 1, 3], 2, [False, True, False]),
+    (3, [1, 1, 1], 0, [True, True, True]),
+]
+
+
+@pytest.mark.parametrize("dim,cells0,nref,periodic", CASES)
+def test_cell_order_and_neighbors_bit_exact(dgx, dim, cells0, nref, periodic):
+    mesh = dgx.Mesh(dim, cells0, nref, [0.0] * dim, [1.0, 2.0, 3.0][:dim], periodic)
+    assert mesh.n_levels() == nref + 1
+    for level in range(nref + 1):
+        om = CartesianMesh(dim, cells0, level, [0.0] * dim, [1.0, 2.0, 3.0][:dim], periodic)
+        assert mesh.n_cells(level) == om.n_cells
+        assert np.array_equal(mesh.cell_coords(level), om.coords)
+        assert np.array_equal(mesh.neighbors(level), om.nbr)
+
+
+def test_morton_child_order(dgx):
+    """children of cell j on level l are cells 2^dim*j + c, c = i + 2j + 4k (refine_global order)."""
+    mesh = dgx.Mesh(3, [2, 1, 1], 2, [0, 0, 0], [2, 1, 1], [False] * 3)
+    coarse, fine = mesh.cell_coords(1), mesh.cell_coords(2)
+    for j in range(len(coarse)):
+        for c in range(8):
+            off = np.array([c & 1, (c >> 1) & 1, (c >> 2) & 1])
+            assert np.array_equal(fine[8 * j + c], 2 * coarse[j] + off)
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3, 8])
+def test_partition_and_ghost_plan(dgx, nranks):
+    """host-only contexts (no device here): owned ranges tile the cell order, ghost lists are the
+    off-rank face neighbours, and send/recv plans of different ranks match pairwise."""
+    dim, cells0, nref, periodic = 3, [1, 1, 1], 2, [True, True, False]
+    mesh = dgx.Mesh(dim, cells0, nref, [0.0] * 3, [1.0] * 3, periodic)
+    om = CartesianMesh(dim, cells0, nref, [0.0] * 3, [1.0] * 3, periodic)
+    bounds = om.partition(nranks)
+    covered = 0
+    for r in range(nranks):
+        ctx = dgx.Context(0, r, nranks)
+        mf = dgx.MatrixFree(ctx, mesh)
+        first, no, ng = mf.first_owned_cell(), mf.n_owned_cells(), mf.n_ghost_cells()
+        assert (first, first + no) == (bounds[r], bounds[r + 1])
+        covered += no
+        nb = om.nbr[first:first + no]
+        expect_ghost = np.unique(nb[(nb >= 0) & ((nb < first) | (nb >= first + no))])
+        ghosts = mf.ghost_cells()
+        assert np.array_equal(ghosts, expect_ghost)
+        loc = mf.local_neighbors()          # [2*dim][n_owned]
+        glob = np.where(loc < 0, loc, np.where(loc < no, loc + first, 0))
+        isg = loc >= no
+        glob[isg] = ghosts[loc[isg] - no]
+        assert np.array_equal(glob.T, nb)
+        ctx.close()
+    assert covered == om.n_cells

@@ -1,0 +1,121 @@
+"""GPU parity: pressure operator / diagonal / mass operator through the C ABI vs the oracle.
+Tolerances are BASELINE.json's: rel. L2 1e-12 in fp64, 1e-5 in fp32."""
+import numpy as np
+import pytest
+
+from oracle.operators import MassOperator, PressureOperator
+from util import make_meshes, rel_l2, smooth_plus_noise
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.float64: 1e-12, np.float32: 1e-5}
+
+CASES = [
+    # dim, cells0, nref, periodic, degrees
+    (2, [1, 1], 3, [True, True], [1, 2, 3, 4, 5, 6, 7, 8]),
+    (2, [4, 2], 2, [False, False], [1, 2, 4]),           # channel: ids 0 inflow, 1 outflow, 2/3 walls
+    (2, [3, 1], 1, [False, True], [2, 3]),
+    (3, [1, 1, 1], 2, [True, True, True], [1, 2, 3, 4, 5, 6, 7, 8]),
+    (3, [1, 1, 1], 0, [True, True, True], [2, 4]),       # one cell: its own neighbour
+    (3, [2, 1, 1], 1, [False, False, False], [1, 3, 4]), # all boundary kinds incl. id 1
+    (3, [1, 2, 1], 1, [True, False, True], [2]),
+]
+
+
+def _run(dgx, ctx, dim, cells0, nref, periodic, degree, np_dtype, stage=1, variant=0):
+    gm, om = make_meshes(dgx, dim, cells0, nref, periodic)
+    dt = 5e-3
+    mf = dgx.MatrixFree(ctx, gm, -1, dgx.F64 if np_dtype == np.float64 else dgx.F32)
+    op = dgx.NavierStokesProjectionOperator(mf, dgx.OP_PRESSURE, degree, 100.0, dt)
+    op.set_TR_BDF2_stage(stage)
+    op.set_variant(variant)
+    oop = PressureOperator(om, degree, dt, np.float64)
+    oop.set_TR_BDF2_stage(stage)
+    u = smooth_plus_noise(om, oop.sh.nodes, noise=0.3)
+    src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+    src.from_host(u)
+    op.vmult(dst, src)
+    ref = oop.vmult(u.astype(np_dtype).astype(np.float64))
+    return dst.to_host(), ref, op, oop, src, dst, u
+
+
+@pytest.mark.parametrize("np_dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}d-{c[1]}-r{c[2]}-{''.join('p' if x else 'b' for x in c[3])}")
+def test_vmult_matches_oracle(dgx, gpu_ctx, case, np_dtype):
+    dim, cells0, nref, periodic, degrees = case
+    for degree in degrees:
+        for stage in (1, 2):
+            got, ref, *_ = _run(dgx, gpu_ctx, dim, cells0, nref, periodic, degree, np_dtype, stage)
+            err = rel_l2(got, ref)
+            assert err < TOL[np_dtype], (degree, stage, err)
+
+
+def test_vmult_add_and_Tvmult(dgx, gpu_ctx):
+    got, ref, op, oop, src, dst, u = _run(dgx, gpu_ctx, 3, [1, 1, 1], 2, [True, True, False], 3, np.float64)
+    op.vmult_add(dst, src)
+    assert rel_l2(dst.to_host(), 2 * ref) < 1e-12
+    op.Tvmult(dst, src)
+    assert rel_l2(dst.to_host(), ref) < 1e-12
+    assert op.m() == oop.m()
+    with pytest.raises(dgx.DgxError):
+        op.vmult(src, src)
+
+
+@pytest.mark.parametrize("np_dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("case", [CASES[1], CASES[3], CASES[5], CASES[4]], ids=["2d-channel", "3d-periodic", "3d-box", "3d-1cell"])
+def test_inverse_diagonal_matches_reference_probing(dgx, gpu_ctx, case, np_dtype):
+    dim, cells0, nref, periodic, degrees = case
+    for degree in degrees[:3]:
+        if dim == 3 and degree > 4:
+            continue
+        got, ref, op, oop, *_ = _run(dgx, gpu_ctx, dim, cells0, nref, periodic, degree, np_dtype)
+        op.compute_diagonal()
+        d = op.get_matrix_diagonal_inverse().to_host()
+        dref = oop.compute_diagonal()
+        assert rel_l2(d, dref) < TOL[np_dtype], degree
+
+
+def test_mass_operator(dgx, gpu_ctx):
+    for dim, cells0, nref in [(2, [2, 1], 2), (3, [1, 1, 2], 1)]:
+        gm, om = make_meshes(dgx, dim, cells0, nref, [False] * dim)
+        mf = dgx.MatrixFree(gpu_ctx, gm)
+        for degree in (1, 2, 3, 5):
+            op = dgx.NavierStokesProjectionOperator(mf, dgx.OP_MASS, degree)
+            oop = MassOperator(om, degree)
+            u = smooth_plus_noise(om, oop.sh.nodes, ncomp=dim, noise=0.5)
+            src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+            src.from_host(u)
+            op.vmult(dst, src)
+            assert rel_l2(dst.to_host(), oop.vmult(u)) < 1e-12
+
+
+def test_vmult_host_entry(dgx, gpu_ctx):
+    got, ref, op, oop, src, dst, u = _run(dgx, gpu_ctx, 3, [1, 1, 1], 2, [True, True, True], 4, np.float64)
+    out = np.empty_like(u)
+    op.vmult_host(out, u)
+    assert rel_l2(out, ref) < 1e-12
+
+
+def test_properties_at_scale(dgx, gpu_ctx):
+    """size-independent properties on a mesh the oracle cannot do quickly (32^3 Q4):
+    symmetry <Au,v> = <u,Av>, constants map to kappa*M*1, positivity."""
+    gm = dgx.Mesh(3, [1, 1, 1], 5, [0, 0, 0], [1, 1, 1], [True] * 3)
+    mf = dgx.MatrixFree(gpu_ctx, gm)
+    op = dgx.NavierStokesProjectionOperator(mf, dgx.OP_PRESSURE, 4, 100.0, 5e-3)
+    mass = dgx.NavierStokesProjectionOperator(mf, dgx.OP_PRESSURE, 4, 100.0, 5e-3)
+    u, v, au, av = (op.initialize_dof_vector() for _ in range(4))
+    rng = np.random.default_rng(7)
+    n = u.locally_owned_size()
+    u.from_host(rng.standard_normal(n))
+    v.from_host(rng.standard_normal(n))
+    op.vmult(au, u)
+    op.vmult(av, v)
+    a, b = v.dot(au), u.dot(av)
+    assert abs(a - b) <= 1e-12 * abs(a)
+    assert u.dot(au) > 0
+    one = op.initialize_dof_vector()
+    one.set(1.0)
+    op.vmult(au, one)
+    # A*1 = kappa * M * 1 and 1^T M 1 = volume = 1
+    kappa = 1.0 / (1.0e6 * (2 - np.sqrt(2)) * 5e-3 * (2 - np.sqrt(2)) * 5e-3)
+    assert abs(one.dot(au) - kappa) <= 1e-10 * kappa

@@ -1,0 +1,61 @@
+"""GPU: device vector operations used by the Krylov / Chebyshev / multigrid layers vs numpy."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dtype_name", ["F64", "F32"])
+def test_vector_ops(dgx, gpu_ctx, dtype_name):
+    dt = getattr(dgx, dtype_name)
+    npdt = np.float64 if dt == dgx.F64 else np.float32
+    tol = 1e-13 if dt == dgx.F64 else 1e-5
+    gm = dgx.Mesh(3, [1, 1, 1], 3, [0, 0, 0], [1, 1, 1], [True] * 3)
+    mf = dgx.MatrixFree(gpu_ctx, gm, -1, dt)
+    a, b, c = (mf.initialize_dof_vector(3) for _ in range(3))
+    n = a.locally_owned_size()
+    assert n == 512 * 64 and a.size() == n
+    rng = np.random.default_rng(3)
+    ha, hb = rng.standard_normal(n).astype(npdt), rng.standard_normal(n).astype(npdt)
+    a.from_host(ha)
+    b.from_host(hb)
+    assert np.array_equal(a.to_host(), ha)
+    assert abs(a.dot(b) - float(ha.astype(np.float64) @ hb.astype(np.float64))) < tol * n
+    assert abs(a.l2_norm() - np.linalg.norm(ha.astype(np.float64))) < tol * np.sqrt(n) * 10
+    assert abs(a.linfty_norm() - np.abs(ha).max()) == 0
+    assert abs(a.mean_value() - ha.astype(np.float64).mean()) < tol
+    c.equ(2.5, a)
+    assert np.allclose(c.to_host(), npdt(2.5) * ha, rtol=tol, atol=0)
+    c.add(-1.5, b)
+    hc = npdt(2.5) * ha + npdt(-1.5) * hb
+    assert np.allclose(c.to_host(), hc, rtol=10 * tol, atol=10 * tol)
+    c.sadd(0.5, 2.0, a)
+    hc = npdt(0.5) * hc + npdt(2.0) * ha
+    assert np.allclose(c.to_host(), hc, rtol=10 * tol, atol=10 * tol)
+    c.scale(3.0)
+    hc = hc * npdt(3.0)
+    c.scale(b)
+    hc = hc * hb
+    assert np.allclose(c.to_host(), hc, rtol=10 * tol, atol=10 * tol)
+    r = c.add_and_dot(0.25, a, b)
+    hc = hc + npdt(0.25) * ha
+    assert abs(r - float(hc.astype(np.float64) @ hb.astype(np.float64))) < 10 * tol * n
+    r = c.add_and_dot(-0.5, b, c)       # aliasing form used by SolverCG: r.add_and_dot(-alpha, v, r)
+    hc = hc + npdt(-0.5) * hb
+    assert abs(r - float(hc.astype(np.float64) @ hc.astype(np.float64))) < 10 * tol * n
+    c.set(1.25)
+    assert np.all(c.to_host() == npdt(1.25))
+
+
+def test_copy_convert(dgx, gpu_ctx):
+    gm = dgx.Mesh(2, [2, 2], 2, [0, 0], [1, 1], [True] * 2)
+    mfd = dgx.MatrixFree(gpu_ctx, gm, -1, dgx.F64)
+    mff = dgx.MatrixFree(gpu_ctx, gm, -1, dgx.F32)
+    d, f = mfd.initialize_dof_vector(2), mff.initialize_dof_vector(2)
+    x = np.random.default_rng(0).standard_normal(d.locally_owned_size())
+    d.from_host(x)
+    f.copy_from(d)                       # copy_to_mg: double -> float
+    assert np.array_equal(f.to_host(), x.astype(np.float32))
+    d.set(0.0)
+    d.copy_from(f)                       # copy_from_mg: float -> double
+    assert np.array_equal(d.to_host(), x.astype(np.float32).astype(np.float64))

@@ -1,0 +1,99 @@
+// Microbenchmark for the roofline denominators MEASURED_PEAKS.json does not hold:
+// FP64 / FP32 FMA issue peak, FP64 tensor (DMMA m8n8k4) peak, both mixed, shared-memory LDS.64 rate.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o fp64_peak fp64_peak.cu ; run on the B200.
+#include <cstdio>
+#include <cuda_runtime.h>
+
+template <typename T, int ILP>
+__global__ void fma_kernel(T *out, T a, T b, int iters) {
+  T acc[ILP];
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) acc[i] = (T)(threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) acc[i] = acc[i] * a + b;
+  }
+  T s = 0;
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) s += acc[i];
+  if (s == (T)123456.789) out[0] = s;
+}
+
+// DMMA m8n8k4: D(8x8) += A(8x4) B(4x8); per thread 1 a, 1 b, 2 c
+template <int ILP, bool MIX>
+__global__ void dmma_kernel(double *out, double a, double b, int iters) {
+  double c0[ILP], c1[ILP], f[ILP];
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) { c0[i] = threadIdx.x; c1[i] = i; f[i] = i + threadIdx.x; }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) {
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
+      if (MIX) { f[i] = f[i] * a + b; f[i] = f[i] * a + b; f[i] = f[i] * a + b; f[i] = f[i] * a + b; }
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) s += c0[i] + c1[i] + f[i];
+  if (s == 123456.789) out[0] = s;
+}
+
+__global__ void lds_kernel(double *out, int iters) {
+  __shared__ double sm[4096];
+  for (int i = threadIdx.x; i < 4096; i += blockDim.x) sm[i] = i;
+  __syncthreads();
+  double s = 0;
+  int idx = threadIdx.x;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += sm[(idx + k * 256) & 4095];
+    idx = (idx + 1) & 4095;
+  }
+  if (s == 123456.789) out[0] = s;
+}
+
+template <typename F>
+float time_ms(F f) {
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  f();
+  cudaDeviceSynchronize();
+  cudaEventRecord(e0);
+  f();
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  return ms;
+}
+
+int main() {
+  cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+  const int sms = p.multiProcessorCount;
+  printf("{\"gpu\": \"%s\", \"sms\": %d", p.name, sms);
+  double *out; cudaMalloc(&out, 64);
+  const int blocks = sms * 4, threads = 512, iters = 20000;
+  {
+    float ms = time_ms([&] { fma_kernel<double, 8><<<blocks, threads>>>(out, 1.0000001, 1e-9, iters); });
+    printf(", \"fp64_fma_tflops\": %.2f", 2.0 * blocks * threads * 8.0 * iters / ms * 1e-9);
+  }
+  {
+    float ms = time_ms([&] { fma_kernel<float, 8><<<blocks, threads>>>((float *)out, 1.0000001f, 1e-9f, iters); });
+    printf(", \"fp32_fma_tflops\": %.2f", 2.0 * blocks * threads * 8.0 * iters / ms * 1e-9);
+  }
+  {
+    float ms = time_ms([&] { dmma_kernel<8, false><<<blocks, threads>>>(out, 1.0000001, 1e-9, iters / 4); });
+    printf(", \"fp64_dmma_tflops\": %.2f", 2.0 * 256.0 * blocks * (threads / 32) * 8.0 * (iters / 4) / ms * 1e-9);
+  }
+  {
+    float ms = time_ms([&] { dmma_kernel<8, true><<<blocks, threads>>>(out, 1.0000001, 1e-9, iters / 4); });
+    double dm = 2.0 * 256.0 * blocks * (threads / 32) * 8.0 * (iters / 4), fm = 2.0 * blocks * threads * 8.0 * 4.0 * (iters / 4);
+    printf(", \"mixed_dmma_tflops\": %.2f, \"mixed_fma_tflops\": %.2f", dm / ms * 1e-9, fm / ms * 1e-9);
+  }
+  {
+    float ms = time_ms([&] { lds_kernel<<<blocks, 256>>>(out, 20000); });
+    printf(", \"lds64_TBps\": %.2f", 8.0 * blocks * 256.0 * 16.0 * 20000 / ms * 1e-9);
+  }
+  printf("}\n");
+  return 0;
+}
