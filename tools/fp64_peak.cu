@@ -53,6 +53,17 @@ __global__ void lds_kernel(double *out, int iters) {
   if (s == 123456.789) out[0] = s;
 }
 
+// streaming read of `n` double2 elements, repeated `reps` times (L2-resident when the buffer is < 126 MB)
+__global__ void read_kernel(const double2 *__restrict__ in, size_t n, int reps, double *out) {
+  double s = 0;
+  for (int r = 0; r < reps; ++r)
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+      double2 v = __ldcg(in + ((i + (size_t)r * 977) % n));
+      s += v.x + v.y;
+    }
+  if (s == 123456.789) out[0] = s;
+}
+
 template <typename F>
 float time_ms(F f) {
   cudaEvent_t e0, e1;
@@ -93,6 +104,20 @@ int main() {
   {
     float ms = time_ms([&] { lds_kernel<<<blocks, 256>>>(out, 20000); });
     printf(", \"lds64_TBps\": %.2f", 8.0 * blocks * 256.0 * 16.0 * 20000 / ms * 1e-9);
+  }
+  {
+    const size_t bytes = 48ull << 20, n = bytes / 16;   // L2-resident
+    double2 *buf; cudaMalloc(&buf, bytes); cudaMemset(buf, 0, bytes);
+    float ms = time_ms([&] { read_kernel<<<sms * 8, 512>>>(buf, n, 20, out); });
+    printf(", \"l2_read_TBps\": %.2f", bytes * 20.0 / ms * 1e-9);
+    cudaFree(buf);
+  }
+  {
+    const size_t bytes = 4ull << 30, n = bytes / 16;    // DRAM
+    double2 *buf; cudaMalloc(&buf, bytes); cudaMemset(buf, 0, bytes);
+    float ms = time_ms([&] { read_kernel<<<sms * 8, 512>>>(buf, n, 1, out); });
+    printf(", \"dram_read_TBps\": %.2f", bytes * 1.0 / ms * 1e-9);
+    cudaFree(buf);
   }
   printf("}\n");
   return 0;
