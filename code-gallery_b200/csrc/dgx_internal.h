@@ -96,6 +96,9 @@ struct dgx_mf {
   std::vector<long long> ghost_global;  // [n_ghost]
   int *d_nbr = nullptr;
   bool all_interior = false;            // no boundary faces at all (periodic everywhere)
+  // owned cells == the box [box_lo, box_lo + box_ext) of cell coordinates (true for Morton-aligned partitions)
+  bool box_ok = false;
+  int box_lo[dgx::MAX_DIM] = {0, 0, 0}, box_ext[dgx::MAX_DIM] = {1, 1, 1};
   // ghost exchange plan: per peer rank, the local owned cells to send and the ghost slot range to receive
   struct Peer {
     int rank;

@@ -151,6 +151,18 @@ int dgx_mf_create(dgx_ctx *ctx, dgx_mesh *mesh, int level, int dtype, dgx_mf **o
       if (g < 0) all_interior = false;
     }
   mf->all_interior = all_interior;
+  // bounding box of the owned cells; the marching kernels need owned set == box
+  {
+    int lo[MAX_DIM] = {1 << 30, 1 << 30, 1 << 30}, hi[MAX_DIM] = {-1, -1, -1};
+    for (long long c = 0; c < no; ++c) {
+      int cc[MAX_DIM] = {0, 0, 0};
+      m.coords_of(level, mf->first_cell + c, cc);
+      for (int d = 0; d < m.dim; ++d) { lo[d] = std::min(lo[d], cc[d]); hi[d] = std::max(hi[d], cc[d]); }
+    }
+    long long vol = no > 0 ? 1 : 0;
+    for (int d = 0; d < m.dim; ++d) { mf->box_lo[d] = no > 0 ? lo[d] : 0; mf->box_ext[d] = no > 0 ? hi[d] - lo[d] + 1 : 0; vol *= mf->box_ext[d]; }
+    mf->box_ok = no > 0 && vol == no;
+  }
   // ghost set (sorted by global index => grouped by owner rank)
   std::vector<long long> ghosts;
   if (R > 1) {

@@ -119,3 +119,30 @@ def test_properties_at_scale(dgx, gpu_ctx):
     # A*1 = kappa * M * 1 and 1^T M 1 = volume = 1
     kappa = 1.0 / (1.0e6 * (2 - np.sqrt(2)) * 5e-3 * (2 - np.sqrt(2)) * 5e-3)
     assert abs(one.dot(au) - kappa) <= 1e-10 * kappa
+
+
+FAST_CASES = [
+    # cells0, nref  (fully periodic 3-D boxes: the marching kernel, variant 2 = fail if it does not apply)
+    ([1, 1, 1], 3),
+    ([2, 1, 1], 3),
+    ([1, 1, 2], 3),
+    ([1, 1, 1], 4),
+]
+
+
+@pytest.mark.parametrize("np_dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("degree", [3, 4])
+@pytest.mark.parametrize("case", FAST_CASES, ids=lambda c: f"{c[0]}-r{c[1]}")
+def test_marching_kernel_matches_oracle(dgx, gpu_ctx, case, degree, np_dtype):
+    cells0, nref = case
+    for stage in (1, 2):
+        got, ref, op, oop, src, dst, u = _run(dgx, gpu_ctx, 3, cells0, nref, [True] * 3, degree, np_dtype, stage, variant=2)
+        err = rel_l2(got, ref)
+        assert err < TOL[np_dtype], (degree, stage, err)
+    # vmult_add through the same kernel
+    op.vmult_add(dst, src)
+    assert rel_l2(dst.to_host(), 2 * ref) < TOL[np_dtype]
+    # and the generic kernel agrees (variant 1)
+    op.set_variant(1)
+    op.vmult(dst, src)
+    assert rel_l2(dst.to_host(), ref) < TOL[np_dtype]
