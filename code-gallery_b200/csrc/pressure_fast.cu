@@ -19,6 +19,9 @@
 //   H warps   read the x / y halo cells of the tile and reduce them to (V', G') traces.
 //
 // Hand-offs use named barriers (bar.arrive / bar.sync), stages are double buffered.
+#include <type_traits>
+#include <utility>
+
 #include "pressure_op.cuh"
 
 namespace dgx {
@@ -54,10 +57,11 @@ struct Roles {
   static constexpr int NH = 2;                        // halo warps
   static constexpr int NW = NXY + NZW + NH;
   static constexpr int NCOL = (n * n + NZW - 1) / NZW;  // column units (32 columns each) per Z warp
+  static constexpr int NSTAGE = 3;                    // stages of the u planes
 };
 
 // barrier ids (0 is __syncthreads)
-enum { B_FULL = 1, B_UFREE = 3, B_QREADY = 5, B_XY = 7 };
+enum { B_FULL = 1, B_QREADY = 3, B_XY = 5 };
 
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int count) {
@@ -67,6 +71,28 @@ __device__ __forceinline__ void bar_arrive(int id, int count) {
 template <typename T> __device__ __forceinline__ void keep(T &v);
 template <> __device__ __forceinline__ void keep<double>(double &v) { asm volatile("" : "+d"(v)::"memory"); }
 template <> __device__ __forceinline__ void keep<float>(float &v) { asm volatile("" : "+f"(v)::"memory"); }
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  const unsigned addr = smem_u32(bar);
+  unsigned ok = 0;
+  for (int spin = 0; !ok; ++spin) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (spin > (1 << 24)) __trap();   // never hang the device on a lost copy
+  }
+}
+// 1-D bulk async copy global -> shared, completion counted on an mbarrier (TMA engine, SASS UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 __device__ __forceinline__ unsigned part1by2(unsigned x) {
   x &= 0x3ffu;
@@ -84,22 +110,35 @@ __device__ __forceinline__ int cell_index(const FastGeom &G, int X, int Y, int Z
   const unsigned loc = part1by2(X & mask) | (part1by2(Y & mask) << 1) | (part1by2(Z & mask) << 2);
   return (int)((coarse << (3 * G.L)) + loc - G.first_cell);
 }
+// z-dependent part of the index (the tile lies inside one coarse cell in x and y)
+__device__ __forceinline__ long long plane_term(const FastGeom &G, int z) {
+  const int mask = (1 << G.L) - 1;
+  return ((long long)G.c0x * G.c0y * (z >> G.L) << (3 * G.L)) + ((long long)part1by2(z & mask) << 2);
+}
 
-template <int n, typename T>
+// Cells of a tile plane are kept in shared memory in their memory (Morton) order, so that a plane is 8 bulk
+// copies of 4 consecutive cells: slot bits (x0, y0, x1, y1, x2).  One lane of an XY warp per slot.
+__device__ __forceinline__ int slot_cx(int s) { return (s & 1) | ((s >> 1) & 2) | ((s >> 2) & 4); }
+__device__ __forceinline__ int slot_cy(int s) { return ((s >> 1) & 1) | ((s >> 2) & 2); }
+__device__ __forceinline__ int slot_of(int cx, int cy) { return (cx & 1) | ((cy & 1) << 1) | ((cx & 2) << 1) | ((cy & 2) << 2) | ((cx & 4) << 2); }
+
+template <int n, typename T, bool ADD>
 __global__ void __launch_bounds__(Roles<n>::NW * 32, 1)
 pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_constant__ FastGeom G,
-                      const int *__restrict__ nbr, const T *__restrict__ src, T *__restrict__ dst, int add) {
+                      const int *__restrict__ nbr, const T *__restrict__ src, T *__restrict__ dst) {
   using R = Roles<n>;
-  constexpr int NL = n * n, ND = NL * n;
-  constexpr int CNT_FULL = (R::NXY + R::NZW + R::NH) * 32, CNT_UFREE = (R::NXY + R::NZW) * 32,
+  constexpr int NL = n * n, ND = NL * n, NS = R::NSTAGE;
+  constexpr int CNT_FULL = (R::NXY + R::NZW + R::NH) * 32,
                 CNT_QREADY = (R::NXY + R::NZW + R::NH) * 32, CNT_XY = R::NXY * 32;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T *U = reinterpret_cast<T *>(smem_raw);          // [2][TC][ND]
-  T *W = U + 2 * TC * ND;                          // [2][TC][ND]
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T *U = reinterpret_cast<T *>(smem_raw);          // [NS][TC][ND]   u planes (bulk-copied)
+  T *W = U + NS * TC * ND;                         // [2][TC][ND]    z-partial sums, then the xy result
   T *TX = W + 2 * TC * ND;                         // [2 side][NL][TC]   own outward-normal-derivative traces, x faces
   T *TY = TX + 2 * NL * TC;                        // [2 side][NL][TC]
-  T *HX = TY + 2 * NL * TC;                        // [2 buf][2 side][TYC][NL][2]  (V', G') of the x halo
-  T *HY = HX + 2 * 2 * TYC * NL * 2;               // [2 buf][2 side][TXC][NL][2]
+  T *HXY = TY + 2 * NL * TC;                       // [2 buf]{[2 side][TYC][NL][2], [2 side][TXC][NL][2]}  (V', G') of the x / y halo
+  constexpr int HBUF = (2 * TYC + 2 * TXC) * NL * 2;
+  unsigned long long *ubar = reinterpret_cast<unsigned long long *>(HXY + 2 * HBUF);   // [NS]
+  int *ucnt = reinterpret_cast<int *>(ubar + NS);   // XY warps that have finished reading the current u plane
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // role assignment balanced over the 4 sub-partitions (warp % 4): XY warps carry twice the work
@@ -112,295 +151,368 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
     role = warp < R::NXY ? 0 : (warp < R::NXY + R::NZW ? 1 : 2);
     ridx = warp < R::NXY ? warp : (warp < R::NXY + R::NZW ? warp - R::NXY : warp - R::NXY - R::NZW);
   }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) mbar_init(&ubar[s], 1);
+    *ucnt = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
 
   const int job = blockIdx.x;
   const int tx = job % G.ntx, ty = (job / G.ntx) % G.nty, sz = job / (G.ntx * G.nty);
   const int x0 = G.lox + tx * TXC, y0 = G.loy + ty * TYC, z0 = G.loz + sz * G.NZ;
   const int NZ = G.NZ;
   const size_t no = (size_t)G.n_owned;
+  const long long pt0 = plane_term(G, z0);
+
+  // one thread streams plane p of the tile into its stage: 8 bulk copies of 4 consecutive cells (TMA engine)
+  auto issue_plane = [&](int p) {
+    unsigned long long *bar = &ubar[p % NS];
+    mbar_expect_tx(bar, (unsigned)(TC * ND * sizeof(T)));
+    const long long sh = plane_term(G, z0 + p) - pt0;
+    T *stage = U + (size_t)(p % NS) * TC * ND;
+#pragma unroll
+    for (int g = 0; g < TC / 4; ++g) {
+      const int ci = cell_index(G, x0 + slot_cx(4 * g), y0 + slot_cy(4 * g), z0);
+      bulk_g2s(stage + (size_t)4 * g * ND, src + (size_t)(ci + sh) * ND, (unsigned)(4 * ND * sizeof(T)), bar);
+    }
+  };
 
   if (role == 1) {
     // ------------------------------------------------------------------ Z warps (column threads)
     const int zw = ridx;
-    int ccell[R::NCOL], cij[R::NCOL], cxy[R::NCOL];
+    int coff[R::NCOL], cxy[R::NCOL];   // shared-memory offset of the column inside a stage; cell index at plane z0
     bool cval[R::NCOL];
+    int cij0 = 0;
 #pragma unroll
     for (int m = 0; m < R::NCOL; ++m) {
       const int unit = zw + R::NZW * m;
       cval[m] = unit < NL;
       const int id = (cval[m] ? unit : 0) * 32 + lane;
-      ccell[m] = id / NL;
-      cij[m] = id - ccell[m] * NL;
-      cxy[m] = cell_index(G, x0 + (ccell[m] & (TXC - 1)), y0 + ccell[m] / TXC, z0);   // index at plane z0
+      const int slot = id / NL, ij = id - slot * NL;
+      coff[m] = slot * ND + ij;
+      cxy[m] = cell_index(G, x0 + slot_cx(slot), y0 + slot_cy(slot), z0) * ND + ij;   // element offset at plane z0
+      (void)cij0;
     }
-    T r[R::NCOL][n], wz[R::NCOL][n], Gt[R::NCOL], Vt[R::NCOL];
-    // z-dependent part of the index relative to plane z0 (tile lies inside one coarse cell in x, y)
-    auto plane_shift = [&](int z) -> long long {
-      const int mask = (1 << G.L) - 1;
-      const long long c1 = ((long long)G.c0x * G.c0y * (z >> G.L) << (3 * G.L)) + ((long long)part1by2(z & mask) << 2);
-      const long long c0 = ((long long)G.c0x * G.c0y * (z0 >> G.L) << (3 * G.L)) + ((long long)part1by2(z0 & mask) << 2);
-      return c1 - c0;
-    };
-    auto load_plane = [&](int q) {   // q in -1 .. NZ : plane z0 + q (ghost planes through the neighbour table)
-#pragma unroll
-      for (int m = 0; m < R::NCOL; ++m) {
-        if (!cval[m]) continue;
-        long long ci;
-        if (q < 0) ci = nbr[4 * no + cxy[m]];
-        else if (q >= NZ) ci = nbr[5 * no + (cxy[m] + plane_shift(z0 + NZ - 1))];
-        else ci = cxy[m] + plane_shift(z0 + q);
-        const T *p = src + (size_t)ci * ND + cij[m];
-#pragma unroll
-        for (int k = 0; k < n; ++k) r[m][k] = __ldg(p + k * NL);
-      }
-    };
-    auto top_traces = [&]() {
-#pragma unroll
-      for (int m = 0; m < R::NCOL; ++m) {
-        T gsum = 0;
-#pragma unroll
-        for (int k = 0; k < n; ++k) gsum += P.g[1][k] * r[m][k];
-        Gt[m] = gsum; Vt[m] = r[m][n - 1];
-      }
-    };
-    auto apply_mz_store = [&](int p) {   // Z2: dst(plane p) = Mz q
+    T uc[R::NCOL][n], Gt[R::NCOL], Vt[R::NCOL];
+    auto apply_mz_store = [&](int p) {   // dst(plane p) = Mz q
       const T *Ws = W + (size_t)(p & 1) * TC * ND;
-      const long long sh = plane_shift(z0 + p);
+      const long long sh = (plane_term(G, z0 + p) - pt0) * ND;
 #pragma unroll
       for (int m = 0; m < R::NCOL; ++m) {
         if (!cval[m]) continue;
         T qv[n];
 #pragma unroll
-        for (int k = 0; k < n; ++k) qv[k] = Ws[ccell[m] * ND + cij[m] + k * NL];
-        T *o = dst + (size_t)(cxy[m] + sh) * ND + cij[m];
+        for (int k = 0; k < n; ++k) qv[k] = Ws[coff[m] + k * NL];
+        T *o = dst + ((long long)cxy[m] + sh);
 #pragma unroll
         for (int k = 0; k < n; ++k) {
-          T acc = 0;
+          T acc = ADD ? o[k * NL] : T(0);
 #pragma unroll
-          for (int kk = 0; kk < n; ++kk) acc += P.Mh[2][k * n + kk] * qv[kk];
-          o[k * NL] = add ? o[k * NL] + acc : acc;
+          for (int kk = 0; kk < n; ++kk) acc = fma(P.Mh[2][k * n + kk], qv[kk], acc);
+          o[k * NL] = acc;
         }
       }
     };
-
-    load_plane(-1);
-    top_traces();
-    load_plane(0);
-    for (int p = -1; p < NZ; ++p) {
-      const int q = p + 1;   // plane currently held in r
-      if (p >= 0) {
-        // finalise plane p with the bottom traces of plane q, publish the z-partial sum
-        T *Ws = W + (size_t)(p & 1) * TC * ND;
+    // one group of columns: finalise plane q (held in uc) with the bottom traces of the plane in stage Un
+    auto z_group = [&](auto m0c, auto m1c, const T *Un, T *Ws) {
+      constexpr int m0 = decltype(m0c)::value, m1 = decltype(m1c)::value, NG = m1 - m0;
+      T nw[NG][n], gb[NG], gt[NG];
+#pragma unroll
+      for (int g = 0; g < NG; ++g)
+#pragma unroll
+        for (int k = 0; k < n; ++k) nw[g][k] = cval[m0 + g] ? Un[coff[m0 + g] + k * NL] : T(0);
+#pragma unroll
+      for (int g = 0; g < NG; ++g) { gb[g] = 0; gt[g] = 0; }
+#pragma unroll
+      for (int k = 0; k < n; ++k)
+#pragma unroll
+        for (int g = 0; g < NG; ++g) { gb[g] = fma(P.g[0][k], nw[g][k], gb[g]); gt[g] = fma(P.g[1][k], uc[m0 + g][k], gt[g]); }
+#pragma unroll
+      for (int k = 0; k < n; ++k) {
+        T acc[NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) acc[g] = P.cG[2][0][k] * Gt[m0 + g];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) acc[g] = fma(P.cV[2][0][k], Vt[m0 + g], acc[g]);
+#pragma unroll
+        for (int g = 0; g < NG; ++g) acc[g] = fma(P.cG[2][1][k], gb[g], acc[g]);
+#pragma unroll
+        for (int g = 0; g < NG; ++g) acc[g] = fma(P.cV[2][1][k], nw[g][0], acc[g]);
+#pragma unroll
+        for (int kk = 0; kk < n; ++kk)
+#pragma unroll
+          for (int g = 0; g < NG; ++g) acc[g] = fma(P.Kt[2][k * n + kk], uc[m0 + g][kk], acc[g]);   // kappa sits on the diagonal
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+          if (cval[m0 + g]) Ws[coff[m0 + g] + k * NL] = acc[g];
+      }
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        Gt[m0 + g] = gt[g]; Vt[m0 + g] = uc[m0 + g][n - 1];
+#pragma unroll
+        for (int k = 0; k < n; ++k) uc[m0 + g][k] = nw[g][k];
+      }
+    };
+    // ghost plane below the segment: only its top traces are needed
+#pragma unroll
+    for (int m = 0; m < R::NCOL; ++m) {
+      Gt[m] = 0; Vt[m] = 0;
+      if (!cval[m]) continue;
+      const int cell = cxy[m] / ND;
+      const T *p = src + (size_t)nbr[4 * no + cell] * ND + (cxy[m] - cell * ND);
+      T gsum = 0, last = 0;
+#pragma unroll
+      for (int k = 0; k < n; ++k) { const T x = __ldg(p + k * NL); gsum = fma(P.g[1][k], x, gsum); last = x; }
+      Gt[m] = gsum; Vt[m] = last;
+    }
+    mbar_wait(&ubar[0], 0);
+#pragma unroll
+    for (int m = 0; m < R::NCOL; ++m)
+#pragma unroll
+      for (int k = 0; k < n; ++k) uc[m][k] = cval[m] ? U[coff[m] + k * NL] : T(0);
+    for (int q = 0; q < NZ; ++q) {
+      T *Un = U + (size_t)((q + 1) % NS) * TC * ND;
+      T *Ws = W + (size_t)(q & 1) * TC * ND;
+      if (q + 1 < NZ) {
+        mbar_wait(&ubar[(q + 1) % NS], (unsigned)(((q + 1) / NS) & 1));
+      } else {
+        // ghost plane above the segment: each thread copies its own columns into the (free) stage, then the
+        // common path reads them back
+        const long long shl = plane_term(G, z0 + NZ - 1) - pt0;
 #pragma unroll
         for (int m = 0; m < R::NCOL; ++m) {
           if (!cval[m]) continue;
-          T gb = 0;
+          const int cell = cxy[m] / ND;
+          const T *p = src + (size_t)nbr[5 * no + (cell + shl)] * ND + (cxy[m] - cell * ND);
 #pragma unroll
-          for (int k = 0; k < n; ++k) gb += P.g[0][k] * r[m][k];
-          const T vb = r[m][0];
-#pragma unroll
-          for (int k = 0; k < n; ++k) Ws[ccell[m] * ND + cij[m] + k * NL] = wz[m][k] + P.cG[2][1][k] * gb + P.cV[2][1][k] * vb;
+          for (int k = 0; k < n; ++k) Un[coff[m] + k * NL] = __ldg(p + k * NL);
         }
-        bar_arrive(B_FULL + (p & 1), CNT_FULL);
       }
-      if (q < NZ) {
-#pragma unroll
-        for (int m = 0; m < R::NCOL; ++m) {
-#pragma unroll
-          for (int k = 0; k < n; ++k) {
-            T acc = P.kappa * r[m][k] + P.cG[2][0][k] * Gt[m] + P.cV[2][0][k] * Vt[m];
-#pragma unroll
-            for (int kk = 0; kk < n; ++kk) acc += P.Kt[2][k * n + kk] * r[m][kk];
-            wz[m][k] = acc;
-          }
-        }
-        top_traces();
-        if (q >= 2) bar_sync(B_UFREE + (q & 1), CNT_UFREE);
-        T *Us = U + (size_t)(q & 1) * TC * ND;
-#pragma unroll
-        for (int m = 0; m < R::NCOL; ++m) {
-          if (!cval[m]) continue;
-#pragma unroll
-          for (int k = 0; k < n; ++k) Us[ccell[m] * ND + cij[m] + k * NL] = r[m][k];
-        }
-        load_plane(q + 1);
-      }
-      if (p >= 1) {
-        bar_sync(B_QREADY + ((p - 1) & 1), CNT_QREADY);
-        apply_mz_store(p - 1);
+      constexpr int MH = (R::NCOL + 1) / 2;
+      z_group(std::integral_constant<int, 0>{}, std::integral_constant<int, MH>{}, Un, Ws);
+      z_group(std::integral_constant<int, MH>{}, std::integral_constant<int, R::NCOL>{}, Un, Ws);
+      bar_arrive(B_FULL + (q & 1), CNT_FULL);
+      if (q >= 1) {
+        bar_sync(B_QREADY + ((q - 1) & 1), CNT_QREADY);
+        apply_mz_store(q - 1);
       }
     }
-    // drain: the UFREE arrivals of the last two planes, then the last result plane
-    if (NZ >= 2) bar_sync(B_UFREE + ((NZ - 2) & 1), CNT_UFREE);
-    bar_sync(B_UFREE + ((NZ - 1) & 1), CNT_UFREE);
     bar_sync(B_QREADY + ((NZ - 1) & 1), CNT_QREADY);
     apply_mz_store(NZ - 1);
   } else if (role == 0) {
     // ------------------------------------------------------------------ XY warps (layer threads)
-    const int k = ridx, c = lane, cx = c & (TXC - 1), cy = c / TXC;
+    // The n x n layer is streamed from shared memory row by row (y sweep) and column by column (x sweep) and
+    // both sweeps are accumulated as outer products into one static register tile: the loops stay rolled, so
+    // the instruction footprint of this role is a fraction of the unrolled form.
+    const int k = ridx, c = lane, cx = slot_cx(c), cy = slot_cy(c);
+    if (k == 0 && lane == 0)
+      for (int p = 0; p < NS && p < NZ; ++p) issue_plane(p);
+    // neighbour descriptors per (direction, side): where G' and V' of the facing cell live
+    //   inside the tile: G' in TX/TY (stride TC per face point), V' in the u stage (stride n or 1)
+    //   halo:            (V', G') pairs in the halo buffer (stride 2)
+    int g_off[2][2], v_off[2][2];
+    bool ins[2][2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      ins[0][s] = s ? (cx < TXC - 1) : (cx > 0);
+      ins[1][s] = s ? (cy < TYC - 1) : (cy > 0);
+      const int cnx = slot_of(s ? cx + 1 : cx - 1, cy), cny = slot_of(cx, s ? cy + 1 : cy - 1);
+      // x faces: face point = row j (of layer k)
+      g_off[0][s] = ins[0][s] ? (int)(TX - U) + ((1 - s) * NL + n * k) * TC + cnx : (int)(HXY - U) + ((s * TYC + cy) * NL + n * k) * 2 + 1;
+      v_off[0][s] = ins[0][s] ? cnx * ND + k * NL + (1 - s) * (n - 1) : (int)(HXY - U) + ((s * TYC + cy) * NL + n * k) * 2;
+      // y faces: face point = column i
+      g_off[1][s] = ins[1][s] ? (int)(TY - U) + ((1 - s) * NL + n * k) * TC + cny : (int)(HXY - U) + 2 * TYC * NL * 2 + ((s * TXC + cx) * NL + n * k) * 2 + 1;
+      v_off[1][s] = ins[1][s] ? cny * ND + k * NL + (1 - s) * (n - 1) * n : (int)(HXY - U) + 2 * TYC * NL * 2 + ((s * TXC + cx) * NL + n * k) * 2;
+    }
     for (int p = 0; p < NZ; ++p) {
       const int st = p & 1;
       bar_sync(B_FULL + st, CNT_FULL);
-      const T *Uc = U + (size_t)st * TC * ND;
+      mbar_wait(&ubar[p % NS], (unsigned)((p / NS) & 1));   // already complete: orders the async-proxy writes
+      const int ustage = (p % NS) * TC * ND;
       T *Wp = W + (size_t)st * TC * ND + c * ND + k * NL;
-      const T *Up = Uc + c * ND + k * NL;
-      T u[n][n], acc[n][n];
+      const T *Up = U + ustage + c * ND + k * NL;
+      T acc[n][n], gx[2][n], gy[2][n];
 #pragma unroll
       for (int j = 0; j < n; ++j)
 #pragma unroll
-        for (int i = 0; i < n; ++i) { u[j][i] = Up[j * n + i]; acc[j][i] = Wp[j * n + i]; }
-      // own traces (outward normal derivative, reference scaling) on the 4 lateral faces of the layer
+        for (int i = 0; i < n; ++i) acc[j][i] = Wp[j * n + i];
 #pragma unroll
+      for (int a = 0; a < n; ++a) { gx[0][a] = 0; gx[1][a] = 0; gy[0][a] = 0; gy[1][a] = 0; }
+      // y sweep: rows of u, acc[jj][i] += Kt_y[jj][j] u[j][i]; traces of the y faces
+#pragma unroll 1
       for (int j = 0; j < n; ++j) {
-        T g0 = 0, g1 = 0;
+        T row[n], kc[n];
 #pragma unroll
-        for (int i = 0; i < n; ++i) { g0 += P.g[0][i] * u[j][i]; g1 += P.g[1][i] * u[j][i]; }
-        TX[(0 * NL + j + n * k) * TC + c] = g0;
-        TX[(1 * NL + j + n * k) * TC + c] = g1;
+        for (int i = 0; i < n; ++i) row[i] = Up[j * n + i];
+#pragma unroll
+        for (int jj = 0; jj < n; ++jj) kc[jj] = P.Kt[1][jj * n + j];
+        const T g0 = P.g[0][j], g1 = P.g[1][j];
+#pragma unroll
+        for (int jj = 0; jj < n; ++jj)
+#pragma unroll
+          for (int i = 0; i < n; ++i) acc[jj][i] = fma(kc[jj], row[i], acc[jj][i]);
+#pragma unroll
+        for (int i = 0; i < n; ++i) { gy[0][i] = fma(g0, row[i], gy[0][i]); gy[1][i] = fma(g1, row[i], gy[1][i]); }
+      }
+      // x sweep: columns of u, acc[j][ii] += Kt_x[ii][i] u[j][i]; traces of the x faces
+#pragma unroll 1
+      for (int i = 0; i < n; ++i) {
+        T col[n], kc[n];
+#pragma unroll
+        for (int j = 0; j < n; ++j) col[j] = Up[j * n + i];
+#pragma unroll
+        for (int ii = 0; ii < n; ++ii) kc[ii] = P.Kt[0][ii * n + i];
+        const T g0 = P.g[0][i], g1 = P.g[1][i];
+#pragma unroll
+        for (int j = 0; j < n; ++j)
+#pragma unroll
+          for (int ii = 0; ii < n; ++ii) acc[j][ii] = fma(kc[ii], col[j], acc[j][ii]);
+#pragma unroll
+        for (int j = 0; j < n; ++j) { gx[0][j] = fma(g0, col[j], gx[0][j]); gx[1][j] = fma(g1, col[j], gx[1][j]); }
       }
 #pragma unroll
-      for (int i = 0; i < n; ++i) {
-        T g0 = 0, g1 = 0;
-#pragma unroll
-        for (int j = 0; j < n; ++j) { g0 += P.g[0][j] * u[j][i]; g1 += P.g[1][j] * u[j][i]; }
-        TY[(0 * NL + i + n * k) * TC + c] = g0;
-        TY[(1 * NL + i + n * k) * TC + c] = g1;
+      for (int a = 0; a < n; ++a) {
+        TX[(0 * NL + a + n * k) * TC + c] = gx[0][a];
+        TX[(1 * NL + a + n * k) * TC + c] = gx[1][a];
+        TY[(0 * NL + a + n * k) * TC + c] = gy[0][a];
+        TY[(1 * NL + a + n * k) * TC + c] = gy[1][a];
       }
       bar_sync(B_XY, CNT_XY);
-      // neighbour traces: x faces
-      const T *hx = HX + (size_t)st * (2 * TYC * NL * 2);
-      const T *hy = HY + (size_t)st * (2 * TXC * NL * 2);
-#pragma unroll
+      // neighbour terms; stage / buffer dependent part of the descriptors
+      const int hsh = st * HBUF;
+#pragma unroll 1
       for (int s = 0; s < 2; ++s) {
-        const bool inside = s ? (cx < TXC - 1) : (cx > 0);
-        const int cn = s ? c + 1 : c - 1;
+        const bool in = s ? ins[0][1] : ins[0][0];
+        const T *gp = U + (s ? g_off[0][1] : g_off[0][0]) + (in ? 0 : hsh);
+        const T *vp = U + (s ? v_off[0][1] : v_off[0][0]) + (in ? ustage : hsh);
+        const int gs = in ? TC : 2, vs = in ? n : 2;
+        T cg[n], cv[n];
+#pragma unroll
+        for (int i = 0; i < n; ++i) { cg[i] = P.cG[0][s][i]; cv[i] = P.cV[0][s][i]; }
 #pragma unroll
         for (int j = 0; j < n; ++j) {
-          const T *h = hx + ((s * TYC + cy) * NL + j + n * k) * 2;
-          const T gn = *(inside ? &TX[((1 - s) * NL + j + n * k) * TC + cn] : h + 1);
-          const T vn = *(inside ? &Uc[cn * ND + k * NL + j * n + (1 - s) * (n - 1)] : h);
+          const T gn = gp[j * gs], vn = vp[j * vs];
 #pragma unroll
-          for (int i = 0; i < n; ++i) acc[j][i] += P.cG[0][s][i] * gn + P.cV[0][s][i] * vn;
+          for (int i = 0; i < n; ++i) acc[j][i] = fma(cv[i], vn, fma(cg[i], gn, acc[j][i]));
         }
       }
-      // y faces
-#pragma unroll
+#pragma unroll 1
       for (int s = 0; s < 2; ++s) {
-        const bool inside = s ? (cy < TYC - 1) : (cy > 0);
-        const int cn = s ? c + TXC : c - TXC;
+        const bool in = s ? ins[1][1] : ins[1][0];
+        const T *gp = U + (s ? g_off[1][1] : g_off[1][0]) + (in ? 0 : hsh);
+        const T *vp = U + (s ? v_off[1][1] : v_off[1][0]) + (in ? ustage : hsh);
+        const int gs = in ? TC : 2, vs = in ? 1 : 2;
+        T cg[n], cv[n];
+#pragma unroll
+        for (int j = 0; j < n; ++j) { cg[j] = P.cG[1][s][j]; cv[j] = P.cV[1][s][j]; }
 #pragma unroll
         for (int i = 0; i < n; ++i) {
-          const T *h = hy + ((s * TXC + cx) * NL + i + n * k) * 2;
-          const T gn = *(inside ? &TY[((1 - s) * NL + i + n * k) * TC + cn] : h + 1);
-          const T vn = *(inside ? &Uc[cn * ND + k * NL + (1 - s) * (n - 1) * n + i] : h);
+          const T gn = gp[i * gs], vn = vp[i * vs];
 #pragma unroll
-          for (int j = 0; j < n; ++j) acc[j][i] += P.cG[1][s][j] * gn + P.cV[1][s][j] * vn;
+          for (int j = 0; j < n; ++j) acc[j][i] = fma(cv[j], vn, fma(cg[j], gn, acc[j][i]));
         }
       }
       // all shared-memory reads of this plane's u and traces are done: make sure they have landed
 #pragma unroll
       for (int j = 0; j < n; ++j)
 #pragma unroll
-        for (int i = 0; i < n; ++i) { keep(u[j][i]); keep(acc[j][i]); }
-      bar_arrive(B_UFREE + st, CNT_UFREE);
+        for (int i = 0; i < n; ++i) keep(acc[j][i]);
+      if (lane == 0) {   // the last XY warp to finish reading plane p refills its stage with plane p + NS
+        const int old = atomicAdd(ucnt, 1);
+        if (old == R::NXY - 1) {
+          *ucnt = 0;
+          if (p + NS < NZ) issue_plane(p + NS);
+        }
+      }
       bar_sync(B_XY, CNT_XY);   // nobody overwrites TX / TY before every layer thread has read them
-      // folded 1-D operators in x and y
+      // mass in x, then y
+      T tmp[n][n];
 #pragma unroll
       for (int j = 0; j < n; ++j)
 #pragma unroll
         for (int i = 0; i < n; ++i) {
-          T a = acc[j][i];
+          T a = P.Mh[0][i * n] * acc[j][0];
 #pragma unroll
-          for (int l = 0; l < n; ++l) a += P.Kt[0][i * n + l] * u[j][l];
-#pragma unroll
-          for (int l = 0; l < n; ++l) a += P.Kt[1][j * n + l] * u[l][i];
-          acc[j][i] = a;
-        }
-      // mass in x, then y (u is dead: reuse it as the temporary)
-#pragma unroll
-      for (int j = 0; j < n; ++j)
-#pragma unroll
-        for (int i = 0; i < n; ++i) {
-          T a = 0;
-#pragma unroll
-          for (int l = 0; l < n; ++l) a += P.Mh[0][i * n + l] * acc[j][l];
-          u[j][i] = a;
+          for (int l = 1; l < n; ++l) a = fma(P.Mh[0][i * n + l], acc[j][l], a);
+          tmp[j][i] = a;
         }
 #pragma unroll
       for (int j = 0; j < n; ++j)
 #pragma unroll
         for (int i = 0; i < n; ++i) {
-          T a = 0;
+          T a = P.Mh[1][j * n] * tmp[0][i];
 #pragma unroll
-          for (int l = 0; l < n; ++l) a += P.Mh[1][j * n + l] * u[l][i];
+          for (int l = 1; l < n; ++l) a = fma(P.Mh[1][j * n + l], tmp[l][i], a);
           Wp[j * n + i] = a;
         }
       bar_arrive(B_QREADY + st, CNT_QREADY);
     }
   } else {
     // ------------------------------------------------------------------ H warps (halo traces)
-    constexpr int NI = (2 * TYC + 2 * TXC) * NL, NT = R::NH * 32, NIT = (NI + NT - 1) / NT;
+    // The (halo cell, face point) items are dealt to the 64 threads in slots whose face (direction, side) is a
+    // compile-time constant, so that every slot is a short straight-line sequence: one neighbour-table lookup
+    // (prefetched one plane ahead), n loads, n FMAs, one (V', G') store.
+    constexpr int NT = R::NH * 32;
+    constexpr int SX = (TYC * NL + NT - 1) / NT, SY = (TXC * NL + NT - 1) / NT;   // slots per x side / y side
+    constexpr int NSLOT = 2 * SX + 2 * SY;
     const int t = ridx * 32 + lane;
-    // static description of this thread's items
-    int hcell[NIT], hoff[NIT], hstr[NIT], hface[NIT], hslot[NIT];
-    bool hval[NIT];
-#pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-      const int item = t + it * NT;
-      hval[it] = item < NI;
-      const int e = hval[it] ? item : 0;
-      if (e < 2 * TYC * NL) {            // x halo: side s, row cy, face point fp = j + n k  -> line along i
-        const int s = e / (TYC * NL), rem = e - s * TYC * NL, cy = rem / NL, fp = rem - cy * NL;
-        hcell[it] = (s ? TXC - 1 : 0) + TXC * cy;
-        hface[it] = s;
-        hoff[it] = fp * n; hstr[it] = 1;
-        hslot[it] = ((s * TYC + cy) * NL + fp) * 2;                      // into HX
-      } else {                            // y halo: side s, column cx, face point fp = i + n k -> line along j
-        const int e2 = e - 2 * TYC * NL;
-        const int s = e2 / (TXC * NL), rem = e2 - s * TXC * NL, cx = rem / NL, fp = rem - cx * NL;
-        hcell[it] = cx + TXC * (s ? TYC - 1 : 0);
-        hface[it] = 2 + s;
-        hoff[it] = (fp % n) + (fp / n) * NL; hstr[it] = n;
-        hslot[it] = 2 * 2 * TYC * NL * 2 + ((s * TXC + cx) * NL + fp) * 2;   // into HY (relative to HX base, buffer 0)
-      }
-      hcell[it] = cell_index(G, x0 + (hcell[it] & (TXC - 1)), y0 + hcell[it] / TXC, z0);
-    }
-    const int mask = (1 << G.L) - 1;
-    const long long sh0 = ((long long)G.c0x * G.c0y * (z0 >> G.L) << (3 * G.L)) + ((long long)part1by2(z0 & mask) << 2);
+    int hcell[NSLOT], hline[NSLOT], hcn[NSLOT];   // adjacent tile cell (index at plane z0), line offset, halo cell
+    auto for_slots = [&](auto &&f) {
+      // f(slot, direction, side, item-within-side)
+#define DGX_SLOT(SL) f(std::integral_constant<int, SL>{})
+      [&]<int... I>(std::integer_sequence<int, I...>) { (DGX_SLOT(I), ...); }(std::make_integer_sequence<int, NSLOT>{});
+#undef DGX_SLOT
+    };
+    auto slot_dir = [](int sl) { return sl < 2 * SX ? 0 : 1; };
+    auto slot_side = [](int sl) { return sl < 2 * SX ? sl / SX : (sl - 2 * SX) / SY; };
+    auto slot_round = [](int sl) { return sl < 2 * SX ? sl % SX : (sl - 2 * SX) % SY; };
+    for_slots([&](auto slc) {
+      constexpr int sl = decltype(slc)::value;
+      constexpr int dir = sl < 2 * SX ? 0 : 1, side = dir == 0 ? sl / SX : (sl - 2 * SX) / SY, rnd = dir == 0 ? sl % SX : (sl - 2 * SX) % SY;
+      constexpr int per_side = (dir == 0 ? TYC : TXC) * NL;
+      int e = t + rnd * NT;                    // item within this side; clamp: invalid items redo the last one
+      if (e >= per_side) e = per_side - 1;
+      const int cellrow = e / NL, fp = e - cellrow * NL;
+      const int hcx = dir == 0 ? (side ? TXC - 1 : 0) : cellrow, hcy = dir == 0 ? cellrow : (side ? TYC - 1 : 0);
+      hcell[sl] = cell_index(G, x0 + hcx, y0 + hcy, z0);
+      hline[sl] = dir == 0 ? fp * n : (fp % n) + (fp / n) * NL;
+      hcn[sl] = nbr[(size_t)(2 * dir + side) * no + hcell[sl]];
+    });
+    (void)slot_dir; (void)slot_side; (void)slot_round;
     for (int p = 0; p < NZ + 2; ++p) {
-      T hv[NIT], hg[NIT];
+      if (p >= 2) bar_sync(B_QREADY + (p & 1), CNT_QREADY);   // plane p - 2 is done: buffer p & 1 is free
       if (p < NZ) {
-        const int z = z0 + p;
-        const long long sh = ((long long)G.c0x * G.c0y * (z >> G.L) << (3 * G.L)) + ((long long)part1by2(z & mask) << 2) - sh0;
+        T x[NSLOT][n];
+        for_slots([&](auto slc) {
+          constexpr int sl = decltype(slc)::value;
+          constexpr int str = sl < 2 * SX ? 1 : n;
+          const T *ptr = src + (size_t)hcn[sl] * ND + hline[sl];
 #pragma unroll
-        for (int it = 0; it < NIT; ++it) {
-          hv[it] = 0; hg[it] = 0;
-          if (!hval[it]) continue;
-          const int s = hface[it] & 1;
-          const long long hc = nbr[(size_t)hface[it] * no + (hcell[it] + sh)];
-          const T *ptr = src + (size_t)hc * ND + hoff[it];
-          T gsum = 0, last = 0;
+          for (int l = 0; l < n; ++l) x[sl][l] = __ldg(ptr + l * str);
+        });
+        const long long sh = plane_term(G, z0 + (p + 1 < NZ ? p + 1 : p)) - pt0;
+        for_slots([&](auto slc) {
+          constexpr int sl = decltype(slc)::value;
+          constexpr int dir = sl < 2 * SX ? 0 : 1, side = dir == 0 ? sl / SX : (sl - 2 * SX) / SY;
+          hcn[sl] = nbr[(size_t)(2 * dir + side) * no + (hcell[sl] + sh)];
+        });
+        T *hb = HXY + (size_t)(p & 1) * HBUF;
+        for_slots([&](auto slc) {
+          constexpr int sl = decltype(slc)::value;
+          constexpr int dir = sl < 2 * SX ? 0 : 1, side = dir == 0 ? sl / SX : (sl - 2 * SX) / SY, rnd = dir == 0 ? sl % SX : (sl - 2 * SX) % SY;
+          constexpr int per_side = (dir == 0 ? TYC : TXC) * NL;
+          constexpr int base = (dir == 0 ? 0 : 2 * TYC * NL) + side * per_side;
+          T gsum = 0;
 #pragma unroll
-          for (int l = 0; l < n; ++l) {
-            const T x = __ldg(ptr + l * hstr[it]);
-            gsum += (s ? P.g[0][l] : P.g[1][l]) * x;    // neighbour's facing side is 1 - s
-            if (l == (s ? 0 : n - 1)) last = x;
+          for (int l = 0; l < n; ++l) gsum = fma(P.g[1 - side][l], x[sl][l], gsum);    // the neighbour's facing side is 1 - side
+          const int e = t + rnd * NT;
+          if (e < per_side) {
+            hb[2 * (base + e)] = side ? x[sl][0] : x[sl][n - 1];
+            hb[2 * (base + e) + 1] = gsum;
           }
-          hv[it] = last; hg[it] = gsum;
-        }
-      }
-      if (p >= 2) bar_sync(B_QREADY + (p & 1), CNT_QREADY);
-      if (p < NZ) {
-        const int st = p & 1;
-#pragma unroll
-        for (int it = 0; it < NIT; ++it) {
-          if (!hval[it]) continue;
-          // HX buffers are [2][...], HY buffers follow; hslot for HY was computed relative to the HX base
-          T *base = (hface[it] < 2) ? (HX + (size_t)st * (2 * TYC * NL * 2) + hslot[it])
-                                    : (HY + (size_t)st * (2 * TXC * NL * 2) + (hslot[it] - 2 * 2 * TYC * NL * 2));
-          base[0] = hv[it]; base[1] = hg[it];
-        }
-        bar_arrive(B_FULL + st, CNT_FULL);
+        });
+        bar_arrive(B_FULL + (p & 1), CNT_FULL);
       }
     }
   }
@@ -424,6 +536,7 @@ void fill_fast_params(FastParams<T, n> &F, const dgx_op *op) {
         F.cV[d][sd][i] = (T)(-C * a + 0.5 * b);
       }
     }
+    if (d == 2) for (int i = 0; i < n; ++i) Kt[i * n + i] += pressure_kappa(op);   // the Helmholtz term rides on the z sweep
     for (int i = 0; i < n * n; ++i) { F.Kt[d][i] = (T)Kt[i]; F.Mh[d][i] = (T)(h * s.M[i]); }
   }
   for (int sd = 0; sd < 2; ++sd)
@@ -437,14 +550,16 @@ int launch_march(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const F
   constexpr int NL = n * n, ND = NL * n;
   FastParams<T, n> F;
   fill_fast_params<T, n>(F, op);
-  const size_t smem = sizeof(T) * (size_t)(4 * TC * ND + 4 * NL * TC + 2 * 2 * TYC * NL * 2 + 2 * 2 * TXC * NL * 2);
+  const size_t smem = sizeof(T) * (size_t)((R::NSTAGE + 2) * TC * ND + 4 * NL * TC + 2 * 2 * TYC * NL * 2 + 2 * 2 * TXC * NL * 2) + 8 * R::NSTAGE + 16;
   static bool configured = false;
   if (!configured) {
-    DGX_CUDA_CHECK(cudaFuncSetAttribute(pressure_march_kernel<n, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DGX_CUDA_CHECK(cudaFuncSetAttribute(pressure_march_kernel<n, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DGX_CUDA_CHECK(cudaFuncSetAttribute(pressure_march_kernel<n, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   const int grid = G.ntx * G.nty * G.nsz;
-  pressure_march_kernel<n, T><<<grid, R::NW * 32, smem, op->mf->ctx->stream>>>(F, G, op->mf->d_nbr, (const T *)src->d, (T *)dst->d, add ? 1 : 0);
+  if (add) pressure_march_kernel<n, T, true><<<grid, R::NW * 32, smem, op->mf->ctx->stream>>>(F, G, op->mf->d_nbr, (const T *)src->d, (T *)dst->d);
+  else pressure_march_kernel<n, T, false><<<grid, R::NW * 32, smem, op->mf->ctx->stream>>>(F, G, op->mf->d_nbr, (const T *)src->d, (T *)dst->d);
   count_launch();
   DGX_CUDA_CHECK(cudaGetLastError());
   return DGX_OK;
@@ -464,7 +579,7 @@ int pressure_apply_fast(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) 
   G.c0x = m.cells0[0]; G.c0y = m.cells0[1];
   G.lox = mf->box_lo[0]; G.loy = mf->box_lo[1]; G.loz = mf->box_lo[2];
   const int EX = mf->box_ext[0], EY = mf->box_ext[1], EZ = mf->box_ext[2];
-  if (G.L < 3 || EX % TXC || EY % TYC || EZ < 2) return DGX_ERR_UNSUPPORTED;
+  if (G.L < 3 || EX % TXC || EY % TYC || EZ < 2 || mf->first_cell % 4) return DGX_ERR_UNSUPPORTED;
   G.ntx = EX / TXC; G.nty = EY / TYC;
   int NZ = EZ;
   while (NZ > 64 && NZ % 2 == 0) NZ /= 2;
