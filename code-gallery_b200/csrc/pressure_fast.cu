@@ -572,7 +572,8 @@ int launch_march(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const F
 int pressure_apply_fast(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) {
   dgx_mf *mf = op->mf;
   if (mf->dim != 3 || !mf->all_interior || !mf->box_ok) return DGX_ERR_UNSUPPORTED;
-  if (op->degree != 4 && op->degree != 3) return DGX_ERR_UNSUPPORTED;
+  // Q3 also runs through this kernel (tests) but is slower than the generic kernel so far: only forced (variant 2)
+  if (op->degree != 4 && !(op->degree == 3 && op->variant == 2)) return DGX_ERR_UNSUPPORTED;
   const Mesh &m = mf->mesh->m;
   FastGeom G;
   G.L = mf->level;

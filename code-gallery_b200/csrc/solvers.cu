@@ -1,0 +1,615 @@
+// Device-resident Krylov / Chebyshev / multigrid layer: the deal.II solver objects the reference wires around
+// the operator in diffusion_step / projection_step / project_grad (NS.cc:2424-2577), restated for the device
+// vector.  Algebra follows deal.II exactly so that iteration counts can be compared:
+//   SolverCG                 -> dgx_solve_cg            (NS.cc:2487, 2542/2546; mass solve NS.cc:2575-2576)
+//   SolverGMRES              -> dgx_solve_gmres         (NS.cc:2451, 2463)
+//   PreconditionChebyshev    -> dgx_cheb_*              (NS.cc:2493-2516)
+//   MGTransferMatrixFree     -> dgx_transfer_*          (NS.cc:2490-2491)
+//   Multigrid + PreconditionMG + MGCoarseGridIterativeSolver -> dgx_mg_* (NS.cc:2519-2537)
+// The host only sequences kernel launches and reads back the few scalars (dot products) the algorithms
+// branch on; all vectors and all arithmetic on them stay on the device.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "pressure_op.cuh"
+
+using namespace dgx;
+
+struct dgx_cheb {
+  dgx_op *op = nullptr;
+  int degree = 3;
+  double smoothing_range = 15.0;
+  int eig_cg_n_iterations = 10;
+  bool initialized = false;
+  double theta = 1.0, delta = 0.0, max_eig_est = 0.0, min_eig_est = 0.0;
+  dgx_vec *t = nullptr, *x_old = nullptr, *x_tmp = nullptr;   // work vectors
+};
+
+struct dgx_mg {
+  dgx_ctx *ctx = nullptr;
+  dgx_mesh *mesh = nullptr;
+  int degree = 1, n_levels = 0;
+  double Re = 1.0, dt = 1.0;
+  int stage = 1;
+  std::vector<dgx_mf *> mf;
+  std::vector<dgx_op *> op;
+  std::vector<dgx_cheb *> smoother;          // [level], level 0 unused (coarse CG)
+  std::vector<dgx_vec *> defect, sol, t;     // [level]
+  dgx_mf *mf_fine64 = nullptr;               // not owned: the caller's fp64 MatrixFree (for shape checks)
+  double coarse_tol = 0.0;
+  int coarse_max_it = 10000;
+  std::vector<int> coarse_its;               // iterations of every coarse solve of the last outer solve
+  // coarse CG work vectors
+  dgx_vec *cg_r = nullptr, *cg_p = nullptr, *cg_v = nullptr;
+};
+
+namespace {
+
+constexpr int kThreads = 256;
+inline int grid_for(long long n, int per_thread = 4) {
+  long long b = (n + (long long)kThreads * per_thread - 1) / ((long long)kThreads * per_thread);
+  return (int)std::max<long long>(1, std::min<long long>(b, 148 * 8));
+}
+
+// out = a * x + b * xold + c * d .* (rhs - t)   (null pointers drop their term)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) cheb_update_kernel(T *__restrict__ out, const T *x, const T *xold, const T *__restrict__ d,
+                                                               const T *__restrict__ rhs, const T *t, T a, T b, T c, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    T r = rhs[i];
+    if (t) r -= t[i];
+    T v = c * d[i] * r;
+    if (x) v += a * x[i];
+    if (xold) v += b * xold[i];
+    out[i] = v;
+  }
+}
+
+// v[i] = (global index) % 11   (PreconditionChebyshev::set_initial_guess)
+template <typename T>
+__global__ void iota_mod11_kernel(T *v, long long first, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    v[i] = (T)((first + i) % 11);
+}
+
+template <typename T>
+__global__ void add_scalar_kernel(T *v, T a, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) v[i] += a;
+}
+
+// ---- MGTransferMatrixFree for FE_DGQ: child = (P_cx (x) P_cy (x) P_cz) parent ---------------------------
+template <typename T, int n>
+struct TransferParams {
+  T P[2][n * n];   // P[c][j*n+i] = l_i((x_j + c)/2)
+};
+
+// one block per parent cell; thread = (child, line).  PROLONG: fine[child] += P parent;  else coarse += P^T fine[child]
+template <int dim, int n, typename T, bool PROLONG>
+__global__ void __launch_bounds__((1 << dim) * ipow(n, dim - 1))
+transfer_kernel(const __grid_constant__ TransferParams<T, n> P, long long n_parents, T *__restrict__ dst, const T *__restrict__ src) {
+  constexpr int NC = 1 << dim, NL = ipow(n, dim - 1), ND = NL * n, NT = NC * NL;
+  __shared__ T buf[NC][ND];
+  __shared__ T par[ND];
+  const long long parent = blockIdx.x;
+  const int tid = threadIdx.x, c = tid / NL, l = tid % NL;
+  if (PROLONG) {
+    for (int i = tid; i < ND; i += NT) par[i] = src[parent * ND + i];
+  } else {
+    for (int i = tid; i < NC * ND; i += NT) buf[i / ND][i % ND] = src[parent * NC * ND + i];
+  }
+  __syncthreads();
+  if (PROLONG)
+    for (int i = l; i < ND; i += NL) buf[c][i] = par[i];
+  __syncthreads();
+#pragma unroll
+  for (int d = 0; d < dim; ++d) {
+    int base, stride;
+    if (d == 0) { base = l * n; stride = 1; }
+    else if (d == 1 && dim == 3) { base = (l % n) + n * n * (l / n); stride = n; }
+    else if (d == 1) { base = l; stride = n; }
+    else { base = l; stride = n * n; }
+    const int cd = (c >> d) & 1;
+    T u[n];
+#pragma unroll
+    for (int i = 0; i < n; ++i) u[i] = buf[c][base + stride * i];
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+      T acc = 0;
+#pragma unroll
+      for (int i = 0; i < n; ++i) acc += (PROLONG ? P.P[cd][j * n + i] : P.P[cd][i * n + j]) * u[i];
+      buf[c][base + stride * j] = acc;
+    }
+    __syncthreads();
+  }
+  if (PROLONG) {
+    for (int i = tid; i < NC * ND; i += NT) dst[parent * NC * ND + i] += buf[i / ND][i % ND];
+  } else {
+    for (int i = tid; i < ND; i += NT) {
+      T s = 0;
+#pragma unroll
+      for (int cc = 0; cc < NC; ++cc) s += buf[cc][i];
+      dst[parent * ND + i] += s;
+    }
+  }
+}
+
+template <int dim, int n, typename T>
+int launch_transfer(dgx_ctx *ctx, bool prolong, long long n_parents, void *dst, const void *src) {
+  const Shape1D &s = get_shape(n - 1, n);
+  TransferParams<T, n> P;
+  for (int c = 0; c < 2; ++c)
+    for (int i = 0; i < n * n; ++i) P.P[c][i] = (T)s.P[c][i];
+  constexpr int NT = (1 << dim) * ipow(n, dim - 1);
+  if (n_parents == 0) return DGX_OK;
+  if (prolong) transfer_kernel<dim, n, T, true><<<(unsigned)n_parents, NT, 0, ctx->stream>>>(P, n_parents, (T *)dst, (const T *)src);
+  else transfer_kernel<dim, n, T, false><<<(unsigned)n_parents, NT, 0, ctx->stream>>>(P, n_parents, (T *)dst, (const T *)src);
+  count_launch();
+  DGX_CUDA_CHECK(cudaGetLastError());
+  return DGX_OK;
+}
+
+template <int dim, typename T>
+int transfer_by_degree(int degree, dgx_ctx *ctx, bool prolong, long long np, void *dst, const void *src) {
+  switch (degree) {
+    case 1: return launch_transfer<dim, 2, T>(ctx, prolong, np, dst, src);
+    case 2: return launch_transfer<dim, 3, T>(ctx, prolong, np, dst, src);
+    case 3: return launch_transfer<dim, 4, T>(ctx, prolong, np, dst, src);
+    case 4: return launch_transfer<dim, 5, T>(ctx, prolong, np, dst, src);
+    case 5: return launch_transfer<dim, 6, T>(ctx, prolong, np, dst, src);
+    case 6: return launch_transfer<dim, 7, T>(ctx, prolong, np, dst, src);
+    default: set_error("transfer: degree must be in 1..6"); return DGX_ERR_UNSUPPORTED;
+  }
+}
+
+int transfer(bool prolong, dgx_vec *dst, const dgx_vec *src) {
+  DGX_REQUIRE(dst && src, "null argument");
+  const dgx_vec *fine = prolong ? dst : src, *coarse = prolong ? src : dst;
+  DGX_REQUIRE(fine->mf->level == coarse->mf->level + 1 && fine->mf->mesh == coarse->mf->mesh, "vectors must live on consecutive levels of one mesh");
+  DGX_REQUIRE(fine->degree == coarse->degree && fine->ncomp == 1 && coarse->ncomp == 1 && fine->dtype == coarse->dtype, "transfer: scalar spaces of equal degree and number type");
+  const int dim = fine->mf->dim, nc = 1 << dim;
+  if (fine->mf->first_cell != coarse->mf->first_cell * nc || fine->mf->n_owned != coarse->mf->n_owned * nc) {
+    set_error("transfer: children of an owned parent cell must be owned by the same rank");
+    return DGX_ERR_UNSUPPORTED;
+  }
+  dgx_ctx *ctx = fine->mf->ctx;
+  const long long np = coarse->mf->n_owned;
+  if (dim == 2) return fine->dtype == DGX_F64 ? transfer_by_degree<2, double>(fine->degree, ctx, prolong, np, dst->d, src->d)
+                                              : transfer_by_degree<2, float>(fine->degree, ctx, prolong, np, dst->d, src->d);
+  return fine->dtype == DGX_F64 ? transfer_by_degree<3, double>(fine->degree, ctx, prolong, np, dst->d, src->d)
+                                : transfer_by_degree<3, float>(fine->degree, ctx, prolong, np, dst->d, src->d);
+}
+
+int cheb_update(dgx_vec *out, const dgx_vec *x, const dgx_vec *xold, const dgx_vec *d, const dgx_vec *rhs, const dgx_vec *t, double a, double b, double c) {
+  const long long n = out->n_owned;
+  cudaStream_t st = out->mf->ctx->stream;
+  if (n == 0) return DGX_OK;
+  if (out->dtype == DGX_F64)
+    cheb_update_kernel<double><<<grid_for(n), kThreads, 0, st>>>((double *)out->d, x ? (const double *)x->d : nullptr, xold ? (const double *)xold->d : nullptr,
+                                                                  (const double *)d->d, (const double *)rhs->d, t ? (const double *)t->d : nullptr, a, b, c, n);
+  else
+    cheb_update_kernel<float><<<grid_for(n), kThreads, 0, st>>>((float *)out->d, x ? (const float *)x->d : nullptr, xold ? (const float *)xold->d : nullptr,
+                                                                 (const float *)d->d, (const float *)rhs->d, t ? (const float *)t->d : nullptr, (float)a, (float)b, (float)c, n);
+  count_launch();
+  DGX_CUDA_CHECK(cudaGetLastError());
+  return DGX_OK;
+}
+
+// eigenvalues of a symmetric tridiagonal matrix (n <= ~30): cyclic Jacobi on the dense form
+void tridiag_eigenvalues(const std::vector<double> &diag, const std::vector<double> &off, std::vector<double> &ev) {
+  const int n = (int)diag.size();
+  std::vector<double> A((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) A[i * n + i] = diag[i];
+  for (int i = 0; i + 1 < n; ++i) A[i * n + i + 1] = A[(i + 1) * n + i] = off[i];
+  for (int sweep = 0; sweep < 100; ++sweep) {
+    double offn = 0;
+    for (int i = 0; i < n; ++i)
+      for (int j = i + 1; j < n; ++j) offn += A[i * n + j] * A[i * n + j];
+    if (offn < 1e-300) break;
+    for (int p = 0; p < n; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const double apq = A[p * n + q];
+        if (std::fabs(apq) < 1e-300) continue;
+        const double tau = (A[q * n + q] - A[p * n + p]) / (2 * apq);
+        const double t = (tau >= 0 ? 1.0 : -1.0) / (std::fabs(tau) + std::sqrt(1 + tau * tau));
+        const double c = 1 / std::sqrt(1 + t * t), s = t * c;
+        for (int k = 0; k < n; ++k) {
+          const double akp = A[k * n + p], akq = A[k * n + q];
+          A[k * n + p] = c * akp - s * akq; A[k * n + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double apk = A[p * n + k], aqk = A[q * n + k];
+          A[p * n + k] = c * apk - s * aqk; A[q * n + k] = s * apk + c * aqk;
+        }
+      }
+  }
+  ev.resize(n);
+  for (int i = 0; i < n; ++i) ev[i] = A[i * n + i];
+  std::sort(ev.begin(), ev.end());
+}
+
+struct Precond {
+  int kind = 0;            // 0 identity, 1 Jacobi (inverse diagonal of `op`), 2 multigrid, 3 inverse diagonal vector
+  dgx_op *op = nullptr;
+  dgx_mg *mg = nullptr;
+  dgx_vec *diag = nullptr;
+};
+
+int apply_precond(const Precond &pc, dgx_vec *dst, dgx_vec *src) {
+  switch (pc.kind) {
+    case 0: return dgx_vec_copy(dst, src);
+    case 1: return dgx_op_precondition_Jacobi(pc.op, dst, src, 1.0);
+    case 2: return dgx_mg_vmult(pc.mg, dst, src);
+    case 3: { int rc = dgx_vec_copy(dst, src); return rc ? rc : dgx_vec_scale_by(dst, pc.diag); }
+    default: set_error("unknown preconditioner kind"); return DGX_ERR_INVALID;
+  }
+}
+
+#define RC(expr) do { int rc__ = (expr); if (rc__) return rc__; } while (0)
+
+// deal.II SolverCG.  work: r, p, v, z.  Optional Lanczos coefficients for eigenvalue estimates.
+int cg_core(dgx_op *A, dgx_vec *x, dgx_vec *b, const Precond &pc, int max_it, double tol, dgx_vec *r, dgx_vec *p, dgx_vec *v, dgx_vec *z,
+            int *iters, double *final_res, std::vector<double> *lz_diag, std::vector<double> *lz_off, bool throw_on_fail) {
+  double res = 0, r_dot_z = 0, prev_rz = 0, alpha = 0, beta = 0, prev_alpha = 0, eigen_beta_alpha = 0, pv = 0;
+  RC(dgx_op_vmult(A, r, x));
+  RC(dgx_vec_sadd(r, -1.0, 1.0, b));          // r = b - A x
+  RC(dgx_vec_l2_norm(r, &res));
+  int it = 0;
+  bool converged = res <= tol;
+  while (!converged && it < max_it && std::isfinite(res)) {
+    ++it;
+    prev_alpha = alpha;
+    dgx_vec *zz = z;
+    if (pc.kind == 0) zz = r; else RC(apply_precond(pc, z, r));
+    if (it > 1) {
+      prev_rz = r_dot_z;
+      RC(dgx_vec_dot(r, zz, &r_dot_z));
+      beta = r_dot_z / prev_rz;
+      RC(dgx_vec_sadd(p, beta, 1.0, zz));     // p = beta p + z
+    } else {
+      RC(dgx_vec_copy(p, zz));
+      RC(dgx_vec_dot(r, zz, &r_dot_z));
+    }
+    RC(dgx_op_vmult(A, v, p));
+    RC(dgx_vec_dot(p, v, &pv));
+    alpha = r_dot_z / pv;
+    RC(dgx_vec_add(x, alpha, p));
+    double rr = 0;
+    RC(dgx_vec_add_and_dot(r, -alpha, v, r, &rr));   // r -= alpha v ; rr = r.r
+    res = std::sqrt(rr);
+    if (it > 1 && lz_diag) {
+      lz_diag->push_back(1.0 / prev_alpha + eigen_beta_alpha);
+      eigen_beta_alpha = beta / prev_alpha;
+      lz_off->push_back(std::sqrt(beta) / prev_alpha);
+    }
+    converged = res <= tol;
+  }
+  if (iters) *iters = it;
+  if (final_res) *final_res = res;
+  if (!converged && throw_on_fail) {
+    set_error("SolverCG: no convergence after " + std::to_string(it) + " steps, residual " + std::to_string(res));
+    return DGX_ERR_NO_CONVERGENCE;
+  }
+  return DGX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- MGTransferMatrixFree ----------------------------------------------------------------------------
+int dgx_transfer_prolongate_and_add(dgx_vec *dst_fine, const dgx_vec *src_coarse) { return transfer(true, dst_fine, src_coarse); }
+int dgx_transfer_restrict_and_add(dgx_vec *dst_coarse, const dgx_vec *src_fine) { return transfer(false, dst_coarse, src_fine); }
+
+// ---- PreconditionChebyshev ----------------------------------------------------------------------------
+int dgx_cheb_create(dgx_op *op, int degree, double smoothing_range, int eig_cg_n_iterations, dgx_cheb **out) {
+  DGX_REQUIRE(op && out, "null argument");
+  DGX_REQUIRE(degree >= 1, "Chebyshev degree");
+  auto *c = new dgx_cheb();
+  c->op = op; c->degree = degree; c->smoothing_range = smoothing_range; c->eig_cg_n_iterations = eig_cg_n_iterations;
+  for (dgx_vec **v : {&c->t, &c->x_old, &c->x_tmp}) {
+    int rc = dgx_vec_create(op->mf, op->degree, op->ncomp, v);
+    if (rc) { delete c; return rc; }
+  }
+  *out = c;
+  return DGX_OK;
+}
+
+int dgx_cheb_destroy(dgx_cheb *c) {
+  if (!c) return DGX_OK;
+  for (dgx_vec *v : {c->t, c->x_old, c->x_tmp}) dgx_vec_destroy(v);
+  delete c;
+  return DGX_OK;
+}
+
+// eigenvalue estimate: eig_cg_n_iterations CG steps on D^-1 A from v = (global index mod 11) - mean
+int dgx_cheb_estimate(dgx_cheb *c) {
+  DGX_REQUIRE(c && c->op->inv_diag, "compute_diagonal() must precede the eigenvalue estimate");
+  dgx_op *op = c->op;
+  dgx_vec *rhs = nullptr, *x = nullptr, *r = nullptr, *p = nullptr;
+  for (dgx_vec **v : {&rhs, &x, &r, &p}) RC(dgx_vec_create(op->mf, op->degree, op->ncomp, v));
+  const long long n = rhs->n_owned, first = op->mf->first_cell * rhs->dofs_per_cell;
+  cudaStream_t st = op->mf->ctx->stream;
+  if (n) {
+    if (rhs->dtype == DGX_F64) iota_mod11_kernel<double><<<grid_for(n), kThreads, 0, st>>>((double *)rhs->d, first, n);
+    else iota_mod11_kernel<float><<<grid_for(n), kThreads, 0, st>>>((float *)rhs->d, first, n);
+    count_launch();
+  }
+  double mean = 0;
+  RC(dgx_vec_mean_value(rhs, &mean));
+  if (n) {
+    if (rhs->dtype == DGX_F64) add_scalar_kernel<double><<<grid_for(n), kThreads, 0, st>>>((double *)rhs->d, -mean, n);
+    else add_scalar_kernel<float><<<grid_for(n), kThreads, 0, st>>>((float *)rhs->d, (float)-mean, n);
+    count_launch();
+  }
+  std::vector<double> dg, off, ev;
+  Precond pc; pc.kind = 3; pc.diag = op->inv_diag;
+  int its = 0; double res = 0;
+  int rc = cg_core(op, x, rhs, pc, c->eig_cg_n_iterations, 1e-10, r, p, c->t, c->x_tmp, &its, &res, &dg, &off, false);
+  for (dgx_vec *v : {rhs, x, r, p}) dgx_vec_destroy(v);
+  if (rc) return rc;
+  if (dg.empty()) { c->min_eig_est = c->max_eig_est = 1.0; }
+  else {
+    off.resize(dg.size() - 1);
+    tridiag_eigenvalues(dg, off, ev);
+    c->min_eig_est = ev.front(); c->max_eig_est = ev.back();
+  }
+  const double max_eig = 1.2 * c->max_eig_est;
+  const double alpha = c->smoothing_range > 1.0 ? max_eig / c->smoothing_range : std::min(0.9 * max_eig, c->min_eig_est);
+  c->delta = (max_eig - alpha) * 0.5;
+  c->theta = (max_eig + alpha) * 0.5;
+  c->initialized = true;
+  return DGX_OK;
+}
+
+int dgx_cheb_get_estimates(const dgx_cheb *c, double *min_eig, double *max_eig, double *theta, double *delta) {
+  DGX_REQUIRE(c, "null argument");
+  if (min_eig) *min_eig = c->min_eig_est;
+  if (max_eig) *max_eig = c->max_eig_est;
+  if (theta) *theta = c->theta;
+  if (delta) *delta = c->delta;
+  return DGX_OK;
+}
+
+static int cheb_iterate(dgx_cheb *c, dgx_vec *x, dgx_vec *x_old_or_null, dgx_vec *b) {
+  // x holds x_1; x_old_or_null holds x_0 (null = zero).  The result ends in x.  Three buffers rotate.
+  dgx_op *op = c->op;
+  double rhok = c->delta / c->theta;
+  const double sigma = c->theta / c->delta;
+  dgx_vec *cur = x, *old = x_old_or_null;
+  dgx_vec *free1 = old ? c->x_tmp : c->x_old, *free2 = old ? nullptr : c->x_tmp;
+  for (int k = 0; k < c->degree - 1; ++k) {
+    const double rhokp = 1.0 / (2.0 * sigma - rhok);
+    const double f1 = rhokp * rhok, f2 = 2.0 * rhokp / c->delta;
+    rhok = rhokp;
+    RC(dgx_op_vmult(op, c->t, cur));
+    dgx_vec *outv = free1;
+    RC(cheb_update(outv, cur, old, op->inv_diag, b, c->t, 1.0 + f1, -f1, f2));
+    if (old) free1 = old; else { free1 = free2; free2 = nullptr; }
+    old = cur; cur = outv;
+  }
+  if (cur != x) RC(dgx_vec_copy(x, cur));
+  return DGX_OK;
+}
+
+// PreconditionChebyshev::vmult: zero initial guess, degree - 1 operator applications
+int dgx_cheb_vmult(dgx_cheb *c, dgx_vec *dst, dgx_vec *src) {
+  DGX_REQUIRE(c && dst && src, "null argument");
+  if (!c->initialized) RC(dgx_cheb_estimate(c));
+  RC(cheb_update(dst, nullptr, nullptr, c->op->inv_diag, src, nullptr, 0.0, 0.0, 1.0 / c->theta));
+  if (c->degree < 2 || std::fabs(c->delta) < 1e-40) return DGX_OK;
+  return cheb_iterate(c, dst, nullptr, src);
+}
+
+// PreconditionChebyshev::step: non-zero initial guess, degree operator applications
+int dgx_cheb_step(dgx_cheb *c, dgx_vec *x, dgx_vec *b) {
+  DGX_REQUIRE(c && x && b, "null argument");
+  if (!c->initialized) RC(dgx_cheb_estimate(c));
+  RC(dgx_op_vmult(c->op, c->t, x));
+  RC(dgx_vec_copy(c->x_old, x));
+  RC(cheb_update(x, c->x_old, nullptr, c->op->inv_diag, b, c->t, 1.0, 0.0, 1.0 / c->theta));
+  if (c->degree < 2 || std::fabs(c->delta) < 1e-40) return DGX_OK;
+  return cheb_iterate(c, x, c->x_old, b);
+}
+
+// ---- Multigrid / PreconditionMG -------------------------------------------------------------------------
+int dgx_mg_create(dgx_ctx *ctx, dgx_mesh *mesh, int degree, int level_dtype, double Re, double dt, dgx_mg **out) {
+  DGX_REQUIRE(ctx && mesh && out, "null argument");
+  auto *mg = new dgx_mg();
+  mg->ctx = ctx; mg->mesh = mesh; mg->degree = degree; mg->Re = Re; mg->dt = dt;
+  mg->n_levels = mesh->m.n_refine + 1;
+  for (int l = 0; l < mg->n_levels; ++l) {
+    dgx_mf *mf = nullptr; dgx_op *op = nullptr; dgx_vec *a = nullptr, *b = nullptr, *c = nullptr; dgx_cheb *sm = nullptr;
+    int rc = dgx_mf_create(ctx, mesh, l, level_dtype, &mf);                       // NS.cc:2353-2375
+    if (!rc) rc = dgx_op_create(mf, DGX_OP_PRESSURE, degree, Re, dt, &op);        // NS.cc:2376-2379
+    if (!rc) rc = dgx_vec_create(mf, degree, 1, &a);
+    if (!rc) rc = dgx_vec_create(mf, degree, 1, &b);
+    if (!rc) rc = dgx_vec_create(mf, degree, 1, &c);
+    if (!rc && l > 0) rc = dgx_cheb_create(op, 3, 15.0, 10, &sm);                  // NS.cc:2504-2508
+    if (rc) { delete mg; return rc; }
+    mg->mf.push_back(mf); mg->op.push_back(op); mg->defect.push_back(a); mg->sol.push_back(b); mg->t.push_back(c); mg->smoother.push_back(sm);
+  }
+  int rc = dgx_vec_create(mg->mf[0], degree, 1, &mg->cg_r);
+  if (!rc) rc = dgx_vec_create(mg->mf[0], degree, 1, &mg->cg_p);
+  if (!rc) rc = dgx_vec_create(mg->mf[0], degree, 1, &mg->cg_v);
+  if (rc) { delete mg; return rc; }
+  *out = mg;
+  return DGX_OK;
+}
+
+int dgx_mg_destroy(dgx_mg *mg) {
+  if (!mg) return DGX_OK;
+  for (dgx_vec *v : {mg->cg_r, mg->cg_p, mg->cg_v}) dgx_vec_destroy(v);
+  for (int l = 0; l < mg->n_levels; ++l) {
+    dgx_cheb_destroy(mg->smoother[l]);
+    dgx_vec_destroy(mg->defect[l]); dgx_vec_destroy(mg->sol[l]); dgx_vec_destroy(mg->t[l]);
+    dgx_op_destroy(mg->op[l]);
+    dgx_mf_destroy(mg->mf[l]);
+  }
+  delete mg;
+  return DGX_OK;
+}
+
+int dgx_mg_n_levels(const dgx_mg *mg) { return mg ? mg->n_levels : 0; }
+
+int dgx_mg_set_dt(dgx_mg *mg, double dt) {
+  DGX_REQUIRE(mg, "null argument");
+  mg->dt = dt;
+  for (dgx_op *op : mg->op) RC(dgx_op_set_dt(op, dt));
+  return DGX_OK;
+}
+
+int dgx_mg_set_TR_BDF2_stage(dgx_mg *mg, int stage) {   // NS.cc:2941-2943, 2967-2969
+  DGX_REQUIRE(mg, "null argument");
+  mg->stage = stage;
+  for (dgx_op *op : mg->op) RC(dgx_op_set_TR_BDF2_stage(op, stage));
+  return DGX_OK;
+}
+
+// what projection_step rebuilds before every solve (NS.cc:2490-2517): level diagonals, smoother eigenvalue estimates
+int dgx_mg_setup(dgx_mg *mg, double coarse_abs_tol, int coarse_max_it) {
+  DGX_REQUIRE(mg, "null argument");
+  mg->coarse_tol = coarse_abs_tol;
+  mg->coarse_max_it = coarse_max_it;
+  mg->coarse_its.clear();
+  for (int l = 0; l < mg->n_levels; ++l) {
+    RC(dgx_op_compute_diagonal(mg->op[l]));
+    if (l > 0) { mg->smoother[l]->initialized = false; RC(dgx_cheb_estimate(mg->smoother[l])); }
+  }
+  return DGX_OK;
+}
+
+static int mg_level(dgx_mg *mg, int l) {
+  // input: defect[l]; output: sol[l]        (Multigrid::level_v_step)
+  if (l == 0) {
+    RC(dgx_vec_set(mg->sol[0], 0.0));
+    Precond pc;   // identity
+    int its = 0; double res = 0;
+    int rc = cg_core(mg->op[0], mg->sol[0], mg->defect[0], pc, mg->coarse_max_it, mg->coarse_tol, mg->cg_r, mg->cg_p, mg->cg_v, mg->t[0], &its, &res, nullptr, nullptr, true);
+    mg->coarse_its.push_back(its);
+    return rc;
+  }
+  RC(dgx_cheb_vmult(mg->smoother[l], mg->sol[l], mg->defect[l]));                  // pre-smoothing from zero
+  RC(dgx_op_vmult(mg->op[l], mg->t[l], mg->sol[l]));
+  RC(dgx_vec_sadd(mg->t[l], -1.0, 1.0, mg->defect[l]));                             // t = defect - A sol
+  RC(dgx_vec_set(mg->defect[l - 1], 0.0));
+  RC(dgx_transfer_restrict_and_add(mg->defect[l - 1], mg->t[l]));
+  RC(mg_level(mg, l - 1));
+  RC(dgx_transfer_prolongate_and_add(mg->sol[l], mg->sol[l - 1]));
+  return dgx_cheb_step(mg->smoother[l], mg->sol[l], mg->defect[l]);                 // post-smoothing
+}
+
+// PreconditionMG::vmult: copy_to_mg (double -> float), V-cycle, copy_from_mg
+int dgx_mg_vmult(dgx_mg *mg, dgx_vec *dst, dgx_vec *src) {
+  DGX_REQUIRE(mg && dst && src, "null argument");
+  const int L = mg->n_levels - 1;
+  RC(dgx_vec_copy(mg->defect[L], src));
+  RC(mg_level(mg, L));
+  return dgx_vec_copy(dst, mg->sol[L]);
+}
+
+int dgx_mg_coarse_iterations(const dgx_mg *mg, int *out, int capacity, int *count) {
+  DGX_REQUIRE(mg && count, "null argument");
+  *count = (int)mg->coarse_its.size();
+  for (int i = 0; i < *count && i < capacity; ++i) out[i] = mg->coarse_its[i];
+  return DGX_OK;
+}
+
+int dgx_mg_level_op(dgx_mg *mg, int level, dgx_op **op) {
+  DGX_REQUIRE(mg && op && level >= 0 && level < mg->n_levels, "level");
+  *op = mg->op[level];
+  return DGX_OK;
+}
+
+// ---- Krylov solvers --------------------------------------------------------------------------------------
+int dgx_solve_cg(dgx_op *A, dgx_vec *x, dgx_vec *b, int precond_kind, void *precond, int max_it, double abs_tol, int *iters, double *final_res) {
+  DGX_REQUIRE(A && x && b, "null argument");
+  Precond pc;
+  pc.kind = precond_kind;
+  if (precond_kind == 1) pc.op = precond ? (dgx_op *)precond : A;
+  else if (precond_kind == 2) { pc.mg = (dgx_mg *)precond; DGX_REQUIRE(pc.mg, "multigrid handle"); }
+  else DGX_REQUIRE(precond_kind == 0, "precond_kind: 0 identity, 1 Jacobi, 2 multigrid");
+  dgx_vec *w[4] = {nullptr, nullptr, nullptr, nullptr};
+  for (auto &v : w) RC(dgx_vec_create(A->mf, A->degree, A->ncomp, &v));
+  int rc = cg_core(A, x, b, pc, max_it, abs_tol, w[0], w[1], w[2], w[3], iters, final_res, nullptr, nullptr, true);
+  for (auto &v : w) dgx_vec_destroy(v);
+  return rc;
+}
+
+// SolverGMRES, deal.II defaults: left preconditioning, restart length max_basis - 2, the monitored
+// residual is the preconditioned one from the Givens recurrence, classical Gram-Schmidt with one re-orthogonalisation.
+int dgx_solve_gmres(dgx_op *A, dgx_vec *x, dgx_vec *b, int precond_kind, void *precond, int max_it, double abs_tol, int max_basis, int *iters, double *final_res) {
+  DGX_REQUIRE(A && x && b, "null argument");
+  Precond pc;
+  pc.kind = precond_kind;
+  if (precond_kind == 1) pc.op = precond ? (dgx_op *)precond : A;
+  else if (precond_kind == 2) pc.mg = (dgx_mg *)precond;
+  const int kdim = std::max(1, max_basis - 2);
+  std::vector<dgx_vec *> V(kdim + 1, nullptr);
+  dgx_vec *w = nullptr, *tmp = nullptr;
+  auto cleanup = [&]() { for (auto v : V) dgx_vec_destroy(v); dgx_vec_destroy(w); dgx_vec_destroy(tmp); };
+#define RCG(expr) do { int rc__ = (expr); if (rc__) { cleanup(); return rc__; } } while (0)
+  RCG(dgx_vec_create(A->mf, A->degree, A->ncomp, &w));
+  RCG(dgx_vec_create(A->mf, A->degree, A->ncomp, &tmp));
+  int it_total = 0;
+  double rho = 0;
+  bool done = false, failed = false;
+  while (!done) {
+    RCG(dgx_op_vmult(A, tmp, x));
+    RCG(dgx_vec_sadd(tmp, -1.0, 1.0, b));
+    if (!V[0]) RCG(dgx_vec_create(A->mf, A->degree, A->ncomp, &V[0]));
+    RCG(apply_precond(pc, V[0], tmp));
+    RCG(dgx_vec_l2_norm(V[0], &rho));
+    if (rho <= abs_tol) break;
+    if (it_total >= max_it || !std::isfinite(rho)) { failed = true; break; }
+    RCG(dgx_vec_scale(V[0], 1.0 / rho));
+    std::vector<double> H((size_t)(kdim + 1) * kdim, 0.0), g(kdim + 1, 0.0), cs(kdim, 0.0), sn(kdim, 0.0);
+    g[0] = rho;
+    int k_used = 0;
+    for (int k = 0; k < kdim; ++k) {
+      RCG(dgx_op_vmult(A, tmp, V[k]));
+      RCG(apply_precond(pc, w, tmp));
+      for (int pass = 0; pass < 2; ++pass) {
+        std::vector<double> h(k + 1);
+        for (int j = 0; j <= k; ++j) RCG(dgx_vec_dot(w, V[j], &h[j]));
+        for (int j = 0; j <= k; ++j) { RCG(dgx_vec_add(w, -h[j], V[j])); H[(size_t)j * kdim + k] += h[j]; }
+      }
+      double hn = 0;
+      RCG(dgx_vec_l2_norm(w, &hn));
+      H[(size_t)(k + 1) * kdim + k] = hn;
+      for (int j = 0; j < k; ++j) {
+        const double a = H[(size_t)j * kdim + k], c = H[(size_t)(j + 1) * kdim + k];
+        H[(size_t)j * kdim + k] = cs[j] * a + sn[j] * c;
+        H[(size_t)(j + 1) * kdim + k] = -sn[j] * a + cs[j] * c;
+      }
+      const double den = std::hypot(H[(size_t)k * kdim + k], H[(size_t)(k + 1) * kdim + k]);
+      cs[k] = H[(size_t)k * kdim + k] / den; sn[k] = H[(size_t)(k + 1) * kdim + k] / den;
+      H[(size_t)k * kdim + k] = den; H[(size_t)(k + 1) * kdim + k] = 0;
+      g[k + 1] = -sn[k] * g[k];
+      g[k] = cs[k] * g[k];
+      ++it_total; k_used = k + 1;
+      rho = std::fabs(g[k + 1]);
+      if (rho <= abs_tol) { done = true; break; }
+      if (it_total >= max_it || !std::isfinite(rho)) { failed = true; done = true; break; }
+      if (hn == 0.0) break;
+      if (!V[k + 1]) RCG(dgx_vec_create(A->mf, A->degree, A->ncomp, &V[k + 1]));
+      RCG(dgx_vec_equ(V[k + 1], 1.0 / hn, w));
+    }
+    // back substitution and update
+    std::vector<double> y(k_used, 0.0);
+    for (int i = k_used - 1; i >= 0; --i) {
+      double s = g[i];
+      for (int j = i + 1; j < k_used; ++j) s -= H[(size_t)i * kdim + j] * y[j];
+      y[i] = s / H[(size_t)i * kdim + i];
+    }
+    for (int j = 0; j < k_used; ++j) RCG(dgx_vec_add(x, y[j], V[j]));
+  }
+  cleanup();
+  if (iters) *iters = it_total;
+  if (final_res) *final_res = rho;
+  if (failed) { set_error("SolverGMRES: no convergence after " + std::to_string(it_total) + " steps"); return DGX_ERR_NO_CONVERGENCE; }
+  return DGX_OK;
+}
+
+}  // extern "C"

@@ -310,3 +310,106 @@ class NavierStokesProjectionOperator:
         """End-to-end entry: host buffers, H2D + vmult + D2H inside."""
         assert dst.flags.c_contiguous and src.flags.c_contiguous and dst.dtype == src.dtype
         _check(lib.dgx_op_vmult_host(self.h, dst.ctypes.data_as(c_vp), src.ctypes.data_as(c_vp), c_ll(src.size)))
+
+
+# ---- solver layer (deal.II objects wired up in NS.cc:2424-2577) ------------------------------------------
+PRECOND_IDENTITY, PRECOND_JACOBI, PRECOND_MG = 0, 1, 2
+
+
+def transfer_prolongate_and_add(dst_fine: Vector, src_coarse: Vector):
+    """MGTransferMatrixFree::prolongate_and_add (NS.cc:2490-2491)"""
+    _check(lib.dgx_transfer_prolongate_and_add(dst_fine.h, src_coarse.h))
+
+
+def transfer_restrict_and_add(dst_coarse: Vector, src_fine: Vector):
+    """MGTransferMatrixFree::restrict_and_add"""
+    _check(lib.dgx_transfer_restrict_and_add(dst_coarse.h, src_fine.h))
+
+
+class PreconditionChebyshev:
+    """PreconditionChebyshev<Op, Vector> with the operator's inverse diagonal (NS.cc:2493-2516)."""
+
+    def __init__(self, op: NavierStokesProjectionOperator, degree=3, smoothing_range=15.0, eig_cg_n_iterations=10):
+        self.op = op
+        self.h = c_vp()
+        _check(lib.dgx_cheb_create(op.h, degree, c_dbl(smoothing_range), eig_cg_n_iterations, C.byref(self.h)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib.dgx_cheb_destroy(self.h)
+            self.h = None
+
+    def estimate_eigenvalues(self):
+        _check(lib.dgx_cheb_estimate(self.h))
+        v = [c_dbl() for _ in range(4)]
+        _check(lib.dgx_cheb_get_estimates(self.h, *[C.byref(x) for x in v]))
+        return {"min_eig": v[0].value, "max_eig": v[1].value, "theta": v[2].value, "delta": v[3].value}
+
+    def vmult(self, dst, src):
+        _check(lib.dgx_cheb_vmult(self.h, dst.h, src.h))
+
+    def step(self, x, b):
+        _check(lib.dgx_cheb_step(self.h, x.h, b.h))
+
+
+class Multigrid:
+    """Multigrid V-cycle + PreconditionMG + coarse CG for the pressure operator (NS.cc:2490-2537)."""
+
+    def __init__(self, ctx: Context, mesh: Mesh, degree, Re=1.0, dt=1.0, level_dtype=F32):
+        self.ctx, self.mesh = ctx, mesh
+        self.h = c_vp()
+        _check(lib.dgx_mg_create(ctx.h, mesh.h, degree, level_dtype, c_dbl(Re), c_dbl(dt), C.byref(self.h)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib.dgx_mg_destroy(self.h)
+            self.h = None
+
+    def n_levels(self):
+        return lib.dgx_mg_n_levels(self.h)
+
+    def set_dt(self, dt):
+        _check(lib.dgx_mg_set_dt(self.h, c_dbl(dt)))
+
+    def set_TR_BDF2_stage(self, stage):
+        _check(lib.dgx_mg_set_TR_BDF2_stage(self.h, stage))
+
+    def setup(self, coarse_abs_tol, coarse_max_it=10000):
+        _check(lib.dgx_mg_setup(self.h, c_dbl(coarse_abs_tol), coarse_max_it))
+
+    def vmult(self, dst, src):
+        _check(lib.dgx_mg_vmult(self.h, dst.h, src.h))
+
+    def coarse_iterations(self):
+        n = c_int()
+        buf = (c_int * 4096)()
+        _check(lib.dgx_mg_coarse_iterations(self.h, buf, 4096, C.byref(n)))
+        return list(buf[: min(n.value, 4096)])
+
+
+def _solve(fn, op, x, b, precond, max_it, abs_tol, *extra):
+    kind, handle = PRECOND_IDENTITY, None
+    if isinstance(precond, Multigrid):
+        kind, handle = PRECOND_MG, precond.h
+    elif isinstance(precond, NavierStokesProjectionOperator):
+        kind, handle = PRECOND_JACOBI, precond.h
+    elif precond == "jacobi":
+        kind = PRECOND_JACOBI
+    its, res = c_int(), c_dbl()
+    rc = fn(op.h, x.h, b.h, kind, handle, max_it, c_dbl(abs_tol), *extra, C.byref(its), C.byref(res))
+    if rc == ERR_NO_CONVERGENCE:
+        e = NoConvergence(rc, lib.dgx_last_error().decode())
+        e.last_step, e.last_residual = its.value, res.value
+        raise e
+    _check(rc)
+    return its.value, res.value
+
+
+def solve_cg(op, x, b, precond=None, max_it=10000, abs_tol=0.0):
+    """SolverCG<Vector>::solve(op, x, b, precond) with SolverControl(max_it, abs_tol); returns (iterations, residual)."""
+    return _solve(lib.dgx_solve_cg, op, x, b, precond, max_it, abs_tol)
+
+
+def solve_gmres(op, x, b, precond=None, max_it=10000, abs_tol=0.0, max_basis=30):
+    """SolverGMRES<Vector>::solve with deal.II defaults (left preconditioning, max_n_tmp_vectors = 30)."""
+    return _solve(lib.dgx_solve_gmres, op, x, b, precond, max_it, abs_tol, c_int(max_basis))

@@ -36,6 +36,7 @@ typedef struct dgx_mf dgx_mf;
 typedef struct dgx_vec dgx_vec;
 typedef struct dgx_op dgx_op;
 typedef struct dgx_mg dgx_mg;
+typedef struct dgx_cheb dgx_cheb;
 
 enum { DGX_F64 = 0, DGX_F32 = 1 };
 enum { DGX_OP_VELOCITY = 1, DGX_OP_PRESSURE = 2, DGX_OP_MASS = 3 }; /* = NS_stage, NS.cc:432-443 */
@@ -142,6 +143,40 @@ int dgx_op_precondition_Jacobi(dgx_op *op, dgx_vec *dst, const dgx_vec *src, dou
 int dgx_op_set_variant(dgx_op *op, int variant);
 /* end-to-end entry: host buffers in the DG layout, H2D + vmult + D2H on the context stream */
 int dgx_op_vmult_host(dgx_op *op, void *dst_host, const void *src_host, long long n);
+
+/* ---- MGTransferMatrixFree<dim,float> (NS.cc:2490-2491): DG embedding of a parent cell into its children ---- */
+/* dst_fine += P src_coarse ; dst_coarse += P^T src_fine (vectors on consecutive levels of one mesh) */
+int dgx_transfer_prolongate_and_add(dgx_vec *dst_fine, const dgx_vec *src_coarse);
+int dgx_transfer_restrict_and_add(dgx_vec *dst_coarse, const dgx_vec *src_fine);
+
+/* ---- PreconditionChebyshev<LevelOp, Vector<float>> with the inverse diagonal inside (NS.cc:2493-2516) ------- */
+int dgx_cheb_create(dgx_op *op, int degree, double smoothing_range, int eig_cg_n_iterations, dgx_cheb **out);
+int dgx_cheb_destroy(dgx_cheb *c);
+int dgx_cheb_estimate(dgx_cheb *c);   /* eigenvalue estimate (lazy in deal.II; needs compute_diagonal first) */
+int dgx_cheb_get_estimates(const dgx_cheb *c, double *min_eig, double *max_eig, double *theta, double *delta);
+int dgx_cheb_vmult(dgx_cheb *c, dgx_vec *dst, dgx_vec *src);   /* zero initial guess (pre-smoothing) */
+int dgx_cheb_step(dgx_cheb *c, dgx_vec *x, dgx_vec *b);        /* non-zero initial guess (post-smoothing) */
+
+/* ---- Multigrid V-cycle + PreconditionMG + MGCoarseGridIterativeSolver (NS.cc:2519-2537) ---------------------- */
+/* builds one MatrixFree / pressure operator / Chebyshev(3, 15, 10) smoother per level 0..n_levels-1 (NS.cc:2351-2379,
+ * 2501-2517); level 0 is solved by plain CG with the tolerance given to dgx_mg_setup (the outer SolverControl,
+ * NS.cc:2486, 2520) */
+int dgx_mg_create(dgx_ctx *ctx, dgx_mesh *mesh, int degree, int level_dtype, double Re, double dt, dgx_mg **out);
+int dgx_mg_destroy(dgx_mg *mg);
+int dgx_mg_n_levels(const dgx_mg *mg);
+int dgx_mg_set_dt(dgx_mg *mg, double dt);
+int dgx_mg_set_TR_BDF2_stage(dgx_mg *mg, int stage);
+int dgx_mg_setup(dgx_mg *mg, double coarse_abs_tol, int coarse_max_it);   /* diagonals + eigenvalue estimates */
+int dgx_mg_vmult(dgx_mg *mg, dgx_vec *dst, dgx_vec *src);                 /* PreconditionMG::vmult (fp64 in/out) */
+int dgx_mg_coarse_iterations(const dgx_mg *mg, int *out, int capacity, int *count);
+int dgx_mg_level_op(dgx_mg *mg, int level, dgx_op **op);                  /* borrowed */
+
+/* ---- SolverCG / SolverGMRES (NS.cc:2451-2463, 2487, 2542-2546, 2575-2576) -------------------------------------- */
+/* precond_kind: 0 PreconditionIdentity, 1 PreconditionJacobi (precond = dgx_op* or NULL for A itself),
+ * 2 PreconditionMG (precond = dgx_mg*).  abs_tol as SolverControl(max_it, tol).  Returns DGX_ERR_NO_CONVERGENCE
+ * (SolverControl::NoConvergence) when max_it is reached; iters / final_res are filled either way. */
+int dgx_solve_cg(dgx_op *A, dgx_vec *x, dgx_vec *b, int precond_kind, void *precond, int max_it, double abs_tol, int *iters, double *final_res);
+int dgx_solve_gmres(dgx_op *A, dgx_vec *x, dgx_vec *b, int precond_kind, void *precond, int max_it, double abs_tol, int max_basis, int *iters, double *final_res);
 
 #ifdef __cplusplus
 }
