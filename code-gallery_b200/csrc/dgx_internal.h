@@ -47,6 +47,9 @@ struct Shape1D {
   std::vector<double> Kt;           // Minv K
   std::vector<double> a[2], b[2];   // Minv f_s, Minv g_s
   std::vector<double> P[2];         // [n][n] P_c[j][i] = l_i((x_j + c)/2)
+  // collocation (Lagrange basis on the Gauss points) tables, only when nq == n:
+  std::vector<double> Dhat;         // [nq][nq] derivative of the Gauss-point Lagrange basis at the Gauss points (= D S^-1)
+  std::vector<double> fhat[2], ghat[2];   // value / derivative of that basis at the end points (= f S^-1, g S^-1)
 };
 const Shape1D &get_shape(int degree, int nq);
 

@@ -139,6 +139,21 @@ Shape1D build(int degree, int nq) {
   s.nodes = to_d(nodes); s.xq = to_d(xq); s.wq = to_d(wq);
   s.S = to_d(S); s.D = to_d(D); s.M = to_d(M); s.K = to_d(K); s.Minv = to_d(Minv); s.Kt = to_d(Kt);
   for (int sd = 0; sd < 2; ++sd) { s.f[sd] = to_d(f[sd]); s.g[sd] = to_d(g[sd]); s.a[sd] = to_d(a[sd]); s.b[sd] = to_d(b[sd]); }
+  if (nq == n) {
+    // change of basis to the Lagrange polynomials on the Gauss points: u_hat = S u
+    std::vector<ld> Sinv, Dh(n * n, 0);
+    invert(n, S, Sinv);
+    for (int q = 0; q < n; ++q)
+      for (int r = 0; r < n; ++r)
+        for (int i = 0; i < n; ++i) Dh[q * n + r] += D[q * n + i] * Sinv[i * n + r];
+    s.Dhat = to_d(Dh);
+    for (int sd = 0; sd < 2; ++sd) {
+      std::vector<ld> fh(n, 0), gh(n, 0);
+      for (int r = 0; r < n; ++r)
+        for (int i = 0; i < n; ++i) { fh[r] += f[sd][i] * Sinv[i * n + r]; gh[r] += g[sd][i] * Sinv[i * n + r]; }
+      s.fhat[sd] = to_d(fh); s.ghat[sd] = to_d(gh);
+    }
+  }
   for (int c = 0; c < 2; ++c) {
     std::vector<ld> P(n * n);
     for (int j = 0; j < n; ++j) {

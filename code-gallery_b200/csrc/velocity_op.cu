@@ -1,7 +1,368 @@
-// Velocity operator (NS_stage == 1, NS.cc:1399-1406): placeholder until the kernels land.
+// Velocity operator, NS_stage == 1 branch of apply_add (NS.cc:1399-1406): assemble_cell_term_velocity
+// (NS.cc:933-988), assemble_face_term_velocity (:995-1085), assemble_boundary_term_velocity (:1092-1223), and its
+// diagonal as the reference probes it (compute_diagonal NS.cc:2018-2060 with assemble_diagonal_*_velocity
+// :1431-1850).  The advecting field u_extr makes the form variable-coefficient, so unlike the pressure operator
+// it is evaluated at the quadrature points:
+//   1. u and u_extr of a cell are moved to the Lagrange basis on the Gauss points (u_hat = (S x S x S) u): in that
+//      basis values at quadrature points are the coefficients themselves, gradients are a 1-D collocation
+//      derivative, and face values need a contraction along the face normal only;
+//   2. cell term and the 2*dim face terms are accumulated per direction by the thread that owns the line;
+//      the neighbour's traces (value, normal derivative, advecting value) are read from the neighbour's dofs and
+//      interpolated to the face's Gauss points; each cell computes its own side of every face (no atomics, no
+//      compress(add));
+//   3. the result is moved back with the transposed basis change.
+// Cell-centric outward-normal form of the face flux (equivalent to NS.cc:1028-1036 on both sides of the face):
+//   FV = a/Re (-1/2 (dn u + dn u') + sigma (u - u')) + a/2 (u (ue.n) + u' (ue'.n)) + a/2 lambda (u - u'),  tests phi
+//   FG = -theta a/Re 1/2 (u - u'),                                                                  tests dn phi
 #include "pressure_op.cuh"
 
 namespace dgx {
-int velocity_apply(dgx_op *, dgx_vec *, const dgx_vec *, bool) { set_error("velocity operator not implemented yet"); return DGX_ERR_UNSUPPORTED; }
-int velocity_diagonal(dgx_op *, dgx_vec *) { set_error("velocity diagonal not implemented yet"); return DGX_ERR_UNSUPPORTED; }
+namespace {
+
+template <typename T, int n>
+struct VelParams {
+  T S[n * n];        // S[q*n+i] = l_i(xi_q)
+  T Dh[n * n];       // collocation derivative on the Gauss points
+  T fh[2][n], gh[2][n];   // end-point value / derivative of the Gauss-point basis
+  T gN[2][n];        // l_i'(s) of the nodal basis (neighbour traces are taken from nodal dofs)
+  T w[n];
+  T h[MAX_DIM], ih[MAX_DIM];
+  T alpha, a, aRe, C, theta;
+};
+
+template <int dim, int n>
+__host__ __device__ constexpr int vel_cpb() { return (64 / ipow(n, dim - 1)) > 0 ? (64 / ipow(n, dim - 1)) : 1; }
+
+template <int dim, int n>
+__device__ __forceinline__ void vline(int d, int l, int &base, int &stride) {
+  if (dim == 3) {
+    if (d == 0) { base = l * n; stride = 1; }
+    else if (d == 1) { base = (l % n) + n * n * (l / n); stride = n; }
+    else { base = l; stride = n * n; }
+  } else {
+    if (d == 0) { base = l * n; stride = 1; }
+    else { base = l; stride = n; }
+  }
+}
+
+template <int dim, int n, typename T>
+__global__ void __launch_bounds__(vel_cpb<dim, n>() * ipow(n, dim - 1))
+velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict__ nbr, int n_owned, const T *__restrict__ src,
+                const T *__restrict__ ue, T *__restrict__ dst, int add) {
+  constexpr int NL = ipow(n, dim - 1), ND = NL * n, CPB = vel_cpb<dim, n>(), NT = CPB * NL;
+  constexpr int NF = 3 * dim;   // face fields: V (dim), G (dim), E (dim)
+  extern __shared__ __align__(16) unsigned char vsm[];
+  T *sm = reinterpret_cast<T *>(vsm);
+  const int tid = threadIdx.x, ci = tid / NL, l = tid % NL;
+  const int cell = blockIdx.x * CPB + ci;
+  const bool active = cell < n_owned;
+  T *A = sm + (size_t)ci * (3 * dim * ND + 4 * NF * NL);   // [2*dim][ND]
+  T *R = A + 2 * dim * ND;                                 // [dim][ND]
+  T *NTa = R + dim * ND;                                   // [2 faces][NF][NL]
+  T *NTb = NTa + 2 * NF * NL;
+  // 1. load u, u_extr
+  if (active)
+    for (int f = 0; f < 2 * dim; ++f) {
+      const T *g = (f < dim ? src : ue) + ((size_t)cell * dim + (f % dim)) * ND;
+      for (int i = l; i < ND; i += NL) A[f * ND + i] = g[i];
+    }
+  __syncthreads();
+  // 2. to the Gauss-point basis
+#pragma unroll
+  for (int d = 0; d < dim; ++d) {
+    if (active) {
+      int base, stride;
+      vline<dim, n>(d, l, base, stride);
+      for (int f = 0; f < 2 * dim; ++f) {
+        T u[n];
+#pragma unroll
+        for (int i = 0; i < n; ++i) u[i] = A[f * ND + base + stride * i];
+#pragma unroll
+        for (int q = 0; q < n; ++q) {
+          T acc = 0;
+#pragma unroll
+          for (int i = 0; i < n; ++i) acc += P.S[q * n + i] * u[i];
+          A[f * ND + base + stride * q] = acc;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // 3. mass part of the cell term: alpha * JxW * u
+  T vol = 1;
+#pragma unroll
+  for (int d = 0; d < dim; ++d) vol *= P.h[d];
+  if (active)
+    for (int i = l; i < ND; i += NL) {
+      int r = i;
+      T jxw = vol;
+#pragma unroll
+      for (int d = 0; d < dim; ++d) { jxw *= P.w[r % n]; r /= n; }
+      for (int c = 0; c < dim; ++c) R[c * ND + i] = P.alpha * jxw * A[c * ND + i];
+    }
+  __syncthreads();
+  // 4. per direction: gradient part of the cell term and the two faces normal to d
+  const int t0 = l % n, t1 = l / n;
+  const T wt = dim == 3 ? P.w[t0] * P.w[t1] : P.w[t0];
+#pragma unroll
+  for (int d = 0; d < dim; ++d) {
+    int base, stride;
+    vline<dim, n>(d, l, base, stride);
+    int nb[2] = {-1, -1};
+    if (active) {
+      // 4a. nodal traces of the neighbours at the nodal tangential point l
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        nb[s] = nbr[(size_t)(2 * d + s) * n_owned + cell];
+        if (nb[s] < 0) continue;
+        for (int c = 0; c < dim; ++c) {
+          const T *gu = src + ((size_t)nb[s] * dim + c) * ND + base;
+          const T *ge = ue + ((size_t)nb[s] * dim + c) * ND + base;
+          T gsum = 0, v = 0;
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            const T x = gu[stride * i];
+            gsum += P.gN[1 - s][i] * x;
+            if (i == (1 - s) * (n - 1)) v = x;
+          }
+          NTa[(s * NF + c) * NL + l] = v;
+          NTa[(s * NF + dim + c) * NL + l] = P.ih[d] * gsum;
+          NTa[(s * NF + 2 * dim + c) * NL + l] = ge[stride * (1 - s) * (n - 1)];
+        }
+      }
+    }
+    __syncthreads();
+    // tangential interpolation to the face Gauss points (dim - 1 passes)
+    if (active) {
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        if (nb[s] < 0) continue;
+        for (int f = 0; f < NF; ++f) {
+          T acc = 0;
+#pragma unroll
+          for (int a2 = 0; a2 < n; ++a2) acc += P.S[t0 * n + a2] * NTa[(s * NF + f) * NL + a2 + n * t1];
+          NTb[(s * NF + f) * NL + l] = acc;
+        }
+      }
+    }
+    __syncthreads();
+    if (dim == 3) {
+      if (active) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (nb[s] < 0) continue;
+          for (int f = 0; f < NF; ++f) {
+            T acc = 0;
+#pragma unroll
+            for (int b2 = 0; b2 < n; ++b2) acc += P.S[t1 * n + b2] * NTb[(s * NF + f) * NL + t0 + n * b2];
+            NTa[(s * NF + f) * NL + l] = acc;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    const T *NTf = dim == 3 ? NTa : NTb;
+    if (active) {
+      // advecting component normal to the faces, own traces
+      T Ed[2] = {0, 0};
+      {
+        const T *e = A + (dim + d) * ND + base;
+#pragma unroll
+        for (int q = 0; q < n; ++q) { const T x = e[stride * q]; Ed[0] += P.fh[0][q] * x; Ed[1] += P.fh[1][q] * x; }
+      }
+      T area = 1;
+#pragma unroll
+      for (int e2 = 0; e2 < dim; ++e2) if (e2 != d) area *= P.h[e2];
+      const T wf = area * wt, sigma = P.C * P.ih[d];
+      for (int c = 0; c < dim; ++c) {
+        T u[n], ed[n], r[n];
+#pragma unroll
+        for (int q = 0; q < n; ++q) { u[q] = A[c * ND + base + stride * q]; ed[q] = A[(dim + d) * ND + base + stride * q]; }
+        // cell term, direction d: flux = JxW (a/Re du/dx_d - a u ue_d), tested with d(phi)/dx_d
+        T fl[n];
+#pragma unroll
+        for (int q = 0; q < n; ++q) {
+          T dl = 0;
+#pragma unroll
+          for (int q2 = 0; q2 < n; ++q2) dl += P.Dh[q * n + q2] * u[q2];
+          fl[q] = vol * wt * P.w[q] * (P.aRe * P.ih[d] * dl - P.a * u[q] * ed[q]);
+        }
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+          T acc = 0;
+#pragma unroll
+          for (int q = 0; q < n; ++q) acc += P.Dh[q * n + i] * fl[q];
+          r[i] = P.ih[d] * acc;
+        }
+        // faces
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const T ns = s ? T(1) : T(-1);
+          T V = 0, G = 0;
+#pragma unroll
+          for (int q = 0; q < n; ++q) { V += P.fh[s][q] * u[q]; G += P.gh[s][q] * u[q]; }
+          G *= P.ih[d];
+          T FV, FG;
+          if (nb[s] >= 0) {
+            const T Vn = NTf[(s * NF + c) * NL + l], Gn = NTf[(s * NF + dim + c) * NL + l], En = NTf[(s * NF + 2 * dim + d) * NL + l];
+            const T lam = fmax(fabs(Ed[s]), fabs(En)), jump = V - Vn;
+            FV = P.aRe * (T(-0.5) * ns * (G + Gn) + sigma * jump) + P.a * T(0.5) * ns * (V * Ed[s] + Vn * En) + T(0.5) * P.a * lam * jump;
+            FG = -P.theta * P.aRe * T(0.5) * jump;
+          } else if (nb[s] != -2) {   // boundary_id != 1: weak Dirichlet, coef_trasp = 0 (NS.cc:1113-1128)
+            const T lam = fabs(Ed[s]);
+            FV = P.aRe * (-ns * G + T(2) * sigma * V) + P.a * lam * V;
+            FG = -P.theta * P.aRe * V;
+          } else {                    // boundary_id == 1: mirror state u_m = (u_0, -u_1, u_2), NS.cc:1139-1155
+            const T lam = fabs(Ed[s]);
+            const T dV = (c == 1) ? T(2) * V : T(0);          // u - u_m
+            const T aV = (c == 1) ? T(0) : V;                 // (u + u_m) / 2
+            const T dn = (c == 0 && d < 2) ? T(0) : ns * G;   // (1/2 (grad u + grad u_m) n)_c
+            FV = P.aRe * (-dn + sigma * dV) + P.a * aV * (ns * Ed[s]) + T(0.5) * P.a * lam * dV;
+            FG = -P.theta * P.aRe * dV;
+          }
+#pragma unroll
+          for (int q = 0; q < n; ++q) r[q] += wf * (P.fh[s][q] * FV + ns * P.ih[d] * P.gh[s][q] * FG);
+        }
+#pragma unroll
+        for (int q = 0; q < n; ++q) R[c * ND + base + stride * q] += r[q];
+      }
+    }
+    __syncthreads();
+  }
+  // 5. back to the nodal basis (transposed basis change)
+#pragma unroll
+  for (int d = 0; d < dim; ++d) {
+    if (active) {
+      int base, stride;
+      vline<dim, n>(d, l, base, stride);
+      for (int c = 0; c < dim; ++c) {
+        T u[n];
+#pragma unroll
+        for (int q = 0; q < n; ++q) u[q] = R[c * ND + base + stride * q];
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+          T acc = 0;
+#pragma unroll
+          for (int q = 0; q < n; ++q) acc += P.S[q * n + i] * u[q];
+          R[c * ND + base + stride * i] = acc;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (active)
+    for (int c = 0; c < dim; ++c) {
+      T *o = dst + ((size_t)cell * dim + c) * ND;
+      for (int i = l; i < ND; i += NL) o[i] = add ? o[i] + R[c * ND + i] : R[c * ND + i];
+    }
+}
+
+// probe vector of compute_diagonal: dof `i` of every component of every cell (ghosts included) is one
+template <typename T>
+__global__ void probe_fill_kernel(T *v, long long total, int ND, int i) {
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) v[g] = (g % ND == i) ? T(1) : T(0);
+}
+template <typename T>
+__global__ void probe_pick_kernel(T *diag, const T *res, long long n_blocks, int ND, int i) {
+  for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < n_blocks; b += (long long)gridDim.x * blockDim.x) diag[b * ND + i] = res[b * ND + i];
+}
+template <typename T>
+__global__ void reciprocal_kernel(T *v, long long n) {
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n; g += (long long)gridDim.x * blockDim.x) v[g] = T(1) / v[g];
+}
+
+template <int dim, int n, typename T>
+int launch_velocity(dgx_op *op, T *dst, const T *src, bool add) {
+  dgx_mf *mf = op->mf;
+  const Shape1D &s = get_shape(n - 1, n);
+  VelParams<T, n> P;
+  for (int i = 0; i < n * n; ++i) { P.S[i] = (T)s.S[i]; P.Dh[i] = (T)s.Dhat[i]; }
+  for (int sd = 0; sd < 2; ++sd)
+    for (int i = 0; i < n; ++i) { P.fh[sd][i] = (T)s.fhat[sd][i]; P.gh[sd][i] = (T)s.ghat[sd][i]; P.gN[sd][i] = (T)s.g[sd][i]; }
+  for (int i = 0; i < n; ++i) P.w[i] = (T)s.wq[i];
+  for (int d = 0; d < MAX_DIM; ++d) { const double h = d < dim ? mf->h[d] : 1.0; P.h[d] = (T)h; P.ih[d] = (T)(1.0 / h); }
+  // stage constants exactly as NS.cc:957-958 / 982-983, 286-287, 396-397
+  const double gamma = gamma_trbdf2();
+  const double a22 = 0.5, a33 = 1.0 / (2.0 - gamma);
+  const double a = op->stage == 1 ? a22 : a33;
+  P.alpha = (T)(op->stage == 1 ? 1.0 / (gamma * op->dt) : 1.0 / ((1.0 - gamma) * op->dt));
+  P.a = (T)a; P.aRe = (T)(a / op->Re);
+  P.C = (T)((double)n * n);   // C_u = (p_v + 1)^2, NS.cc:293
+  P.theta = (T)1.0;           // theta_v, NS.cc:290
+  constexpr int NL = ipow(n, dim - 1), ND = NL * n, CPB = vel_cpb<dim, n>(), NT = CPB * NL;
+  const size_t smem = sizeof(T) * (size_t)CPB * (3 * dim * ND + 4 * 3 * dim * NL);
+  static bool configured = false;
+  if (!configured) {
+    DGX_CUDA_CHECK(cudaFuncSetAttribute(velocity_kernel<dim, n, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int n_owned = (int)mf->n_owned;
+  if (n_owned == 0) return DGX_OK;
+  const int grid = (n_owned + CPB - 1) / CPB;
+  velocity_kernel<dim, n, T><<<grid, NT, smem, mf->ctx->stream>>>(P, mf->d_nbr, n_owned, src, (const T *)op->u_extr->d, dst, add ? 1 : 0);
+  count_launch();
+  DGX_CUDA_CHECK(cudaGetLastError());
+  return DGX_OK;
+}
+
+template <int dim, typename T>
+int velocity_by_degree(dgx_op *op, T *dst, const T *src, bool add) {
+  switch (op->degree) {
+    case 1: return launch_velocity<dim, 2, T>(op, dst, src, add);
+    case 2: return launch_velocity<dim, 3, T>(op, dst, src, add);
+    case 3: return launch_velocity<dim, 4, T>(op, dst, src, add);
+    case 4: return launch_velocity<dim, 5, T>(op, dst, src, add);
+    case 5: return launch_velocity<dim, 6, T>(op, dst, src, add);
+    case 6: return launch_velocity<dim, 7, T>(op, dst, src, add);
+    default: set_error("velocity operator: degree must be in 1..6"); return DGX_ERR_UNSUPPORTED;
+  }
+}
+
+template <typename T>
+int velocity_dispatch(dgx_op *op, T *dst, const T *src, bool add) {
+  return op->mf->dim == 2 ? velocity_by_degree<2, T>(op, dst, src, add) : velocity_by_degree<3, T>(op, dst, src, add);
+}
+
+template <typename T>
+int diagonal_by_probing(dgx_op *op, dgx_vec *out) {
+  dgx_mf *mf = op->mf;
+  long long ND = 1;
+  for (int d = 0; d < mf->dim; ++d) ND *= op->degree + 1;
+  dgx_vec *probe = nullptr, *res = nullptr;
+  int rc = dgx_vec_create(mf, op->degree, op->ncomp, &probe);
+  if (!rc) rc = dgx_vec_create(mf, op->degree, op->ncomp, &res);
+  if (rc) return rc;
+  const long long total = probe->n_owned + probe->n_ghost, nblocks = probe->n_owned / ND;
+  cudaStream_t st = mf->ctx->stream;
+  const int g1 = (int)std::min<long long>((total + 255) / 256 + 1, 148 * 8), g2 = (int)std::min<long long>((nblocks + 255) / 256 + 1, 148 * 8);
+  for (int i = 0; i < ND && !rc; ++i) {
+    probe_fill_kernel<T><<<g1, 256, 0, st>>>((T *)probe->d, total, (int)ND, i);
+    count_launch();
+    rc = velocity_dispatch<T>(op, (T *)res->d, (const T *)probe->d, false);
+    if (rc) break;
+    if (nblocks) { probe_pick_kernel<T><<<g2, 256, 0, st>>>((T *)out->d, (const T *)res->d, nblocks, (int)ND, i); count_launch(); }
+  }
+  if (!rc && out->n_owned) { reciprocal_kernel<T><<<g1, 256, 0, st>>>((T *)out->d, out->n_owned); count_launch(); }   // NS.cc:2055-2059
+  if (!rc && cudaGetLastError() != cudaSuccess) { set_error("velocity diagonal: kernel launch failed"); rc = DGX_ERR_CUDA; }
+  cudaStreamSynchronize(st);
+  dgx_vec_destroy(probe); dgx_vec_destroy(res);
+  return rc;
+}
+
+}  // namespace
+
+int velocity_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) {
+  if (!op->u_extr) { set_error("velocity operator: set_u_extr() has not been called"); return DGX_ERR_INVALID; }
+  if (op->mf->dtype == DGX_F64) return velocity_dispatch<double>(op, (double *)dst->d, (const double *)src->d, add);
+  return velocity_dispatch<float>(op, (float *)dst->d, (const float *)src->d, add);
+}
+
+// compute_diagonal, NS_stage == 1: unit-vector probing exactly as NS.cc:1442-1471, 1527-1530 do it -- the probe sets
+// dof i of ALL components, on BOTH sides of every face, and keeps the entries of dof i.  Probing all cells at once
+// with the operator kernel reproduces that (n^dim operator applications, as in the reference).
+int velocity_diagonal(dgx_op *op, dgx_vec *out) {
+  if (!op->u_extr) { set_error("velocity operator: set_u_extr() has not been called"); return DGX_ERR_INVALID; }
+  return op->mf->dtype == DGX_F64 ? diagonal_by_probing<double>(op, out) : diagonal_by_probing<float>(op, out);
+}
+
 }  // namespace dgx
