@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-refine", type=int, default=5)
+    ap.add_argument("--no-solve", action="store_true", help="skip the (untimed-region) MG-CG pressure solve report")
+    ap.add_argument("--solve-refine", type=int, default=6)
+    ap.add_argument("--solve-degree", type=int, default=3)
     return ap.parse_args()
 
 
@@ -89,6 +92,34 @@ def cpu_baseline(degree, refine, dtype, steps=3):
     """Oracle C port (oracle/cpu_vmult.c) on all host cores; falls back to the numpy oracle."""
     from oracle import cpu_port
     return cpu_port.time_vmult(degree, refine, dtype, steps)
+
+
+def pressure_solve_report(dgx, ctx, args):
+    """one CG solve preconditioned by the fp32 Chebyshev/V-cycle on a periodic cube (not part of the timed region)"""
+    R, p = args.solve_refine, args.solve_degree
+    mesh = dgx.Mesh(3, [1, 1, 1], R, [0, 0, 0], [1, 1, 1], [True, True, True])
+    mf = dgx.MatrixFree(ctx, mesh)
+    op = dgx.NavierStokesProjectionOperator(mf, dgx.OP_PRESSURE, p, 100.0, 5e-3)
+    mg = dgx.Multigrid(ctx, mesh, p, 100.0, 5e-3)
+    x, b = op.initialize_dof_vector(), op.initialize_dof_vector()
+    n = b.locally_owned_size()
+    rhs = np.sin(np.arange(n) * 7e-4) + 1e-2 * np.random.default_rng(5).uniform(-1, 1, n)
+    rhs -= rhs.mean()
+    b.from_host(rhs)
+    tol = 1e-8 * float(np.linalg.norm(rhs))
+    out = {}
+    for rep in range(2):            # first pass warms up
+        x.set(0.0)
+        ctx.synchronize()
+        l0 = dgx.kernel_launch_count()
+        ctx.timer_start()
+        mg.setup(tol, 10000)        # the reference rebuilds diagonals / eigenvalue estimates per solve (NS.cc:2490-2517)
+        its, res = dgx.solve_cg(op, x, b, mg, 10000, tol)
+        ms = ctx.timer_stop()
+        out = {"workload": f"pressure MG-CG, 3D Q{p}, {2**R}^3 cells periodic, {n} DoFs, fp64 outer / fp32 V-cycle, tol 1e-8*||rhs||",
+               "ms_per_solve": ms, "cg_iterations": its, "levels": mg.n_levels(), "final_residual": res,
+               "gpu_launches": dgx.kernel_launch_count() - l0, "includes": "level diagonals + Chebyshev eigenvalue estimates + solve"}
+    return out
 
 
 def run_reference(args):
@@ -208,15 +239,39 @@ def main():
     peaks, which = measured_peaks()
     bytes_per_dof = 2 * host.element_size()
     achieved = (n_local * bytes_per_dof) / (ms_per_step * 1e-3) / 1e9
+    marching = args.variant != 1 and args.degree == 4 and args.refine >= 3
+    kernel = "pressure_march_kernel" if marching else "pressure_generic_kernel"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                 "traffic": None, "peak_source": which, "algorithmic_bytes_per_dof": bytes_per_dof,
-                "kernel": "pressure vmult (1 launch per step)"}
+                "kernel": kernel + " (1 launch per step)"}
+    # DRAM bytes per launch of the same kernel on the same workload from the committed ncu --set full capture
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
-            roofline["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
+            ent = json.load(open(tr)).get(f"{kernel}:Q{args.degree}:{args.dtype}:r{args.refine}")
+            if ent and world == 1:
+                roofline["traffic"] = ent["dram_bytes_per_launch"]
+                roofline["traffic_source"] = ent["source"]
         except Exception:
             pass
+    # the operator is also bound by the FP64 pipe: report the executed-flop fraction beside the HBM one
+    try:
+        pk = json.load(open(os.path.join(ROOT, "profiles", "r1_peaks.json")))
+        flop_per_dof = {"pressure_march_kernel": 96.0, "pressure_generic_kernel": 112.0}[kernel]
+        key = "fp64_fma_tflops" if args.dtype == "f64" else "fp32_fma_tflops"
+        tf = n_local * flop_per_dof / (ms_per_step * 1e-3) / 1e12
+        roofline["fma_pipe"] = {"achieved_tflops": tf, "peak_tflops": pk[key], "frac": tf / pk[key], "flop_per_dof": flop_per_dof,
+                                "peak_source": "tools/fp64_peak.cu on this pool's B200 (profiles/r1_peaks.json)"}
+    except Exception:
+        pass
+
+    # MG-preconditioned pressure solve (projection_step's solver, NS.cc:2486-2546), reported beside the vmult metric
+    mg_solve = None
+    if not args.no_solve and world == 1:
+        try:
+            mg_solve = pressure_solve_report(dgx, ctx, args)
+        except Exception as exc:  # noqa: BLE001
+            mg_solve = {"error": str(exc)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -235,6 +290,7 @@ def main():
                                    f"{n_global} DoFs {args.dtype}", "l2": "inputs (2 vectors) exceed the 126 MB L2; no flush needed",
                        "partition": f"{world} contiguous Morton chunks" if world > 1 else "single GPU"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(),
+            "mg_solve": mg_solve,
         }
         print(json.dumps(line))
     if world > 1:

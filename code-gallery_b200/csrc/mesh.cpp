@@ -250,6 +250,24 @@ int dgx_mf_local_neighbors(const dgx_mf *mf, int *out) {
   return DGX_OK;
 }
 
+int dgx_mf_n_peers(const dgx_mf *mf) { return mf ? (int)mf->peers.size() : 0; }
+
+int dgx_mf_peer_info(const dgx_mf *mf, int i, int *rank, long long *n_send, long long *recv_first, long long *recv_count) {
+  DGX_REQUIRE(mf && i >= 0 && i < (int)mf->peers.size(), "peer index");
+  const auto &p = mf->peers[i];
+  if (rank) *rank = p.rank;
+  if (n_send) *n_send = (long long)p.send_cells.size();
+  if (recv_first) *recv_first = p.recv_first;
+  if (recv_count) *recv_count = p.recv_count;
+  return DGX_OK;
+}
+
+int dgx_mf_peer_send_cells(const dgx_mf *mf, int i, int *out) {
+  DGX_REQUIRE(mf && out && i >= 0 && i < (int)mf->peers.size(), "peer index");
+  std::copy(mf->peers[i].send_cells.begin(), mf->peers[i].send_cells.end(), out);
+  return DGX_OK;
+}
+
 int dgx_mf_ghost_cells(const dgx_mf *mf, long long *out) {
   DGX_REQUIRE(mf && out, "null argument");
   std::copy(mf->ghost_global.begin(), mf->ghost_global.end(), out);

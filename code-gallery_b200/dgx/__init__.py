@@ -156,6 +156,18 @@ class MatrixFree:
         _check(lib.dgx_mf_ghost_cells(self.h, out.ctypes.data_as(c_vp)))
         return out
 
+    def peers(self):
+        """ghost-exchange plan: list of (rank, send_cells[local], recv_first, recv_count)"""
+        out = []
+        for i in range(lib.dgx_mf_n_peers(self.h)):
+            rank, ns, rf, rc = c_int(), c_ll(), c_ll(), c_ll()
+            _check(lib.dgx_mf_peer_info(self.h, i, C.byref(rank), C.byref(ns), C.byref(rf), C.byref(rc)))
+            cells = np.empty(ns.value, dtype=np.int32)
+            if ns.value:
+                _check(lib.dgx_mf_peer_send_cells(self.h, i, cells.ctypes.data_as(c_vp)))
+            out.append((rank.value, cells, rf.value, rc.value))
+        return out
+
     def initialize_dof_vector(self, degree, ncomp=1):
         return Vector(self, degree, ncomp)
 

@@ -95,6 +95,10 @@ long long dgx_mf_first_owned_cell(const dgx_mf *mf);
 int dgx_mf_local_neighbors(const dgx_mf *mf, int *out);
 /* global cell index of every ghost slot, out[n_ghost] */
 int dgx_mf_ghost_cells(const dgx_mf *mf, long long *out);
+/* ghost-exchange plan (Utilities::MPI::Partitioner import / export lists): peers in ascending rank order */
+int dgx_mf_n_peers(const dgx_mf *mf);
+int dgx_mf_peer_info(const dgx_mf *mf, int i, int *rank, long long *n_send, long long *recv_first, long long *recv_count);
+int dgx_mf_peer_send_cells(const dgx_mf *mf, int i, int *out_local_cells);
 
 /* ---- LinearAlgebra::distributed::Vector<Number> (NS.cc:2102-2115, 2330-2341) ---------------- */
 /* MatrixFree::initialize_dof_vector for FESystem(FE_DGQ(degree), ncomp); zero-initialised */
