@@ -34,7 +34,7 @@ UNIT = "DoF/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--refine", type=int, default=7, help="refine_global level per GPU-count 1 (128^3 cells)")
     ap.add_argument("--degree", type=int, default=4)
@@ -50,26 +50,32 @@ def parse():
     return ap.parse_args()
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe): one nvidia-smi process
+    streaming every 50 ms, started before and killed after the timed steps."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
-        super().__init__(daemon=True)
-        self.device, self.samples, self.stop_flag = device, [], False
+        self.device, self.proc, self.samples = device, None, []
 
-    def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.device)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.device), "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return
+        try:
+            self.proc.terminate()
+            out, _ = self.proc.communicate(timeout=5)
+            self.samples = [[x.strip() for x in ln.split(",")] for ln in out.strip().splitlines() if ln.strip()]
+        except Exception:
+            pass
 
     def summary(self):
         if not self.samples:
@@ -197,6 +203,10 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    time.sleep(0.3)                       # let the sampler come up; the GPU idles meanwhile
+    for _ in range(3):                    # re-warm after the pause (untimed)
+        op.vmult(dst, src)
+    barrier()
     launches0 = dgx.kernel_launch_count()
     ctx.timer_start()
     for _ in range(args.steps):
@@ -204,8 +214,7 @@ def main():
     ms = ctx.timer_stop()
     barrier()
     launches = dgx.kernel_launch_count() - launches0
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
+    sampler.stop()
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
