@@ -59,6 +59,11 @@ struct Roles {
   static constexpr int NCOL = (n * n + NZW - 1) / NZW;  // column units (32 columns each) per Z warp
   static constexpr int NSTAGE = 3;                    // stages of the u planes
 };
+// resident CTAs per SM the register allocation is sized for (shared memory allows as many)
+template <int n, typename T> struct MinBlocks { static constexpr int value = 1; };
+template <> struct MinBlocks<5, float> { static constexpr int value = 2; };
+template <> struct MinBlocks<4, double> { static constexpr int value = 2; };
+template <> struct MinBlocks<4, float> { static constexpr int value = 3; };
 
 // barrier ids (0 is __syncthreads)
 enum { B_FULL = 1, B_QREADY = 3, B_XY = 5 };
@@ -123,7 +128,7 @@ __device__ __forceinline__ int slot_cy(int s) { return ((s >> 1) & 1) | ((s >> 2
 __device__ __forceinline__ int slot_of(int cx, int cy) { return (cx & 1) | ((cy & 1) << 1) | ((cx & 2) << 1) | ((cy & 2) << 2) | ((cx & 4) << 2); }
 
 template <int n, typename T, bool ADD>
-__global__ void __launch_bounds__(Roles<n>::NW * 32, 1)
+__global__ void __launch_bounds__(Roles<n>::NW * 32, MinBlocks<n, T>::value)
 pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_constant__ FastGeom G,
                       const int *__restrict__ nbr, const T *__restrict__ src, T *__restrict__ dst) {
   using R = Roles<n>;
@@ -131,14 +136,19 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
   constexpr int CNT_FULL = (R::NXY + R::NZW + R::NH) * 32,
                 CNT_QREADY = (R::NXY + R::NZW + R::NH) * 32, CNT_XY = R::NXY * 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  T *U = reinterpret_cast<T *>(smem_raw);          // [NS][TC][ND]   u planes (bulk-copied)
-  T *W = U + NS * TC * ND;                         // [2][TC][ND]    z-partial sums, then the xy result
-  T *TX = W + 2 * TC * ND;                         // [2 side][NL][TC]   own outward-normal-derivative traces, x faces
+  // For even n the cell stride n^3 maps every lane (= cell) of an XY warp to the same bank: those instantiations keep a
+  // second, padded copy of u (written by the Z warps, which hold the columns in registers anyway) and a padded W.
+  constexpr bool PAD = (n % 2 == 0);
+  constexpr int NDP = PAD ? ND + 1 : ND;
+  T *U = reinterpret_cast<T *>(smem_raw);          // [NS][TC][ND]   u planes (bulk-copied, memory order)
+  T *W = U + NS * TC * ND;                         // [2][TC][NDP]   z-partial sums, then the xy result
+  T *UP = W + 2 * TC * NDP;                        // [2][TC][NDP]   padded u planes (PAD only)
+  T *TX = UP + (PAD ? 2 * TC * NDP : 0);           // [2 side][NL][TC]   own outward-normal-derivative traces, x faces
   T *TY = TX + 2 * NL * TC;                        // [2 side][NL][TC]
   T *HXY = TY + 2 * NL * TC;                       // [2 buf]{[2 side][TYC][NL][2], [2 side][TXC][NL][2]}  (V', G') of the x / y halo
   constexpr int HBUF = (2 * TYC + 2 * TXC) * NL * 2;
   unsigned long long *ubar = reinterpret_cast<unsigned long long *>(HXY + 2 * HBUF);   // [NS]
-  int *ucnt = reinterpret_cast<int *>(ubar + NS);   // XY warps that have finished reading the current u plane
+  int *ucnt = reinterpret_cast<int *>(ubar + NS);   // [NS] warps that have finished reading the plane held by each stage
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // role assignment balanced over the 4 sub-partitions (warp % 4): XY warps carry twice the work
@@ -153,7 +163,7 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) mbar_init(&ubar[s], 1);
-    *ucnt = 0;
+    for (int s = 0; s < NS; ++s) ucnt[s] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -181,7 +191,7 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
   if (role == 1) {
     // ------------------------------------------------------------------ Z warps (column threads)
     const int zw = ridx;
-    int coff[R::NCOL], cxy[R::NCOL];   // shared-memory offset of the column inside a stage; cell index at plane z0
+    int coff[R::NCOL], cofp[R::NCOL], cxy[R::NCOL];   // offset of the column inside a u stage / padded plane; global element offset at z0
     bool cval[R::NCOL];
     int cij0 = 0;
 #pragma unroll
@@ -191,19 +201,20 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
       const int id = (cval[m] ? unit : 0) * 32 + lane;
       const int slot = id / NL, ij = id - slot * NL;
       coff[m] = slot * ND + ij;
+      cofp[m] = slot * NDP + ij;
       cxy[m] = cell_index(G, x0 + slot_cx(slot), y0 + slot_cy(slot), z0) * ND + ij;   // element offset at plane z0
       (void)cij0;
     }
     T uc[R::NCOL][n], Gt[R::NCOL], Vt[R::NCOL];
     auto apply_mz_store = [&](int p) {   // dst(plane p) = Mz q
-      const T *Ws = W + (size_t)(p & 1) * TC * ND;
+      const T *Ws = W + (size_t)(p & 1) * TC * NDP;
       const long long sh = (plane_term(G, z0 + p) - pt0) * ND;
 #pragma unroll
       for (int m = 0; m < R::NCOL; ++m) {
         if (!cval[m]) continue;
         T qv[n];
 #pragma unroll
-        for (int k = 0; k < n; ++k) qv[k] = Ws[coff[m] + k * NL];
+        for (int k = 0; k < n; ++k) qv[k] = Ws[cofp[m] + k * NL];
         T *o = dst + ((long long)cxy[m] + sh);
 #pragma unroll
         for (int k = 0; k < n; ++k) {
@@ -215,7 +226,7 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
       }
     };
     // one group of columns: finalise plane q (held in uc) with the bottom traces of the plane in stage Un
-    auto z_group = [&](auto m0c, auto m1c, const T *Un, T *Ws) {
+    auto z_group = [&](auto m0c, auto m1c, const T *Un, T *Ws, T *Ups) {
       constexpr int m0 = decltype(m0c)::value, m1 = decltype(m1c)::value, NG = m1 - m0;
       T nw[NG][n], gb[NG], gt[NG];
 #pragma unroll
@@ -245,7 +256,10 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
           for (int g = 0; g < NG; ++g) acc[g] = fma(P.Kt[2][k * n + kk], uc[m0 + g][kk], acc[g]);   // kappa sits on the diagonal
 #pragma unroll
         for (int g = 0; g < NG; ++g)
-          if (cval[m0 + g]) Ws[coff[m0 + g] + k * NL] = acc[g];
+          if (cval[m0 + g]) {
+            Ws[cofp[m0 + g] + k * NL] = acc[g];
+            if (PAD) Ups[cofp[m0 + g] + k * NL] = uc[m0 + g][k];
+          }
       }
 #pragma unroll
       for (int g = 0; g < NG; ++g) {
@@ -266,14 +280,33 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
       for (int k = 0; k < n; ++k) { const T x = __ldg(p + k * NL); gsum = fma(P.g[1][k], x, gsum); last = x; }
       Gt[m] = gsum; Vt[m] = last;
     }
+    // PAD only: plane `pl` now lives in the registers of this warp; the last Z warp to say so refills its stage
+    auto z_release_stage = [&](int pl) {
+      if (!PAD) return;
+#pragma unroll
+      for (int m = 0; m < R::NCOL; ++m)
+#pragma unroll
+        for (int k = 0; k < n; ++k) keep(uc[m][k]);
+      __syncwarp();
+      if (lane == 0) {
+        const int old = atomicAdd(&ucnt[pl % NS], 1);
+        if (old == R::NZW - 1) {
+          ucnt[pl % NS] = 0;
+          __threadfence_block();
+          if (pl + NS < NZ) issue_plane(pl + NS);
+        }
+      }
+    };
     mbar_wait(&ubar[0], 0);
 #pragma unroll
     for (int m = 0; m < R::NCOL; ++m)
 #pragma unroll
       for (int k = 0; k < n; ++k) uc[m][k] = cval[m] ? U[coff[m] + k * NL] : T(0);
+    z_release_stage(0);
     for (int q = 0; q < NZ; ++q) {
       T *Un = U + (size_t)((q + 1) % NS) * TC * ND;
-      T *Ws = W + (size_t)(q & 1) * TC * ND;
+      T *Ws = W + (size_t)(q & 1) * TC * NDP;
+      T *Ups = UP + (size_t)(q & 1) * TC * NDP;
       if (q + 1 < NZ) {
         mbar_wait(&ubar[(q + 1) % NS], (unsigned)(((q + 1) / NS) & 1));
       } else {
@@ -290,8 +323,9 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
         }
       }
       constexpr int MH = (R::NCOL + 1) / 2;
-      z_group(std::integral_constant<int, 0>{}, std::integral_constant<int, MH>{}, Un, Ws);
-      z_group(std::integral_constant<int, MH>{}, std::integral_constant<int, R::NCOL>{}, Un, Ws);
+      z_group(std::integral_constant<int, 0>{}, std::integral_constant<int, MH>{}, Un, Ws, Ups);
+      z_group(std::integral_constant<int, MH>{}, std::integral_constant<int, R::NCOL>{}, Un, Ws, Ups);
+      if (q + 1 < NZ) z_release_stage(q + 1);
       bar_arrive(B_FULL + (q & 1), CNT_FULL);
       if (q >= 1) {
         bar_sync(B_QREADY + ((q - 1) & 1), CNT_QREADY);
@@ -320,18 +354,18 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
       const int cnx = slot_of(s ? cx + 1 : cx - 1, cy), cny = slot_of(cx, s ? cy + 1 : cy - 1);
       // x faces: face point = row j (of layer k)
       g_off[0][s] = ins[0][s] ? (int)(TX - U) + ((1 - s) * NL + n * k) * TC + cnx : (int)(HXY - U) + ((s * TYC + cy) * NL + n * k) * 2 + 1;
-      v_off[0][s] = ins[0][s] ? cnx * ND + k * NL + (1 - s) * (n - 1) : (int)(HXY - U) + ((s * TYC + cy) * NL + n * k) * 2;
+      v_off[0][s] = ins[0][s] ? cnx * NDP + k * NL + (1 - s) * (n - 1) : (int)(HXY - U) + ((s * TYC + cy) * NL + n * k) * 2;
       // y faces: face point = column i
       g_off[1][s] = ins[1][s] ? (int)(TY - U) + ((1 - s) * NL + n * k) * TC + cny : (int)(HXY - U) + 2 * TYC * NL * 2 + ((s * TXC + cx) * NL + n * k) * 2 + 1;
-      v_off[1][s] = ins[1][s] ? cny * ND + k * NL + (1 - s) * (n - 1) * n : (int)(HXY - U) + 2 * TYC * NL * 2 + ((s * TXC + cx) * NL + n * k) * 2;
+      v_off[1][s] = ins[1][s] ? cny * NDP + k * NL + (1 - s) * (n - 1) * n : (int)(HXY - U) + 2 * TYC * NL * 2 + ((s * TXC + cx) * NL + n * k) * 2;
     }
     for (int p = 0; p < NZ; ++p) {
       const int st = p & 1;
       bar_sync(B_FULL + st, CNT_FULL);
-      mbar_wait(&ubar[p % NS], (unsigned)((p / NS) & 1));   // already complete: orders the async-proxy writes
-      const int ustage = (p % NS) * TC * ND;
-      T *Wp = W + (size_t)st * TC * ND + c * ND + k * NL;
-      const T *Up = U + ustage + c * ND + k * NL;
+      if (!PAD) mbar_wait(&ubar[p % NS], (unsigned)((p / NS) & 1));   // already complete: orders the async-proxy writes
+      const int ustage = PAD ? (int)(UP - U) + st * TC * NDP : (p % NS) * TC * ND;   // this plane's u, relative to U
+      T *Wp = W + (size_t)st * TC * NDP + c * NDP + k * NL;
+      const T *Up = U + ustage + c * NDP + k * NL;
       T acc[n][n], gx[2][n], gy[2][n];
 #pragma unroll
       for (int j = 0; j < n; ++j)
@@ -418,10 +452,10 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
       for (int j = 0; j < n; ++j)
 #pragma unroll
         for (int i = 0; i < n; ++i) keep(acc[j][i]);
-      if (lane == 0) {   // the last XY warp to finish reading plane p refills its stage with plane p + NS
-        const int old = atomicAdd(ucnt, 1);
+      if (!PAD && lane == 0) {   // the last XY warp to finish reading plane p refills its stage with plane p + NS
+        const int old = atomicAdd(&ucnt[p % NS], 1);
         if (old == R::NXY - 1) {
-          *ucnt = 0;
+          ucnt[p % NS] = 0;
           if (p + NS < NZ) issue_plane(p + NS);
         }
       }
@@ -550,7 +584,8 @@ int launch_march(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const F
   constexpr int NL = n * n, ND = NL * n;
   FastParams<T, n> F;
   fill_fast_params<T, n>(F, op);
-  const size_t smem = sizeof(T) * (size_t)((R::NSTAGE + 2) * TC * ND + 4 * NL * TC + 2 * 2 * TYC * NL * 2 + 2 * 2 * TXC * NL * 2) + 8 * R::NSTAGE + 16;
+  constexpr int NDP = (n % 2 == 0) ? ND + 1 : ND;
+  const size_t smem = sizeof(T) * (size_t)(R::NSTAGE * TC * ND + (n % 2 == 0 ? 4 : 2) * TC * NDP + 4 * NL * TC + 2 * 2 * TYC * NL * 2 + 2 * 2 * TXC * NL * 2) + 8 * R::NSTAGE + 4 * R::NSTAGE + 16;
   static bool configured = false;
   if (!configured) {
     DGX_CUDA_CHECK(cudaFuncSetAttribute(pressure_march_kernel<n, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -572,8 +607,8 @@ int launch_march(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const F
 int pressure_apply_fast(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) {
   dgx_mf *mf = op->mf;
   if (mf->dim != 3 || !mf->all_interior || !mf->box_ok) return DGX_ERR_UNSUPPORTED;
-  // Q3 also runs through this kernel (tests) but is slower than the generic kernel so far: only forced (variant 2)
-  if (op->degree != 4 && !(op->degree == 3 && op->variant == 2)) return DGX_ERR_UNSUPPORTED;
+  // Q3 fp32 is still slower here than in the generic kernel (small planes: fixed per-plane costs): only on request (variant 2)
+  if (op->degree != 4 && !(op->degree == 3 && (op->variant == 2 || mf->dtype == DGX_F64))) return DGX_ERR_UNSUPPORTED;
   const Mesh &m = mf->mesh->m;
   FastGeom G;
   G.L = mf->level;
