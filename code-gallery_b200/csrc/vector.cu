@@ -332,6 +332,26 @@ int dgx_vec_add_and_dot(dgx_vec *dst, double a, const dgx_vec *v, const dgx_vec 
   return reduce_dispatch<0, true>(dst->mf->ctx, dst->dtype, nullptr, w->d, dst->d, v->d, a, dst->n_owned, out, false);
 }
 
+// interpolate_velocity (NS.cc:2403-2418) fused into one pass: dst = a * x - (b * y), with the reference's rounding
+// order (equ, equ, -=): a * x and b * y are rounded separately before the subtraction.
+int dgx_vec_interpolate(dgx_vec *dst, double a, const dgx_vec *x, double b, const dgx_vec *y) {
+  DGX_REQUIRE(same_shape(dst, x) && same_shape(dst, y) && dst->dtype == x->dtype && dst->dtype == y->dtype, "vector shape / dtype mismatch");
+  const long long n = dst->n_owned;
+  cudaStream_t st = dst->mf->ctx->stream;
+  if (n == 0) return DGX_OK;
+  if (dst->dtype == DGX_F64) {
+    const double *xp = (const double *)x->d, *yp = (const double *)y->d;
+    map1_kernel<double><<<grid_for(n), kThreads, 0, st>>>((double *)dst->d, n, [=] __device__(double, long long i) { return __dsub_rn(__dmul_rn(a, xp[i]), __dmul_rn(b, yp[i])); });
+  } else {
+    const float *xp = (const float *)x->d, *yp = (const float *)y->d;
+    const float af = (float)a, bf = (float)b;
+    map1_kernel<float><<<grid_for(n), kThreads, 0, st>>>((float *)dst->d, n, [=] __device__(float, long long i) { return __fsub_rn(__fmul_rn(af, xp[i]), __fmul_rn(bf, yp[i])); });
+  }
+  count_launch();
+  DGX_CUDA_CHECK(cudaGetLastError());
+  return DGX_OK;
+}
+
 int dgx_vec_update_ghost_values(dgx_vec *v) {
   DGX_REQUIRE(v, "null argument");
   return ghost_exchange(v);

@@ -253,6 +253,10 @@ class Vector:
         _check(lib.dgx_vec_add_and_dot(self.h, c_dbl(a), v.h, w.h, C.byref(out)))
         return out.value
 
+    def interpolate(self, a, x, b, y):
+        """dst = a*x - b*y (interpolate_velocity, NS.cc:2403-2418)"""
+        _check(lib.dgx_vec_interpolate(self.h, c_dbl(a), x.h, c_dbl(b), y.h))
+
     def update_ghost_values(self):
         _check(lib.dgx_vec_update_ghost_values(self.h))
 
@@ -425,3 +429,16 @@ def solve_cg(op, x, b, precond=None, max_it=10000, abs_tol=0.0):
 def solve_gmres(op, x, b, precond=None, max_it=10000, abs_tol=0.0, max_basis=30):
     """SolverGMRES<Vector>::solve with deal.II defaults (left preconditioning, max_n_tmp_vectors = 30)."""
     return _solve(lib.dgx_solve_gmres, op, x, b, precond, max_it, abs_tol, c_int(max_basis))
+
+
+GAMMA = 2.0 - 2.0 ** 0.5      # NS.cc:396, 2210
+
+
+def interpolate_velocity(u_extr: Vector, TR_BDF2_stage: int, u_a: Vector, u_b: Vector):
+    """NavierStokesProjection::interpolate_velocity (NS.cc:2403-2418): stage 1: (u_a, u_b) = (u_n, u_n_minus_1),
+    stage 2: (u_a, u_b) = (u_n_gamma, u_n)."""
+    g = GAMMA
+    if TR_BDF2_stage == 1:
+        u_extr.interpolate(1.0 + g / (2.0 * (1.0 - g)), u_a, g / (2.0 * (1.0 - g)), u_b)
+    else:
+        u_extr.interpolate(1.0 + (1.0 - g) / g, u_a, (1.0 - g) / g, u_b)

@@ -59,3 +59,22 @@ def test_copy_convert(dgx, gpu_ctx):
     d.set(0.0)
     d.copy_from(f)                       # copy_from_mg: float -> double
     assert np.array_equal(d.to_host(), x.astype(np.float32).astype(np.float64))
+
+
+def test_interpolate_velocity_bit_exact(dgx, gpu_ctx):
+    """fused interpolate_velocity == equ, equ, -= of the reference (NS.cc:2403-2418), bit for bit"""
+    gm = dgx.Mesh(2, [2, 2], 2, [0, 0], [1, 1], [True] * 2)
+    mf = dgx.MatrixFree(gpu_ctx, gm)
+    a, b, e, tmp, ref = (mf.initialize_dof_vector(3, 2) for _ in range(5))
+    rng = np.random.default_rng(9)
+    ha, hb = rng.standard_normal(a.locally_owned_size()), rng.standard_normal(a.locally_owned_size())
+    a.from_host(ha)
+    b.from_host(hb)
+    g = 2.0 - np.sqrt(2.0)
+    for stage, (c1, c2) in {1: (1.0 + g / (2.0 * (1.0 - g)), g / (2.0 * (1.0 - g))), 2: (1.0 + (1.0 - g) / g, (1.0 - g) / g)}.items():
+        dgx.interpolate_velocity(e, stage, a, b)
+        ref.equ(c1, a)
+        tmp.equ(c2, b)
+        ref.add(-1.0, tmp)
+        assert np.array_equal(e.to_host(), ref.to_host())
+        assert np.array_equal(e.to_host(), c1 * ha - c2 * hb)
