@@ -114,7 +114,7 @@ int dgx_op_create(dgx_mf *mf, int kind, int degree, double Re, double dt, dgx_op
 
 int dgx_op_destroy(dgx_op *op) {
   if (!op) return DGX_OK;
-  for (dgx_vec *v : {op->u_extr, op->inv_diag, op->h_src, op->h_dst})
+  for (dgx_vec *v : {op->u_extr, op->inv_diag, op->h_src, op->h_dst, op->work[0], op->work[1], op->work[2], op->work[3]})
     if (v) { v->borrowed = false; dgx_vec_destroy(v); }
   delete op;
   return DGX_OK;

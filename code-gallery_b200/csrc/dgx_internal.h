@@ -133,6 +133,7 @@ struct dgx_op {
   dgx_vec *u_extr = nullptr;
   dgx_vec *inv_diag = nullptr;
   dgx_vec *h_src = nullptr, *h_dst = nullptr;   // staging vectors of the host entry point
+  dgx_vec *work[4] = {nullptr, nullptr, nullptr, nullptr};   // Krylov work vectors, allocated on first use and kept
 };
 
 namespace dgx {
@@ -141,6 +142,13 @@ double gamma_trbdf2();
 // kernel launchers (defined in .cu files); all enqueue on mf->ctx->stream
 int pressure_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add);
 int pressure_diagonal(dgx_op *op, dgx_vec *diag_inv);
+// fused operator + vector update: dst = a x + b xold + c d .* (rhs - A x)   (xold, d may be null)
+struct FusedUpdate {
+  const dgx_vec *xold = nullptr, *d = nullptr, *rhs = nullptr;
+  double a = 0, b = 0, c = 0;
+};
+int pressure_apply_fused(dgx_op *op, dgx_vec *dst, dgx_vec *x, const FusedUpdate &fu);
+int pressure_coarse_cg(dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_vec *r, dgx_vec *p, dgx_vec *v, double tol, int max_it, int *d_info, double *d_res);
 int mass_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add);
 int velocity_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add);
 int velocity_diagonal(dgx_op *op, dgx_vec *diag_inv);

@@ -38,15 +38,24 @@ __host__ __device__ constexpr int cells_per_block() {
   return (192 / ipow(n, dim - 1)) > 0 ? (192 / ipow(n, dim - 1)) : 1;
 }
 
+// Optional fused epilogue of the operator: instead of dst = A x the kernel writes
+//   dst = a * x + b * xold + c * d .* (rhs - A x)        (null pointers drop their term; d == null means d = 1)
+// which is one Chebyshev step (PreconditionChebyshev) or the multigrid residual, without the extra
+// passes over t = A x.
+template <typename T>
+struct Epilogue {
+  const T *xold = nullptr, *d = nullptr, *rhs = nullptr;
+  T a = 0, b = 0, c = 0;
+  int on = 0;
+};
+
+// one batch of CPB cells: dst[cells] (+)= A src.  Shared by the generic kernel (one batch per block) and the
+// single-CTA coarse-grid CG kernel (loops over the batches of a tiny level).
 template <int dim, int n, typename T>
-__global__ void __launch_bounds__(cells_per_block<dim, n>() * ipow(n, dim - 1))
-pressure_generic_kernel(const __grid_constant__ PresParams<T, n> P, const int *__restrict__ nbr, int n_owned,
-                        const T *__restrict__ src, T *__restrict__ dst, int add) {
+__device__ __forceinline__ void pressure_cell_batch(const PresParams<T, n> &P, const int *nbr, int n_owned, const T *src, T *dst, int add,
+                                                    int cell0, T *su, T *sa, const Epilogue<T> &E = Epilogue<T>()) {
   constexpr int NL = ipow(n, dim - 1), ND = NL * n, CPB = cells_per_block<dim, n>(), NT = CPB * NL;
-  __shared__ T su[CPB * ND];
-  __shared__ T sa[CPB * ND];
   const int tid = threadIdx.x;
-  const int cell0 = blockIdx.x * CPB;
   const int nblk = min(CPB, n_owned - cell0);
   for (int idx = tid; idx < nblk * ND; idx += NT) su[idx] = src[(size_t)cell0 * ND + idx];
   __syncthreads();
@@ -126,8 +135,89 @@ pressure_generic_kernel(const __grid_constant__ PresParams<T, n> P, const int *_
   }
   for (int idx = tid; idx < nblk * ND; idx += NT) {
     const size_t o = (size_t)cell0 * ND + idx;
-    dst[o] = add ? dst[o] + sa[idx] : sa[idx];
+    if (E.on) {
+      T v = E.c * (E.rhs[o] - sa[idx]);
+      if (E.d) v *= E.d[o];
+      v += E.a * su[idx];
+      if (E.xold) v += E.b * E.xold[o];
+      dst[o] = v;
+    } else {
+      dst[o] = add ? dst[o] + sa[idx] : sa[idx];
+    }
   }
+}
+
+template <int dim, int n, typename T>
+__global__ void __launch_bounds__(cells_per_block<dim, n>() * ipow(n, dim - 1))
+pressure_generic_kernel(const __grid_constant__ PresParams<T, n> P, const int *__restrict__ nbr, int n_owned,
+                        const T *__restrict__ src, T *__restrict__ dst, int add, const __grid_constant__ Epilogue<T> E) {
+  constexpr int ND = ipow(n, dim), CPB = cells_per_block<dim, n>();
+  __shared__ T su[CPB * ND];
+  __shared__ T sa[CPB * ND];
+  pressure_cell_batch<dim, n, T>(P, nbr, n_owned, src, dst, add, blockIdx.x * CPB, su, sa, E);
+}
+
+// MGCoarseGridIterativeSolver<SolverCG, PreconditionIdentity> (NS.cc:2519-2529) for a level of a few cells, entirely inside
+// ONE CTA: no launch and no host round trip per iteration.  Same algebra as cg_core (solvers.cu) with x0 = 0.
+// info[0] = iterations, info[1] = 1 if converged; res[0] = final residual norm.
+template <int dim, int n, typename T>
+__global__ void __launch_bounds__(cells_per_block<dim, n>() * ipow(n, dim - 1))
+pressure_coarse_cg_kernel(const __grid_constant__ PresParams<T, n> P, const int *nbr, int n_cells, const T *b, T *x, T *r, T *p, T *v,
+                          double tol, int max_it, int *info, double *res_out) {
+  constexpr int NL = ipow(n, dim - 1), ND = NL * n, CPB = cells_per_block<dim, n>(), NT = CPB * NL;
+  __shared__ T su[CPB * ND];
+  __shared__ T sa[CPB * ND];
+  __shared__ double red[32];
+  __shared__ double bc;
+  const int tid = threadIdx.x, N = n_cells * ND;
+  auto block_sum = [&](double val) -> double {
+    for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(0xffffffffu, val, o);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = val;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0;
+      for (int w = 0; w < (NT + 31) / 32; ++w) s += red[w];
+      bc = s;
+    }
+    __syncthreads();
+    return bc;
+  };
+  double acc = 0;
+  for (int i = tid; i < N; i += NT) { const T bi = b[i]; r[i] = bi; x[i] = 0; acc += (double)bi * (double)bi; }
+  double rr = block_sum(acc), res = sqrt(rr), prev_rr = 0;
+  int it = 0;
+  bool conv = res <= tol;
+  while (!conv && it < max_it && isfinite(res)) {
+    ++it;
+    if (it > 1) {
+      const T beta = (T)(rr / prev_rr);
+      for (int i = tid; i < N; i += NT) p[i] = beta * p[i] + r[i];
+    } else {
+      for (int i = tid; i < N; i += NT) p[i] = r[i];
+    }
+    __syncthreads();
+    for (int c0 = 0; c0 < n_cells; c0 += CPB) {
+      pressure_cell_batch<dim, n, T>(P, nbr, n_cells, p, v, 0, c0, su, sa);
+      __syncthreads();
+    }
+    acc = 0;
+    for (int i = tid; i < N; i += NT) acc += (double)p[i] * (double)v[i];
+    const double pv = block_sum(acc);
+    const T alpha = (T)(rr / pv);
+    acc = 0;
+    for (int i = tid; i < N; i += NT) {
+      x[i] += alpha * p[i];
+      const T ri = r[i] - alpha * v[i];
+      r[i] = ri;
+      acc += (double)ri * (double)ri;
+    }
+    prev_rr = rr;
+    rr = block_sum(acc);
+    res = sqrt(rr);
+    conv = res <= tol;
+  }
+  if (tid == 0) { info[0] = it; info[1] = conv ? 1 : 0; res_out[0] = res; }
 }
 
 // Inverse "diagonal" exactly as the reference probes it (NS.cc:1857-2008): the interior-face probe sets
@@ -176,7 +266,7 @@ __global__ void pressure_diag_kernel(const __grid_constant__ DiagParams<T, n> P,
 }
 
 template <int dim, int n, typename T>
-int launch_generic(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) {
+int launch_generic(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const FusedUpdate *fu = nullptr) {
   dgx_mf *mf = op->mf;
   PresParams<T, n> P;
   fill_pres_params<T, n>(P, op, pressure_kappa(op));
@@ -184,7 +274,15 @@ int launch_generic(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) {
   const int n_owned = (int)mf->n_owned;
   if (n_owned == 0) return DGX_OK;
   const int grid = (n_owned + CPB - 1) / CPB;
-  pressure_generic_kernel<dim, n, T><<<grid, NT, 0, mf->ctx->stream>>>(P, mf->d_nbr, n_owned, (const T *)src->d, (T *)dst->d, add ? 1 : 0);
+  Epilogue<T> E;
+  if (fu) {
+    E.on = 1;
+    E.xold = fu->xold ? (const T *)fu->xold->d : nullptr;
+    E.d = fu->d ? (const T *)fu->d->d : nullptr;
+    E.rhs = (const T *)fu->rhs->d;
+    E.a = (T)fu->a; E.b = (T)fu->b; E.c = (T)fu->c;
+  }
+  pressure_generic_kernel<dim, n, T><<<grid, NT, 0, mf->ctx->stream>>>(P, mf->d_nbr, n_owned, (const T *)src->d, (T *)dst->d, add ? 1 : 0, E);
   count_launch();
   DGX_CUDA_CHECK(cudaGetLastError());
   return DGX_OK;
@@ -240,8 +338,8 @@ int launch_diag(dgx_op *op, dgx_vec *out) {
   }
 
 template <int dim, typename T>
-int generic_by_degree(int degree, dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) {
-#define CALL(N) launch_generic<dim, N, T>(op, dst, src, add)
+int generic_by_degree(int degree, dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const FusedUpdate *fu = nullptr) {
+#define CALL(N) launch_generic<dim, N, T>(op, dst, src, add, fu)
   DGX_DEGREE_SWITCH(CALL)
 #undef CALL
 }
@@ -255,6 +353,37 @@ int diag_by_degree(int degree, dgx_op *op, dgx_vec *out) {
 
 }  // namespace
 
+template <int dim, int n, typename T>
+int launch_coarse_cg(dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_vec *r, dgx_vec *p, dgx_vec *v, double tol, int max_it, int *d_info, double *d_res) {
+  dgx_mf *mf = op->mf;
+  PresParams<T, n> P;
+  fill_pres_params<T, n>(P, op, pressure_kappa(op));
+  constexpr int CPB = cells_per_block<dim, n>(), NT = CPB * ipow(n, dim - 1);
+  pressure_coarse_cg_kernel<dim, n, T><<<1, NT, 0, mf->ctx->stream>>>(P, mf->d_nbr, (int)mf->n_owned, (const T *)b->d, (T *)x->d, (T *)r->d, (T *)p->d,
+                                                                      (T *)v->d, tol, max_it, d_info, d_res);
+  count_launch();
+  DGX_CUDA_CHECK(cudaGetLastError());
+  return DGX_OK;
+}
+
+template <int dim, typename T>
+int coarse_by_degree(int degree, dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_vec *r, dgx_vec *p, dgx_vec *v, double tol, int max_it, int *d_info, double *d_res) {
+#define CALL(N) launch_coarse_cg<dim, N, T>(op, x, b, r, p, v, tol, max_it, d_info, d_res)
+  DGX_DEGREE_SWITCH(CALL)
+#undef CALL
+}
+
+// single-CTA coarse solve; DGX_ERR_UNSUPPORTED when the level is not tiny / not on one rank (caller falls back to cg_core)
+int pressure_coarse_cg(dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_vec *r, dgx_vec *p, dgx_vec *v, double tol, int max_it, int *d_info, double *d_res) {
+  dgx_mf *mf = op->mf;
+  if (op->kind != DGX_OP_PRESSURE || mf->ctx->nranks != 1 || mf->n_ghost != 0 || mf->n_owned < 1 || mf->n_owned > 64) return DGX_ERR_UNSUPPORTED;
+  const int degree = op->degree;
+  if (mf->dim == 2) return mf->dtype == DGX_F64 ? coarse_by_degree<2, double>(degree, op, x, b, r, p, v, tol, max_it, d_info, d_res)
+                                                 : coarse_by_degree<2, float>(degree, op, x, b, r, p, v, tol, max_it, d_info, d_res);
+  return mf->dtype == DGX_F64 ? coarse_by_degree<3, double>(degree, op, x, b, r, p, v, tol, max_it, d_info, d_res)
+                              : coarse_by_degree<3, float>(degree, op, x, b, r, p, v, tol, max_it, d_info, d_res);
+}
+
 int pressure_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) {
   dgx_mf *mf = op->mf;
   if (op->variant != 1) {
@@ -266,6 +395,18 @@ int pressure_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) {
                                                  : generic_by_degree<2, float>(op->degree, op, dst, src, add);
   return mf->dtype == DGX_F64 ? generic_by_degree<3, double>(op->degree, op, dst, src, add)
                               : generic_by_degree<3, float>(op->degree, op, dst, src, add);
+}
+
+// dst = a x + b xold + c d .* (rhs - A x) in ONE kernel (generic path).  dst must differ from x (neighbour cells read x).
+int pressure_apply_fused(dgx_op *op, dgx_vec *dst, dgx_vec *x, const FusedUpdate &fu) {
+  dgx_mf *mf = op->mf;
+  if (op->kind != DGX_OP_PRESSURE || dst->d == x->d) return DGX_ERR_UNSUPPORTED;
+  int rc = ghost_exchange(x);
+  if (rc) return rc;
+  if (mf->dim == 2) return mf->dtype == DGX_F64 ? generic_by_degree<2, double>(op->degree, op, dst, x, false, &fu)
+                                                 : generic_by_degree<2, float>(op->degree, op, dst, x, false, &fu);
+  return mf->dtype == DGX_F64 ? generic_by_degree<3, double>(op->degree, op, dst, x, false, &fu)
+                              : generic_by_degree<3, float>(op->degree, op, dst, x, false, &fu);
 }
 
 int pressure_diagonal(dgx_op *op, dgx_vec *out) {

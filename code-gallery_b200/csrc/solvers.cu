@@ -43,6 +43,11 @@ struct dgx_mg {
   std::vector<int> coarse_its;               // iterations of every coarse solve of the last outer solve
   // coarse CG work vectors
   dgx_vec *cg_r = nullptr, *cg_p = nullptr, *cg_v = nullptr;
+  // device-side log of the single-CTA coarse solves since the last setup: (iterations, converged) pairs, residuals
+  static constexpr int kLog = 8192;
+  int *d_info = nullptr;
+  double *d_res = nullptr;
+  int n_dev_solves = 0;
 };
 
 namespace {
@@ -239,14 +244,25 @@ struct Precond {
 int apply_precond(const Precond &pc, dgx_vec *dst, dgx_vec *src) {
   switch (pc.kind) {
     case 0: return dgx_vec_copy(dst, src);
-    case 1: return dgx_op_precondition_Jacobi(pc.op, dst, src, 1.0);
+    case 1:
+      if (!pc.op->inv_diag) { set_error("compute_diagonal() has not been called"); return DGX_ERR_INVALID; }
+      return cheb_update(dst, nullptr, nullptr, pc.op->inv_diag, src, nullptr, 0.0, 0.0, 1.0);
     case 2: return dgx_mg_vmult(pc.mg, dst, src);
-    case 3: { int rc = dgx_vec_copy(dst, src); return rc ? rc : dgx_vec_scale_by(dst, pc.diag); }
+    case 3: return cheb_update(dst, nullptr, nullptr, pc.diag, src, nullptr, 0.0, 0.0, 1.0);   // dst = diag .* src in one pass
     default: set_error("unknown preconditioner kind"); return DGX_ERR_INVALID;
   }
 }
 
 #define RC(expr) do { int rc__ = (expr); if (rc__) return rc__; } while (0)
+
+// Krylov work vectors live with the operator: cudaMalloc / cudaFree (which synchronises the device) stay out of the solves
+int op_work(dgx_op *op, dgx_vec **w, int count) {
+  for (int i = 0; i < count; ++i) {
+    if (!op->work[i]) { RC(dgx_vec_create(op->mf, op->degree, op->ncomp, &op->work[i])); op->work[i]->borrowed = true; }
+    w[i] = op->work[i];
+  }
+  return DGX_OK;
+}
 
 // deal.II SolverCG.  work: r, p, v, z.  Optional Lanczos coefficients for eigenvalue estimates.
 int cg_core(dgx_op *A, dgx_vec *x, dgx_vec *b, const Precond &pc, int max_it, double tol, dgx_vec *r, dgx_vec *p, dgx_vec *v, dgx_vec *z,
@@ -327,8 +343,10 @@ int dgx_cheb_destroy(dgx_cheb *c) {
 int dgx_cheb_estimate(dgx_cheb *c) {
   DGX_REQUIRE(c && c->op->inv_diag, "compute_diagonal() must precede the eigenvalue estimate");
   dgx_op *op = c->op;
-  dgx_vec *rhs = nullptr, *x = nullptr, *r = nullptr, *p = nullptr;
-  for (dgx_vec **v : {&rhs, &x, &r, &p}) RC(dgx_vec_create(op->mf, op->degree, op->ncomp, v));
+  dgx_vec *w4[4];
+  RC(op_work(op, w4, 4));
+  dgx_vec *rhs = w4[0], *x = w4[1], *r = w4[2], *p = w4[3];
+  RC(dgx_vec_set(x, 0.0));
   const long long n = rhs->n_owned, first = op->mf->first_cell * rhs->dofs_per_cell;
   cudaStream_t st = op->mf->ctx->stream;
   if (n) {
@@ -347,7 +365,6 @@ int dgx_cheb_estimate(dgx_cheb *c) {
   Precond pc; pc.kind = 3; pc.diag = op->inv_diag;
   int its = 0; double res = 0;
   int rc = cg_core(op, x, rhs, pc, c->eig_cg_n_iterations, 1e-10, r, p, c->t, c->x_tmp, &its, &res, &dg, &off, false);
-  for (dgx_vec *v : {rhs, x, r, p}) dgx_vec_destroy(v);
   if (rc) return rc;
   if (dg.empty()) { c->min_eig_est = c->max_eig_est = 1.0; }
   else {
@@ -383,9 +400,14 @@ static int cheb_iterate(dgx_cheb *c, dgx_vec *x, dgx_vec *x_old_or_null, dgx_vec
     const double rhokp = 1.0 / (2.0 * sigma - rhok);
     const double f1 = rhokp * rhok, f2 = 2.0 * rhokp / c->delta;
     rhok = rhokp;
-    RC(dgx_op_vmult(op, c->t, cur));
     dgx_vec *outv = free1;
-    RC(cheb_update(outv, cur, old, op->inv_diag, b, c->t, 1.0 + f1, -f1, f2));
+    FusedUpdate fu;
+    fu.xold = old; fu.d = op->inv_diag; fu.rhs = b; fu.a = 1.0 + f1; fu.b = -f1; fu.c = f2;
+    int frc = pressure_apply_fused(op, outv, cur, fu);          // one kernel: operator + Chebyshev update
+    if (frc == DGX_ERR_UNSUPPORTED) {
+      RC(dgx_op_vmult(op, c->t, cur));
+      RC(cheb_update(outv, cur, old, op->inv_diag, b, c->t, 1.0 + f1, -f1, f2));
+    } else if (frc) return frc;
     if (old) free1 = old; else { free1 = free2; free2 = nullptr; }
     old = cur; cur = outv;
   }
@@ -406,9 +428,16 @@ int dgx_cheb_vmult(dgx_cheb *c, dgx_vec *dst, dgx_vec *src) {
 int dgx_cheb_step(dgx_cheb *c, dgx_vec *x, dgx_vec *b) {
   DGX_REQUIRE(c && x && b, "null argument");
   if (!c->initialized) RC(dgx_cheb_estimate(c));
-  RC(dgx_op_vmult(c->op, c->t, x));
   RC(dgx_vec_copy(c->x_old, x));
-  RC(cheb_update(x, c->x_old, nullptr, c->op->inv_diag, b, c->t, 1.0, 0.0, 1.0 / c->theta));
+  {
+    FusedUpdate fu;
+    fu.d = c->op->inv_diag; fu.rhs = b; fu.a = 1.0; fu.c = 1.0 / c->theta;
+    int frc = pressure_apply_fused(c->op, x, c->x_old, fu);      // x = x_old + 1/theta D^-1 (b - A x_old)
+    if (frc == DGX_ERR_UNSUPPORTED) {
+      RC(dgx_op_vmult(c->op, c->t, c->x_old));
+      RC(cheb_update(x, c->x_old, nullptr, c->op->inv_diag, b, c->t, 1.0, 0.0, 1.0 / c->theta));
+    } else if (frc) return frc;
+  }
   if (c->degree < 2 || std::fabs(c->delta) < 1e-40) return DGX_OK;
   return cheb_iterate(c, x, c->x_old, b);
 }
@@ -434,12 +463,18 @@ int dgx_mg_create(dgx_ctx *ctx, dgx_mesh *mesh, int degree, int level_dtype, dou
   if (!rc) rc = dgx_vec_create(mg->mf[0], degree, 1, &mg->cg_p);
   if (!rc) rc = dgx_vec_create(mg->mf[0], degree, 1, &mg->cg_v);
   if (rc) { delete mg; return rc; }
+  if (cudaMalloc(&mg->d_info, 2 * dgx_mg::kLog * sizeof(int)) != cudaSuccess || cudaMalloc(&mg->d_res, dgx_mg::kLog * sizeof(double)) != cudaSuccess) {
+    cudaGetLastError();
+    mg->d_info = nullptr;   // fall back to the host-sequenced coarse solve
+  }
   *out = mg;
   return DGX_OK;
 }
 
 int dgx_mg_destroy(dgx_mg *mg) {
   if (!mg) return DGX_OK;
+  if (mg->d_info) cudaFree(mg->d_info);
+  if (mg->d_res) cudaFree(mg->d_res);
   for (dgx_vec *v : {mg->cg_r, mg->cg_p, mg->cg_v}) dgx_vec_destroy(v);
   for (int l = 0; l < mg->n_levels; ++l) {
     dgx_cheb_destroy(mg->smoother[l]);
@@ -473,6 +508,7 @@ int dgx_mg_setup(dgx_mg *mg, double coarse_abs_tol, int coarse_max_it) {
   mg->coarse_tol = coarse_abs_tol;
   mg->coarse_max_it = coarse_max_it;
   mg->coarse_its.clear();
+  mg->n_dev_solves = 0;
   for (int l = 0; l < mg->n_levels; ++l) {
     RC(dgx_op_compute_diagonal(mg->op[l]));
     if (l > 0) { mg->smoother[l]->initialized = false; RC(dgx_cheb_estimate(mg->smoother[l])); }
@@ -483,6 +519,13 @@ int dgx_mg_setup(dgx_mg *mg, double coarse_abs_tol, int coarse_max_it) {
 static int mg_level(dgx_mg *mg, int l) {
   // input: defect[l]; output: sol[l]        (Multigrid::level_v_step)
   if (l == 0) {
+    if (mg->d_info) {   // tiny level: the whole CG runs inside one CTA (no host round trips)
+      const int slot = mg->n_dev_solves % dgx_mg::kLog;
+      int rc = pressure_coarse_cg(mg->op[0], mg->sol[0], mg->defect[0], mg->cg_r, mg->cg_p, mg->cg_v, mg->coarse_tol, mg->coarse_max_it,
+                                  mg->d_info + 2 * slot, mg->d_res + slot);
+      if (rc == DGX_OK) { ++mg->n_dev_solves; return DGX_OK; }
+      if (rc != DGX_ERR_UNSUPPORTED) return rc;
+    }
     RC(dgx_vec_set(mg->sol[0], 0.0));
     Precond pc;   // identity
     int its = 0; double res = 0;
@@ -491,8 +534,15 @@ static int mg_level(dgx_mg *mg, int l) {
     return rc;
   }
   RC(dgx_cheb_vmult(mg->smoother[l], mg->sol[l], mg->defect[l]));                  // pre-smoothing from zero
-  RC(dgx_op_vmult(mg->op[l], mg->t[l], mg->sol[l]));
-  RC(dgx_vec_sadd(mg->t[l], -1.0, 1.0, mg->defect[l]));                             // t = defect - A sol
+  {
+    FusedUpdate fu;
+    fu.rhs = mg->defect[l]; fu.c = 1.0;
+    int frc = pressure_apply_fused(mg->op[l], mg->t[l], mg->sol[l], fu);           // t = defect - A sol in one kernel
+    if (frc == DGX_ERR_UNSUPPORTED) {
+      RC(dgx_op_vmult(mg->op[l], mg->t[l], mg->sol[l]));
+      RC(dgx_vec_sadd(mg->t[l], -1.0, 1.0, mg->defect[l]));
+    } else if (frc) return frc;
+  }
   RC(dgx_vec_set(mg->defect[l - 1], 0.0));
   RC(dgx_transfer_restrict_and_add(mg->defect[l - 1], mg->t[l]));
   RC(mg_level(mg, l - 1));
@@ -511,6 +561,18 @@ int dgx_mg_vmult(dgx_mg *mg, dgx_vec *dst, dgx_vec *src) {
 
 int dgx_mg_coarse_iterations(const dgx_mg *mg, int *out, int capacity, int *count) {
   DGX_REQUIRE(mg && count, "null argument");
+  if (mg->n_dev_solves > 0) {   // read the device-side log (also the place where a failed coarse solve surfaces)
+    const int nlog = std::min(mg->n_dev_solves, (int)dgx_mg::kLog);
+    std::vector<int> info(2 * nlog);
+    DGX_CUDA_CHECK(cudaStreamSynchronize(mg->ctx->stream));
+    DGX_CUDA_CHECK(cudaMemcpy(info.data(), mg->d_info, info.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    *count = nlog;
+    for (int i = 0; i < nlog; ++i) {
+      if (i < capacity) out[i] = info[2 * i];
+      if (!info[2 * i + 1]) { set_error("coarse SolverCG: no convergence after " + std::to_string(info[2 * i]) + " steps"); return DGX_ERR_NO_CONVERGENCE; }
+    }
+    return DGX_OK;
+  }
   *count = (int)mg->coarse_its.size();
   for (int i = 0; i < *count && i < capacity; ++i) out[i] = mg->coarse_its[i];
   return DGX_OK;
@@ -530,11 +592,9 @@ int dgx_solve_cg(dgx_op *A, dgx_vec *x, dgx_vec *b, int precond_kind, void *prec
   if (precond_kind == 1) pc.op = precond ? (dgx_op *)precond : A;
   else if (precond_kind == 2) { pc.mg = (dgx_mg *)precond; DGX_REQUIRE(pc.mg, "multigrid handle"); }
   else DGX_REQUIRE(precond_kind == 0, "precond_kind: 0 identity, 1 Jacobi, 2 multigrid");
-  dgx_vec *w[4] = {nullptr, nullptr, nullptr, nullptr};
-  for (auto &v : w) RC(dgx_vec_create(A->mf, A->degree, A->ncomp, &v));
-  int rc = cg_core(A, x, b, pc, max_it, abs_tol, w[0], w[1], w[2], w[3], iters, final_res, nullptr, nullptr, true);
-  for (auto &v : w) dgx_vec_destroy(v);
-  return rc;
+  dgx_vec *w[4];
+  RC(op_work(A, w, 4));
+  return cg_core(A, x, b, pc, max_it, abs_tol, w[0], w[1], w[2], w[3], iters, final_res, nullptr, nullptr, true);
 }
 
 // SolverGMRES, deal.II defaults: left preconditioning, restart length max_basis - 2, the monitored
