@@ -322,6 +322,24 @@ class NavierStokesProjectionOperator:
     def precondition_Jacobi(self, dst, src, omega=1.0):
         _check(lib.dgx_op_precondition_Jacobi(self.h, dst.h, src.h, c_dbl(omega)))
 
+    def _srcs(self, srcs):
+        arr = (c_vp * len(srcs))(*[v.h for v in srcs])
+        return arr, len(srcs)
+
+    def vmult_rhs_velocity(self, dst, srcs):
+        """NS.cc:788: stage 1 srcs = [u_n, u_extr, pres_n]; stage 2 srcs = [u_n, u_n_gamma, pres_int, u_extr]"""
+        arr, n = self._srcs(srcs)
+        _check(lib.dgx_op_vmult_rhs_velocity(self.h, dst.h, arr, n))
+
+    def vmult_rhs_pressure(self, dst, srcs):
+        """NS.cc:915: srcs = [u_star, pres_old]"""
+        arr, n = self._srcs(srcs)
+        _check(lib.dgx_op_vmult_rhs_pressure(self.h, dst.h, arr, n))
+
+    def vmult_grad_p_projection(self, dst, src):
+        """NS.cc:1363: dst = int grad(p) . phi on the velocity space"""
+        _check(lib.dgx_op_vmult_grad_p_projection(self.h, dst.h, src.h))
+
     def vmult_host(self, dst: np.ndarray, src: np.ndarray):
         """End-to-end entry: host buffers, H2D + vmult + D2H inside."""
         assert dst.flags.c_contiguous and src.flags.c_contiguous and dst.dtype == src.dtype
