@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--no-solve", action="store_true", help="skip the (untimed-region) MG-CG pressure solve report")
     ap.add_argument("--solve-refine", type=int, default=6)
     ap.add_argument("--solve-degree", type=int, default=3)
+    ap.add_argument("--no-step", action="store_true", help="skip the (untimed-region) TR-BDF2 step report")
+    ap.add_argument("--step-refine", type=int, default=5)
     return ap.parse_args()
 
 
@@ -125,6 +127,49 @@ def pressure_solve_report(dgx, ctx, args):
         out = {"workload": f"pressure MG-CG, 3D Q{p}, {2**R}^3 cells periodic, {n} DoFs, fp64 outer / fp32 V-cycle, tol 1e-8*||rhs||",
                "ms_per_solve": ms, "cg_iterations": its, "levels": mg.n_levels(), "final_residual": res,
                "gpu_launches": dgx.kernel_launch_count() - l0, "includes": "level diagonals + Chebyshev eigenvalue estimates + solve"}
+    return out
+
+
+def trbdf2_step_report(dgx, ctx, args):
+    """time per TR-BDF2 step (NS.cc:2934-2986) of the 3-D periodic Taylor-Green vortex, velocity Q3 / pressure Q2"""
+    from dgx.navier_stokes import NavierStokesProjection
+    R, dp = args.step_refine, 2
+    L = 2 * np.pi
+    mesh = dgx.Mesh(3, [1, 1, 1], R, [0, 0, 0], [L, L, L], [True, True, True])
+    h = L / 2 ** R
+    dt = 0.2 * h / (dp + 2)
+    ns = NavierStokesProjection(ctx, mesh, dp, 1600.0, dt)
+    # TGV initial state interpolated at the dof support points (Gauss-Lobatto nodes), cells in the library's order
+    def nodes(n):
+        from numpy.polynomial import legendre as leg
+        if n == 2:
+            return np.array([0.0, 1.0])
+        c = np.zeros(n); c[-1] = 1.0
+        return np.concatenate(([0.0], (np.sort(leg.legroots(leg.legder(c))) + 1) / 2, [1.0]))
+    coords = mesh.cell_coords().astype(np.float64)                       # [cells, 3]
+    def field(n, f):
+        x1 = nodes(n)
+        X = (coords[:, None, None, None, 0] + x1[None, None, None, :]) * h
+        Y = (coords[:, None, None, None, 1] + x1[None, None, :, None]) * h
+        Z = (coords[:, None, None, None, 2] + x1[None, :, None, None]) * h
+        return f(X + 0 * Y + 0 * Z, Y + 0 * X + 0 * Z, Z + 0 * X + 0 * Y)
+    nv, npn = dp + 2, dp + 1
+    u = np.stack([field(nv, lambda x, y, z: np.sin(x) * np.cos(y) * np.cos(z)), field(nv, lambda x, y, z: -np.cos(x) * np.sin(y) * np.cos(z)),
+                  field(nv, lambda x, y, z: 0 * x)], axis=1).reshape(-1)
+    p = field(npn, lambda x, y, z: (np.cos(2 * x) + np.cos(2 * y)) * (np.cos(2 * z) + 2) / 16).reshape(-1)
+    ns.u_n.from_host(u); ns.u_n_minus_1.from_host(u); ns.pres_n.from_host(p)
+    out = {}
+    for rep in range(2):
+        ns.iterations.clear()
+        ctx.synchronize()
+        l0 = dgx.kernel_launch_count()
+        ctx.timer_start()
+        vmax = ns.advance()
+        ms = ctx.timer_stop()
+        out = {"workload": f"TR-BDF2 step, 3D periodic Taylor-Green vortex, {2**R}^3 cells, velocity Q{dp+1} ({u.size} DoFs) / pressure Q{dp} ({p.size} DoFs), Re 1600, dt {dt:.3e}",
+               "ms_per_step": ms, "max_velocity": vmax, "iterations": dict((k + f"#{i}", v) for i, (k, v) in enumerate(ns.iterations)),
+               "gpu_launches": dgx.kernel_launch_count() - l0,
+               "note": "2 GMRES + 2 MG-CG + 3 mass CG solves, 2 probed velocity diagonals (n^3 operator applications each, as NS.cc:1431-1471)"}
     return out
 
 
@@ -282,6 +327,13 @@ def main():
         except Exception as exc:  # noqa: BLE001
             mg_solve = {"error": str(exc)}
 
+    step = None
+    if not args.no_step and world == 1:
+        try:
+            step = trbdf2_step_report(dgx, ctx, args)
+        except Exception as exc:  # noqa: BLE001
+            step = {"error": str(exc)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
@@ -299,7 +351,7 @@ def main():
                                    f"{n_global} DoFs {args.dtype}", "l2": "inputs (2 vectors) exceed the 126 MB L2; no flush needed",
                        "partition": f"{world} contiguous Morton chunks" if world > 1 else "single GPU"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(),
-            "mg_solve": mg_solve,
+            "mg_solve": mg_solve, "trbdf2_step": step,
         }
         print(json.dumps(line))
     if world > 1:

@@ -13,6 +13,19 @@ long long g_launch_count = 0;
 void set_error(const std::string &msg) { g_error = msg; }
 }  // namespace dgx
 
+namespace dgx {
+int op_pool_vec(dgx_op *op, int i, dgx_vec **out) {
+  if ((int)op->pool.size() <= i) op->pool.resize(i + 1, nullptr);
+  if (!op->pool[i]) {
+    int rc = dgx_vec_create(op->mf, op->degree, op->ncomp, &op->pool[i]);
+    if (rc) return rc;
+    op->pool[i]->borrowed = true;
+  }
+  *out = op->pool[i];
+  return DGX_OK;
+}
+}  // namespace dgx
+
 using namespace dgx;
 
 extern "C" {
@@ -99,6 +112,7 @@ int dgx_ctx_timer_stop(dgx_ctx *ctx, double *ms) {
   return DGX_OK;
 }
 
+
 // ---- operator ---------------------------------------------------------------------------------
 int dgx_op_create(dgx_mf *mf, int kind, int degree, double Re, double dt, dgx_op **out) {
   DGX_REQUIRE(mf && out, "null argument");
@@ -114,6 +128,8 @@ int dgx_op_create(dgx_mf *mf, int kind, int degree, double Re, double dt, dgx_op
 
 int dgx_op_destroy(dgx_op *op) {
   if (!op) return DGX_OK;
+  for (dgx_vec *v : op->pool)
+    if (v) { v->borrowed = false; dgx_vec_destroy(v); }
   for (dgx_vec *v : {op->u_extr, op->inv_diag, op->h_src, op->h_dst, op->work[0], op->work[1], op->work[2], op->work[3]})
     if (v) { v->borrowed = false; dgx_vec_destroy(v); }
   delete op;

@@ -134,6 +134,7 @@ struct dgx_op {
   dgx_vec *inv_diag = nullptr;
   dgx_vec *h_src = nullptr, *h_dst = nullptr;   // staging vectors of the host entry point
   dgx_vec *work[4] = {nullptr, nullptr, nullptr, nullptr};   // Krylov work vectors, allocated on first use and kept
+  std::vector<dgx_vec *> pool;                                // further work vectors (GMRES basis, diagonal probes), kept
 };
 
 namespace dgx {
@@ -148,6 +149,8 @@ struct FusedUpdate {
   double a = 0, b = 0, c = 0;
 };
 int pressure_apply_fused(dgx_op *op, dgx_vec *dst, dgx_vec *x, const FusedUpdate &fu);
+// i-th pooled work vector of the operator's space (created on first use, lives as long as the operator)
+int op_pool_vec(dgx_op *op, int i, dgx_vec **out);
 int pressure_coarse_cg(dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_vec *r, dgx_vec *p, dgx_vec *v, double tol, int max_it, int *d_info, double *d_res);
 int mass_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add);
 int velocity_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add);

@@ -608,17 +608,17 @@ int dgx_solve_gmres(dgx_op *A, dgx_vec *x, dgx_vec *b, int precond_kind, void *p
   const int kdim = std::max(1, max_basis - 2);
   std::vector<dgx_vec *> V(kdim + 1, nullptr);
   dgx_vec *w = nullptr, *tmp = nullptr;
-  auto cleanup = [&]() { for (auto v : V) dgx_vec_destroy(v); dgx_vec_destroy(w); dgx_vec_destroy(tmp); };
+  auto cleanup = [&]() {};   // all work vectors are pooled with the operator
 #define RCG(expr) do { int rc__ = (expr); if (rc__) { cleanup(); return rc__; } } while (0)
-  RCG(dgx_vec_create(A->mf, A->degree, A->ncomp, &w));
-  RCG(dgx_vec_create(A->mf, A->degree, A->ncomp, &tmp));
+  RCG(op_pool_vec(A, 2, &w));
+  RCG(op_pool_vec(A, 3, &tmp));
   int it_total = 0;
   double rho = 0;
   bool done = false, failed = false;
   while (!done) {
     RCG(dgx_op_vmult(A, tmp, x));
     RCG(dgx_vec_sadd(tmp, -1.0, 1.0, b));
-    if (!V[0]) RCG(dgx_vec_create(A->mf, A->degree, A->ncomp, &V[0]));
+    if (!V[0]) RCG(op_pool_vec(A, 4, &V[0]));
     RCG(apply_precond(pc, V[0], tmp));
     RCG(dgx_vec_l2_norm(V[0], &rho));
     if (rho <= abs_tol) break;
@@ -653,7 +653,7 @@ int dgx_solve_gmres(dgx_op *A, dgx_vec *x, dgx_vec *b, int precond_kind, void *p
       if (rho <= abs_tol) { done = true; break; }
       if (it_total >= max_it || !std::isfinite(rho)) { failed = true; done = true; break; }
       if (hn == 0.0) break;
-      if (!V[k + 1]) RCG(dgx_vec_create(A->mf, A->degree, A->ncomp, &V[k + 1]));
+      if (!V[k + 1]) RCG(op_pool_vec(A, 5 + k, &V[k + 1]));
       RCG(dgx_vec_equ(V[k + 1], 1.0 / hn, w));
     }
     // back substitution and update

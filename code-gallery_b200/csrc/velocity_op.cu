@@ -30,8 +30,13 @@ struct VelParams {
   T alpha, a, aRe, C, theta;
 };
 
-template <int dim, int n>
-__host__ __device__ constexpr int vel_cpb() { return (64 / ipow(n, dim - 1)) > 0 ? (64 / ipow(n, dim - 1)) : 1; }
+// cells per block: as many as keep the block's shared memory near 72 KB (3 blocks per SM), at most 16
+template <int dim, int n, typename T>
+__host__ __device__ constexpr int vel_cpb() {
+  constexpr int per_cell = (int)sizeof(T) * (3 * dim * ipow(n, dim) + 4 * 3 * dim * ipow(n, dim - 1));
+  return (72 * 1024 / per_cell) < 1 ? 1 : ((72 * 1024 / per_cell) > 16 ? 16 : (72 * 1024 / per_cell));
+}
+constexpr int kVelThreads = 256;
 
 template <int dim, int n>
 __device__ __forceinline__ void vline(int d, int l, int &base, int &stride) {
@@ -45,45 +50,48 @@ __device__ __forceinline__ void vline(int d, int l, int &base, int &stride) {
   }
 }
 
+// Every phase is a block-wide loop over work items (cell, field or component, line or point), so the number of
+// threads is independent of n and all 256 threads have work in every phase.
 template <int dim, int n, typename T>
-__global__ void __launch_bounds__(vel_cpb<dim, n>() * ipow(n, dim - 1))
+__global__ void __launch_bounds__(kVelThreads)
 velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict__ nbr, int n_owned, const T *__restrict__ src,
                 const T *__restrict__ ue, T *__restrict__ dst, int add) {
-  constexpr int NL = ipow(n, dim - 1), ND = NL * n, CPB = vel_cpb<dim, n>(), NT = CPB * NL;
+  constexpr int NL = ipow(n, dim - 1), ND = NL * n, CPB = vel_cpb<dim, n, T>(), NT = kVelThreads;
   constexpr int NF = 3 * dim;   // face fields: V (dim), G (dim), E (dim)
+  constexpr int PER_CELL = 3 * dim * ND + 4 * NF * NL;
   extern __shared__ __align__(16) unsigned char vsm[];
   T *sm = reinterpret_cast<T *>(vsm);
-  const int tid = threadIdx.x, ci = tid / NL, l = tid % NL;
-  const int cell = blockIdx.x * CPB + ci;
-  const bool active = cell < n_owned;
-  T *A = sm + (size_t)ci * (3 * dim * ND + 4 * NF * NL);   // [2*dim][ND]
-  T *R = A + 2 * dim * ND;                                 // [dim][ND]
-  T *NTa = R + dim * ND;                                   // [2 faces][NF][NL]
-  T *NTb = NTa + 2 * NF * NL;
-  // 1. load u, u_extr
-  if (active)
-    for (int f = 0; f < 2 * dim; ++f) {
-      const T *g = (f < dim ? src : ue) + ((size_t)cell * dim + (f % dim)) * ND;
-      for (int i = l; i < ND; i += NL) A[f * ND + i] = g[i];
-    }
+  const int tid = threadIdx.x;
+  const int cell0 = blockIdx.x * CPB;
+  const int ncell = min(CPB, n_owned - cell0);
+  auto Ac = [&](int ci) { return sm + (size_t)ci * PER_CELL; };                 // [2*dim][ND]
+  auto Rc = [&](int ci) { return sm + (size_t)ci * PER_CELL + 2 * dim * ND; };  // [dim][ND]
+  auto Na = [&](int ci) { return sm + (size_t)ci * PER_CELL + 3 * dim * ND; };  // [2 faces][NF][NL]
+  auto Nb = [&](int ci) { return sm + (size_t)ci * PER_CELL + 3 * dim * ND + 2 * NF * NL; };
+  // 1. load u, u_extr (contiguous per cell: dim * ND values each)
+  for (int it = tid; it < ncell * 2 * dim * ND; it += NT) {
+    const int ci = it / (2 * dim * ND), r = it - ci * (2 * dim * ND);
+    const int f = r / ND, i = r - f * ND;
+    Ac(ci)[r] = (f < dim ? src : ue)[((size_t)(cell0 + ci) * dim + (f % dim)) * ND + i];
+  }
   __syncthreads();
   // 2. to the Gauss-point basis
 #pragma unroll
   for (int d = 0; d < dim; ++d) {
-    if (active) {
+    for (int it = tid; it < ncell * 2 * dim * NL; it += NT) {
+      const int ci = it / (2 * dim * NL), r = it - ci * (2 * dim * NL), f = r / NL, l = r - f * NL;
       int base, stride;
       vline<dim, n>(d, l, base, stride);
-      for (int f = 0; f < 2 * dim; ++f) {
-        T u[n];
+      T *A = Ac(ci) + f * ND;
+      T u[n];
 #pragma unroll
-        for (int i = 0; i < n; ++i) u[i] = A[f * ND + base + stride * i];
+      for (int i = 0; i < n; ++i) u[i] = A[base + stride * i];
 #pragma unroll
-        for (int q = 0; q < n; ++q) {
-          T acc = 0;
+      for (int q = 0; q < n; ++q) {
+        T acc = 0;
 #pragma unroll
-          for (int i = 0; i < n; ++i) acc += P.S[q * n + i] * u[i];
-          A[f * ND + base + stride * q] = acc;
-        }
+        for (int i = 0; i < n; ++i) acc += P.S[q * n + i] * u[i];
+        A[base + stride * q] = acc;
       }
     }
     __syncthreads();
@@ -92,169 +100,162 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
   T vol = 1;
 #pragma unroll
   for (int d = 0; d < dim; ++d) vol *= P.h[d];
-  if (active)
-    for (int i = l; i < ND; i += NL) {
-      int r = i;
-      T jxw = vol;
+  for (int it = tid; it < ncell * dim * ND; it += NT) {
+    const int ci = it / (dim * ND), r = it - ci * (dim * ND), i = r % ND;
+    int rr = i;
+    T jxw = vol;
 #pragma unroll
-      for (int d = 0; d < dim; ++d) { jxw *= P.w[r % n]; r /= n; }
-      for (int c = 0; c < dim; ++c) R[c * ND + i] = P.alpha * jxw * A[c * ND + i];
-    }
+    for (int d = 0; d < dim; ++d) { jxw *= P.w[rr % n]; rr /= n; }
+    Rc(ci)[r] = P.alpha * jxw * Ac(ci)[r];
+  }
   __syncthreads();
   // 4. per direction: gradient part of the cell term and the two faces normal to d
-  const int t0 = l % n, t1 = l / n;
-  const T wt = dim == 3 ? P.w[t0] * P.w[t1] : P.w[t0];
 #pragma unroll
   for (int d = 0; d < dim; ++d) {
-    int base, stride;
-    vline<dim, n>(d, l, base, stride);
-    int nb[2] = {-1, -1};
-    if (active) {
-      // 4a. nodal traces of the neighbours at the nodal tangential point l
+    // 4a. nodal traces of the neighbours: item = (cell, side, component, nodal tangential point)
+    for (int it = tid; it < ncell * 2 * dim * NL; it += NT) {
+      const int ci = it / (2 * dim * NL), r = it - ci * (2 * dim * NL), s = r / (dim * NL), r2 = r - s * (dim * NL), c = r2 / NL, l = r2 - c * NL;
+      const int nbc = nbr[(size_t)(2 * d + s) * n_owned + cell0 + ci];
+      if (nbc < 0) continue;
+      int base, stride;
+      vline<dim, n>(d, l, base, stride);
+      const T *gu = src + ((size_t)nbc * dim + c) * ND + base;
+      const T *ge = ue + ((size_t)nbc * dim + c) * ND + base;
+      T gsum = 0, v = 0;
 #pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        nb[s] = nbr[(size_t)(2 * d + s) * n_owned + cell];
-        if (nb[s] < 0) continue;
-        for (int c = 0; c < dim; ++c) {
-          const T *gu = src + ((size_t)nb[s] * dim + c) * ND + base;
-          const T *ge = ue + ((size_t)nb[s] * dim + c) * ND + base;
-          T gsum = 0, v = 0;
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-            const T x = gu[stride * i];
-            gsum += P.gN[1 - s][i] * x;
-            if (i == (1 - s) * (n - 1)) v = x;
-          }
-          NTa[(s * NF + c) * NL + l] = v;
-          NTa[(s * NF + dim + c) * NL + l] = P.ih[d] * gsum;
-          NTa[(s * NF + 2 * dim + c) * NL + l] = ge[stride * (1 - s) * (n - 1)];
-        }
+      for (int i = 0; i < n; ++i) {
+        const T x = gu[stride * i];
+        gsum += P.gN[1 - s][i] * x;
+        if (i == (1 - s) * (n - 1)) v = x;
       }
+      T *NTa = Na(ci);
+      NTa[(s * NF + c) * NL + l] = v;
+      NTa[(s * NF + dim + c) * NL + l] = P.ih[d] * gsum;
+      NTa[(s * NF + 2 * dim + c) * NL + l] = ge[stride * (1 - s) * (n - 1)];
     }
     __syncthreads();
-    // tangential interpolation to the face Gauss points (dim - 1 passes)
-    if (active) {
+    // tangential interpolation to the face Gauss points (dim - 1 passes): item = (cell, side, face field, point)
+    for (int it = tid; it < ncell * 2 * NF * NL; it += NT) {
+      const int ci = it / (2 * NF * NL), r = it - ci * (2 * NF * NL), sf = r / NL, l = r - sf * NL;
+      const int t0 = l % n, t1 = l / n;
+      const T *in = Na(ci) + sf * NL;
+      T acc = 0;
 #pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        if (nb[s] < 0) continue;
-        for (int f = 0; f < NF; ++f) {
-          T acc = 0;
-#pragma unroll
-          for (int a2 = 0; a2 < n; ++a2) acc += P.S[t0 * n + a2] * NTa[(s * NF + f) * NL + a2 + n * t1];
-          NTb[(s * NF + f) * NL + l] = acc;
-        }
-      }
+      for (int a2 = 0; a2 < n; ++a2) acc += P.S[t0 * n + a2] * in[a2 + n * t1];
+      Nb(ci)[sf * NL + l] = acc;
     }
     __syncthreads();
     if (dim == 3) {
-      if (active) {
+      for (int it = tid; it < ncell * 2 * NF * NL; it += NT) {
+        const int ci = it / (2 * NF * NL), r = it - ci * (2 * NF * NL), sf = r / NL, l = r - sf * NL;
+        const int t0 = l % n, t1 = l / n;
+        const T *in = Nb(ci) + sf * NL;
+        T acc = 0;
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          if (nb[s] < 0) continue;
-          for (int f = 0; f < NF; ++f) {
-            T acc = 0;
-#pragma unroll
-            for (int b2 = 0; b2 < n; ++b2) acc += P.S[t1 * n + b2] * NTb[(s * NF + f) * NL + t0 + n * b2];
-            NTa[(s * NF + f) * NL + l] = acc;
-          }
-        }
+        for (int b2 = 0; b2 < n; ++b2) acc += P.S[t1 * n + b2] * in[t0 + n * b2];
+        Na(ci)[sf * NL + l] = acc;
       }
       __syncthreads();
     }
-    const T *NTf = dim == 3 ? NTa : NTb;
-    if (active) {
-      // advecting component normal to the faces, own traces
-      T Ed[2] = {0, 0};
-      {
-        const T *e = A + (dim + d) * ND + base;
-#pragma unroll
-        for (int q = 0; q < n; ++q) { const T x = e[stride * q]; Ed[0] += P.fh[0][q] * x; Ed[1] += P.fh[1][q] * x; }
-      }
+    // 4b. item = (cell, component, line along d)
+    for (int it = tid; it < ncell * dim * NL; it += NT) {
+      const int ci = it / (dim * NL), r = it - ci * (dim * NL), c = r / NL, l = r - c * NL;
+      const int cell = cell0 + ci;
+      const T *A = Ac(ci);
+      T *R = Rc(ci);
+      const T *NTf = dim == 3 ? Na(ci) : Nb(ci);
+      int base, stride;
+      vline<dim, n>(d, l, base, stride);
+      const int t0 = l % n, t1 = l / n;
+      const T wt = dim == 3 ? P.w[t0] * P.w[t1] : P.w[t0];
       T area = 1;
 #pragma unroll
       for (int e2 = 0; e2 < dim; ++e2) if (e2 != d) area *= P.h[e2];
       const T wf = area * wt, sigma = P.C * P.ih[d];
-      for (int c = 0; c < dim; ++c) {
-        T u[n], ed[n], r[n];
+      T u[n], ed[n], rl[n];
+      T Ed[2] = {0, 0};
 #pragma unroll
-        for (int q = 0; q < n; ++q) { u[q] = A[c * ND + base + stride * q]; ed[q] = A[(dim + d) * ND + base + stride * q]; }
-        // cell term, direction d: flux = JxW (a/Re du/dx_d - a u ue_d), tested with d(phi)/dx_d
-        T fl[n];
-#pragma unroll
-        for (int q = 0; q < n; ++q) {
-          T dl = 0;
-#pragma unroll
-          for (int q2 = 0; q2 < n; ++q2) dl += P.Dh[q * n + q2] * u[q2];
-          fl[q] = vol * wt * P.w[q] * (P.aRe * P.ih[d] * dl - P.a * u[q] * ed[q]);
-        }
-#pragma unroll
-        for (int i = 0; i < n; ++i) {
-          T acc = 0;
-#pragma unroll
-          for (int q = 0; q < n; ++q) acc += P.Dh[q * n + i] * fl[q];
-          r[i] = P.ih[d] * acc;
-        }
-        // faces
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          const T ns = s ? T(1) : T(-1);
-          T V = 0, G = 0;
-#pragma unroll
-          for (int q = 0; q < n; ++q) { V += P.fh[s][q] * u[q]; G += P.gh[s][q] * u[q]; }
-          G *= P.ih[d];
-          T FV, FG;
-          if (nb[s] >= 0) {
-            const T Vn = NTf[(s * NF + c) * NL + l], Gn = NTf[(s * NF + dim + c) * NL + l], En = NTf[(s * NF + 2 * dim + d) * NL + l];
-            const T lam = fmax(fabs(Ed[s]), fabs(En)), jump = V - Vn;
-            FV = P.aRe * (T(-0.5) * ns * (G + Gn) + sigma * jump) + P.a * T(0.5) * ns * (V * Ed[s] + Vn * En) + T(0.5) * P.a * lam * jump;
-            FG = -P.theta * P.aRe * T(0.5) * jump;
-          } else if (nb[s] != -2) {   // boundary_id != 1: weak Dirichlet, coef_trasp = 0 (NS.cc:1113-1128)
-            const T lam = fabs(Ed[s]);
-            FV = P.aRe * (-ns * G + T(2) * sigma * V) + P.a * lam * V;
-            FG = -P.theta * P.aRe * V;
-          } else {                    // boundary_id == 1: mirror state u_m = (u_0, -u_1, u_2), NS.cc:1139-1155
-            const T lam = fabs(Ed[s]);
-            const T dV = (c == 1) ? T(2) * V : T(0);          // u - u_m
-            const T aV = (c == 1) ? T(0) : V;                 // (u + u_m) / 2
-            const T dn = (c == 0 && d < 2) ? T(0) : ns * G;   // (1/2 (grad u + grad u_m) n)_c
-            FV = P.aRe * (-dn + sigma * dV) + P.a * aV * (ns * Ed[s]) + T(0.5) * P.a * lam * dV;
-            FG = -P.theta * P.aRe * dV;
-          }
-#pragma unroll
-          for (int q = 0; q < n; ++q) r[q] += wf * (P.fh[s][q] * FV + ns * P.ih[d] * P.gh[s][q] * FG);
-        }
-#pragma unroll
-        for (int q = 0; q < n; ++q) R[c * ND + base + stride * q] += r[q];
+      for (int q = 0; q < n; ++q) {
+        u[q] = A[c * ND + base + stride * q];
+        ed[q] = A[(dim + d) * ND + base + stride * q];
+        Ed[0] += P.fh[0][q] * ed[q]; Ed[1] += P.fh[1][q] * ed[q];
       }
+      // cell term, direction d: flux = JxW (a/Re du/dx_d - a u ue_d), tested with d(phi)/dx_d
+      T fl[n];
+#pragma unroll
+      for (int q = 0; q < n; ++q) {
+        T dl = 0;
+#pragma unroll
+        for (int q2 = 0; q2 < n; ++q2) dl += P.Dh[q * n + q2] * u[q2];
+        fl[q] = vol * wt * P.w[q] * (P.aRe * P.ih[d] * dl - P.a * u[q] * ed[q]);
+      }
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        T acc = 0;
+#pragma unroll
+        for (int q = 0; q < n; ++q) acc += P.Dh[q * n + i] * fl[q];
+        rl[i] = P.ih[d] * acc;
+      }
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int nbc = nbr[(size_t)(2 * d + s) * n_owned + cell];
+        const T ns = s ? T(1) : T(-1);
+        T V = 0, G = 0;
+#pragma unroll
+        for (int q = 0; q < n; ++q) { V += P.fh[s][q] * u[q]; G += P.gh[s][q] * u[q]; }
+        G *= P.ih[d];
+        T FV, FG;
+        if (nbc >= 0) {
+          const T Vn = NTf[(s * NF + c) * NL + l], Gn = NTf[(s * NF + dim + c) * NL + l], En = NTf[(s * NF + 2 * dim + d) * NL + l];
+          const T lam = fmax(fabs(Ed[s]), fabs(En)), jump = V - Vn;
+          FV = P.aRe * (T(-0.5) * ns * (G + Gn) + sigma * jump) + P.a * T(0.5) * ns * (V * Ed[s] + Vn * En) + T(0.5) * P.a * lam * jump;
+          FG = -P.theta * P.aRe * T(0.5) * jump;
+        } else if (nbc != -2) {   // boundary_id != 1: weak Dirichlet, coef_trasp = 0 (NS.cc:1113-1128)
+          const T lam = fabs(Ed[s]);
+          FV = P.aRe * (-ns * G + T(2) * sigma * V) + P.a * lam * V;
+          FG = -P.theta * P.aRe * V;
+        } else {                    // boundary_id == 1: mirror state u_m = (u_0, -u_1, u_2), NS.cc:1139-1155
+          const T lam = fabs(Ed[s]);
+          const T dV = (c == 1) ? T(2) * V : T(0);          // u - u_m
+          const T aV = (c == 1) ? T(0) : V;                 // (u + u_m) / 2
+          const T dn = (c == 0 && d < 2) ? T(0) : ns * G;   // (1/2 (grad u + grad u_m) n)_c
+          FV = P.aRe * (-dn + sigma * dV) + P.a * aV * (ns * Ed[s]) + T(0.5) * P.a * lam * dV;
+          FG = -P.theta * P.aRe * dV;
+        }
+#pragma unroll
+        for (int q = 0; q < n; ++q) rl[q] += wf * (P.fh[s][q] * FV + ns * P.ih[d] * P.gh[s][q] * FG);
+      }
+#pragma unroll
+      for (int q = 0; q < n; ++q) R[c * ND + base + stride * q] += rl[q];
     }
     __syncthreads();
   }
   // 5. back to the nodal basis (transposed basis change)
 #pragma unroll
   for (int d = 0; d < dim; ++d) {
-    if (active) {
+    for (int it = tid; it < ncell * dim * NL; it += NT) {
+      const int ci = it / (dim * NL), r = it - ci * (dim * NL), c = r / NL, l = r - c * NL;
       int base, stride;
       vline<dim, n>(d, l, base, stride);
-      for (int c = 0; c < dim; ++c) {
-        T u[n];
+      T *R = Rc(ci) + c * ND;
+      T u[n];
 #pragma unroll
-        for (int q = 0; q < n; ++q) u[q] = R[c * ND + base + stride * q];
+      for (int q = 0; q < n; ++q) u[q] = R[base + stride * q];
 #pragma unroll
-        for (int i = 0; i < n; ++i) {
-          T acc = 0;
+      for (int i = 0; i < n; ++i) {
+        T acc = 0;
 #pragma unroll
-          for (int q = 0; q < n; ++q) acc += P.S[q * n + i] * u[q];
-          R[c * ND + base + stride * i] = acc;
-        }
+        for (int q = 0; q < n; ++q) acc += P.S[q * n + i] * u[q];
+        R[base + stride * i] = acc;
       }
     }
     __syncthreads();
   }
-  if (active)
-    for (int c = 0; c < dim; ++c) {
-      T *o = dst + ((size_t)cell * dim + c) * ND;
-      for (int i = l; i < ND; i += NL) o[i] = add ? o[i] + R[c * ND + i] : R[c * ND + i];
-    }
+  for (int it = tid; it < ncell * dim * ND; it += NT) {
+    const int ci = it / (dim * ND), r = it - ci * (dim * ND);
+    T *o = dst + (size_t)(cell0 + ci) * dim * ND + r;
+    *o = add ? *o + Rc(ci)[r] : Rc(ci)[r];
+  }
 }
 
 // probe vector of compute_diagonal: dof `i` of every component of every cell (ghosts included) is one
@@ -289,7 +290,7 @@ int launch_velocity(dgx_op *op, T *dst, const T *src, bool add) {
   P.a = (T)a; P.aRe = (T)(a / op->Re);
   P.C = (T)((double)n * n);   // C_u = (p_v + 1)^2, NS.cc:293
   P.theta = (T)1.0;           // theta_v, NS.cc:290
-  constexpr int NL = ipow(n, dim - 1), ND = NL * n, CPB = vel_cpb<dim, n>(), NT = CPB * NL;
+  constexpr int NL = ipow(n, dim - 1), ND = NL * n, CPB = vel_cpb<dim, n, T>(), NT = kVelThreads;
   const size_t smem = sizeof(T) * (size_t)CPB * (3 * dim * ND + 4 * 3 * dim * NL);
   static bool configured = false;
   if (!configured) {
@@ -328,9 +329,9 @@ int diagonal_by_probing(dgx_op *op, dgx_vec *out) {
   dgx_mf *mf = op->mf;
   long long ND = 1;
   for (int d = 0; d < mf->dim; ++d) ND *= op->degree + 1;
-  dgx_vec *probe = nullptr, *res = nullptr;
-  int rc = dgx_vec_create(mf, op->degree, op->ncomp, &probe);
-  if (!rc) rc = dgx_vec_create(mf, op->degree, op->ncomp, &res);
+  dgx_vec *probe = nullptr, *res = nullptr;   // pooled with the operator: no cudaMalloc / cudaFree per call
+  int rc = op_pool_vec(op, 0, &probe);
+  if (!rc) rc = op_pool_vec(op, 1, &res);
   if (rc) return rc;
   const long long total = probe->n_owned + probe->n_ghost, nblocks = probe->n_owned / ND;
   cudaStream_t st = mf->ctx->stream;
@@ -344,8 +345,6 @@ int diagonal_by_probing(dgx_op *op, dgx_vec *out) {
   }
   if (!rc && out->n_owned) { reciprocal_kernel<T><<<g1, 256, 0, st>>>((T *)out->d, out->n_owned); count_launch(); }   // NS.cc:2055-2059
   if (!rc && cudaGetLastError() != cudaSuccess) { set_error("velocity diagonal: kernel launch failed"); rc = DGX_ERR_CUDA; }
-  cudaStreamSynchronize(st);
-  dgx_vec_destroy(probe); dgx_vec_destroy(res);
   return rc;
 }
 
