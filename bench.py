@@ -198,6 +198,10 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
+    # libraries (NCCL's version banner) may print to stdout: keep stdout clean for the ONE JSON line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import dgx
@@ -353,7 +357,10 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(),
             "mg_solve": mg_solve, "trbdf2_step": step,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
     ctx.close()

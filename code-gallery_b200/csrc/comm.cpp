@@ -103,14 +103,14 @@ int allreduce_max(dgx_ctx *ctx, double *dvals, int n) {
 }
 
 // grouped point-to-point: send[i] -> peers, recv[i] <- peers (bytes)
-int comm_exchange(dgx_ctx *ctx, int npeers, const int *ranks, const void *const *sendbuf, const size_t *sendbytes,
+int comm_exchange(dgx_ctx *ctx, cudaStream_t stream, int npeers, const int *ranks, const void *const *sendbuf, const size_t *sendbytes,
                   void *const *recvbuf, const size_t *recvbytes) {
   if (ctx->nranks == 1 || npeers == 0) return DGX_OK;
   ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
   DGX_NCCL_CHECK(api().GroupStart());
   for (int i = 0; i < npeers; ++i) {
-    if (sendbytes[i]) DGX_NCCL_CHECK(api().Send(sendbuf[i], sendbytes[i], ncclChar, ranks[i], comm, ctx->stream));
-    if (recvbytes[i]) DGX_NCCL_CHECK(api().Recv(recvbuf[i], recvbytes[i], ncclChar, ranks[i], comm, ctx->stream));
+    if (sendbytes[i]) DGX_NCCL_CHECK(api().Send(sendbuf[i], sendbytes[i], ncclChar, ranks[i], comm, stream));
+    if (recvbytes[i]) DGX_NCCL_CHECK(api().Recv(recvbuf[i], recvbytes[i], ncclChar, ranks[i], comm, stream));
   }
   DGX_NCCL_CHECK(api().GroupEnd());
   return DGX_OK;

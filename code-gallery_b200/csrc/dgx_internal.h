@@ -81,6 +81,9 @@ struct dgx_ctx {
   int device = 0, rank = 0, nranks = 1;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // ghost exchange overlapped with interior work: pack + NCCL run on comm_stream between these two events
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_src_ready = nullptr, ev_ghosts_done = nullptr;
   void *nccl_comm = nullptr;
   double *d_scratch = nullptr;   // reduction scratch (device)
   double *h_scratch = nullptr;   // pinned
@@ -110,6 +113,9 @@ struct dgx_mf {
     int *d_send_cells = nullptr;
   };
   std::vector<Peer> peers;
+  // marching kernel job lists (tile columns that need no ghost data / that do), built on first use for jobs_NZ
+  int *d_jobs = nullptr;
+  int n_jobs_interior = 0, n_jobs_boundary = 0, jobs_NZ = 0;
 };
 
 struct dgx_vec {
@@ -142,6 +148,7 @@ namespace dgx {
 double gamma_trbdf2();
 // kernel launchers (defined in .cu files); all enqueue on mf->ctx->stream
 int pressure_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add);
+int pressure_apply_fast_overlapped(dgx_op *op, dgx_vec *dst, dgx_vec *src, bool add);
 int pressure_diagonal(dgx_op *op, dgx_vec *diag_inv);
 // fused operator + vector update: dst = a x + b xold + c d .* (rhs - A x)   (xold, d may be null)
 struct FusedUpdate {
@@ -156,6 +163,10 @@ int mass_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add);
 int velocity_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add);
 int velocity_diagonal(dgx_op *op, dgx_vec *diag_inv);
 int ghost_exchange(dgx_vec *v);
+// same exchange on the context's communication stream: starts when the work already queued on the compute stream is
+// done; ghost_exchange_wait makes the compute stream wait for the ghosts
+int ghost_exchange_start(dgx_vec *v);
+int ghost_exchange_wait(dgx_ctx *ctx);
 int allreduce_sum(dgx_ctx *ctx, double *vals, int n);
 int allreduce_max(dgx_ctx *ctx, double *vals, int n);
 int comm_init(dgx_ctx *ctx, const void *id);

@@ -21,6 +21,7 @@
 // Hand-offs use named barriers (bar.arrive / bar.sync), stages are double buffered.
 #include <type_traits>
 #include <utility>
+#include <vector>
 
 #include "pressure_op.cuh"
 
@@ -130,7 +131,7 @@ __device__ __forceinline__ int slot_of(int cx, int cy) { return (cx & 1) | ((cy 
 template <int n, typename T, bool ADD>
 __global__ void __launch_bounds__(Roles<n>::NW * 32, MinBlocks<n, T>::value)
 pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_constant__ FastGeom G,
-                      const int *__restrict__ nbr, const T *__restrict__ src, T *__restrict__ dst) {
+                      const int *__restrict__ nbr, const T *__restrict__ src, T *__restrict__ dst, const int *__restrict__ jobs) {
   using R = Roles<n>;
   constexpr int NL = n * n, ND = NL * n, NS = R::NSTAGE;
   constexpr int CNT_FULL = (R::NXY + R::NZW + R::NH) * 32,
@@ -168,7 +169,7 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
   }
   __syncthreads();
 
-  const int job = blockIdx.x;
+  const int job = jobs ? jobs[blockIdx.x] : blockIdx.x;
   const int tx = job % G.ntx, ty = (job / G.ntx) % G.nty, sz = job / (G.ntx * G.nty);
   const int x0 = G.lox + tx * TXC, y0 = G.loy + ty * TYC, z0 = G.loz + sz * G.NZ;
   const int NZ = G.NZ;
@@ -374,11 +375,17 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
 #pragma unroll
       for (int a = 0; a < n; ++a) { gx[0][a] = 0; gx[1][a] = 0; gy[0][a] = 0; gy[1][a] = 0; }
       // y sweep: rows of u, acc[jj][i] += Kt_y[jj][j] u[j][i]; traces of the y faces
+      T nxt[n];
+#pragma unroll
+      for (int i = 0; i < n; ++i) nxt[i] = Up[i];
 #pragma unroll 1
       for (int j = 0; j < n; ++j) {
         T row[n], kc[n];
 #pragma unroll
-        for (int i = 0; i < n; ++i) row[i] = Up[j * n + i];
+        for (int i = 0; i < n; ++i) row[i] = nxt[i];
+        const int jn = j + 1 < n ? j + 1 : 0;          // software pipelining: the next row is in flight during the FMAs
+#pragma unroll
+        for (int i = 0; i < n; ++i) nxt[i] = Up[jn * n + i];
 #pragma unroll
         for (int jj = 0; jj < n; ++jj) kc[jj] = P.Kt[1][jj * n + j];
         const T g0 = P.g[0][j], g1 = P.g[1][j];
@@ -390,11 +397,16 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
         for (int i = 0; i < n; ++i) { gy[0][i] = fma(g0, row[i], gy[0][i]); gy[1][i] = fma(g1, row[i], gy[1][i]); }
       }
       // x sweep: columns of u, acc[j][ii] += Kt_x[ii][i] u[j][i]; traces of the x faces
+#pragma unroll
+      for (int j = 0; j < n; ++j) nxt[j] = Up[j * n];
 #pragma unroll 1
       for (int i = 0; i < n; ++i) {
         T col[n], kc[n];
 #pragma unroll
-        for (int j = 0; j < n; ++j) col[j] = Up[j * n + i];
+        for (int j = 0; j < n; ++j) col[j] = nxt[j];
+        const int in_ = i + 1 < n ? i + 1 : 0;
+#pragma unroll
+        for (int j = 0; j < n; ++j) nxt[j] = Up[j * n + in_];
 #pragma unroll
         for (int ii = 0; ii < n; ++ii) kc[ii] = P.Kt[0][ii * n + i];
         const T g0 = P.g[0][i], g1 = P.g[1][i];
@@ -405,6 +417,7 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
 #pragma unroll
         for (int j = 0; j < n; ++j) { gx[0][j] = fma(g0, col[j], gx[0][j]); gx[1][j] = fma(g1, col[j], gx[1][j]); }
       }
+      if (p > 0) bar_sync(B_XY, CNT_XY);   // every layer thread has read the previous plane's traces: TX / TY may be overwritten
 #pragma unroll
       for (int a = 0; a < n; ++a) {
         TX[(0 * NL + a + n * k) * TC + c] = gx[0][a];
@@ -459,7 +472,6 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
           if (p + NS < NZ) issue_plane(p + NS);
         }
       }
-      bar_sync(B_XY, CNT_XY);   // nobody overwrites TX / TY before every layer thread has read them
       // mass in x, then y
       T tmp[n][n];
 #pragma unroll
@@ -579,7 +591,7 @@ void fill_fast_params(FastParams<T, n> &F, const dgx_op *op) {
 }
 
 template <int n, typename T>
-int launch_march(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const FastGeom &G) {
+int launch_march(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const FastGeom &G, const int *d_jobs, int n_jobs, cudaStream_t stream) {
   using R = Roles<n>;
   constexpr int NL = n * n, ND = NL * n;
   FastParams<T, n> F;
@@ -592,12 +604,41 @@ int launch_march(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const F
     DGX_CUDA_CHECK(cudaFuncSetAttribute(pressure_march_kernel<n, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  const int grid = G.ntx * G.nty * G.nsz;
-  if (add) pressure_march_kernel<n, T, true><<<grid, R::NW * 32, smem, op->mf->ctx->stream>>>(F, G, op->mf->d_nbr, (const T *)src->d, (T *)dst->d);
-  else pressure_march_kernel<n, T, false><<<grid, R::NW * 32, smem, op->mf->ctx->stream>>>(F, G, op->mf->d_nbr, (const T *)src->d, (T *)dst->d);
+  const int grid = d_jobs ? n_jobs : G.ntx * G.nty * G.nsz;
+  if (grid == 0) return DGX_OK;
+  if (add) pressure_march_kernel<n, T, true><<<grid, R::NW * 32, smem, stream>>>(F, G, op->mf->d_nbr, (const T *)src->d, (T *)dst->d, d_jobs);
+  else pressure_march_kernel<n, T, false><<<grid, R::NW * 32, smem, stream>>>(F, G, op->mf->d_nbr, (const T *)src->d, (T *)dst->d, d_jobs);
   count_launch();
   DGX_CUDA_CHECK(cudaGetLastError());
   return DGX_OK;
+}
+
+int march_dispatch(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const FastGeom &G, const int *d_jobs, int n_jobs, cudaStream_t stream = nullptr) {
+  dgx_mf *mf = op->mf;
+  if (!stream) stream = mf->ctx->stream;
+  if (mf->dtype == DGX_F64) return op->degree == 4 ? launch_march<5, double>(op, dst, src, add, G, d_jobs, n_jobs, stream) : launch_march<4, double>(op, dst, src, add, G, d_jobs, n_jobs, stream);
+  return op->degree == 4 ? launch_march<5, float>(op, dst, src, add, G, d_jobs, n_jobs, stream) : launch_march<4, float>(op, dst, src, add, G, d_jobs, n_jobs, stream);
+}
+
+// geometry of the march for this operator, or false when the marching kernel does not apply
+bool march_geometry(const dgx_op *op, FastGeom &G) {
+  const dgx_mf *mf = op->mf;
+  if (mf->dim != 3 || !mf->all_interior || !mf->box_ok) return false;
+  // Q3 fp32 is still slower here than in the generic kernel (small planes: fixed per-plane costs): only on request (variant 2)
+  if (op->degree != 4 && !(op->degree == 3 && (op->variant == 2 || mf->dtype == DGX_F64))) return false;
+  const Mesh &m = mf->mesh->m;
+  G.L = mf->level;
+  G.c0x = m.cells0[0]; G.c0y = m.cells0[1];
+  G.lox = mf->box_lo[0]; G.loy = mf->box_lo[1]; G.loz = mf->box_lo[2];
+  const int EX = mf->box_ext[0], EY = mf->box_ext[1], EZ = mf->box_ext[2];
+  if (G.L < 3 || EX % TXC || EY % TYC || EZ < 2 || mf->first_cell % 4) return false;
+  G.ntx = EX / TXC; G.nty = EY / TYC;
+  int NZ = EZ;
+  while (NZ > 64 && NZ % 2 == 0) NZ /= 2;
+  G.NZ = NZ; G.nsz = EZ / NZ;
+  G.first_cell = mf->first_cell;
+  G.n_owned = (int)mf->n_owned;
+  return true;
 }
 
 }  // namespace
@@ -605,25 +646,54 @@ int launch_march(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const F
 // The marching kernel applies when every face is interior (fully periodic mesh) and the owned cells form a
 // box of the hierarchical order whose extents are multiples of the tile.
 int pressure_apply_fast(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) {
-  dgx_mf *mf = op->mf;
-  if (mf->dim != 3 || !mf->all_interior || !mf->box_ok) return DGX_ERR_UNSUPPORTED;
-  // Q3 fp32 is still slower here than in the generic kernel (small planes: fixed per-plane costs): only on request (variant 2)
-  if (op->degree != 4 && !(op->degree == 3 && (op->variant == 2 || mf->dtype == DGX_F64))) return DGX_ERR_UNSUPPORTED;
-  const Mesh &m = mf->mesh->m;
   FastGeom G;
-  G.L = mf->level;
-  G.c0x = m.cells0[0]; G.c0y = m.cells0[1];
-  G.lox = mf->box_lo[0]; G.loy = mf->box_lo[1]; G.loz = mf->box_lo[2];
-  const int EX = mf->box_ext[0], EY = mf->box_ext[1], EZ = mf->box_ext[2];
-  if (G.L < 3 || EX % TXC || EY % TYC || EZ < 2 || mf->first_cell % 4) return DGX_ERR_UNSUPPORTED;
-  G.ntx = EX / TXC; G.nty = EY / TYC;
-  int NZ = EZ;
-  while (NZ > 64 && NZ % 2 == 0) NZ /= 2;
-  G.NZ = NZ; G.nsz = EZ / NZ;
-  G.first_cell = mf->first_cell;
-  G.n_owned = (int)mf->n_owned;
-  if (mf->dtype == DGX_F64) return op->degree == 4 ? launch_march<5, double>(op, dst, src, add, G) : launch_march<4, double>(op, dst, src, add, G);
-  return op->degree == 4 ? launch_march<5, float>(op, dst, src, add, G) : launch_march<4, float>(op, dst, src, add, G);
+  if (!march_geometry(op, G)) return DGX_ERR_UNSUPPORTED;
+  return march_dispatch(op, dst, src, add, G, nullptr, 0);
+}
+
+// Multi-rank: MatrixFree::loop's update_ghost_values_start / cells without ghost dependence / finish / remaining cells
+// (SURVEY 9.10).  Tile columns on the surface of the owned box may read ghost cells (halo traces, ghost planes); all the
+// others run while the ghost import is in flight on the communication stream.
+int pressure_apply_fast_overlapped(dgx_op *op, dgx_vec *dst, dgx_vec *src, bool add) {
+  FastGeom G;
+  if (!march_geometry(op, G)) return DGX_ERR_UNSUPPORTED;
+  dgx_mf *mf = op->mf;
+  if (!mf->d_jobs || mf->jobs_NZ != G.NZ) {
+    // which faces of the owned box border another rank (the partition is a box, so one cell per face tells)
+    const Mesh &m = mf->mesh->m;
+    bool ghost_face[6];
+    for (int f = 0; f < 6; ++f) {
+      int c[3] = {mf->box_lo[0], mf->box_lo[1], mf->box_lo[2]};
+      if (f & 1) c[f / 2] += mf->box_ext[f / 2] - 1;
+      const long long local = m.index_of(mf->level, c) - mf->first_cell;
+      ghost_face[f] = mf->nbr_host[(size_t)f * mf->n_owned + local] >= mf->n_owned;
+    }
+    std::vector<int> interior, boundary;
+    for (int sz = 0; sz < G.nsz; ++sz)
+      for (int ty = 0; ty < G.nty; ++ty)
+        for (int tx = 0; tx < G.ntx; ++tx) {
+          const bool surf = (tx == 0 && ghost_face[0]) || (tx == G.ntx - 1 && ghost_face[1]) || (ty == 0 && ghost_face[2]) ||
+                            (ty == G.nty - 1 && ghost_face[3]) || (sz == 0 && ghost_face[4]) || (sz == G.nsz - 1 && ghost_face[5]);
+          (surf ? boundary : interior).push_back(tx + G.ntx * (ty + G.nty * sz));
+        }
+    mf->n_jobs_interior = (int)interior.size(); mf->n_jobs_boundary = (int)boundary.size();
+    interior.insert(interior.end(), boundary.begin(), boundary.end());
+    if (mf->d_jobs) cudaFree(mf->d_jobs);
+    DGX_CUDA_CHECK(cudaMalloc(&mf->d_jobs, interior.size() * sizeof(int)));
+    DGX_CUDA_CHECK(cudaMemcpy(mf->d_jobs, interior.data(), interior.size() * sizeof(int), cudaMemcpyHostToDevice));
+    mf->jobs_NZ = G.NZ;
+  }
+  // communication stream: pack, NCCL send/recv, then the tile columns that read ghosts; compute stream: all other tile
+  // columns.  The two kernels write disjoint cells of dst and fill each other's idle SMs; the compute stream joins at the end.
+  dgx_ctx *ctx = mf->ctx;
+  int rc = ghost_exchange_start(src);
+  if (rc) return rc;
+  rc = march_dispatch(op, dst, src, add, G, mf->d_jobs + mf->n_jobs_interior, mf->n_jobs_boundary, ctx->comm_stream);
+  if (rc) return rc;
+  DGX_CUDA_CHECK(cudaEventRecord(ctx->ev_ghosts_done, ctx->comm_stream));
+  rc = march_dispatch(op, dst, src, add, G, mf->d_jobs, mf->n_jobs_interior);
+  if (rc) return rc;
+  return ghost_exchange_wait(ctx);
 }
 
 }  // namespace dgx

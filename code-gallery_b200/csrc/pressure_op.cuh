@@ -50,5 +50,7 @@ double pressure_kappa(const dgx_op *op);
 
 // blocked fast path (pressure_fast.cu): returns DGX_ERR_UNSUPPORTED when the shape does not qualify
 int pressure_apply_fast(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add);
+// multi-rank form: starts the ghost import of src itself, runs the tile columns that need no ghosts meanwhile
+int pressure_apply_fast_overlapped(dgx_op *op, dgx_vec *dst, dgx_vec *src, bool add);
 
 }  // namespace dgx

@@ -10,7 +10,7 @@
 #include "dgx_internal.h"
 
 namespace dgx {
-int comm_exchange(dgx_ctx *ctx, int npeers, const int *ranks, const void *const *sendbuf, const size_t *sendbytes,
+int comm_exchange(dgx_ctx *ctx, cudaStream_t stream, int npeers, const int *ranks, const void *const *sendbuf, const size_t *sendbytes,
                   void *const *recvbuf, const size_t *recvbytes);
 
 namespace {
@@ -120,7 +120,7 @@ int reduce_dispatch(dgx_ctx *ctx, int dtype, const void *a, const void *b, void 
 bool same_shape(const dgx_vec *a, const dgx_vec *b) { return a && b && a->n_owned == b->n_owned; }
 }  // namespace
 
-int ghost_exchange(dgx_vec *v) {
+static int ghost_exchange_on(dgx_vec *v, cudaStream_t stream) {
   dgx_mf *mf = v->mf;
   dgx_ctx *ctx = mf->ctx;
   if (ctx->nranks == 1 || mf->peers.empty()) return DGX_OK;
@@ -145,9 +145,9 @@ int ghost_exchange(dgx_vec *v) {
     if (nc) {
       const int grid = grid_for(nc * dpc);
       if (v->dtype == DGX_F64)
-        pack_cells_kernel<double><<<grid, kThreads, 0, ctx->stream>>>((double *)dstp, (const double *)v->d, p.d_send_cells, nc, dpc);
+        pack_cells_kernel<double><<<grid, kThreads, 0, stream>>>((double *)dstp, (const double *)v->d, p.d_send_cells, nc, dpc);
       else
-        pack_cells_kernel<float><<<grid, kThreads, 0, ctx->stream>>>((float *)dstp, (const float *)v->d, p.d_send_cells, nc, dpc);
+        pack_cells_kernel<float><<<grid, kThreads, 0, stream>>>((float *)dstp, (const float *)v->d, p.d_send_cells, nc, dpc);
       count_launch();
     }
     ranks.push_back(p.rank);
@@ -158,7 +158,27 @@ int ghost_exchange(dgx_vec *v) {
     off += (size_t)nc * dpc * es;
   }
   DGX_CUDA_CHECK(cudaGetLastError());
-  return comm_exchange(ctx, (int)ranks.size(), ranks.data(), sb.data(), sbytes.data(), rb.data(), rbytes.data());
+  return comm_exchange(ctx, stream, (int)ranks.size(), ranks.data(), sb.data(), sbytes.data(), rb.data(), rbytes.data());
+}
+
+
+int ghost_exchange(dgx_vec *v) { return ghost_exchange_on(v, v->mf->ctx->stream); }
+
+int ghost_exchange_start(dgx_vec *v) {
+  dgx_ctx *ctx = v->mf->ctx;
+  if (ctx->nranks == 1 || v->mf->peers.empty()) return DGX_OK;
+  DGX_CUDA_CHECK(cudaEventRecord(ctx->ev_src_ready, ctx->stream));
+  DGX_CUDA_CHECK(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_src_ready, 0));
+  int rc = ghost_exchange_on(v, ctx->comm_stream);
+  if (rc) return rc;
+  DGX_CUDA_CHECK(cudaEventRecord(ctx->ev_ghosts_done, ctx->comm_stream));
+  return DGX_OK;
+}
+
+int ghost_exchange_wait(dgx_ctx *ctx) {
+  if (ctx->nranks == 1) return DGX_OK;
+  DGX_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_ghosts_done, 0));
+  return DGX_OK;
 }
 
 }  // namespace dgx

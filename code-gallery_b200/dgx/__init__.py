@@ -184,7 +184,7 @@ class Vector:
         self.dtype = _NP[lib.dgx_vec_dtype(self.h)]
 
     def __del__(self):
-        if getattr(self, "h", None) and not self._borrowed:
+        if getattr(self, "h", None) and not self._borrowed and lib is not None:
             lib.dgx_vec_destroy(self.h)
             self.h = None
 
@@ -277,7 +277,7 @@ class NavierStokesProjectionOperator:
         _check(lib.dgx_op_create(mf.h, NS_stage, degree, c_dbl(Re), c_dbl(dt), C.byref(self.h)))
 
     def __del__(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:
             lib.dgx_op_destroy(self.h)
             self.h = None
 
@@ -369,7 +369,7 @@ class PreconditionChebyshev:
         _check(lib.dgx_cheb_create(op.h, degree, c_dbl(smoothing_range), eig_cg_n_iterations, C.byref(self.h)))
 
     def __del__(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:
             lib.dgx_cheb_destroy(self.h)
             self.h = None
 
@@ -395,7 +395,7 @@ class Multigrid:
         _check(lib.dgx_mg_create(ctx.h, mesh.h, degree, level_dtype, c_dbl(Re), c_dbl(dt), C.byref(self.h)))
 
     def __del__(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:
             lib.dgx_mg_destroy(self.h)
             self.h = None
 
