@@ -54,8 +54,36 @@ for name, cells0, nref, periodic, kind, degree in [
         dist.all_reduce(e[:2])
         errs.append({"dtype": "f64" if dt == dgx.F64 else "f32", "rel_l2": float(torch.sqrt(e[0] / e[1])), "dot_abs_err": float(e[2])})
     report[name] = errs
+# MG-preconditioned pressure solve across ranks (projection_step's solver): same iteration count and solution as on one GPU
+cells0, nref, degree = [world, 1, 1], 3, 3
+mesh = dgx.Mesh(3, cells0, nref, [0, 0, 0], [float(world), 1, 1], [True] * 3)
+res = {}
+sols = {}
+for tag, c in (("multi", ctx), ("solo", solo)):
+    mf = dgx.MatrixFree(c, mesh)
+    op = dgx.NavierStokesProjectionOperator(mf, dgx.OP_PRESSURE, degree, 100.0, 5e-3)
+    mg = dgx.Multigrid(c, mesh, degree, 100.0, 5e-3)
+    dpc = (degree + 1) ** 3
+    N = mesh.n_cells() * dpc
+    g = np.sin(np.arange(N) * 3e-3) + 0.1 * np.random.default_rng(1).standard_normal(N)
+    g -= g.mean()
+    lo, n = mf.first_owned_cell() * dpc, mf.n_owned_cells() * dpc
+    x, b = op.initialize_dof_vector(), op.initialize_dof_vector()
+    b.from_host(g[lo:lo + n])
+    tol = 1e-8 * float(np.linalg.norm(g))
+    mg.setup(tol, 10000)
+    its, r = dgx.solve_cg(op, x, b, mg, 10000, tol)
+    res[tag] = its
+    sols[tag] = (x.to_host(), lo, n)
+xm, lo, n = sols["multi"]
+xs = sols["solo"][0][lo:lo + n]
+e = torch.tensor([float(np.sum((xm - xs) ** 2)), float(np.sum(xs ** 2))], dtype=torch.float64, device="cuda")
+dist.all_reduce(e)
+mg_rel = float(torch.sqrt(e[0] / e[1]))
 if rank == 0:
-    print(json.dumps({"world": world, "checks": report}))
+    print(json.dumps({"world": world, "checks": report, "mg_cg": {"iterations_multi": res["multi"], "iterations_solo": res["solo"], "solution_rel_l2": mg_rel}}))
+    if abs(res["multi"] - res["solo"]) > 1 or mg_rel > 1e-5:
+        report["mg_cg"] = [{"dtype": "f64", "rel_l2": 1.0}]
     bad = [k for k, v in report.items() for x in v if x["rel_l2"] > (1e-12 if x["dtype"] == "f64" else 1e-5)]
     print("MULTI-GPU CHECK", "FAILED " + str(bad) if bad else "PASSED")
 dist.destroy_process_group()
