@@ -214,6 +214,14 @@ int dgx_op_vmult_add(dgx_op *op, dgx_vec *dst, dgx_vec *src) { return apply(op, 
 int dgx_op_Tvmult(dgx_op *op, dgx_vec *dst, dgx_vec *src) { return apply(op, dst, src, false); }
 int dgx_op_Tvmult_add(dgx_op *op, dgx_vec *dst, dgx_vec *src) { return apply(op, dst, src, true); }
 
+// exact inverse of the DG mass operator (replaces project_grad's unpreconditioned CG, NS.cc:2574-2576, when the caller opts in)
+int dgx_op_mass_inverse(dgx_op *op, dgx_vec *dst, dgx_vec *src) {
+  int rc = check_vecs(op, dst, src);
+  if (rc) return rc;
+  DGX_REQUIRE(op->kind == DGX_OP_MASS, "mass_inverse needs the mass operator (NS_stage 3)");
+  return mass_inverse_apply(op, dst, src);
+}
+
 int dgx_op_compute_diagonal(dgx_op *op) {
   DGX_REQUIRE(op, "null argument");
   DGX_REQUIRE(op->kind == DGX_OP_VELOCITY || op->kind == DGX_OP_PRESSURE, "compute_diagonal needs NS_stage 1 or 2");  // NS.cc:2019

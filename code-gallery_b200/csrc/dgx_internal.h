@@ -160,6 +160,8 @@ int pressure_apply_fused(dgx_op *op, dgx_vec *dst, dgx_vec *x, const FusedUpdate
 int op_pool_vec(dgx_op *op, int i, dgx_vec **out);
 int pressure_coarse_cg(dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_vec *r, dgx_vec *p, dgx_vec *v, double tol, int max_it, int *d_info, double *d_res);
 int mass_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add);
+int mass_apply_any(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, bool inverse);
+int mass_inverse_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src);
 int velocity_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add);
 int velocity_diagonal(dgx_op *op, dgx_vec *diag_inv);
 int ghost_exchange(dgx_vec *v);

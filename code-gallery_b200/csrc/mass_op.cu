@@ -54,13 +54,13 @@ mass_kernel(const __grid_constant__ MassParams<T, n> P, long long n_items, const
 }
 
 template <int dim, int n, typename T>
-int launch_mass(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) {
+int launch_mass(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, bool inverse) {
   dgx_mf *mf = op->mf;
   const Shape1D &s = get_shape(n - 1, n);
   MassParams<T, n> P;
   for (int d = 0; d < MAX_DIM; ++d) {
     const double h = d < dim ? mf->h[d] : 1.0;
-    for (int i = 0; i < n * n; ++i) P.Mh[d][i] = (T)(h * s.M[i]);
+    for (int i = 0; i < n * n; ++i) P.Mh[d][i] = (T)(inverse ? s.Minv[i] / h : h * s.M[i]);   // (h M)^-1 = M^-1 / h
   }
   const long long items = mf->n_owned * op->ncomp;
   if (items == 0) return DGX_OK;
@@ -73,25 +73,31 @@ int launch_mass(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) {
 }
 
 template <int dim, typename T>
-int mass_by_degree(int degree, dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) {
+int mass_by_degree(int degree, dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, bool inverse) {
   switch (degree) {
-    case 1: return launch_mass<dim, 2, T>(op, dst, src, add);
-    case 2: return launch_mass<dim, 3, T>(op, dst, src, add);
-    case 3: return launch_mass<dim, 4, T>(op, dst, src, add);
-    case 4: return launch_mass<dim, 5, T>(op, dst, src, add);
-    case 5: return launch_mass<dim, 6, T>(op, dst, src, add);
-    case 6: return launch_mass<dim, 7, T>(op, dst, src, add);
-    case 7: return launch_mass<dim, 8, T>(op, dst, src, add);
-    case 8: return launch_mass<dim, 9, T>(op, dst, src, add);
+    case 1: return launch_mass<dim, 2, T>(op, dst, src, add, inverse);
+    case 2: return launch_mass<dim, 3, T>(op, dst, src, add, inverse);
+    case 3: return launch_mass<dim, 4, T>(op, dst, src, add, inverse);
+    case 4: return launch_mass<dim, 5, T>(op, dst, src, add, inverse);
+    case 5: return launch_mass<dim, 6, T>(op, dst, src, add, inverse);
+    case 6: return launch_mass<dim, 7, T>(op, dst, src, add, inverse);
+    case 7: return launch_mass<dim, 8, T>(op, dst, src, add, inverse);
+    case 8: return launch_mass<dim, 9, T>(op, dst, src, add, inverse);
     default: set_error("degree must be in 1..8"); return DGX_ERR_UNSUPPORTED;
   }
 }
 }  // namespace
 
-int mass_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) {
+int mass_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) { return mass_apply_any(op, dst, src, add, false); }
+
+// dst = M^-1 src: the cell mass matrix is (h_x M) (x) (h_y M) (x) (h_z M), so its inverse is the same three sweeps with
+// M^-1 / h_d -- the exact solution of project_grad's CG solve (NS.cc:2574-2576) in one kernel.
+int mass_inverse_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src) { return mass_apply_any(op, dst, src, false, true); }
+
+int mass_apply_any(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, bool inverse) {
   dgx_mf *mf = op->mf;
-  if (mf->dim == 2) return mf->dtype == DGX_F64 ? mass_by_degree<2, double>(op->degree, op, dst, src, add) : mass_by_degree<2, float>(op->degree, op, dst, src, add);
-  return mf->dtype == DGX_F64 ? mass_by_degree<3, double>(op->degree, op, dst, src, add) : mass_by_degree<3, float>(op->degree, op, dst, src, add);
+  if (mf->dim == 2) return mf->dtype == DGX_F64 ? mass_by_degree<2, double>(op->degree, op, dst, src, add, inverse) : mass_by_degree<2, float>(op->degree, op, dst, src, add, inverse);
+  return mf->dtype == DGX_F64 ? mass_by_degree<3, double>(op->degree, op, dst, src, add, inverse) : mass_by_degree<3, float>(op->degree, op, dst, src, add, inverse);
 }
 
 }  // namespace dgx

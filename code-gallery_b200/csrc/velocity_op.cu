@@ -258,6 +258,234 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
   }
 }
 
+// ---- tensorised diagonal -------------------------------------------------------------------------------------
+// The reference probes the diagonal with n^dim operator applications per cell (NS.cc:1442-1471, 1527-1530: dof i of
+// every component is set to one on BOTH sides of every face and entry i is kept).  Because the probe phi_i is a
+// rank-1 tensor, every term of [A phi_i]_i is a contraction of a field (1, u_extr . e_d, its face traces, lambda)
+// with squared 1-D shape values: sum_q w_q ue_d(q) phi_i(q) d_d phi_i(q) etc.  These are sum-factorised moments, so
+// the whole diagonal costs about ONE operator application instead of n^dim.  Same numbers as the probing to round-off.
+template <typename T, int n>
+struct VelDiagParams {
+  T S[n * n];          // nodal -> Gauss points
+  T P2[n * n];         // P2[i][q] = S[q][i]^2
+  T PD[n * n];         // PD[i][q] = S[q][i] * l_i'(xi_q)
+  T fh[2][n];          // end-point values of the Gauss-point basis (own traces of u_extr)
+  T f[2][n], g[2][n];  // nodal basis: l_i(s), l_i'(s)
+  T w[n], Md[n], Kd[n];   // weights, diag of the 1-D mass / stiffness matrix
+  T h[MAX_DIM], ih[MAX_DIM];
+  T alpha, a, aRe, C, theta;
+};
+
+template <int dim, int n, typename T>
+__host__ __device__ constexpr int veld_cpb() {
+  constexpr int per_cell = (int)sizeof(T) * ((dim + 2) * ipow(n, dim) + (2 * 3 + 2 * dim * 3) * ipow(n, dim - 1));
+  return (64 * 1024 / per_cell) < 1 ? 1 : ((64 * 1024 / per_cell) > 16 ? 16 : (64 * 1024 / per_cell));
+}
+
+template <int dim, int n, typename T>
+__global__ void __launch_bounds__(kVelThreads)
+velocity_diag_kernel(const __grid_constant__ VelDiagParams<T, n> P, const int *__restrict__ nbr, int n_owned, const T *__restrict__ ue,
+                     T *__restrict__ out) {
+  constexpr int NL = ipow(n, dim - 1), ND = NL * n, CPB = veld_cpb<dim, n, T>(), NT = kVelThreads;
+  constexpr int PER_CELL = (dim + 2) * ND + (2 * 3 + 2 * dim * 3) * NL;
+  extern __shared__ __align__(16) unsigned char dsm[];
+  T *sm = reinterpret_cast<T *>(dsm);
+  const int tid = threadIdx.x, cell0 = blockIdx.x * CPB, ncell = min(CPB, n_owned - cell0);
+  auto Ec = [&](int ci) { return sm + (size_t)ci * PER_CELL; };                          // [dim][ND] u_extr at the Gauss points
+  auto Tm = [&](int ci) { return sm + (size_t)ci * PER_CELL + dim * ND; };               // [ND] scratch
+  auto Ts = [&](int ci) { return sm + (size_t)ci * PER_CELL + (dim + 1) * ND; };         // [ND] sum_d T_d
+  auto Fa = [&](int ci) { return sm + (size_t)ci * PER_CELL + (dim + 2) * ND; };         // [3][NL] face fields (ping)
+  auto Fb = [&](int ci) { return Fa(ci) + 3 * NL; };                                     // [3][NL] (pong)
+  auto Mf = [&](int ci) { return Fa(ci) + 6 * NL; };                                     // [2*dim faces][3][NL] face moments
+  for (int it = tid; it < ncell * dim * ND; it += NT) {
+    const int ci = it / (dim * ND), r = it - ci * (dim * ND);
+    Ec(ci)[r] = ue[(size_t)(cell0 + ci) * dim * ND + r];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int d = 0; d < dim; ++d) {
+    for (int it = tid; it < ncell * dim * NL; it += NT) {
+      const int ci = it / (dim * NL), r = it - ci * (dim * NL), f = r / NL, l = r - f * NL;
+      int base, stride;
+      vline<dim, n>(d, l, base, stride);
+      T *A = Ec(ci) + f * ND;
+      T u[n];
+#pragma unroll
+      for (int i = 0; i < n; ++i) u[i] = A[base + stride * i];
+#pragma unroll
+      for (int q = 0; q < n; ++q) {
+        T acc = 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) acc += P.S[q * n + i] * u[i];
+        A[base + stride * q] = acc;
+      }
+    }
+    __syncthreads();
+  }
+  T vol = 1;
+#pragma unroll
+  for (int d = 0; d < dim; ++d) vol *= P.h[d];
+  for (int it = tid; it < ncell * ND; it += NT) Ts(it / ND)[it % ND] = 0;
+  // cell moments T_d[i] = vol/h_d sum_q w_q ue_d(q) phi_i(q) d(phi_i)/d(xi_d)(q): three sweeps per direction
+#pragma unroll
+  for (int d = 0; d < dim; ++d) {
+#pragma unroll
+    for (int e = 0; e < dim; ++e) {
+      for (int it = tid; it < ncell * NL; it += NT) {
+        const int ci = it / NL, l = it - ci * NL;
+        int base, stride;
+        vline<dim, n>(e, l, base, stride);
+        const T *in = e == 0 ? Ec(ci) + d * ND : Tm(ci);
+        T u[n];
+#pragma unroll
+        for (int q = 0; q < n; ++q) u[q] = in[base + stride * q] * P.w[q];
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+          T acc = 0;
+#pragma unroll
+          for (int q = 0; q < n; ++q) acc += (e == d ? P.PD[i * n + q] : P.P2[i * n + q]) * u[q];
+          Tm(ci)[base + stride * i] = acc;
+        }
+      }
+      __syncthreads();
+    }
+    for (int it = tid; it < ncell * ND; it += NT) Ts(it / ND)[it % ND] += vol * P.ih[d] * Tm(it / ND)[it % ND];
+    __syncthreads();
+  }
+  // face moments: for every face, the three fields w*E_own, w*E_nbr, w*lambda contracted with S^2 (x) S^2
+#pragma unroll
+  for (int d = 0; d < dim; ++d) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      // nodal trace of the neighbour's advecting component d (field 1, ping buffer), interpolated below
+      for (int it = tid; it < ncell * NL; it += NT) {
+        const int ci = it / NL, l = it - ci * NL;
+        const int nbc = nbr[(size_t)(2 * d + s) * n_owned + cell0 + ci];
+        int base, stride;
+        vline<dim, n>(d, l, base, stride);
+        Fa(ci)[1 * NL + l] = nbc >= 0 ? ue[((size_t)nbc * dim + d) * ND + base + stride * (1 - s) * (n - 1)] : T(0);
+      }
+      __syncthreads();
+      for (int it = tid; it < ncell * NL; it += NT) {
+        const int ci = it / NL, l = it - ci * NL, t0 = l % n, t1 = l / n;
+        T acc = 0;
+#pragma unroll
+        for (int a2 = 0; a2 < n; ++a2) acc += P.S[t0 * n + a2] * Fa(ci)[1 * NL + a2 + n * t1];
+        Fb(ci)[1 * NL + l] = acc;
+      }
+      __syncthreads();
+      if (dim == 3) {
+        for (int it = tid; it < ncell * NL; it += NT) {
+          const int ci = it / NL, l = it - ci * NL, t0 = l % n, t1 = l / n;
+          T acc = 0;
+#pragma unroll
+          for (int b2 = 0; b2 < n; ++b2) acc += P.S[t1 * n + b2] * Fb(ci)[1 * NL + t0 + n * b2];
+          Fa(ci)[1 * NL + l] = acc;
+        }
+        __syncthreads();
+      }
+      // own trace, lambda, quadrature weights -> Fb[0..2]
+      for (int it = tid; it < ncell * NL; it += NT) {
+        const int ci = it / NL, l = it - ci * NL, t0 = l % n, t1 = l / n;
+        const int nbc = nbr[(size_t)(2 * d + s) * n_owned + cell0 + ci];
+        int base, stride;
+        vline<dim, n>(d, l, base, stride);
+        T Eo = 0;
+#pragma unroll
+        for (int q = 0; q < n; ++q) Eo += P.fh[s][q] * Ec(ci)[d * ND + base + stride * q];
+        const T En = dim == 3 ? Fa(ci)[1 * NL + l] : Fb(ci)[1 * NL + l];
+        const T wt = dim == 3 ? P.w[t0] * P.w[t1] : P.w[t0];
+        const T lam = nbc >= 0 ? fmax(fabs(Eo), fabs(En)) : fabs(Eo);
+        T *o = dim == 3 ? Fb(ci) : Fa(ci);
+        o[0 * NL + l] = wt * Eo; o[1 * NL + l] = wt * En; o[2 * NL + l] = wt * lam;
+      }
+      __syncthreads();
+      // moments: contract both tangential directions with S^2
+      {
+        for (int it = tid; it < ncell * 3 * NL; it += NT) {
+          const int ci = it / (3 * NL), r = it - ci * (3 * NL), f = r / NL, l = r - f * NL, t0 = l % n, t1 = l / n;
+          const T *in = (dim == 3 ? Fb(ci) : Fa(ci)) + f * NL;
+          T acc = 0;
+#pragma unroll
+          for (int a2 = 0; a2 < n; ++a2) acc += P.P2[t0 * n + a2] * in[a2 + n * t1];
+          if (dim == 3) Fa(ci)[f * NL + l] = acc;
+          else Mf(ci)[((2 * d + s) * 3 + f) * NL + l] = acc;
+        }
+        __syncthreads();
+        if (dim == 3) {
+          for (int it = tid; it < ncell * 3 * NL; it += NT) {
+            const int ci = it / (3 * NL), r = it - ci * (3 * NL), f = r / NL, l = r - f * NL, t0 = l % n, t1 = l / n;
+            T acc = 0;
+#pragma unroll
+            for (int b2 = 0; b2 < n; ++b2) acc += P.P2[t1 * n + b2] * Fa(ci)[f * NL + t0 + n * b2];
+            Mf(ci)[((2 * d + s) * 3 + f) * NL + l] = acc;
+          }
+          __syncthreads();
+        }
+      }
+    }
+  }
+  // assemble the entries: item = (cell, scalar dof i); all components share everything except boundary_id == 1 faces
+  for (int it = tid; it < ncell * ND; it += NT) {
+    const int ci = it / ND, i = it - ci * ND, cell = cell0 + ci;
+    int idx[3] = {0, 0, 0};
+    { int r = i; for (int d = 0; d < dim; ++d) { idx[d] = r % n; r /= n; } }
+    T mprod = vol, kk = 0;
+#pragma unroll
+    for (int d = 0; d < dim; ++d) mprod *= P.Md[idx[d]];
+#pragma unroll
+    for (int d = 0; d < dim; ++d) kk += P.ih[d] * P.ih[d] * P.Kd[idx[d]] / P.Md[idx[d]];
+    const T base = P.alpha * mprod + P.aRe * mprod * kk - P.a * Ts(ci)[i];
+    T val[dim];
+#pragma unroll
+    for (int c = 0; c < dim; ++c) val[c] = base;
+#pragma unroll
+    for (int d = 0; d < dim; ++d) {
+      // tangential position of dof i on faces normal to d, in the line numbering of vline
+      int l;
+      if (dim == 3) l = d == 0 ? idx[1] + n * idx[2] : (d == 1 ? idx[0] + n * idx[2] : idx[0] + n * idx[1]);
+      else l = d == 0 ? idx[1] : idx[0];
+      T area = 1, m0 = 1;
+#pragma unroll
+      for (int e = 0; e < dim; ++e) if (e != d) { area *= P.h[e]; m0 *= P.Md[idx[e]]; }
+      m0 *= area;
+      const T sigma = P.C * P.ih[d];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int nbc = nbr[(size_t)(2 * d + s) * n_owned + cell];
+        const T ns = s ? T(1) : T(-1);
+        const T *M = Mf(ci) + (2 * d + s) * 3 * NL;
+        const T mE = area * M[0 * NL + l], mEn = area * M[1 * NL + l], mL = area * M[2 * NL + l];
+        const T fs = P.f[s][idx[d]], fp = P.f[1 - s][idx[d]], gs = P.ih[d] * P.g[s][idx[d]], gp = P.ih[d] * P.g[1 - s][idx[d]];
+        if (nbc >= 0) {
+          const T FV = P.aRe * (T(-0.5) * ns * (gs + gp) + sigma * (fs - fp)) * m0 + P.a * T(0.5) * ns * (fs * mE + fp * mEn) + T(0.5) * P.a * (fs - fp) * mL;
+          const T FG = -P.theta * P.aRe * T(0.5) * (fs - fp) * m0;
+          const T add = fs * FV + ns * gs * FG;
+#pragma unroll
+          for (int c = 0; c < dim; ++c) val[c] += add;
+        } else if (nbc != -2) {
+          const T FV = P.aRe * (-ns * gs + T(2) * sigma * fs) * m0 + P.a * fs * mL;
+          const T FG = -P.theta * P.aRe * fs * m0;
+          const T add = fs * FV + ns * gs * FG;
+#pragma unroll
+          for (int c = 0; c < dim; ++c) val[c] += add;
+        } else {
+#pragma unroll
+          for (int c = 0; c < dim; ++c) {
+            const T dV = c == 1 ? T(2) * fs : T(0), aV = c == 1 ? T(0) : fs;
+            const T dn = (c == 0 && d < 2) ? T(0) : ns * gs;
+            const T FV = P.aRe * (-dn + sigma * dV) * m0 + P.a * aV * ns * mE + T(0.5) * P.a * dV * mL;
+            const T FG = -P.theta * P.aRe * dV * m0;
+            val[c] += fs * FV + ns * gs * FG;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < dim; ++c) out[((size_t)cell * dim + c) * ND + i] = T(1) / val[c];   // NS.cc:2055-2059
+  }
+}
+
 // probe vector of compute_diagonal: dof `i` of every component of every cell (ghosts included) is one
 template <typename T>
 __global__ void probe_fill_kernel(T *v, long long total, int ND, int i) {
@@ -324,6 +552,53 @@ int velocity_dispatch(dgx_op *op, T *dst, const T *src, bool add) {
   return op->mf->dim == 2 ? velocity_by_degree<2, T>(op, dst, src, add) : velocity_by_degree<3, T>(op, dst, src, add);
 }
 
+template <int dim, int n, typename T>
+int launch_velocity_diag(dgx_op *op, T *out) {
+  dgx_mf *mf = op->mf;
+  const Shape1D &s = get_shape(n - 1, n);
+  VelDiagParams<T, n> P;
+  for (int q = 0; q < n; ++q)
+    for (int i = 0; i < n; ++i) {
+      P.S[q * n + i] = (T)s.S[q * n + i];
+      P.P2[i * n + q] = (T)(s.S[q * n + i] * s.S[q * n + i]);
+      P.PD[i * n + q] = (T)(s.S[q * n + i] * s.D[q * n + i]);
+    }
+  for (int sd = 0; sd < 2; ++sd)
+    for (int i = 0; i < n; ++i) { P.fh[sd][i] = (T)s.fhat[sd][i]; P.f[sd][i] = (T)s.f[sd][i]; P.g[sd][i] = (T)s.g[sd][i]; }
+  for (int i = 0; i < n; ++i) { P.w[i] = (T)s.wq[i]; P.Md[i] = (T)s.M[i * n + i]; P.Kd[i] = (T)s.K[i * n + i]; }
+  for (int d = 0; d < MAX_DIM; ++d) { const double h = d < dim ? mf->h[d] : 1.0; P.h[d] = (T)h; P.ih[d] = (T)(1.0 / h); }
+  const double gamma = gamma_trbdf2();
+  const double a = op->stage == 1 ? 0.5 : 1.0 / (2.0 - gamma);
+  P.alpha = (T)(op->stage == 1 ? 1.0 / (gamma * op->dt) : 1.0 / ((1.0 - gamma) * op->dt));
+  P.a = (T)a; P.aRe = (T)(a / op->Re); P.C = (T)((double)n * n); P.theta = (T)1.0;
+  constexpr int NL = ipow(n, dim - 1), ND = NL * n, CPB = veld_cpb<dim, n, T>();
+  const size_t smem = sizeof(T) * (size_t)CPB * ((dim + 2) * ND + (2 * 3 + 2 * dim * 3) * NL);
+  static bool configured = false;
+  if (!configured) {
+    DGX_CUDA_CHECK(cudaFuncSetAttribute(velocity_diag_kernel<dim, n, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int n_owned = (int)mf->n_owned;
+  if (n_owned == 0) return DGX_OK;
+  velocity_diag_kernel<dim, n, T><<<(n_owned + CPB - 1) / CPB, kVelThreads, smem, mf->ctx->stream>>>(P, mf->d_nbr, n_owned, (const T *)op->u_extr->d, out);
+  count_launch();
+  DGX_CUDA_CHECK(cudaGetLastError());
+  return DGX_OK;
+}
+
+template <int dim, typename T>
+int velocity_diag_by_degree(dgx_op *op, T *out) {
+  switch (op->degree) {
+    case 1: return launch_velocity_diag<dim, 2, T>(op, out);
+    case 2: return launch_velocity_diag<dim, 3, T>(op, out);
+    case 3: return launch_velocity_diag<dim, 4, T>(op, out);
+    case 4: return launch_velocity_diag<dim, 5, T>(op, out);
+    case 5: return launch_velocity_diag<dim, 6, T>(op, out);
+    case 6: return launch_velocity_diag<dim, 7, T>(op, out);
+    default: set_error("velocity diagonal: degree must be in 1..6"); return DGX_ERR_UNSUPPORTED;
+  }
+}
+
 template <typename T>
 int diagonal_by_probing(dgx_op *op, dgx_vec *out) {
   dgx_mf *mf = op->mf;
@@ -361,7 +636,10 @@ int velocity_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) {
 // with the operator kernel reproduces that (n^dim operator applications, as in the reference).
 int velocity_diagonal(dgx_op *op, dgx_vec *out) {
   if (!op->u_extr) { set_error("velocity operator: set_u_extr() has not been called"); return DGX_ERR_INVALID; }
-  return op->mf->dtype == DGX_F64 ? diagonal_by_probing<double>(op, out) : diagonal_by_probing<float>(op, out);
+  if (op->variant == 1)   // literal probing with n^dim operator applications (kept as the cross-check of the tensorised form)
+    return op->mf->dtype == DGX_F64 ? diagonal_by_probing<double>(op, out) : diagonal_by_probing<float>(op, out);
+  if (op->mf->dim == 2) return op->mf->dtype == DGX_F64 ? velocity_diag_by_degree<2, double>(op, (double *)out->d) : velocity_diag_by_degree<2, float>(op, (float *)out->d);
+  return op->mf->dtype == DGX_F64 ? velocity_diag_by_degree<3, double>(op, (double *)out->d) : velocity_diag_by_degree<3, float>(op, (float *)out->d);
 }
 
 }  // namespace dgx

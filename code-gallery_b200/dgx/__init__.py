@@ -311,6 +311,10 @@ class NavierStokesProjectionOperator:
     def Tvmult_add(self, dst, src):
         _check(lib.dgx_op_Tvmult_add(self.h, dst.h, src.h))
 
+    def mass_inverse(self, dst, src):
+        """dst = M^-1 src (exact tensor-product inverse of the DG mass matrix; NS_stage 3 only)"""
+        _check(lib.dgx_op_mass_inverse(self.h, dst.h, src.h))
+
     def compute_diagonal(self):
         _check(lib.dgx_op_compute_diagonal(self.h))
 

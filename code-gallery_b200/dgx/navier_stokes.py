@@ -10,8 +10,10 @@ from . import (GAMMA, OP_MASS, OP_PRESSURE, OP_VELOCITY, MatrixFree, Multigrid, 
 
 
 class NavierStokesProjection:
-    def __init__(self, ctx, mesh, degree_p=1, Re=100.0, dt=5e-3, max_its=10000, eps=1e-8):
-        """Data_Storage values as parameter-file.prm:1-39 (Reynolds, dt, max_iterations, eps)."""
+    def __init__(self, ctx, mesh, degree_p=1, Re=100.0, dt=5e-3, max_its=10000, eps=1e-8, direct_mass_inverse=False):
+        """Data_Storage values as parameter-file.prm:1-39 (Reynolds, dt, max_iterations, eps).  direct_mass_inverse: replace
+        project_grad's CG on the DG mass matrix by its exact tensor-product inverse (not the reference's algorithm: opt-in)."""
+        self.direct_mass_inverse = direct_mass_inverse
         self.ctx, self.mesh, self.dim = ctx, mesh, mesh.dim
         self.degree_p, self.Re, self.dt, self.max_its, self.eps = degree_p, Re, dt, max_its, eps
         self.mf = MatrixFree(ctx, mesh)                                                  # NS.cc:2329
@@ -73,6 +75,10 @@ class NavierStokesProjection:
     def project_grad(self, flag):                                                         # NS.cc:2554-2577
         assert flag in (1, 2)
         self.mass_op.vmult_grad_p_projection(self.rhs_u, self.pres_n if flag == 1 else self.pres_int)
+        if self.direct_mass_inverse:
+            self.mass_op.mass_inverse(self.u_tmp, self.rhs_u)
+            self.iterations.append((f"direct_mass_flag{flag}", 0))
+            return
         tol = 1e-12 * self.rhs_u.l2_norm()
         its, _ = solve_cg(self.mass_op, self.u_tmp, self.rhs_u, None, self.max_its, tol)
         self.iterations.append((f"cg_mass_flag{flag}", its))

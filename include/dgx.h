@@ -142,6 +142,9 @@ int dgx_op_vmult(dgx_op *op, dgx_vec *dst, dgx_vec *src);      /* Base::vmult: d
 int dgx_op_vmult_add(dgx_op *op, dgx_vec *dst, dgx_vec *src);  /* Base::vmult_add -> apply_add NS.cc:1398 */
 int dgx_op_Tvmult(dgx_op *op, dgx_vec *dst, dgx_vec *src);     /* Base::Tvmult = apply_add (NS.cc:281) */
 int dgx_op_Tvmult_add(dgx_op *op, dgx_vec *dst, dgx_vec *src);
+/* dst = M^-1 src for the DG mass operator (NS_stage 3): exact tensor-product inverse, an opt-in replacement of the CG solve
+ * of project_grad (NS.cc:2574-2576) */
+int dgx_op_mass_inverse(dgx_op *op, dgx_vec *dst, dgx_vec *src);
 int dgx_op_compute_diagonal(dgx_op *op);                  /* NS.cc:2018-2060 (stores the INVERSE) */
 int dgx_op_get_matrix_diagonal_inverse(dgx_op *op, dgx_vec **out); /* borrowed handle, NS.cc:2515 */
 int dgx_op_precondition_Jacobi(dgx_op *op, dgx_vec *dst, const dgx_vec *src, double omega);

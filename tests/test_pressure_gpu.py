@@ -89,6 +89,22 @@ def test_mass_operator(dgx, gpu_ctx):
             assert rel_l2(dst.to_host(), oop.vmult(u)) < 1e-12
 
 
+def test_mass_inverse(dgx, gpu_ctx):
+    """exact tensor-product inverse of the DG mass operator: M^-1 (M u) == u"""
+    for dim, cells0, nref in [(2, [2, 1], 2), (3, [1, 1, 2], 1)]:
+        gm, om = make_meshes(dgx, dim, cells0, nref, [False] * dim)
+        mf = dgx.MatrixFree(gpu_ctx, gm)
+        for degree in (1, 3, 4):
+            op = dgx.NavierStokesProjectionOperator(mf, dgx.OP_MASS, degree)
+            oop = MassOperator(om, degree)
+            u = smooth_plus_noise(om, oop.sh.nodes, ncomp=dim, noise=0.5)
+            a, b, c = (op.initialize_dof_vector() for _ in range(3))
+            a.from_host(u)
+            op.vmult(b, a)
+            op.mass_inverse(c, b)
+            assert rel_l2(c.to_host(), u) < 1e-12
+
+
 def test_vmult_host_entry(dgx, gpu_ctx):
     got, ref, op, oop, src, dst, u = _run(dgx, gpu_ctx, 3, [1, 1, 1], 2, [True, True, True], 4, np.float64)
     out = np.empty_like(u)

@@ -68,6 +68,10 @@ def test_velocity_diagonal_matches_reference_probing(dgx, gpu_ctx, case):
     op.compute_diagonal()
     d = op.get_matrix_diagonal_inverse().to_host()
     assert rel_l2(d, oop.compute_diagonal()) < 1e-12
+    # the tensorised form (default) equals literal probing with n^dim operator applications (variant 1)
+    op.set_variant(1)
+    op.compute_diagonal()
+    assert rel_l2(op.get_matrix_diagonal_inverse().to_host(), d) < 1e-12
 
 
 def test_diffusion_step_solve(dgx, gpu_ctx):
