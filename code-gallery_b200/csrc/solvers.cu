@@ -630,10 +630,10 @@ int dgx_solve_gmres(dgx_op *A, dgx_vec *x, dgx_vec *b, int precond_kind, void *p
     for (int k = 0; k < kdim; ++k) {
       RCG(dgx_op_vmult(A, tmp, V[k]));
       RCG(apply_precond(pc, w, tmp));
-      for (int pass = 0; pass < 2; ++pass) {
+      for (int pass = 0; pass < 2; ++pass) {   // classical Gram-Schmidt + one re-orthogonalisation, each sweep fused
         std::vector<double> h(k + 1);
-        for (int j = 0; j <= k; ++j) RCG(dgx_vec_dot(w, V[j], &h[j]));
-        for (int j = 0; j <= k; ++j) { RCG(dgx_vec_add(w, -h[j], V[j])); H[(size_t)j * kdim + k] += h[j]; }
+        RCG(dgx_vec_orthogonalize(w, V.data(), k + 1, h.data()));
+        for (int j = 0; j <= k; ++j) H[(size_t)j * kdim + k] += h[j];
       }
       double hn = 0;
       RCG(dgx_vec_l2_norm(w, &hn));

@@ -96,6 +96,58 @@ __global__ void pack_cells_kernel(T *__restrict__ out, const T *__restrict__ v, 
   }
 }
 
+constexpr int kMaxMulti = 32;
+template <typename T> struct PtrTable { const T *v[kMaxMulti]; double h[kMaxMulti]; };
+
+// out[j] = sum_i w[i] * V_j[i], j < k: ONE pass over w for all k dot products of a Gram-Schmidt sweep (SolverGMRES)
+template <typename T, int KB>
+__global__ void __launch_bounds__(kThreads) multi_dot_kernel(const T *__restrict__ w, const __grid_constant__ PtrTable<T> tab, int k0, int k, long long n,
+                                                             double *partial, double *result) {
+  double acc[KB];
+#pragma unroll
+  for (int j = 0; j < KB; ++j) acc[j] = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double wi = (double)w[i];
+#pragma unroll
+    for (int j = 0; j < KB; ++j)
+      if (k0 + j < k) acc[j] += wi * (double)tab.v[k0 + j][i];
+  }
+  __shared__ double sm[KB][kThreads / 32];
+  __shared__ bool last;
+#pragma unroll
+  for (int j = 0; j < KB; ++j) {
+    double a = acc[j];
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) sm[j][threadIdx.x >> 5] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x < KB) {
+    double s = 0;
+    for (int wv = 0; wv < kThreads / 32; ++wv) s += sm[threadIdx.x][wv];
+    partial[(size_t)blockIdx.x * KB + threadIdx.x] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicInc(&g_ticket, gridDim.x - 1) == gridDim.x - 1);
+  __syncthreads();
+  if (last && threadIdx.x < KB) {
+    __threadfence();
+    double s = 0;
+    for (int b = 0; b < (int)gridDim.x; ++b) s += ((volatile double *)partial)[(size_t)b * KB + threadIdx.x];
+    if (k0 + (int)threadIdx.x < k) result[k0 + threadIdx.x] = s;
+  }
+}
+
+// w -= sum_j h_j V_j in one pass
+template <typename T>
+__global__ void __launch_bounds__(kThreads) multi_axpy_kernel(T *__restrict__ w, const __grid_constant__ PtrTable<T> tab, int k, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double x = (double)w[i];
+    for (int j = 0; j < k; ++j) x -= tab.h[j] * (double)tab.v[j][i];
+    w[i] = (T)x;
+  }
+}
+
 template <int OP, bool FUSED>
 int reduce_dispatch(dgx_ctx *ctx, int dtype, const void *a, const void *b, void *upd, const void *v, double alpha, long long n,
                     double *out, bool is_max) {
@@ -389,4 +441,41 @@ int dgx_vec_compress_add(dgx_vec *v) {
   return DGX_OK;
 }
 
+
+// One Gram-Schmidt sweep of SolverGMRES: h_j = w . V_j for j < k (one pass over w, one all-reduce, one host read-back),
+// then w -= sum_j h_j V_j (one pass).  k <= 32.
+int dgx_vec_orthogonalize(dgx_vec *w, dgx_vec *const *V, int k, double *h) {
+  DGX_REQUIRE(w && V && h && k >= 1 && k <= kMaxMulti, "orthogonalize: 1 <= k <= 32");
+  dgx_ctx *ctx = w->mf->ctx;
+  const long long n = w->n_owned;
+  const int grid = std::min(grid_for(n, 8), 148 * 2);
+  constexpr int KB = 8;
+  DGX_REQUIRE((size_t)grid * KB + 8 + kMaxMulti <= ctx->scratch_doubles, "reduction scratch too small");
+  double *result = ctx->d_scratch, *partial = ctx->d_scratch + 8 + kMaxMulti;
+  auto run = [&](auto tag) -> int {
+    using T = decltype(tag);
+    PtrTable<T> tab;
+    for (int j = 0; j < k; ++j) {
+      DGX_REQUIRE(V[j] && same_shape(w, V[j]) && V[j]->dtype == w->dtype, "basis vector shape / dtype mismatch");
+      tab.v[j] = (const T *)V[j]->d;
+      tab.h[j] = 0;
+    }
+    for (int k0 = 0; k0 < k; k0 += KB) {
+      multi_dot_kernel<T, KB><<<grid, kThreads, 0, ctx->stream>>>((const T *)w->d, tab, k0, k, n, partial, result);
+      count_launch();
+    }
+    DGX_CUDA_CHECK(cudaGetLastError());
+    int rc = allreduce_sum(ctx, result, k);
+    if (rc) return rc;
+    DGX_CUDA_CHECK(cudaMemcpyAsync(ctx->h_scratch, result, k * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DGX_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (int j = 0; j < k; ++j) { h[j] = ctx->h_scratch[j]; tab.h[j] = h[j]; }
+    if (n) { multi_axpy_kernel<T><<<grid_for(n), kThreads, 0, ctx->stream>>>((T *)w->d, tab, k, n); count_launch(); }
+    DGX_CUDA_CHECK(cudaGetLastError());
+    return DGX_OK;
+  };
+  return w->dtype == DGX_F64 ? run(double()) : run(float());
+}
+
 }  // extern "C"
+

@@ -53,7 +53,7 @@ __device__ __forceinline__ void vline(int d, int l, int &base, int &stride) {
 // Every phase is a block-wide loop over work items (cell, field or component, line or point), so the number of
 // threads is independent of n and all 256 threads have work in every phase.
 template <int dim, int n, typename T>
-__global__ void __launch_bounds__(kVelThreads)
+__global__ void __launch_bounds__(kVelThreads, 3)
 velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict__ nbr, int n_owned, const T *__restrict__ src,
                 const T *__restrict__ ue, T *__restrict__ dst, int add) {
   constexpr int NL = ipow(n, dim - 1), ND = NL * n, CPB = vel_cpb<dim, n, T>(), NT = kVelThreads;

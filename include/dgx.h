@@ -125,6 +125,8 @@ int dgx_vec_mean_value(const dgx_vec *a, double *out);
 int dgx_vec_add_and_dot(dgx_vec *dst, double a, const dgx_vec *v, const dgx_vec *w, double *out);
 /* interpolate_velocity (NS.cc:2403-2418): dst = a*x - b*y in one pass, bit-identical to equ / equ / operator-= */
 int dgx_vec_interpolate(dgx_vec *dst, double a, const dgx_vec *x, double b, const dgx_vec *y);
+/* one (classical) Gram-Schmidt sweep: h[j] = w . V[j] (j < k <= 32, one pass + one all-reduce), then w -= sum_j h[j] V[j] */
+int dgx_vec_orthogonalize(dgx_vec *w, dgx_vec *const *V, int k, double *h);
 int dgx_vec_update_ghost_values(dgx_vec *v);
 int dgx_vec_zero_out_ghost_values(dgx_vec *v);
 /* compress(VectorOperation::add): a no-op by construction (cell-centric kernels never write ghosts) */
