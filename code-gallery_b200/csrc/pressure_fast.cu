@@ -19,6 +19,9 @@
 //   H warps   read the x / y halo cells of the tile and reduce them to (V', G') traces.
 //
 // Hand-offs use named barriers (bar.arrive / bar.sync), stages are double buffered.
+#ifndef DGX_XY_UNROLLED
+#define DGX_XY_UNROLLED 1
+#endif
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -140,6 +143,9 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
   // For even n the cell stride n^3 maps every lane (= cell) of an XY warp to the same bank: those instantiations keep a
   // second, padded copy of u (written by the Z warps, which hold the columns in registers anyway) and a padded W.
   constexpr bool PAD = (n % 2 == 0);
+  // straight-line XY sweeps where the register budget allows it (fp64: one CTA per SM, 168 registers); rolled streaming
+  // loops for fp32, which runs 2-3 CTAs per SM at 64-96 registers
+  constexpr bool XY_UNROLLED = DGX_XY_UNROLLED && sizeof(T) == 8;
   constexpr int NDP = PAD ? ND + 1 : ND;
   T *U = reinterpret_cast<T *>(smem_raw);          // [NS][TC][ND]   u planes (bulk-copied, memory order)
   T *W = U + NS * TC * ND;                         // [2][TC][NDP]   z-partial sums, then the xy result
@@ -375,6 +381,32 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
 #pragma unroll
       for (int a = 0; a < n; ++a) { gx[0][a] = 0; gx[1][a] = 0; gy[0][a] = 0; gy[1][a] = 0; }
       // y sweep: rows of u, acc[jj][i] += Kt_y[jj][j] u[j][i]; traces of the y faces
+      if (XY_UNROLLED) {
+        // the layer sits in registers; both sweeps and the four face traces straight-line (more ILP, larger code)
+        T u[n][n];
+#pragma unroll
+        for (int j = 0; j < n; ++j)
+#pragma unroll
+          for (int i = 0; i < n; ++i) u[j][i] = Up[j * n + i];
+#pragma unroll
+        for (int j = 0; j < n; ++j)
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            T a = acc[j][i];
+#pragma unroll
+            for (int l = 0; l < n; ++l) a = fma(P.Kt[0][i * n + l], u[j][l], a);
+#pragma unroll
+            for (int l = 0; l < n; ++l) a = fma(P.Kt[1][j * n + l], u[l][i], a);
+            acc[j][i] = a;
+          }
+#pragma unroll
+        for (int a = 0; a < n; ++a)
+#pragma unroll
+          for (int l = 0; l < n; ++l) {
+            gx[0][a] = fma(P.g[0][l], u[a][l], gx[0][a]); gx[1][a] = fma(P.g[1][l], u[a][l], gx[1][a]);
+            gy[0][a] = fma(P.g[0][l], u[l][a], gy[0][a]); gy[1][a] = fma(P.g[1][l], u[l][a], gy[1][a]);
+          }
+      } else {
       T nxt[n];
 #pragma unroll
       for (int i = 0; i < n; ++i) nxt[i] = Up[i];
@@ -417,6 +449,7 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
 #pragma unroll
         for (int j = 0; j < n; ++j) { gx[0][j] = fma(g0, col[j], gx[0][j]); gx[1][j] = fma(g1, col[j], gx[1][j]); }
       }
+      }
       if (p > 0) bar_sync(B_XY, CNT_XY);   // every layer thread has read the previous plane's traces: TX / TY may be overwritten
 #pragma unroll
       for (int a = 0; a < n; ++a) {
@@ -428,7 +461,7 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
       bar_sync(B_XY, CNT_XY);
       // neighbour terms; stage / buffer dependent part of the descriptors
       const int hsh = st * HBUF;
-#pragma unroll 1
+#pragma unroll XY_UNROLLED ? 2 : 1
       for (int s = 0; s < 2; ++s) {
         const bool in = s ? ins[0][1] : ins[0][0];
         const T *gp = U + (s ? g_off[0][1] : g_off[0][0]) + (in ? 0 : hsh);
@@ -444,7 +477,7 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
           for (int i = 0; i < n; ++i) acc[j][i] = fma(cv[i], vn, fma(cg[i], gn, acc[j][i]));
         }
       }
-#pragma unroll 1
+#pragma unroll XY_UNROLLED ? 2 : 1
       for (int s = 0; s < 2; ++s) {
         const bool in = s ? ins[1][1] : ins[1][0];
         const T *gp = U + (s ? g_off[1][1] : g_off[1][0]) + (in ? 0 : hsh);
