@@ -19,6 +19,9 @@
 //   H warps   read the x / y halo cells of the tile and reduce them to (V', G') traces.
 //
 // Hand-offs use named barriers (bar.arrive / bar.sync), stages are double buffered.
+#ifndef DGX_MB4F
+#define DGX_MB4F 2
+#endif
 #ifndef DGX_XY_UNROLLED
 #define DGX_XY_UNROLLED 1
 #endif
@@ -66,8 +69,8 @@ struct Roles {
 // resident CTAs per SM the register allocation is sized for (shared memory allows as many)
 template <int n, typename T> struct MinBlocks { static constexpr int value = 1; };
 template <> struct MinBlocks<5, float> { static constexpr int value = 2; };
-template <> struct MinBlocks<4, double> { static constexpr int value = 2; };
-template <> struct MinBlocks<4, float> { static constexpr int value = 3; };
+// (4, double): shared memory allows one CTA per SM anyway, so take the registers
+template <> struct MinBlocks<4, float> { static constexpr int value = DGX_MB4F; };
 
 // barrier ids (0 is __syncthreads)
 enum { B_FULL = 1, B_QREADY = 3, B_XY = 5 };
@@ -134,7 +137,8 @@ __device__ __forceinline__ int slot_of(int cx, int cy) { return (cx & 1) | ((cy 
 template <int n, typename T, bool ADD>
 __global__ void __launch_bounds__(Roles<n>::NW * 32, MinBlocks<n, T>::value)
 pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_constant__ FastGeom G,
-                      const int *__restrict__ nbr, const T *__restrict__ src, T *__restrict__ dst, const int *__restrict__ jobs) {
+                      const int *__restrict__ nbr, const T *__restrict__ src, T *__restrict__ dst, const int *__restrict__ jobs,
+                      const __grid_constant__ Epilogue<T> E) {
   using R = Roles<n>;
   constexpr int NL = n * n, ND = NL * n, NS = R::NSTAGE;
   constexpr int CNT_FULL = (R::NXY + R::NZW + R::NH) * 32,
@@ -222,12 +226,20 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
         T qv[n];
 #pragma unroll
         for (int k = 0; k < n; ++k) qv[k] = Ws[cofp[m] + k * NL];
-        T *o = dst + ((long long)cxy[m] + sh);
+        const long long off = (long long)cxy[m] + sh;
+        T *o = dst + off;
 #pragma unroll
         for (int k = 0; k < n; ++k) {
           T acc = ADD ? o[k * NL] : T(0);
 #pragma unroll
           for (int kk = 0; kk < n; ++kk) acc = fma(P.Mh[2][k * n + kk], qv[kk], acc);
+          if (E.on) {   // fused Chebyshev / residual update: dst = a x + b xold + c d .* (rhs - A x)
+            T v = E.c * (E.rhs[off + k * NL] - acc);
+            if (E.d) v *= E.d[off + k * NL];
+            v += E.a * src[off + k * NL];
+            if (E.xold) v += E.b * E.xold[off + k * NL];
+            acc = v;
+          }
           o[k * NL] = acc;
         }
       }
@@ -624,7 +636,8 @@ void fill_fast_params(FastParams<T, n> &F, const dgx_op *op) {
 }
 
 template <int n, typename T>
-int launch_march(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const FastGeom &G, const int *d_jobs, int n_jobs, cudaStream_t stream) {
+int launch_march(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const FastGeom &G, const int *d_jobs, int n_jobs, cudaStream_t stream,
+                 const FusedUpdate *fu) {
   using R = Roles<n>;
   constexpr int NL = n * n, ND = NL * n;
   FastParams<T, n> F;
@@ -639,26 +652,34 @@ int launch_march(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const F
   }
   const int grid = d_jobs ? n_jobs : G.ntx * G.nty * G.nsz;
   if (grid == 0) return DGX_OK;
-  if (add) pressure_march_kernel<n, T, true><<<grid, R::NW * 32, smem, stream>>>(F, G, op->mf->d_nbr, (const T *)src->d, (T *)dst->d, d_jobs);
-  else pressure_march_kernel<n, T, false><<<grid, R::NW * 32, smem, stream>>>(F, G, op->mf->d_nbr, (const T *)src->d, (T *)dst->d, d_jobs);
+  Epilogue<T> E;
+  if (fu) {
+    E.on = 1;
+    E.xold = fu->xold ? (const T *)fu->xold->d : nullptr;
+    E.d = fu->d ? (const T *)fu->d->d : nullptr;
+    E.rhs = (const T *)fu->rhs->d;
+    E.a = (T)fu->a; E.b = (T)fu->b; E.c = (T)fu->c;
+  }
+  if (add) pressure_march_kernel<n, T, true><<<grid, R::NW * 32, smem, stream>>>(F, G, op->mf->d_nbr, (const T *)src->d, (T *)dst->d, d_jobs, E);
+  else pressure_march_kernel<n, T, false><<<grid, R::NW * 32, smem, stream>>>(F, G, op->mf->d_nbr, (const T *)src->d, (T *)dst->d, d_jobs, E);
   count_launch();
   DGX_CUDA_CHECK(cudaGetLastError());
   return DGX_OK;
 }
 
-int march_dispatch(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const FastGeom &G, const int *d_jobs, int n_jobs, cudaStream_t stream = nullptr) {
+int march_dispatch(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const FastGeom &G, const int *d_jobs, int n_jobs, cudaStream_t stream = nullptr,
+                   const FusedUpdate *fu = nullptr) {
   dgx_mf *mf = op->mf;
   if (!stream) stream = mf->ctx->stream;
-  if (mf->dtype == DGX_F64) return op->degree == 4 ? launch_march<5, double>(op, dst, src, add, G, d_jobs, n_jobs, stream) : launch_march<4, double>(op, dst, src, add, G, d_jobs, n_jobs, stream);
-  return op->degree == 4 ? launch_march<5, float>(op, dst, src, add, G, d_jobs, n_jobs, stream) : launch_march<4, float>(op, dst, src, add, G, d_jobs, n_jobs, stream);
+  if (mf->dtype == DGX_F64) return op->degree == 4 ? launch_march<5, double>(op, dst, src, add, G, d_jobs, n_jobs, stream, fu) : launch_march<4, double>(op, dst, src, add, G, d_jobs, n_jobs, stream, fu);
+  return op->degree == 4 ? launch_march<5, float>(op, dst, src, add, G, d_jobs, n_jobs, stream, fu) : launch_march<4, float>(op, dst, src, add, G, d_jobs, n_jobs, stream, fu);
 }
 
 // geometry of the march for this operator, or false when the marching kernel does not apply
 bool march_geometry(const dgx_op *op, FastGeom &G) {
   const dgx_mf *mf = op->mf;
   if (mf->dim != 3 || !mf->all_interior || !mf->box_ok) return false;
-  // Q3 fp32 is still slower here than in the generic kernel (small planes: fixed per-plane costs): only on request (variant 2)
-  if (op->degree != 4 && !(op->degree == 3 && (op->variant == 2 || mf->dtype == DGX_F64))) return false;
+  if (op->degree != 4 && op->degree != 3) return false;
   const Mesh &m = mf->mesh->m;
   G.L = mf->level;
   G.c0x = m.cells0[0]; G.c0y = m.cells0[1];
@@ -666,8 +687,12 @@ bool march_geometry(const dgx_op *op, FastGeom &G) {
   const int EX = mf->box_ext[0], EY = mf->box_ext[1], EZ = mf->box_ext[2];
   if (G.L < 3 || EX % TXC || EY % TYC || EZ < 2 || mf->first_cell % 4) return false;
   G.ntx = EX / TXC; G.nty = EY / TYC;
+  // planes per job: as long as possible (each job pays ~2 extra planes of prologue / epilogue) but at least ~4 waves of jobs;
+  // levels too small for that stay with the generic kernel, which parallelises over all cells
   int NZ = EZ;
   while (NZ > 64 && NZ % 2 == 0) NZ /= 2;
+  while (NZ > 8 && NZ % 2 == 0 && (long long)G.ntx * G.nty * (EZ / NZ) < 4 * 148) NZ /= 2;
+  if ((long long)G.ntx * G.nty * (EZ / NZ) < 2 * 148 && op->variant != 2) return false;
   G.NZ = NZ; G.nsz = EZ / NZ;
   G.first_cell = mf->first_cell;
   G.n_owned = (int)mf->n_owned;
@@ -675,6 +700,13 @@ bool march_geometry(const dgx_op *op, FastGeom &G) {
 }
 
 }  // namespace
+
+// fused operator + vector update through the marching kernel (its Z warps apply the update when they store the result)
+int pressure_apply_fast_fused(dgx_op *op, dgx_vec *dst, const dgx_vec *x, const FusedUpdate &fu) {
+  FastGeom G;
+  if (op->variant == 1 || !march_geometry(op, G)) return DGX_ERR_UNSUPPORTED;
+  return march_dispatch(op, dst, x, false, G, nullptr, 0, nullptr, &fu);
+}
 
 // The marching kernel applies when every face is interior (fully periodic mesh) and the owned cells form a
 // box of the hierarchical order whose extents are multiples of the tile.

@@ -38,17 +38,6 @@ __host__ __device__ constexpr int cells_per_block() {
   return (192 / ipow(n, dim - 1)) > 0 ? (192 / ipow(n, dim - 1)) : 1;
 }
 
-// Optional fused epilogue of the operator: instead of dst = A x the kernel writes
-//   dst = a * x + b * xold + c * d .* (rhs - A x)        (null pointers drop their term; d == null means d = 1)
-// which is one Chebyshev step (PreconditionChebyshev) or the multigrid residual, without the extra
-// passes over t = A x.
-template <typename T>
-struct Epilogue {
-  const T *xold = nullptr, *d = nullptr, *rhs = nullptr;
-  T a = 0, b = 0, c = 0;
-  int on = 0;
-};
-
 // one batch of CPB cells: dst[cells] (+)= A src.  Shared by the generic kernel (one batch per block) and the
 // single-CTA coarse-grid CG kernel (loops over the batches of a tiny level).
 template <int dim, int n, typename T>
@@ -403,6 +392,12 @@ int pressure_apply_fused(dgx_op *op, dgx_vec *dst, dgx_vec *x, const FusedUpdate
   if (op->kind != DGX_OP_PRESSURE || dst->d == x->d) return DGX_ERR_UNSUPPORTED;
   int rc = ghost_exchange(x);
   if (rc) return rc;
+  // The marching kernel can apply the same epilogue in its Z warps (pressure_apply_fast_fused), but measured on 128^3 Q3 fp32 that
+  // puts four more streams on its producer warps and costs 2.1 ms per fused step against 1.0 ms here: opt-in (variant 2) only.
+  if (op->variant == 2) {
+    rc = pressure_apply_fast_fused(op, dst, x, fu);
+    if (rc != DGX_ERR_UNSUPPORTED) return rc;
+  }
   if (mf->dim == 2) return mf->dtype == DGX_F64 ? generic_by_degree<2, double>(op->degree, op, dst, x, false, &fu)
                                                  : generic_by_degree<2, float>(op->degree, op, dst, x, false, &fu);
   return mf->dtype == DGX_F64 ? generic_by_degree<3, double>(op->degree, op, dst, x, false, &fu)

@@ -46,7 +46,19 @@ void fill_pres_params(PresParams<T, n> &P, const dgx_op *op, double kappa) {
   P.C = (T)((double)n * n);
 }
 
+// Optional fused epilogue of the operator kernels: instead of dst = A x they write
+//   dst = a * x + b * xold + c * d .* (rhs - A x)        (null pointers drop their term; d == null means d = 1)
+// which is one Chebyshev step (PreconditionChebyshev) or the multigrid residual, without the extra
+// passes over t = A x.
+template <typename T>
+struct Epilogue {
+  const T *xold = nullptr, *d = nullptr, *rhs = nullptr;
+  T a = 0, b = 0, c = 0;
+  int on = 0;
+};
+
 double pressure_kappa(const dgx_op *op);
+int pressure_apply_fast_fused(dgx_op *op, dgx_vec *dst, const dgx_vec *x, const FusedUpdate &fu);
 
 // blocked fast path (pressure_fast.cu): returns DGX_ERR_UNSUPPORTED when the shape does not qualify
 int pressure_apply_fast(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add);
