@@ -9,6 +9,7 @@
 // The host only sequences kernel launches and reads back the few scalars (dot products) the algorithms
 // branch on; all vectors and all arithmetic on them stay on the device.
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -48,6 +49,12 @@ struct dgx_mg {
   int *d_info = nullptr;
   double *d_res = nullptr;
   int n_dev_solves = 0;
+  // Chebyshev eigenvalue estimates per (TR_BDF2 stage, dt): they depend on nothing else (the level operators are fixed by the
+  // mesh, kappa(stage, dt) and the degree), so a time loop pays the 10 CG iterations per level once per stage, not per solve
+  struct EigKey { int stage; double dt; };
+  std::vector<std::pair<EigKey, std::vector<std::array<double, 4>>>> eig_cache;
+  bool cache_estimates = true;
+  int last_setup_cached = 0;
 };
 
 namespace {
@@ -509,10 +516,35 @@ int dgx_mg_setup(dgx_mg *mg, double coarse_abs_tol, int coarse_max_it) {
   mg->coarse_max_it = coarse_max_it;
   mg->coarse_its.clear();
   mg->n_dev_solves = 0;
+  const std::vector<std::array<double, 4>> *hit = nullptr;
+  if (mg->cache_estimates)
+    for (auto &e : mg->eig_cache)
+      if (e.first.stage == mg->stage && e.first.dt == mg->dt) hit = &e.second;
+  mg->last_setup_cached = hit ? 1 : 0;
+  std::vector<std::array<double, 4>> fresh(mg->n_levels);
   for (int l = 0; l < mg->n_levels; ++l) {
     RC(dgx_op_compute_diagonal(mg->op[l]));
-    if (l > 0) { mg->smoother[l]->initialized = false; RC(dgx_cheb_estimate(mg->smoother[l])); }
+    if (l == 0) continue;
+    dgx_cheb *c = mg->smoother[l];
+    if (hit) {
+      c->min_eig_est = (*hit)[l][0]; c->max_eig_est = (*hit)[l][1]; c->theta = (*hit)[l][2]; c->delta = (*hit)[l][3];
+      c->initialized = true;
+    } else {
+      c->initialized = false;
+      RC(dgx_cheb_estimate(c));
+      fresh[l] = {c->min_eig_est, c->max_eig_est, c->theta, c->delta};
+    }
   }
+  if (!hit && mg->cache_estimates) mg->eig_cache.push_back({{mg->stage, mg->dt}, fresh});
+  return DGX_OK;
+}
+
+// 0: recompute the eigenvalue estimates on every setup, exactly as projection_step does (NS.cc:2501-2517); 1 (default): reuse them
+// for an unchanged (stage, dt).  Returns through *was_cached whether the last setup hit the cache.
+int dgx_mg_cache_estimates(dgx_mg *mg, int enable, int *was_cached) {
+  DGX_REQUIRE(mg, "null argument");
+  if (enable >= 0) { mg->cache_estimates = enable != 0; if (!enable) mg->eig_cache.clear(); }
+  if (was_cached) *was_cached = mg->last_setup_cached;
   return DGX_OK;
 }
 

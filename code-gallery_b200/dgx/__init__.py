@@ -415,6 +415,15 @@ class Multigrid:
     def setup(self, coarse_abs_tol, coarse_max_it=10000):
         _check(lib.dgx_mg_setup(self.h, c_dbl(coarse_abs_tol), coarse_max_it))
 
+    def cache_estimates(self, enable=True):
+        """reuse the Chebyshev eigenvalue estimates for an unchanged (stage, dt) (default) or recompute per setup like the reference"""
+        _check(lib.dgx_mg_cache_estimates(self.h, 1 if enable else 0, None))
+
+    def last_setup_was_cached(self):
+        c = c_int()
+        _check(lib.dgx_mg_cache_estimates(self.h, -1, C.byref(c)))
+        return bool(c.value)
+
     def vmult(self, dst, src):
         _check(lib.dgx_mg_vmult(self.h, dst.h, src.h))
 

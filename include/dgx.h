@@ -182,6 +182,9 @@ int dgx_mg_n_levels(const dgx_mg *mg);
 int dgx_mg_set_dt(dgx_mg *mg, double dt);
 int dgx_mg_set_TR_BDF2_stage(dgx_mg *mg, int stage);
 int dgx_mg_setup(dgx_mg *mg, double coarse_abs_tol, int coarse_max_it);   /* diagonals + eigenvalue estimates */
+/* the Chebyshev eigenvalue estimates depend only on (TR_BDF2 stage, dt): by default a setup with an unchanged pair reuses them
+ * (enable = 0 restores the reference's recomputation per solve, NS.cc:2501-2517; enable < 0 only queries) */
+int dgx_mg_cache_estimates(dgx_mg *mg, int enable, int *was_cached);
 int dgx_mg_vmult(dgx_mg *mg, dgx_vec *dst, dgx_vec *src);                 /* PreconditionMG::vmult (fp64 in/out) */
 int dgx_mg_coarse_iterations(const dgx_mg *mg, int *out, int capacity, int *count);
 int dgx_mg_level_op(dgx_mg *mg, int level, dgx_op **op);                  /* borrowed */

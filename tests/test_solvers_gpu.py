@@ -147,3 +147,11 @@ def test_mg_cg_pressure_solve(dgx, gpu_ctx, dim, cells0, nref, degree):
         assert rel_l2(vx.to_host(), x) < 1e-4
         assert np.linalg.norm(osolver.op.vmult(vx.to_host()) - rhs) <= 1.5 * tol
         assert len(mg.coarse_iterations()) == its
+        # a second setup with the same (stage, dt) reuses the eigenvalue estimates: same iteration count, same solution
+        assert not mg.last_setup_was_cached()
+        mg.setup(tol, 10000)
+        assert mg.last_setup_was_cached()
+        x1 = vx.to_host()
+        vx.set(0.0)
+        its2, _ = dgx.solve_cg(op, vx, vb, mg, 10000, tol)
+        assert its2 == its and np.array_equal(vx.to_host(), x1)
