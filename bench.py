@@ -360,6 +360,12 @@ def main():
         try:
             res = cpu_baseline(args.degree, args.cpu_refine, args.dtype)
             cpu = {"value": res["dofs_per_s"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]}
+            try:    # extra: the kernels' own (Kronecker-factored) algorithm on the host cores, so the ratio is not inflated by the port
+                from oracle import cpu_port
+                k = cpu_port.time_kron(args.degree, args.cpu_refine + 1)
+                cpu["kronecker_algorithm_on_cpu"] = {"value": k["dofs_per_s"], "unit": UNIT, "cores": k["cores"], "what": k["what"]}
+            except Exception as exc:  # noqa: BLE001
+                cpu["kronecker_algorithm_on_cpu"] = {"error": str(exc)}
         except Exception as exc:  # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
 

@@ -173,3 +173,17 @@ def test_c_port_matches_numpy_oracle(case):
     u = np.random.default_rng(0).standard_normal(op.n_dofs)
     a, b = op.vmult(u), cpu_port.pressure_vmult(m, deg, 5e-3, u)
     assert np.linalg.norm(a - b) <= 1e-13 * np.linalg.norm(a)
+
+
+def test_cpu_kronecker_port_matches_oracle():
+    """oracle/cpu_kron.c (the kernels' Kronecker form on the CPU, used as an extra timed baseline) equals the quadrature-point oracle"""
+    from oracle import cpu_port
+    from oracle.mesh import CartesianMesh
+    from oracle.operators import PressureOperator
+    m = CartesianMesh(3, [1, 2, 1], 1, [0, 0, 0], [1.0, 1.5, 0.75], [True] * 3)
+    for degree in (1, 2, 4):
+        op = PressureOperator(m, degree, 5e-3)
+        u = np.random.default_rng(degree).standard_normal(op.n_dofs)
+        got = cpu_port.kron_vmult(m, degree, 5e-3, u)
+        ref = op.vmult(u)
+        assert np.linalg.norm(got - ref) <= 1e-12 * np.linalg.norm(ref)
