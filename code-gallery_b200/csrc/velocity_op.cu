@@ -30,13 +30,30 @@ struct VelParams {
   T alpha, a, aRe, C, theta;
 };
 
-// cells per block: as many as keep the block's shared memory near 72 KB (3 blocks per SM), at most 16
-template <int dim, int n, typename T>
-__host__ __device__ constexpr int vel_cpb() {
-  constexpr int per_cell = (int)sizeof(T) * (3 * dim * ipow(n, dim) + 4 * 3 * dim * ipow(n, dim - 1));
-  return (72 * 1024 / per_cell) < 1 ? 1 : ((72 * 1024 / per_cell) > 16 ? 16 : (72 * 1024 / per_cell));
-}
+// Work decomposition.  A block of 256 threads is cut into independent GROUPS of WPG warps; a group owns CPG cells and all
+// the shared memory they need, runs every phase as a group-wide loop over work items (cell, field or component, line or
+// point) and synchronises only with itself (__syncwarp, or a named barrier when WPG > 1).  Groups of one block drift
+// apart, so one group's global loads overlap another's contractions; no phase ever waits for the whole block (the first
+// version's 16 __syncthreads per block cost 12 % of all issue slots and left 25 % occupancy to hide the rest).
+// Sizes: about 75 KB of shared memory per block (3 blocks per SM); small cells give WPG = 1 and several cells per warp,
+// large cells several warps per cell.
 constexpr int kVelThreads = 256;
+constexpr int kVelSmemBudget = 75 * 1024;
+
+template <int dim, int n, typename T>
+struct VelCfg {
+  static constexpr int NL = ipow(n, dim - 1), ND = NL * n;
+  static constexpr int NF = 2 * dim + 1;                 // face fields: V (dim), G (dim), E_d
+  static constexpr int RS = n + 1, NB = RS * NL;         // x-rows padded to n + 1: no bank conflicts for y-/z-lines
+  static constexpr int PER_CELL = 3 * dim * NB + 4 * NF * NL;
+  static constexpr int fit = kVelSmemBudget / (PER_CELL * (int)sizeof(T));
+  static constexpr int CPBraw = fit < 1 ? 1 : (fit > 16 ? 16 : fit);
+  static constexpr int WPG = CPBraw >= 8 ? 1 : (CPBraw >= 4 ? 2 : (CPBraw >= 2 ? 4 : 8));
+  static constexpr int NG = (kVelThreads / 32) / WPG;    // groups per block
+  static constexpr int CPG = CPBraw >= 8 ? CPBraw / 8 : 1;
+  static constexpr int CPB = NG * CPG;
+  static constexpr size_t smem = sizeof(T) * (size_t)CPB * PER_CELL;
+};
 
 template <int dim, int n>
 __device__ __forceinline__ void vline(int d, int l, int &base, int &stride) {
@@ -50,39 +67,68 @@ __device__ __forceinline__ void vline(int d, int l, int &base, int &stride) {
   }
 }
 
-// Every phase is a block-wide loop over work items (cell, field or component, line or point), so the number of
-// threads is independent of n and all 256 threads have work in every phase.
+// same line in a box whose x-rows are padded to n + 1 entries
+template <int dim, int n>
+__device__ __forceinline__ void pline(int d, int l, int &base, int &stride) {
+  constexpr int RS = n + 1;
+  if (dim == 3) {
+    if (d == 0) { base = l * RS; stride = 1; }
+    else if (d == 1) { base = (l % n) + RS * n * (l / n); stride = RS; }
+    else { base = (l % n) + RS * (l / n); stride = RS * n; }
+  } else {
+    if (d == 0) { base = l * RS; stride = 1; }
+    else { base = l; stride = RS; }
+  }
+}
+
+template <int WPG>
+__device__ __forceinline__ void group_sync(int g) {
+  if (WPG == 1) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(WPG * 32) : "memory");
+}
+
 template <int dim, int n, typename T>
 __global__ void __launch_bounds__(kVelThreads, 3)
 velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict__ nbr, int n_owned, const T *__restrict__ src,
                 const T *__restrict__ ue, T *__restrict__ dst, int add) {
-  constexpr int NL = ipow(n, dim - 1), ND = NL * n, CPB = vel_cpb<dim, n, T>(), NT = kVelThreads;
-  constexpr int NF = 3 * dim;   // face fields: V (dim), G (dim), E (dim)
-  constexpr int PER_CELL = 3 * dim * ND + 4 * NF * NL;
+  using Cfg = VelCfg<dim, n, T>;
+  constexpr int NL = Cfg::NL, ND = Cfg::ND, NF = Cfg::NF, RS = Cfg::RS, NB = Cfg::NB, PER_CELL = Cfg::PER_CELL;
+  constexpr int WPG = Cfg::WPG, CPG = Cfg::CPG, GT = WPG * 32;
   extern __shared__ __align__(16) unsigned char vsm[];
-  T *sm = reinterpret_cast<T *>(vsm);
-  const int tid = threadIdx.x;
-  const int cell0 = blockIdx.x * CPB;
-  const int ncell = min(CPB, n_owned - cell0);
-  auto Ac = [&](int ci) { return sm + (size_t)ci * PER_CELL; };                 // [2*dim][ND]
-  auto Rc = [&](int ci) { return sm + (size_t)ci * PER_CELL + 2 * dim * ND; };  // [dim][ND]
-  auto Na = [&](int ci) { return sm + (size_t)ci * PER_CELL + 3 * dim * ND; };  // [2 faces][NF][NL]
-  auto Nb = [&](int ci) { return sm + (size_t)ci * PER_CELL + 3 * dim * ND + 2 * NF * NL; };
-  // 1. load u, u_extr (contiguous per cell: dim * ND values each)
-  for (int it = tid; it < ncell * 2 * dim * ND; it += NT) {
-    const int ci = it / (2 * dim * ND), r = it - ci * (2 * dim * ND);
-    const int f = r / ND, i = r - f * ND;
-    Ac(ci)[r] = (f < dim ? src : ue)[((size_t)(cell0 + ci) * dim + (f % dim)) * ND + i];
-  }
-  __syncthreads();
-  // 2. to the Gauss-point basis
+  const int g = threadIdx.x / GT, tid = threadIdx.x - g * GT;
+  const int cell0 = (blockIdx.x * Cfg::NG + g) * CPG;
+  const int ncell = min(CPG, n_owned - cell0);
+  if (ncell <= 0) return;                                  // whole group leaves; nobody else waits for it
+  T *sm = reinterpret_cast<T *>(vsm) + (size_t)g * CPG * PER_CELL;
+  auto Ac = [&](int ci) { return sm + (size_t)ci * PER_CELL; };                 // [2*dim][NB]: u_hat, ue_hat
+  auto Rc = [&](int ci) { return sm + (size_t)ci * PER_CELL + 2 * dim * NB; };  // [dim][NB]: result
+  auto Na = [&](int ci) { return sm + (size_t)ci * PER_CELL + 3 * dim * NB; };  // [2 sides][NF][NL]
+  auto Nb = [&](int ci) { return sm + (size_t)ci * PER_CELL + 3 * dim * NB + 2 * NF * NL; };
+  // 1. load u, u_extr one x-row per item and move the row to the Gauss-point basis on the way in
+  for (int it = tid; it < ncell * 2 * dim * NL; it += GT) {
+    const int ci = it / (2 * dim * NL), r = it - ci * (2 * dim * NL), f = r / NL, row = r - f * NL;
+    const T *gp = (f < dim ? src : ue) + ((size_t)(cell0 + ci) * dim + (f % dim)) * ND + row * n;
+    T u[n];
 #pragma unroll
-  for (int d = 0; d < dim; ++d) {
-    for (int it = tid; it < ncell * 2 * dim * NL; it += NT) {
+    for (int i = 0; i < n; ++i) u[i] = gp[i];
+    T *A = Ac(ci) + f * NB + row * RS;
+#pragma unroll
+    for (int q = 0; q < n; ++q) {
+      T acc = 0;
+#pragma unroll
+      for (int i = 0; i < n; ++i) acc += P.S[q * n + i] * u[i];
+      A[q] = acc;
+    }
+  }
+  group_sync<WPG>(g);
+  // 2. remaining directions of the basis change
+#pragma unroll
+  for (int d = 1; d < dim; ++d) {
+    for (int it = tid; it < ncell * 2 * dim * NL; it += GT) {
       const int ci = it / (2 * dim * NL), r = it - ci * (2 * dim * NL), f = r / NL, l = r - f * NL;
       int base, stride;
-      vline<dim, n>(d, l, base, stride);
-      T *A = Ac(ci) + f * ND;
+      pline<dim, n>(d, l, base, stride);
+      T *A = Ac(ci) + f * NB;
       T u[n];
 #pragma unroll
       for (int i = 0; i < n; ++i) u[i] = A[base + stride * i];
@@ -94,33 +140,22 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
         A[base + stride * q] = acc;
       }
     }
-    __syncthreads();
+    group_sync<WPG>(g);
   }
-  // 3. mass part of the cell term: alpha * JxW * u
   T vol = 1;
 #pragma unroll
   for (int d = 0; d < dim; ++d) vol *= P.h[d];
-  for (int it = tid; it < ncell * dim * ND; it += NT) {
-    const int ci = it / (dim * ND), r = it - ci * (dim * ND), i = r % ND;
-    int rr = i;
-    T jxw = vol;
-#pragma unroll
-    for (int d = 0; d < dim; ++d) { jxw *= P.w[rr % n]; rr /= n; }
-    Rc(ci)[r] = P.alpha * jxw * Ac(ci)[r];
-  }
-  __syncthreads();
-  // 4. per direction: gradient part of the cell term and the two faces normal to d
+  // 3. per direction: cell term (mass part with d == 0) and the two faces normal to d
 #pragma unroll
   for (int d = 0; d < dim; ++d) {
-    // 4a. nodal traces of the neighbours: item = (cell, side, component, nodal tangential point)
-    for (int it = tid; it < ncell * 2 * dim * NL; it += NT) {
+    // 3a. nodal traces of the neighbours: item = (cell, side, component, nodal tangential point)
+    for (int it = tid; it < ncell * 2 * dim * NL; it += GT) {
       const int ci = it / (2 * dim * NL), r = it - ci * (2 * dim * NL), s = r / (dim * NL), r2 = r - s * (dim * NL), c = r2 / NL, l = r2 - c * NL;
       const int nbc = nbr[(size_t)(2 * d + s) * n_owned + cell0 + ci];
       if (nbc < 0) continue;
       int base, stride;
       vline<dim, n>(d, l, base, stride);
       const T *gu = src + ((size_t)nbc * dim + c) * ND + base;
-      const T *ge = ue + ((size_t)nbc * dim + c) * ND + base;
       T gsum = 0, v = 0;
 #pragma unroll
       for (int i = 0; i < n; ++i) {
@@ -131,11 +166,11 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
       T *NTa = Na(ci);
       NTa[(s * NF + c) * NL + l] = v;
       NTa[(s * NF + dim + c) * NL + l] = P.ih[d] * gsum;
-      NTa[(s * NF + 2 * dim + c) * NL + l] = ge[stride * (1 - s) * (n - 1)];
+      if (c == d) NTa[(s * NF + 2 * dim) * NL + l] = ue[((size_t)nbc * dim + d) * ND + base + stride * (1 - s) * (n - 1)];
     }
-    __syncthreads();
+    group_sync<WPG>(g);
     // tangential interpolation to the face Gauss points (dim - 1 passes): item = (cell, side, face field, point)
-    for (int it = tid; it < ncell * 2 * NF * NL; it += NT) {
+    for (int it = tid; it < ncell * 2 * NF * NL; it += GT) {
       const int ci = it / (2 * NF * NL), r = it - ci * (2 * NF * NL), sf = r / NL, l = r - sf * NL;
       const int t0 = l % n, t1 = l / n;
       const T *in = Na(ci) + sf * NL;
@@ -144,9 +179,9 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
       for (int a2 = 0; a2 < n; ++a2) acc += P.S[t0 * n + a2] * in[a2 + n * t1];
       Nb(ci)[sf * NL + l] = acc;
     }
-    __syncthreads();
+    group_sync<WPG>(g);
     if (dim == 3) {
-      for (int it = tid; it < ncell * 2 * NF * NL; it += NT) {
+      for (int it = tid; it < ncell * 2 * NF * NL; it += GT) {
         const int ci = it / (2 * NF * NL), r = it - ci * (2 * NF * NL), sf = r / NL, l = r - sf * NL;
         const int t0 = l % n, t1 = l / n;
         const T *in = Nb(ci) + sf * NL;
@@ -155,17 +190,17 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
         for (int b2 = 0; b2 < n; ++b2) acc += P.S[t1 * n + b2] * in[t0 + n * b2];
         Na(ci)[sf * NL + l] = acc;
       }
-      __syncthreads();
+      group_sync<WPG>(g);
     }
-    // 4b. item = (cell, component, line along d)
-    for (int it = tid; it < ncell * dim * NL; it += NT) {
+    // 3b. item = (cell, component, line along d)
+    for (int it = tid; it < ncell * dim * NL; it += GT) {
       const int ci = it / (dim * NL), r = it - ci * (dim * NL), c = r / NL, l = r - c * NL;
       const int cell = cell0 + ci;
       const T *A = Ac(ci);
       T *R = Rc(ci);
       const T *NTf = dim == 3 ? Na(ci) : Nb(ci);
       int base, stride;
-      vline<dim, n>(d, l, base, stride);
+      pline<dim, n>(d, l, base, stride);
       const int t0 = l % n, t1 = l / n;
       const T wt = dim == 3 ? P.w[t0] * P.w[t1] : P.w[t0];
       T area = 1;
@@ -176,8 +211,8 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
       T Ed[2] = {0, 0};
 #pragma unroll
       for (int q = 0; q < n; ++q) {
-        u[q] = A[c * ND + base + stride * q];
-        ed[q] = A[(dim + d) * ND + base + stride * q];
+        u[q] = A[c * NB + base + stride * q];
+        ed[q] = A[(dim + d) * NB + base + stride * q];
         Ed[0] += P.fh[0][q] * ed[q]; Ed[1] += P.fh[1][q] * ed[q];
       }
       // cell term, direction d: flux = JxW (a/Re du/dx_d - a u ue_d), tested with d(phi)/dx_d
@@ -195,6 +230,7 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
 #pragma unroll
         for (int q = 0; q < n; ++q) acc += P.Dh[q * n + i] * fl[q];
         rl[i] = P.ih[d] * acc;
+        if (d == 0) rl[i] += P.alpha * vol * wt * P.w[i] * u[i];   // mass part: alpha JxW u
       }
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
@@ -206,7 +242,7 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
         G *= P.ih[d];
         T FV, FG;
         if (nbc >= 0) {
-          const T Vn = NTf[(s * NF + c) * NL + l], Gn = NTf[(s * NF + dim + c) * NL + l], En = NTf[(s * NF + 2 * dim + d) * NL + l];
+          const T Vn = NTf[(s * NF + c) * NL + l], Gn = NTf[(s * NF + dim + c) * NL + l], En = NTf[(s * NF + 2 * dim) * NL + l];
           const T lam = fmax(fabs(Ed[s]), fabs(En)), jump = V - Vn;
           FV = P.aRe * (T(-0.5) * ns * (G + Gn) + sigma * jump) + P.a * T(0.5) * ns * (V * Ed[s] + Vn * En) + T(0.5) * P.a * lam * jump;
           FG = -P.theta * P.aRe * T(0.5) * jump;
@@ -225,19 +261,24 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
 #pragma unroll
         for (int q = 0; q < n; ++q) rl[q] += wf * (P.fh[s][q] * FV + ns * P.ih[d] * P.gh[s][q] * FG);
       }
+      if (d == 0) {
 #pragma unroll
-      for (int q = 0; q < n; ++q) R[c * ND + base + stride * q] += rl[q];
+        for (int q = 0; q < n; ++q) R[c * NB + base + stride * q] = rl[q];
+      } else {
+#pragma unroll
+        for (int q = 0; q < n; ++q) R[c * NB + base + stride * q] += rl[q];
+      }
     }
-    __syncthreads();
+    group_sync<WPG>(g);
   }
-  // 5. back to the nodal basis (transposed basis change)
+  // 4. back to the nodal basis (transposed basis change): y, z in shared memory, x on the way out
 #pragma unroll
-  for (int d = 0; d < dim; ++d) {
-    for (int it = tid; it < ncell * dim * NL; it += NT) {
+  for (int d = dim - 1; d >= 1; --d) {
+    for (int it = tid; it < ncell * dim * NL; it += GT) {
       const int ci = it / (dim * NL), r = it - ci * (dim * NL), c = r / NL, l = r - c * NL;
       int base, stride;
-      vline<dim, n>(d, l, base, stride);
-      T *R = Rc(ci) + c * ND;
+      pline<dim, n>(d, l, base, stride);
+      T *R = Rc(ci) + c * NB;
       T u[n];
 #pragma unroll
       for (int q = 0; q < n; ++q) u[q] = R[base + stride * q];
@@ -249,12 +290,22 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
         R[base + stride * i] = acc;
       }
     }
-    __syncthreads();
+    group_sync<WPG>(g);
   }
-  for (int it = tid; it < ncell * dim * ND; it += NT) {
-    const int ci = it / (dim * ND), r = it - ci * (dim * ND);
-    T *o = dst + (size_t)(cell0 + ci) * dim * ND + r;
-    *o = add ? *o + Rc(ci)[r] : Rc(ci)[r];
+  for (int it = tid; it < ncell * dim * NL; it += GT) {
+    const int ci = it / (dim * NL), r = it - ci * (dim * NL), c = r / NL, row = r - c * NL;
+    const T *R = Rc(ci) + c * NB + row * RS;
+    T u[n];
+#pragma unroll
+    for (int q = 0; q < n; ++q) u[q] = R[q];
+    T *o = dst + ((size_t)(cell0 + ci) * dim + c) * ND + row * n;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      T acc = 0;
+#pragma unroll
+      for (int q = 0; q < n; ++q) acc += P.S[q * n + i] * u[q];
+      o[i] = add ? o[i] + acc : acc;
+    }
   }
 }
 
@@ -518,8 +569,8 @@ int launch_velocity(dgx_op *op, T *dst, const T *src, bool add) {
   P.a = (T)a; P.aRe = (T)(a / op->Re);
   P.C = (T)((double)n * n);   // C_u = (p_v + 1)^2, NS.cc:293
   P.theta = (T)1.0;           // theta_v, NS.cc:290
-  constexpr int NL = ipow(n, dim - 1), ND = NL * n, CPB = vel_cpb<dim, n, T>(), NT = kVelThreads;
-  const size_t smem = sizeof(T) * (size_t)CPB * (3 * dim * ND + 4 * 3 * dim * NL);
+  constexpr int CPB = VelCfg<dim, n, T>::CPB, NT = kVelThreads;
+  const size_t smem = VelCfg<dim, n, T>::smem;
   static bool configured = false;
   if (!configured) {
     DGX_CUDA_CHECK(cudaFuncSetAttribute(velocity_kernel<dim, n, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
