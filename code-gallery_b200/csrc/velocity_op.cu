@@ -26,6 +26,8 @@ struct VelParams {
   T fh[2][n], gh[2][n];   // end-point value / derivative of the Gauss-point basis
   T gN[2][n];        // l_i'(s) of the nodal basis (neighbour traces are taken from nodal dofs)
   T w[n];
+  T kA[MAX_DIM][n], kB[MAX_DIM][n];   // w_q aRe / h_d^2 and w_q a / h_d: quadrature-point factors of the cell term
+  T aw[n];                            // alpha w_q (mass part)
   T h[MAX_DIM], ih[MAX_DIM];
   T alpha, a, aRe, C, theta;
 };
@@ -106,7 +108,7 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
   auto Nb = [&](int ci) { return sm + (size_t)ci * PER_CELL + 3 * dim * NB + 2 * NF * NL; };
   // 1. load u, u_extr one x-row per item and move the row to the Gauss-point basis on the way in
   for (int it = tid; it < ncell * 2 * dim * NL; it += GT) {
-    const int ci = it / (2 * dim * NL), r = it - ci * (2 * dim * NL), f = r / NL, row = r - f * NL;
+    const int ci = CPG == 1 ? 0 : it / (2 * dim * NL), r = it - ci * (2 * dim * NL), f = r / NL, row = r - f * NL;
     const T *gp = (f < dim ? src : ue) + ((size_t)(cell0 + ci) * dim + (f % dim)) * ND + row * n;
     T u[n];
 #pragma unroll
@@ -125,7 +127,7 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
 #pragma unroll
   for (int d = 1; d < dim; ++d) {
     for (int it = tid; it < ncell * 2 * dim * NL; it += GT) {
-      const int ci = it / (2 * dim * NL), r = it - ci * (2 * dim * NL), f = r / NL, l = r - f * NL;
+      const int ci = CPG == 1 ? 0 : it / (2 * dim * NL), r = it - ci * (2 * dim * NL), f = r / NL, l = r - f * NL;
       int base, stride;
       pline<dim, n>(d, l, base, stride);
       T *A = Ac(ci) + f * NB;
@@ -148,53 +150,68 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
   // 3. per direction: cell term (mass part with d == 0) and the two faces normal to d
 #pragma unroll
   for (int d = 0; d < dim; ++d) {
-    // 3a. nodal traces of the neighbours: item = (cell, side, component, nodal tangential point)
-    for (int it = tid; it < ncell * 2 * dim * NL; it += GT) {
-      const int ci = it / (2 * dim * NL), r = it - ci * (2 * dim * NL), s = r / (dim * NL), r2 = r - s * (dim * NL), c = r2 / NL, l = r2 - c * NL;
-      const int nbc = nbr[(size_t)(2 * d + s) * n_owned + cell0 + ci];
-      if (nbc < 0) continue;
+    // 3a. nodal traces of both neighbours: item = (cell, component, nodal tangential point)
+    for (int it = tid; it < ncell * dim * NL; it += GT) {
+      const int ci = CPG == 1 ? 0 : it / (dim * NL), r = it - ci * (dim * NL), c = r / NL, l = r - c * NL;
       int base, stride;
       vline<dim, n>(d, l, base, stride);
-      const T *gu = src + ((size_t)nbc * dim + c) * ND + base;
-      T gsum = 0, v = 0;
-#pragma unroll
-      for (int i = 0; i < n; ++i) {
-        const T x = gu[stride * i];
-        gsum += P.gN[1 - s][i] * x;
-        if (i == (1 - s) * (n - 1)) v = x;
-      }
       T *NTa = Na(ci);
-      NTa[(s * NF + c) * NL + l] = v;
-      NTa[(s * NF + dim + c) * NL + l] = P.ih[d] * gsum;
-      if (c == d) NTa[(s * NF + 2 * dim) * NL + l] = ue[((size_t)nbc * dim + d) * ND + base + stride * (1 - s) * (n - 1)];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int nbc = nbr[(size_t)(2 * d + s) * n_owned + cell0 + ci];
+        if (nbc < 0) continue;
+        const T *gu = src + ((size_t)nbc * dim + c) * ND + base;
+        T x[n];
+#pragma unroll
+        for (int i = 0; i < n; ++i) x[i] = gu[stride * i];
+        T gsum = 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) gsum += P.gN[1 - s][i] * x[i];
+        NTa[(s * NF + c) * NL + l] = x[(1 - s) * (n - 1)];
+        NTa[(s * NF + dim + c) * NL + l] = P.ih[d] * gsum;
+        if (c == d) NTa[(s * NF + 2 * dim) * NL + l] = ue[((size_t)nbc * dim + d) * ND + base + stride * (1 - s) * (n - 1)];
+      }
     }
     group_sync<WPG>(g);
-    // tangential interpolation to the face Gauss points (dim - 1 passes): item = (cell, side, face field, point)
-    for (int it = tid; it < ncell * 2 * NF * NL; it += GT) {
-      const int ci = it / (2 * NF * NL), r = it - ci * (2 * NF * NL), sf = r / NL, l = r - sf * NL;
-      const int t0 = l % n, t1 = l / n;
-      const T *in = Na(ci) + sf * NL;
-      T acc = 0;
+    // tangential interpolation to the face Gauss points (dim - 1 passes): item = (cell, side, face field, row or column)
+    constexpr int NR = NL / n;
+    for (int it = tid; it < ncell * 2 * NF * NR; it += GT) {
+      const int ci = CPG == 1 ? 0 : it / (2 * NF * NR), r = it - ci * (2 * NF * NR), sf = r / NR, t1 = r - sf * NR;
+      const T *in = Na(ci) + sf * NL + n * t1;
+      T x[n];
 #pragma unroll
-      for (int a2 = 0; a2 < n; ++a2) acc += P.S[t0 * n + a2] * in[a2 + n * t1];
-      Nb(ci)[sf * NL + l] = acc;
+      for (int a2 = 0; a2 < n; ++a2) x[a2] = in[a2];
+      T *out = Nb(ci) + sf * NL + n * t1;
+#pragma unroll
+      for (int t0 = 0; t0 < n; ++t0) {
+        T acc = 0;
+#pragma unroll
+        for (int a2 = 0; a2 < n; ++a2) acc += P.S[t0 * n + a2] * x[a2];
+        out[t0] = acc;
+      }
     }
     group_sync<WPG>(g);
     if (dim == 3) {
-      for (int it = tid; it < ncell * 2 * NF * NL; it += GT) {
-        const int ci = it / (2 * NF * NL), r = it - ci * (2 * NF * NL), sf = r / NL, l = r - sf * NL;
-        const int t0 = l % n, t1 = l / n;
-        const T *in = Nb(ci) + sf * NL;
-        T acc = 0;
+      for (int it = tid; it < ncell * 2 * NF * n; it += GT) {
+        const int ci = CPG == 1 ? 0 : it / (2 * NF * n), r = it - ci * (2 * NF * n), sf = r / n, t0 = r - sf * n;
+        const T *in = Nb(ci) + sf * NL + t0;
+        T x[n];
 #pragma unroll
-        for (int b2 = 0; b2 < n; ++b2) acc += P.S[t1 * n + b2] * in[t0 + n * b2];
-        Na(ci)[sf * NL + l] = acc;
+        for (int b2 = 0; b2 < n; ++b2) x[b2] = in[n * b2];
+        T *out = Na(ci) + sf * NL + t0;
+#pragma unroll
+        for (int t1 = 0; t1 < n; ++t1) {
+          T acc = 0;
+#pragma unroll
+          for (int b2 = 0; b2 < n; ++b2) acc += P.S[t1 * n + b2] * x[b2];
+          out[n * t1] = acc;
+        }
       }
       group_sync<WPG>(g);
     }
-    // 3b. item = (cell, component, line along d)
+    // 3b. item = (cell, component, line along d); everything below carries the common factor cw = vol * w_t0 * w_t1
     for (int it = tid; it < ncell * dim * NL; it += GT) {
-      const int ci = it / (dim * NL), r = it - ci * (dim * NL), c = r / NL, l = r - c * NL;
+      const int ci = CPG == 1 ? 0 : it / (dim * NL), r = it - ci * (dim * NL), c = r / NL, l = r - c * NL;
       const int cell = cell0 + ci;
       const T *A = Ac(ci);
       T *R = Rc(ci);
@@ -202,11 +219,8 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
       int base, stride;
       pline<dim, n>(d, l, base, stride);
       const int t0 = l % n, t1 = l / n;
-      const T wt = dim == 3 ? P.w[t0] * P.w[t1] : P.w[t0];
-      T area = 1;
-#pragma unroll
-      for (int e2 = 0; e2 < dim; ++e2) if (e2 != d) area *= P.h[e2];
-      const T wf = area * wt, sigma = P.C * P.ih[d];
+      const T cw = vol * (dim == 3 ? P.w[t0] * P.w[t1] : P.w[t0]);
+      const T sigma = P.C * P.ih[d];
       T u[n], ed[n], rl[n];
       T Ed[2] = {0, 0};
 #pragma unroll
@@ -215,22 +229,21 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
         ed[q] = A[(dim + d) * NB + base + stride * q];
         Ed[0] += P.fh[0][q] * ed[q]; Ed[1] += P.fh[1][q] * ed[q];
       }
-      // cell term, direction d: flux = JxW (a/Re du/dx_d - a u ue_d), tested with d(phi)/dx_d
+      // cell term, direction d: flux = w_q (a/Re du/dx_d - a u ue_d) / h_d, tested with d(phi)/d(xi_d)
       T fl[n];
 #pragma unroll
       for (int q = 0; q < n; ++q) {
         T dl = 0;
 #pragma unroll
         for (int q2 = 0; q2 < n; ++q2) dl += P.Dh[q * n + q2] * u[q2];
-        fl[q] = vol * wt * P.w[q] * (P.aRe * P.ih[d] * dl - P.a * u[q] * ed[q]);
+        fl[q] = P.kA[d][q] * dl - P.kB[d][q] * (u[q] * ed[q]);
       }
 #pragma unroll
       for (int i = 0; i < n; ++i) {
-        T acc = 0;
+        T acc = d == 0 ? P.aw[i] * u[i] : T(0);   // mass part: alpha w_q u
 #pragma unroll
         for (int q = 0; q < n; ++q) acc += P.Dh[q * n + i] * fl[q];
-        rl[i] = P.ih[d] * acc;
-        if (d == 0) rl[i] += P.alpha * vol * wt * P.w[i] * u[i];   // mass part: alpha JxW u
+        rl[i] = acc;
       }
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
@@ -258,15 +271,16 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
           FV = P.aRe * (-dn + sigma * dV) + P.a * aV * (ns * Ed[s]) + T(0.5) * P.a * lam * dV;
           FG = -P.theta * P.aRe * dV;
         }
+        const T FVs = P.ih[d] * FV, FGs = ns * P.ih[d] * P.ih[d] * FG;   // face area = vol / h_d
 #pragma unroll
-        for (int q = 0; q < n; ++q) rl[q] += wf * (P.fh[s][q] * FV + ns * P.ih[d] * P.gh[s][q] * FG);
+        for (int q = 0; q < n; ++q) rl[q] += P.fh[s][q] * FVs + P.gh[s][q] * FGs;
       }
       if (d == 0) {
 #pragma unroll
-        for (int q = 0; q < n; ++q) R[c * NB + base + stride * q] = rl[q];
+        for (int q = 0; q < n; ++q) R[c * NB + base + stride * q] = cw * rl[q];
       } else {
 #pragma unroll
-        for (int q = 0; q < n; ++q) R[c * NB + base + stride * q] += rl[q];
+        for (int q = 0; q < n; ++q) R[c * NB + base + stride * q] += cw * rl[q];
       }
     }
     group_sync<WPG>(g);
@@ -275,7 +289,7 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
 #pragma unroll
   for (int d = dim - 1; d >= 1; --d) {
     for (int it = tid; it < ncell * dim * NL; it += GT) {
-      const int ci = it / (dim * NL), r = it - ci * (dim * NL), c = r / NL, l = r - c * NL;
+      const int ci = CPG == 1 ? 0 : it / (dim * NL), r = it - ci * (dim * NL), c = r / NL, l = r - c * NL;
       int base, stride;
       pline<dim, n>(d, l, base, stride);
       T *R = Rc(ci) + c * NB;
@@ -293,7 +307,7 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
     group_sync<WPG>(g);
   }
   for (int it = tid; it < ncell * dim * NL; it += GT) {
-    const int ci = it / (dim * NL), r = it - ci * (dim * NL), c = r / NL, row = r - c * NL;
+    const int ci = CPG == 1 ? 0 : it / (dim * NL), r = it - ci * (dim * NL), c = r / NL, row = r - c * NL;
     const T *R = Rc(ci) + c * NB + row * RS;
     T u[n];
 #pragma unroll
@@ -569,6 +583,13 @@ int launch_velocity(dgx_op *op, T *dst, const T *src, bool add) {
   P.a = (T)a; P.aRe = (T)(a / op->Re);
   P.C = (T)((double)n * n);   // C_u = (p_v + 1)^2, NS.cc:293
   P.theta = (T)1.0;           // theta_v, NS.cc:290
+  for (int d = 0; d < MAX_DIM; ++d)
+    for (int q = 0; q < n; ++q) {
+      const double ih = d < dim ? 1.0 / mf->h[d] : 1.0;
+      P.kA[d][q] = (T)(s.wq[q] * (a / op->Re) * ih * ih);
+      P.kB[d][q] = (T)(s.wq[q] * a * ih);
+    }
+  for (int q = 0; q < n; ++q) P.aw[q] = (T)(s.wq[q] * (op->stage == 1 ? 1.0 / (gamma * op->dt) : 1.0 / ((1.0 - gamma) * op->dt)));
   constexpr int CPB = VelCfg<dim, n, T>::CPB, NT = kVelThreads;
   const size_t smem = VelCfg<dim, n, T>::smem;
   static bool configured = false;
