@@ -47,7 +47,8 @@ struct VelCfg {
   static constexpr int NL = ipow(n, dim - 1), ND = NL * n;
   static constexpr int NF = 2 * dim + 1;                 // face fields: V (dim), G (dim), E_d
   static constexpr int RS = n + 1, NB = RS * NL;         // x-rows padded to n + 1: no bank conflicts for y-/z-lines
-  static constexpr int PER_CELL = 3 * dim * NB + 4 * NF * NL;
+  static constexpr int NR = NL / n, NLF = RS * NR;       // face fields: rows padded the same way
+  static constexpr int PER_CELL = 3 * dim * NB + 2 * NF * NLF;
   static constexpr int fit = kVelSmemBudget / (PER_CELL * (int)sizeof(T));
   static constexpr int CPBraw = fit < 1 ? 1 : (fit > 16 ? 16 : fit);
   static constexpr int WPG = CPBraw >= 8 ? 1 : (CPBraw >= 4 ? 2 : (CPBraw >= 2 ? 4 : 8));
@@ -95,6 +96,7 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
                 const T *__restrict__ ue, T *__restrict__ dst, int add) {
   using Cfg = VelCfg<dim, n, T>;
   constexpr int NL = Cfg::NL, ND = Cfg::ND, NF = Cfg::NF, RS = Cfg::RS, NB = Cfg::NB, PER_CELL = Cfg::PER_CELL;
+  constexpr int NR = Cfg::NR, NLF = Cfg::NLF;
   constexpr int WPG = Cfg::WPG, CPG = Cfg::CPG, GT = WPG * 32;
   extern __shared__ __align__(16) unsigned char vsm[];
   const int g = threadIdx.x / GT, tid = threadIdx.x - g * GT;
@@ -104,22 +106,39 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
   T *sm = reinterpret_cast<T *>(vsm) + (size_t)g * CPG * PER_CELL;
   auto Ac = [&](int ci) { return sm + (size_t)ci * PER_CELL; };                 // [2*dim][NB]: u_hat, ue_hat
   auto Rc = [&](int ci) { return sm + (size_t)ci * PER_CELL + 2 * dim * NB; };  // [dim][NB]: result
-  auto Na = [&](int ci) { return sm + (size_t)ci * PER_CELL + 3 * dim * NB; };  // [2 sides][NF][NL]
-  auto Nb = [&](int ci) { return sm + (size_t)ci * PER_CELL + 3 * dim * NB + 2 * NF * NL; };
-  // 1. load u, u_extr one x-row per item and move the row to the Gauss-point basis on the way in
-  for (int it = tid; it < ncell * 2 * dim * NL; it += GT) {
-    const int ci = CPG == 1 ? 0 : it / (2 * dim * NL), r = it - ci * (2 * dim * NL), f = r / NL, row = r - f * NL;
-    const T *gp = (f < dim ? src : ue) + ((size_t)(cell0 + ci) * dim + (f % dim)) * ND + row * n;
-    T u[n];
+  auto Na = [&](int ci) { return sm + (size_t)ci * PER_CELL + 3 * dim * NB; };  // [2 sides][NF][NLF]: neighbour traces
+  // 1. load u, u_extr one x-row per item and move the row to the Gauss-point basis on the way in.  All loads of a
+  //    chunk of rounds are issued before the first contraction (the loop over items is otherwise latency-bound).
+  {
+    constexpr int ITEMS = CPG * 2 * dim * NL, ROUNDS = (ITEMS + GT - 1) / GT;
+    constexpr int RC = (12 * 8) / (n * (int)sizeof(T)) < 1 ? 1 : ((12 * 8) / (n * (int)sizeof(T)) > ROUNDS ? ROUNDS : (12 * 8) / (n * (int)sizeof(T)));
+    for (int r0 = 0; r0 < ROUNDS; r0 += RC) {
+      T u[RC][n];
 #pragma unroll
-    for (int i = 0; i < n; ++i) u[i] = gp[i];
-    T *A = Ac(ci) + f * NB + row * RS;
+      for (int rr = 0; rr < RC; ++rr) {
+        const int it = tid + (r0 + rr) * GT;
+        if (it < ncell * 2 * dim * NL) {
+          const int ci = CPG == 1 ? 0 : it / (2 * dim * NL), r = it - ci * (2 * dim * NL), f = r / NL, row = r - f * NL;
+          const T *gp = (f < dim ? src : ue) + ((size_t)(cell0 + ci) * dim + (f % dim)) * ND + row * n;
 #pragma unroll
-    for (int q = 0; q < n; ++q) {
-      T acc = 0;
+          for (int i = 0; i < n; ++i) u[rr][i] = gp[i];
+        }
+      }
 #pragma unroll
-      for (int i = 0; i < n; ++i) acc += P.S[q * n + i] * u[i];
-      A[q] = acc;
+      for (int rr = 0; rr < RC; ++rr) {
+        const int it = tid + (r0 + rr) * GT;
+        if (it < ncell * 2 * dim * NL) {
+          const int ci = CPG == 1 ? 0 : it / (2 * dim * NL), r = it - ci * (2 * dim * NL), f = r / NL, row = r - f * NL;
+          T *A = Ac(ci) + f * NB + row * RS;
+#pragma unroll
+          for (int q = 0; q < n; ++q) {
+            T acc = 0;
+#pragma unroll
+            for (int i = 0; i < n; ++i) acc += P.S[q * n + i] * u[rr][i];
+            A[q] = acc;
+          }
+        }
+      }
     }
   }
   group_sync<WPG>(g);
@@ -150,61 +169,66 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
   // 3. per direction: cell term (mass part with d == 0) and the two faces normal to d
 #pragma unroll
   for (int d = 0; d < dim; ++d) {
-    // 3a. nodal traces of both neighbours: item = (cell, component, nodal tangential point)
+    // 3a. nodal traces of both neighbours: item = (cell, component, nodal tangential point); loads of both sides first
     for (int it = tid; it < ncell * dim * NL; it += GT) {
       const int ci = CPG == 1 ? 0 : it / (dim * NL), r = it - ci * (dim * NL), c = r / NL, l = r - c * NL;
       int base, stride;
       vline<dim, n>(d, l, base, stride);
       T *NTa = Na(ci);
+      const int lf = (l / n) * RS + (l % n);
+      int nb[2];
+      T x[2][n], e[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) nb[s] = nbr[(size_t)(2 * d + s) * n_owned + cell0 + ci];
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
-        const int nbc = nbr[(size_t)(2 * d + s) * n_owned + cell0 + ci];
-        if (nbc < 0) continue;
-        const T *gu = src + ((size_t)nbc * dim + c) * ND + base;
-        T x[n];
+        const size_t off = ((size_t)max(nb[s], 0) * dim + c) * ND + base;   // boundary sides read the first cell and drop it
 #pragma unroll
-        for (int i = 0; i < n; ++i) x[i] = gu[stride * i];
+        for (int i = 0; i < n; ++i) x[s][i] = src[off + stride * i];
+        if (c == d) e[s] = ue[off + stride * (1 - s) * (n - 1)];
+      }
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        if (nb[s] < 0) continue;
         T gsum = 0;
 #pragma unroll
-        for (int i = 0; i < n; ++i) gsum += P.gN[1 - s][i] * x[i];
-        NTa[(s * NF + c) * NL + l] = x[(1 - s) * (n - 1)];
-        NTa[(s * NF + dim + c) * NL + l] = P.ih[d] * gsum;
-        if (c == d) NTa[(s * NF + 2 * dim) * NL + l] = ue[((size_t)nbc * dim + d) * ND + base + stride * (1 - s) * (n - 1)];
+        for (int i = 0; i < n; ++i) gsum += P.gN[1 - s][i] * x[s][i];
+        NTa[(s * NF + c) * NLF + lf] = x[s][(1 - s) * (n - 1)];
+        NTa[(s * NF + dim + c) * NLF + lf] = P.ih[d] * gsum;
+        if (c == d) NTa[(s * NF + 2 * dim) * NLF + lf] = e[s];
       }
     }
     group_sync<WPG>(g);
-    // tangential interpolation to the face Gauss points (dim - 1 passes): item = (cell, side, face field, row or column)
-    constexpr int NR = NL / n;
+    // tangential interpolation to the face Gauss points, in place (dim - 1 passes): item = (cell, side, face field, row or
+    // column)
     for (int it = tid; it < ncell * 2 * NF * NR; it += GT) {
       const int ci = CPG == 1 ? 0 : it / (2 * NF * NR), r = it - ci * (2 * NF * NR), sf = r / NR, t1 = r - sf * NR;
-      const T *in = Na(ci) + sf * NL + n * t1;
+      T *io = Na(ci) + sf * NLF + RS * t1;
       T x[n];
 #pragma unroll
-      for (int a2 = 0; a2 < n; ++a2) x[a2] = in[a2];
-      T *out = Nb(ci) + sf * NL + n * t1;
+      for (int a2 = 0; a2 < n; ++a2) x[a2] = io[a2];
 #pragma unroll
       for (int t0 = 0; t0 < n; ++t0) {
         T acc = 0;
 #pragma unroll
         for (int a2 = 0; a2 < n; ++a2) acc += P.S[t0 * n + a2] * x[a2];
-        out[t0] = acc;
+        io[t0] = acc;
       }
     }
     group_sync<WPG>(g);
     if (dim == 3) {
       for (int it = tid; it < ncell * 2 * NF * n; it += GT) {
         const int ci = CPG == 1 ? 0 : it / (2 * NF * n), r = it - ci * (2 * NF * n), sf = r / n, t0 = r - sf * n;
-        const T *in = Nb(ci) + sf * NL + t0;
+        T *io = Na(ci) + sf * NLF + t0;
         T x[n];
 #pragma unroll
-        for (int b2 = 0; b2 < n; ++b2) x[b2] = in[n * b2];
-        T *out = Na(ci) + sf * NL + t0;
+        for (int b2 = 0; b2 < n; ++b2) x[b2] = io[RS * b2];
 #pragma unroll
         for (int t1 = 0; t1 < n; ++t1) {
           T acc = 0;
 #pragma unroll
           for (int b2 = 0; b2 < n; ++b2) acc += P.S[t1 * n + b2] * x[b2];
-          out[n * t1] = acc;
+          io[RS * t1] = acc;
         }
       }
       group_sync<WPG>(g);
@@ -215,10 +239,10 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
       const int cell = cell0 + ci;
       const T *A = Ac(ci);
       T *R = Rc(ci);
-      const T *NTf = dim == 3 ? Na(ci) : Nb(ci);
+      const T *NTf = Na(ci);
       int base, stride;
       pline<dim, n>(d, l, base, stride);
-      const int t0 = l % n, t1 = l / n;
+      const int t0 = l % n, t1 = l / n, lf = t1 * RS + t0;
       const T cw = vol * (dim == 3 ? P.w[t0] * P.w[t1] : P.w[t0]);
       const T sigma = P.C * P.ih[d];
       T u[n], ed[n], rl[n];
@@ -255,7 +279,7 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
         G *= P.ih[d];
         T FV, FG;
         if (nbc >= 0) {
-          const T Vn = NTf[(s * NF + c) * NL + l], Gn = NTf[(s * NF + dim + c) * NL + l], En = NTf[(s * NF + 2 * dim) * NL + l];
+          const T Vn = NTf[(s * NF + c) * NLF + lf], Gn = NTf[(s * NF + dim + c) * NLF + lf], En = NTf[(s * NF + 2 * dim) * NLF + lf];
           const T lam = fmax(fabs(Ed[s]), fabs(En)), jump = V - Vn;
           FV = P.aRe * (T(-0.5) * ns * (G + Gn) + sigma * jump) + P.a * T(0.5) * ns * (V * Ed[s] + Vn * En) + T(0.5) * P.a * lam * jump;
           FG = -P.theta * P.aRe * T(0.5) * jump;
