@@ -84,6 +84,45 @@ __device__ __forceinline__ void pline(int d, int l, int &base, int &stride) {
   }
 }
 
+// one x-row of a cell (n contiguous values) from / to global memory, in 16-byte pieces when the row length allows it
+template <typename T, int n>
+__device__ __forceinline__ void load_row(const T *__restrict__ p, T (&u)[n]) {
+  if constexpr (sizeof(T) == 8 && n % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k < n / 2; ++k) { const double2 t = __ldg(reinterpret_cast<const double2 *>(p) + k); u[2 * k] = t.x; u[2 * k + 1] = t.y; }
+  } else if constexpr (sizeof(T) == 4 && n % 4 == 0) {
+#pragma unroll
+    for (int k = 0; k < n / 4; ++k) {
+      const float4 t = __ldg(reinterpret_cast<const float4 *>(p) + k);
+      u[4 * k] = t.x; u[4 * k + 1] = t.y; u[4 * k + 2] = t.z; u[4 * k + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < n; ++i) u[i] = p[i];
+  }
+}
+template <typename T, int n>
+__device__ __forceinline__ void store_row(T *p, const T (&u)[n], int add) {
+  if constexpr (sizeof(T) == 8 && n % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k < n / 2; ++k) {
+      double2 t = make_double2(u[2 * k], u[2 * k + 1]);
+      if (add) { const double2 o = reinterpret_cast<double2 *>(p)[k]; t.x += o.x; t.y += o.y; }
+      reinterpret_cast<double2 *>(p)[k] = t;
+    }
+  } else if constexpr (sizeof(T) == 4 && n % 4 == 0) {
+#pragma unroll
+    for (int k = 0; k < n / 4; ++k) {
+      float4 t = make_float4(u[4 * k], u[4 * k + 1], u[4 * k + 2], u[4 * k + 3]);
+      if (add) { const float4 o = reinterpret_cast<float4 *>(p)[k]; t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w; }
+      reinterpret_cast<float4 *>(p)[k] = t;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < n; ++i) p[i] = add ? p[i] + u[i] : u[i];
+  }
+}
+
 template <int WPG>
 __device__ __forceinline__ void group_sync(int g) {
   if (WPG == 1) __syncwarp();
@@ -120,8 +159,7 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
         if (it < ncell * 2 * dim * NL) {
           const int ci = CPG == 1 ? 0 : it / (2 * dim * NL), r = it - ci * (2 * dim * NL), f = r / NL, row = r - f * NL;
           const T *gp = (f < dim ? src : ue) + ((size_t)(cell0 + ci) * dim + (f % dim)) * ND + row * n;
-#pragma unroll
-          for (int i = 0; i < n; ++i) u[rr][i] = gp[i];
+          load_row<T, n>(gp, u[rr]);
         }
       }
 #pragma unroll
@@ -183,8 +221,11 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         const size_t off = ((size_t)max(nb[s], 0) * dim + c) * ND + base;   // boundary sides read the first cell and drop it
+        if (d == 0) load_row<T, n>(src + off, x[s]);
+        else {
 #pragma unroll
-        for (int i = 0; i < n; ++i) x[s][i] = src[off + stride * i];
+          for (int i = 0; i < n; ++i) x[s][i] = src[off + stride * i];
+        }
         if (c == d) e[s] = ue[off + stride * (1 - s) * (n - 1)];
       }
 #pragma unroll
@@ -336,14 +377,15 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
     T u[n];
 #pragma unroll
     for (int q = 0; q < n; ++q) u[q] = R[q];
-    T *o = dst + ((size_t)(cell0 + ci) * dim + c) * ND + row * n;
+    T v[n];
 #pragma unroll
     for (int i = 0; i < n; ++i) {
       T acc = 0;
 #pragma unroll
       for (int q = 0; q < n; ++q) acc += P.S[q * n + i] * u[q];
-      o[i] = add ? o[i] + acc : acc;
+      v[i] = acc;
     }
+    store_row<T, n>(dst + ((size_t)(cell0 + ci) * dim + c) * ND + row * n, v, add);
   }
 }
 
