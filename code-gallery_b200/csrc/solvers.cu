@@ -274,7 +274,7 @@ int op_work(dgx_op *op, dgx_vec **w, int count) {
 // deal.II SolverCG.  work: r, p, v, z.  Optional Lanczos coefficients for eigenvalue estimates.
 int cg_core(dgx_op *A, dgx_vec *x, dgx_vec *b, const Precond &pc, int max_it, double tol, dgx_vec *r, dgx_vec *p, dgx_vec *v, dgx_vec *z,
             int *iters, double *final_res, std::vector<double> *lz_diag, std::vector<double> *lz_off, bool throw_on_fail) {
-  double res = 0, r_dot_z = 0, prev_rz = 0, alpha = 0, beta = 0, prev_alpha = 0, eigen_beta_alpha = 0, pv = 0;
+  double res = 0, r_dot_z = 0, prev_rz = 0, alpha = 0, beta = 0, prev_alpha = 0, eigen_beta_alpha = 0, pv = 0, rr = 0;
   RC(dgx_op_vmult(A, r, x));
   RC(dgx_vec_sadd(r, -1.0, 1.0, b));          // r = b - A x
   RC(dgx_vec_l2_norm(r, &res));
@@ -287,7 +287,8 @@ int cg_core(dgx_op *A, dgx_vec *x, dgx_vec *b, const Precond &pc, int max_it, do
     if (pc.kind == 0) zz = r; else RC(apply_precond(pc, z, r));
     if (it > 1) {
       prev_rz = r_dot_z;
-      RC(dgx_vec_dot(r, zz, &r_dot_z));
+      if (pc.kind == 0) r_dot_z = rr;           // z == r: r.z is the r.r the previous update already reduced
+      else RC(dgx_vec_dot(r, zz, &r_dot_z));
       beta = r_dot_z / prev_rz;
       RC(dgx_vec_sadd(p, beta, 1.0, zz));     // p = beta p + z
     } else {
@@ -297,9 +298,7 @@ int cg_core(dgx_op *A, dgx_vec *x, dgx_vec *b, const Precond &pc, int max_it, do
     RC(dgx_op_vmult(A, v, p));
     RC(dgx_vec_dot(p, v, &pv));
     alpha = r_dot_z / pv;
-    RC(dgx_vec_add(x, alpha, p));
-    double rr = 0;
-    RC(dgx_vec_add_and_dot(r, -alpha, v, r, &rr));   // r -= alpha v ; rr = r.r
+    RC(dgx_vec_cg_update(x, alpha, p, r, -alpha, v, &rr));   // x += alpha p ; r -= alpha v ; rr = r.r  (one pass)
     res = std::sqrt(rr);
     if (it > 1 && lz_diag) {
       lz_diag->push_back(1.0 / prev_alpha + eigen_beta_alpha);

@@ -39,11 +39,14 @@ __global__ void __launch_bounds__(kThreads) map2_kernel(T *__restrict__ dst, con
 __device__ unsigned int g_ticket = 0;
 
 // op: 0 = sum a*b, 1 = max |a|, 2 = sum a ; optionally fused update dst += alpha*v before dot(dst, w)
+// (upd2 += alpha2 * v2 rides along in the same pass: the x and r updates of one CG iteration)
 template <typename T, int OP, bool FUSED_ADD>
 __global__ void __launch_bounds__(kThreads) reduce_kernel(const T *a, const T *b, T *upd, const T *v, T alpha, long long n,
-                                                          double *partial, double *result) {
+                                                          double *partial, double *result, T *upd2 = nullptr, const T *v2 = nullptr,
+                                                          T alpha2 = T(0)) {
   double acc = 0.0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (FUSED_ADD && upd2) upd2[i] += alpha2 * v2[i];
     if (FUSED_ADD) {
       T x = upd[i] + alpha * v[i];
       const T bv = (b == (const T *)upd) ? x : b[i];   // add_and_dot(a, v, *this) aliases
@@ -99,18 +102,33 @@ __global__ void pack_cells_kernel(T *__restrict__ out, const T *__restrict__ v, 
 constexpr int kMaxMulti = 32;
 template <typename T> struct PtrTable { const T *v[kMaxMulti]; double h[kMaxMulti]; };
 
-// out[j] = sum_i w[i] * V_j[i], j < k: ONE pass over w for all k dot products of a Gram-Schmidt sweep (SolverGMRES)
+// out[j] = sum_i w[i] * V_j[i], j < k: ONE pass over w for all k dot products of a Gram-Schmidt sweep (SolverGMRES).
+// Two elements per thread and iteration (16-byte loads for double), grid = 8 blocks per SM: with one element per
+// iteration and 2 blocks per SM the pass ran at 1.5 TB/s, bound by the loads in flight.
+template <typename T> struct Pair;
+template <> struct Pair<double> { using type = double2; };
+template <> struct Pair<float> { using type = float2; };
+
 template <typename T, int KB>
 __global__ void __launch_bounds__(kThreads) multi_dot_kernel(const T *__restrict__ w, const __grid_constant__ PtrTable<T> tab, int k0, int k, long long n,
                                                              double *partial, double *result) {
+  using P2 = typename Pair<T>::type;
   double acc[KB];
 #pragma unroll
   for (int j = 0; j < KB; ++j) acc[j] = 0.0;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const double wi = (double)w[i];
+  const int kk = min(KB, k - k0);
+  const long long n2 = n / 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    const P2 wi = reinterpret_cast<const P2 *>(w)[i];
 #pragma unroll
     for (int j = 0; j < KB; ++j)
-      if (k0 + j < k) acc[j] += wi * (double)tab.v[k0 + j][i];
+      if (j < kk) {
+        const P2 vj = reinterpret_cast<const P2 *>(tab.v[k0 + j])[i];
+        acc[j] += (double)wi.x * (double)vj.x + (double)wi.y * (double)vj.y;
+      }
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int j = 0; j < kk; ++j) acc[j] += (double)w[n - 1] * (double)tab.v[k0 + j][n - 1];
   }
   __shared__ double sm[KB][kThreads / 32];
   __shared__ bool last;
@@ -130,11 +148,15 @@ __global__ void __launch_bounds__(kThreads) multi_dot_kernel(const T *__restrict
   __syncthreads();
   if (threadIdx.x == 0) last = (atomicInc(&g_ticket, gridDim.x - 1) == gridDim.x - 1);
   __syncthreads();
-  if (last && threadIdx.x < KB) {
+  if (last) {   // fixed-order combination of the block partials: warp j sums column j
     __threadfence();
-    double s = 0;
-    for (int b = 0; b < (int)gridDim.x; ++b) s += ((volatile double *)partial)[(size_t)b * KB + threadIdx.x];
-    if (k0 + (int)threadIdx.x < k) result[k0 + threadIdx.x] = s;
+    const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (j < KB) {
+      double s = 0;
+      for (int b = lane; b < (int)gridDim.x; b += 32) s += ((volatile double *)partial)[(size_t)b * KB + j];
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+      if (lane == 0 && k0 + j < k) result[k0 + j] = s;
+    }
   }
 }
 
@@ -150,15 +172,17 @@ __global__ void __launch_bounds__(kThreads) multi_axpy_kernel(T *__restrict__ w,
 
 template <int OP, bool FUSED>
 int reduce_dispatch(dgx_ctx *ctx, int dtype, const void *a, const void *b, void *upd, const void *v, double alpha, long long n,
-                    double *out, bool is_max) {
+                    double *out, bool is_max, void *upd2 = nullptr, const void *v2 = nullptr, double alpha2 = 0.0) {
   const int grid = grid_for(n, 8);
   double *partial = ctx->d_scratch + 8, *result = ctx->d_scratch;
   if (dtype == DGX_F64)
     reduce_kernel<double, OP, FUSED><<<grid, kThreads, 0, ctx->stream>>>((const double *)a, (const double *)b, (double *)upd,
-                                                                        (const double *)v, alpha, n, partial, result);
+                                                                        (const double *)v, alpha, n, partial, result, (double *)upd2,
+                                                                        (const double *)v2, alpha2);
   else
     reduce_kernel<float, OP, FUSED><<<grid, kThreads, 0, ctx->stream>>>((const float *)a, (const float *)b, (float *)upd,
-                                                                       (const float *)v, (float)alpha, n, partial, result);
+                                                                       (const float *)v, (float)alpha, n, partial, result, (float *)upd2,
+                                                                       (const float *)v2, (float)alpha2);
   count_launch();
   DGX_CUDA_CHECK(cudaGetLastError());
   int rc = is_max ? allreduce_max(ctx, result, 1) : allreduce_sum(ctx, result, 1);
@@ -404,6 +428,13 @@ int dgx_vec_add_and_dot(dgx_vec *dst, double a, const dgx_vec *v, const dgx_vec 
   return reduce_dispatch<0, true>(dst->mf->ctx, dst->dtype, nullptr, w->d, dst->d, v->d, a, dst->n_owned, out, false);
 }
 
+// x += a p ; r += b v ; *out = r . r  -- the two vector updates and the residual norm of one SolverCG iteration, one pass
+int dgx_vec_cg_update(dgx_vec *x, double a, const dgx_vec *p, dgx_vec *r, double b, const dgx_vec *v, double *out) {
+  DGX_REQUIRE(same_shape(x, p) && same_shape(x, r) && same_shape(x, v) && x->dtype == p->dtype && x->dtype == r->dtype && x->dtype == v->dtype && out,
+              "vector mismatch");
+  return reduce_dispatch<0, true>(x->mf->ctx, x->dtype, nullptr, r->d, r->d, v->d, b, x->n_owned, out, false, x->d, p->d, a);
+}
+
 // interpolate_velocity (NS.cc:2403-2418) fused into one pass: dst = a * x - (b * y), with the reference's rounding
 // order (equ, equ, -=): a * x and b * y are rounded separately before the subtraction.
 int dgx_vec_interpolate(dgx_vec *dst, double a, const dgx_vec *x, double b, const dgx_vec *y) {
@@ -448,7 +479,7 @@ int dgx_vec_orthogonalize(dgx_vec *w, dgx_vec *const *V, int k, double *h) {
   DGX_REQUIRE(w && V && h && k >= 1 && k <= kMaxMulti, "orthogonalize: 1 <= k <= 32");
   dgx_ctx *ctx = w->mf->ctx;
   const long long n = w->n_owned;
-  const int grid = std::min(grid_for(n, 8), 148 * 2);
+  const int grid = grid_for(n, 8);
   constexpr int KB = 8;
   DGX_REQUIRE((size_t)grid * KB + 8 + kMaxMulti <= ctx->scratch_doubles, "reduction scratch too small");
   double *result = ctx->d_scratch, *partial = ctx->d_scratch + 8 + kMaxMulti;

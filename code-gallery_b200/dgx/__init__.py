@@ -253,6 +253,20 @@ class Vector:
         _check(lib.dgx_vec_add_and_dot(self.h, c_dbl(a), v.h, w.h, C.byref(out)))
         return out.value
 
+    def cg_update(self, a, p, r, b, v):
+        """self += a*p ; r += b*v ; returns r.r  (the vector work of one SolverCG iteration in one pass)"""
+        out = c_dbl()
+        _check(lib.dgx_vec_cg_update(self.h, c_dbl(a), p.h, r.h, c_dbl(b), v.h, C.byref(out)))
+        return out.value
+
+    def orthogonalize(self, basis):
+        """one classical Gram-Schmidt sweep against `basis` (SolverGMRES): returns h[j] = self . basis[j], self -= sum_j h[j] basis[j]"""
+        k = len(basis)
+        arr = (C.c_void_p * k)(*[v.h for v in basis])
+        h = (c_dbl * k)()
+        _check(lib.dgx_vec_orthogonalize(self.h, arr, C.c_int(k), h))
+        return [h[j] for j in range(k)]
+
     def interpolate(self, a, x, b, y):
         """dst = a*x - b*y (interpolate_velocity, NS.cc:2403-2418)"""
         _check(lib.dgx_vec_interpolate(self.h, c_dbl(a), x.h, c_dbl(b), y.h))

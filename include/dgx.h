@@ -123,6 +123,8 @@ int dgx_vec_l2_norm(const dgx_vec *a, double *out);
 int dgx_vec_linfty_norm(const dgx_vec *a, double *out);
 int dgx_vec_mean_value(const dgx_vec *a, double *out);
 int dgx_vec_add_and_dot(dgx_vec *dst, double a, const dgx_vec *v, const dgx_vec *w, double *out);
+/* the vector work of one SolverCG iteration in one pass: x += a*p ; r += b*v ; *out = r . r */
+int dgx_vec_cg_update(dgx_vec *x, double a, const dgx_vec *p, dgx_vec *r, double b, const dgx_vec *v, double *out);
 /* interpolate_velocity (NS.cc:2403-2418): dst = a*x - b*y in one pass, bit-identical to equ / equ / operator-= */
 int dgx_vec_interpolate(dgx_vec *dst, double a, const dgx_vec *x, double b, const dgx_vec *y);
 /* one (classical) Gram-Schmidt sweep: h[j] = w . V[j] (j < k <= 32, one pass + one all-reduce), then w -= sum_j h[j] V[j] */

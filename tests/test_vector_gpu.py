@@ -47,6 +47,41 @@ def test_vector_ops(dgx, gpu_ctx, dtype_name):
     assert np.all(c.to_host() == npdt(1.25))
 
 
+@pytest.mark.parametrize("dtype_name", ["F64", "F32"])
+def test_cg_update_and_gram_schmidt(dgx, gpu_ctx, dtype_name):
+    """fused SolverCG update and the SolverGMRES Gram-Schmidt sweep (incl. more than 8 basis vectors, 2 kernel batches)"""
+    dt = getattr(dgx, dtype_name)
+    npdt = np.float64 if dt == dgx.F64 else np.float32
+    tol = 1e-13 if dt == dgx.F64 else 2e-5
+    gm = dgx.Mesh(3, [1, 1, 1], 3, [0, 0, 0], [1, 1, 1], [True] * 3)
+    mf = dgx.MatrixFree(gpu_ctx, gm, -1, dt)
+    rng = np.random.default_rng(11)
+    x, p, r, v = (mf.initialize_dof_vector(2) for _ in range(4))
+    n = x.locally_owned_size()
+    hx, hp, hr, hv = (rng.standard_normal(n).astype(npdt) for _ in range(4))
+    for d, h in ((x, hx), (p, hp), (r, hr), (v, hv)):
+        d.from_host(h)
+    rr = x.cg_update(0.75, p, r, -0.25, v)
+    ex, er = hx + npdt(0.75) * hp, hr + npdt(-0.25) * hv
+    assert np.allclose(x.to_host(), ex, rtol=10 * tol, atol=10 * tol)
+    assert np.allclose(r.to_host(), er, rtol=10 * tol, atol=10 * tol)
+    assert abs(rr - float(er.astype(np.float64) @ er.astype(np.float64))) < 10 * tol * n
+    basis, hb = [], []
+    for j in range(11):
+        b = mf.initialize_dof_vector(2)
+        hb.append(rng.standard_normal(n).astype(npdt))
+        b.from_host(hb[-1])
+        basis.append(b)
+    w = mf.initialize_dof_vector(2)
+    hw = rng.standard_normal(n).astype(npdt)
+    w.from_host(hw)
+    h = w.orthogonalize(basis)
+    eh = [float(hw.astype(np.float64) @ b.astype(np.float64)) for b in hb]
+    assert np.allclose(h, eh, rtol=0, atol=10 * tol * n)
+    ew = hw.astype(np.float64) - sum(hj * b.astype(np.float64) for hj, b in zip(eh, hb))
+    assert np.allclose(w.to_host(), ew, rtol=0, atol=200 * tol)
+
+
 def test_copy_convert(dgx, gpu_ctx):
     gm = dgx.Mesh(2, [2, 2], 2, [0, 0], [1, 1], [True] * 2)
     mfd = dgx.MatrixFree(gpu_ctx, gm, -1, dgx.F64)
