@@ -21,8 +21,12 @@ double pressure_kappa(const dgx_op *op) {
 
 namespace {
 
+// Shared-memory boxes pad every x-row to RS entries when n is even: with the natural stride the x- and y-lines of a warp
+// fall on few banks (n = 4: 4-way conflicts, more than half of all shared-memory wavefronts of the fp32 level operator).
+template <int n> __host__ __device__ constexpr int row_stride() { return n % 2 == 0 ? n + 1 : n; }
+
 template <int dim, int n>
-__device__ __forceinline__ void line_base_stride(int d, int l, int &base, int &stride) {
+__device__ __forceinline__ void line_base_stride(int d, int l, int &base, int &stride) {   // global (unpadded) layout
   if (dim == 3) {
     if (d == 0) { base = l * n; stride = 1; }
     else if (d == 1) { base = (l % n) + n * n * (l / n); stride = n; }
@@ -30,6 +34,36 @@ __device__ __forceinline__ void line_base_stride(int d, int l, int &base, int &s
   } else {
     if (d == 0) { base = l * n; stride = 1; }
     else { base = l; stride = n; }
+  }
+}
+template <int dim, int n>
+__device__ __forceinline__ void padded_base_stride(int d, int l, int &base, int &stride) {   // shared-memory box
+  constexpr int RS = row_stride<n>();
+  if (dim == 3) {
+    if (d == 0) { base = l * RS; stride = 1; }
+    else if (d == 1) { base = (l % n) + RS * n * (l / n); stride = RS; }
+    else { base = (l % n) + RS * (l / n); stride = RS * n; }
+  } else {
+    if (d == 0) { base = l * RS; stride = 1; }
+    else { base = l; stride = RS; }
+  }
+}
+
+// n contiguous values, in 16-byte pieces when the row length allows it
+template <typename T, int n>
+__device__ __forceinline__ void load_row(const T *__restrict__ p, T (&u)[n]) {
+  if constexpr (sizeof(T) == 8 && n % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k < n / 2; ++k) { const double2 t = __ldg(reinterpret_cast<const double2 *>(p) + k); u[2 * k] = t.x; u[2 * k + 1] = t.y; }
+  } else if constexpr (sizeof(T) == 4 && n % 4 == 0) {
+#pragma unroll
+    for (int k = 0; k < n / 4; ++k) {
+      const float4 t = __ldg(reinterpret_cast<const float4 *>(p) + k);
+      u[4 * k] = t.x; u[4 * k + 1] = t.y; u[4 * k + 2] = t.z; u[4 * k + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < n; ++i) u[i] = p[i];
   }
 }
 
@@ -44,9 +78,11 @@ template <int dim, int n, typename T>
 __device__ __forceinline__ void pressure_cell_batch(const PresParams<T, n> &P, const int *nbr, int n_owned, const T *src, T *dst, int add,
                                                     int cell0, T *su, T *sa, const Epilogue<T> &E = Epilogue<T>()) {
   constexpr int NL = ipow(n, dim - 1), ND = NL * n, CPB = cells_per_block<dim, n>(), NT = CPB * NL;
+  constexpr int RS = row_stride<n>(), NBX = RS * NL;
+  auto pidx = [](int idx) { return idx + (RS - n) * (idx / n); };   // block-linear dof index -> padded shared-memory index
   const int tid = threadIdx.x;
   const int nblk = min(CPB, n_owned - cell0);
-  for (int idx = tid; idx < nblk * ND; idx += NT) su[idx] = src[(size_t)cell0 * ND + idx];
+  for (int idx = tid; idx < nblk * ND; idx += NT) su[pidx(idx)] = src[(size_t)cell0 * ND + idx];
   __syncthreads();
   const int c = tid / NL, l = tid % NL;
   const bool active = c < nblk;
@@ -54,11 +90,25 @@ __device__ __forceinline__ void pressure_cell_batch(const PresParams<T, n> &P, c
 #pragma unroll
   for (int d = 0; d < dim; ++d) {
     if (active) {
-      int base, stride;
+      int base, stride, pb, ps;
       line_base_stride<dim, n>(d, l, base, stride);
+      padded_base_stride<dim, n>(d, l, pb, ps);
+      // both neighbour lines first: their latency overlaps the own-line work
+      int nb[2];
+      T xn[2][n];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        nb[s] = nbr[(size_t)(2 * d + s) * n_owned + cell];
+        const T *un = src + (size_t)max(nb[s], 0) * ND + base;   // boundary sides read cell 0 and drop it
+        if (d == 0) load_row<T, n>(un, xn[s]);
+        else {
+#pragma unroll
+          for (int j = 0; j < n; ++j) xn[s][j] = un[stride * j];
+        }
+      }
       T u[n], t[n];
 #pragma unroll
-      for (int i = 0; i < n; ++i) u[i] = su[c * ND + base + stride * i];
+      for (int i = 0; i < n; ++i) u[i] = su[c * NBX + pb + ps * i];
 #pragma unroll
       for (int i = 0; i < n; ++i) {
         T acc = 0;
@@ -68,22 +118,17 @@ __device__ __forceinline__ void pressure_cell_batch(const PresParams<T, n> &P, c
       }
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
-        const int nb = nbr[(size_t)(2 * d + s) * n_owned + cell];
-        if (nb >= 0 || nb == -2) {
+        if (nb[s] >= 0 || nb[s] == -2) {
           const T V = u[s * (n - 1)];
           T G = 0;
 #pragma unroll
           for (int j = 0; j < n; ++j) G += P.g[s][j] * u[j];
           T FV, FG;
-          if (nb >= 0) {
-            const T *un = src + (size_t)nb * ND + base;
-            T Gn = 0, Vn = 0;
+          if (nb[s] >= 0) {
+            T Gn = 0;
 #pragma unroll
-            for (int j = 0; j < n; ++j) {
-              const T x = un[stride * j];
-              Gn += P.gn[s][j] * x;
-              if (j == (1 - s) * (n - 1)) Vn = x;
-            }
+            for (int j = 0; j < n; ++j) Gn += P.gn[s][j] * xn[s][j];
+            const T Vn = xn[s][(1 - s) * (n - 1)];
             FV = T(-0.5) * (G + Gn) + P.C * (V - Vn);
             FG = T(-0.5) * (V - Vn);
           } else {   // boundary_id == 1: weak Dirichlet (NS.cc:1308-1322)
@@ -96,7 +141,7 @@ __device__ __forceinline__ void pressure_cell_batch(const PresParams<T, n> &P, c
       }
 #pragma unroll
       for (int i = 0; i < n; ++i) {
-        const int o = c * ND + base + stride * i;
+        const int o = c * NBX + pb + ps * i;
         if (d == 0) sa[o] = P.kappa * u[i] + t[i];
         else sa[o] += t[i];
       }
@@ -107,31 +152,32 @@ __device__ __forceinline__ void pressure_cell_batch(const PresParams<T, n> &P, c
 #pragma unroll
   for (int d = 0; d < dim; ++d) {
     if (active) {
-      int base, stride;
-      line_base_stride<dim, n>(d, l, base, stride);
+      int pb, ps;
+      padded_base_stride<dim, n>(d, l, pb, ps);
       T u[n];
 #pragma unroll
-      for (int i = 0; i < n; ++i) u[i] = sa[c * ND + base + stride * i];
+      for (int i = 0; i < n; ++i) u[i] = sa[c * NBX + pb + ps * i];
 #pragma unroll
       for (int i = 0; i < n; ++i) {
         T acc = 0;
 #pragma unroll
         for (int j = 0; j < n; ++j) acc += P.Mh[d][i * n + j] * u[j];
-        sa[c * ND + base + stride * i] = acc;
+        sa[c * NBX + pb + ps * i] = acc;
       }
     }
     __syncthreads();
   }
   for (int idx = tid; idx < nblk * ND; idx += NT) {
     const size_t o = (size_t)cell0 * ND + idx;
+    const int pi = pidx(idx);
     if (E.on) {
-      T v = E.c * (E.rhs[o] - sa[idx]);
+      T v = E.c * (E.rhs[o] - sa[pi]);
       if (E.d) v *= E.d[o];
-      v += E.a * su[idx];
+      v += E.a * su[pi];
       if (E.xold) v += E.b * E.xold[o];
       dst[o] = v;
     } else {
-      dst[o] = add ? dst[o] + sa[idx] : sa[idx];
+      dst[o] = add ? dst[o] + sa[pi] : sa[pi];
     }
   }
 }
@@ -140,9 +186,9 @@ template <int dim, int n, typename T>
 __global__ void __launch_bounds__(cells_per_block<dim, n>() * ipow(n, dim - 1))
 pressure_generic_kernel(const __grid_constant__ PresParams<T, n> P, const int *__restrict__ nbr, int n_owned,
                         const T *__restrict__ src, T *__restrict__ dst, int add, const __grid_constant__ Epilogue<T> E) {
-  constexpr int ND = ipow(n, dim), CPB = cells_per_block<dim, n>();
-  __shared__ T su[CPB * ND];
-  __shared__ T sa[CPB * ND];
+  constexpr int NBX = row_stride<n>() * ipow(n, dim - 1), CPB = cells_per_block<dim, n>();
+  __shared__ T su[CPB * NBX];
+  __shared__ T sa[CPB * NBX];
   pressure_cell_batch<dim, n, T>(P, nbr, n_owned, src, dst, add, blockIdx.x * CPB, su, sa, E);
 }
 
@@ -154,8 +200,8 @@ __global__ void __launch_bounds__(cells_per_block<dim, n>() * ipow(n, dim - 1))
 pressure_coarse_cg_kernel(const __grid_constant__ PresParams<T, n> P, const int *nbr, int n_cells, const T *b, T *x, T *r, T *p, T *v,
                           double tol, int max_it, int *info, double *res_out) {
   constexpr int NL = ipow(n, dim - 1), ND = NL * n, CPB = cells_per_block<dim, n>(), NT = CPB * NL;
-  __shared__ T su[CPB * ND];
-  __shared__ T sa[CPB * ND];
+  __shared__ T su[CPB * row_stride<n>() * NL];
+  __shared__ T sa[CPB * row_stride<n>() * NL];
   __shared__ double red[32];
   __shared__ double bc;
   const int tid = threadIdx.x, N = n_cells * ND;
