@@ -22,6 +22,9 @@
 #ifndef DGX_MB4F
 #define DGX_MB4F 2
 #endif
+#ifndef DGX_NZW4
+#define DGX_NZW4 8
+#endif
 #ifndef DGX_XY_UNROLLED
 #define DGX_XY_UNROLLED 1
 #endif
@@ -60,7 +63,7 @@ struct FastGeom {
 template <int n>
 struct Roles {
   static constexpr int NXY = n;                       // XY warps: one per z-layer
-  static constexpr int NZW = (n == 5) ? 5 : 4;        // column warps
+  static constexpr int NZW = (n == 5) ? 5 : DGX_NZW4; // column warps
   static constexpr int NH = 2;                        // halo warps
   static constexpr int NW = NXY + NZW + NH;
   static constexpr int NCOL = (n * n + NZW - 1) / NZW;  // column units (32 columns each) per Z warp
@@ -158,8 +161,14 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
   T *TY = TX + 2 * NL * TC;                        // [2 side][NL][TC]
   T *HXY = TY + 2 * NL * TC;                       // [2 buf]{[2 side][TYC][NL][2], [2 side][TXC][NL][2]}  (V', G') of the x / y halo
   constexpr int HBUF = (2 * TYC + 2 * TXC) * NL * 2;
-  unsigned long long *ubar = reinterpret_cast<unsigned long long *>(HXY + 2 * HBUF);   // [NS]
+  // fused update, padded instantiations: the planes of rhs, d and xold that the Z warps need when they store a plane are
+  // bulk-copied one plane ahead into AUX (the loads would otherwise sit on the critical path of the producer warps)
+  const bool AUXON = PAD && E.on;
+  T *AUX = HXY + 2 * HBUF;                         // [3][TC][ND]  rhs, d, xold of the plane being stored (fused + PAD only)
+  unsigned long long *ubar = reinterpret_cast<unsigned long long *>(AUX + (AUXON ? 3 * TC * ND : 0));   // [NS]
   int *ucnt = reinterpret_cast<int *>(ubar + NS);   // [NS] warps that have finished reading the plane held by each stage
+  unsigned long long *abar = ubar + NS + (NS * 4 + 7) / 8;   // behind ucnt, 8-byte aligned
+  int *acnt = reinterpret_cast<int *>(abar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // role assignment balanced over the 4 sub-partitions (warp % 4): XY warps carry twice the work
@@ -175,6 +184,7 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) mbar_init(&ubar[s], 1);
     for (int s = 0; s < NS; ++s) ucnt[s] = 0;
+    if (AUXON) { mbar_init(abar, 1); *acnt = 0; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -187,15 +197,33 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
   const long long pt0 = plane_term(G, z0);
 
   // one thread streams plane p of the tile into its stage: 8 bulk copies of 4 consecutive cells (TMA engine)
+  // Both issue routines are called by a WHOLE warp: lane 0 arms the barrier, then one lane per bulk copy (the index
+  // arithmetic of 8 - 24 copies on a single lane would hold that warp back by a good part of a plane period).
   auto issue_plane = [&](int p) {
     unsigned long long *bar = &ubar[p % NS];
-    mbar_expect_tx(bar, (unsigned)(TC * ND * sizeof(T)));
+    if (lane == 0) mbar_expect_tx(bar, (unsigned)(TC * ND * sizeof(T)));
+    __syncwarp();
     const long long sh = plane_term(G, z0 + p) - pt0;
     T *stage = U + (size_t)(p % NS) * TC * ND;
-#pragma unroll
-    for (int g = 0; g < TC / 4; ++g) {
+    if (lane < TC / 4) {
+      const int g = lane;
       const int ci = cell_index(G, x0 + slot_cx(4 * g), y0 + slot_cy(4 * g), z0);
       bulk_g2s(stage + (size_t)4 * g * ND, src + (size_t)(ci + sh) * ND, (unsigned)(4 * ND * sizeof(T)), bar);
+    }
+  };
+  auto issue_aux = [&](int p) {
+    const int nact = 1 + (E.d ? 1 : 0) + (E.xold ? 1 : 0);
+    if (lane == 0) mbar_expect_tx(abar, (unsigned)(nact * TC * ND * sizeof(T)));
+    __syncwarp();
+    const long long sh = plane_term(G, z0 + p) - pt0;
+    static_assert(3 * (TC / 4) <= 32, "one lane per bulk copy");
+    if (lane < 3 * (TC / 4)) {
+      const int a = lane / (TC / 4), g = lane - a * (TC / 4);
+      const T *arr = a == 0 ? E.rhs : (a == 1 ? E.d : E.xold);
+      if (arr) {
+        const int ci = cell_index(G, x0 + slot_cx(4 * g), y0 + slot_cy(4 * g), z0);
+        bulk_g2s(AUX + (size_t)a * TC * ND + (size_t)4 * g * ND, arr + (size_t)(ci + sh) * ND, (unsigned)(4 * ND * sizeof(T)), abar);
+      }
     }
   };
 
@@ -219,7 +247,9 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
     T uc[R::NCOL][n], Gt[R::NCOL], Vt[R::NCOL];
     auto apply_mz_store = [&](int p) {   // dst(plane p) = Mz q
       const T *Ws = W + (size_t)(p & 1) * TC * NDP;
+      const T *Upl = UP + (size_t)(p & 1) * TC * NDP;   // PAD: plane p of u is still there (this thread wrote these columns)
       const long long sh = (plane_term(G, z0 + p) - pt0) * ND;
+      if (AUXON) mbar_wait(abar, (unsigned)(p & 1));
 #pragma unroll
       for (int m = 0; m < R::NCOL; ++m) {
         if (!cval[m]) continue;
@@ -234,14 +264,32 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
 #pragma unroll
           for (int kk = 0; kk < n; ++kk) acc = fma(P.Mh[2][k * n + kk], qv[kk], acc);
           if (E.on) {   // fused Chebyshev / residual update: dst = a x + b xold + c d .* (rhs - A x)
-            T v = E.c * (E.rhs[off + k * NL] - acc);
-            if (E.d) v *= E.d[off + k * NL];
-            v += E.a * src[off + k * NL];
-            if (E.xold) v += E.b * E.xold[off + k * NL];
-            acc = v;
+            if (PAD) {
+              T v = E.c * (AUX[coff[m] + k * NL] - acc);
+              if (E.d) v *= AUX[TC * ND + coff[m] + k * NL];
+              v += E.a * Upl[cofp[m] + k * NL];
+              if (E.xold) v += E.b * AUX[2 * TC * ND + coff[m] + k * NL];
+              acc = v;
+            } else {
+              T v = E.c * (E.rhs[off + k * NL] - acc);
+              if (E.d) v *= E.d[off + k * NL];
+              v += E.a * src[off + k * NL];
+              if (E.xold) v += E.b * E.xold[off + k * NL];
+              acc = v;
+            }
           }
           o[k * NL] = acc;
         }
+      }
+      if (AUXON) {   // the last Z warp done with this plane's AUX starts the copy of the next one
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) {
+          const int old = atomicAdd(acnt, 1);
+          if (old == R::NZW - 1) { *acnt = 0; __threadfence_block(); last = 1; }
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last && p + 1 < NZ) issue_aux(p + 1);
       }
     };
     // one group of columns: finalise plane q (held in uc) with the bottom traces of the plane in stage Un
@@ -307,14 +355,13 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
 #pragma unroll
         for (int k = 0; k < n; ++k) keep(uc[m][k]);
       __syncwarp();
+      int last = 0;
       if (lane == 0) {
         const int old = atomicAdd(&ucnt[pl % NS], 1);
-        if (old == R::NZW - 1) {
-          ucnt[pl % NS] = 0;
-          __threadfence_block();
-          if (pl + NS < NZ) issue_plane(pl + NS);
-        }
+        if (old == R::NZW - 1) { ucnt[pl % NS] = 0; __threadfence_block(); last = 1; }
       }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last && pl + NS < NZ) issue_plane(pl + NS);
     };
     mbar_wait(&ubar[0], 0);
 #pragma unroll
@@ -359,8 +406,10 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
     // both sweeps are accumulated as outer products into one static register tile: the loops stay rolled, so
     // the instruction footprint of this role is a fraction of the unrolled form.
     const int k = ridx, c = lane, cx = slot_cx(c), cy = slot_cy(c);
-    if (k == 0 && lane == 0)
+    if (k == 0) {
       for (int p = 0; p < NS && p < NZ; ++p) issue_plane(p);
+      if (AUXON) issue_aux(0);
+    }
     // neighbour descriptors per (direction, side): where G' and V' of the facing cell live
     //   inside the tile: G' in TX/TY (stride TC per face point), V' in the u stage (stride n or 1)
     //   halo:            (V', G') pairs in the halo buffer (stride 2)
@@ -510,12 +559,14 @@ pressure_march_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_c
       for (int j = 0; j < n; ++j)
 #pragma unroll
         for (int i = 0; i < n; ++i) keep(acc[j][i]);
-      if (!PAD && lane == 0) {   // the last XY warp to finish reading plane p refills its stage with plane p + NS
-        const int old = atomicAdd(&ucnt[p % NS], 1);
-        if (old == R::NXY - 1) {
-          ucnt[p % NS] = 0;
-          if (p + NS < NZ) issue_plane(p + NS);
+      if (!PAD) {   // the last XY warp to finish reading plane p refills its stage with plane p + NS
+        int last = 0;
+        if (lane == 0) {
+          const int old = atomicAdd(&ucnt[p % NS], 1);
+          if (old == R::NXY - 1) { ucnt[p % NS] = 0; last = 1; }
         }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last && p + NS < NZ) issue_plane(p + NS);
       }
       // mass in x, then y
       T tmp[n][n];
@@ -643,11 +694,13 @@ int launch_march(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const F
   FastParams<T, n> F;
   fill_fast_params<T, n>(F, op);
   constexpr int NDP = (n % 2 == 0) ? ND + 1 : ND;
-  const size_t smem = sizeof(T) * (size_t)(R::NSTAGE * TC * ND + (n % 2 == 0 ? 4 : 2) * TC * NDP + 4 * NL * TC + 2 * 2 * TYC * NL * 2 + 2 * 2 * TXC * NL * 2) + 8 * R::NSTAGE + 4 * R::NSTAGE + 16;
+  const size_t smem_plain = sizeof(T) * (size_t)(R::NSTAGE * TC * ND + (n % 2 == 0 ? 4 : 2) * TC * NDP + 4 * NL * TC + 2 * 2 * TYC * NL * 2 + 2 * 2 * TXC * NL * 2) + 8 * R::NSTAGE + 8 * ((4 * R::NSTAGE + 7) / 8) + 16;
+  const size_t smem_fused = smem_plain + (n % 2 == 0 ? sizeof(T) * (size_t)(3 * TC * ND) : 0);   // + AUX planes of the fused update
+  const size_t smem = fu ? smem_fused : smem_plain;
   static bool configured = false;
   if (!configured) {
-    DGX_CUDA_CHECK(cudaFuncSetAttribute(pressure_march_kernel<n, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DGX_CUDA_CHECK(cudaFuncSetAttribute(pressure_march_kernel<n, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DGX_CUDA_CHECK(cudaFuncSetAttribute(pressure_march_kernel<n, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused));
+    DGX_CUDA_CHECK(cudaFuncSetAttribute(pressure_march_kernel<n, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plain));
     configured = true;
   }
   const int grid = d_jobs ? n_jobs : G.ntx * G.nty * G.nsz;

@@ -8,6 +8,8 @@
 // 2*dim neighbours and writes its own dofs once: no atomics, no compress(add), deterministic) and
 // uses the Kronecker-factored form documented in pressure_op.cuh.  The blocked fast path for large
 // 3-D meshes lives in pressure_fast.cu.
+#include <cstdlib>
+
 #include "pressure_op.cuh"
 
 namespace dgx {
@@ -438,9 +440,10 @@ int pressure_apply_fused(dgx_op *op, dgx_vec *dst, dgx_vec *x, const FusedUpdate
   if (op->kind != DGX_OP_PRESSURE || dst->d == x->d) return DGX_ERR_UNSUPPORTED;
   int rc = ghost_exchange(x);
   if (rc) return rc;
-  // The marching kernel can apply the same epilogue in its Z warps (pressure_apply_fast_fused), but measured on 128^3 Q3 fp32 that
-  // puts four more streams on its producer warps and costs 2.1 ms per fused step against 1.0 ms here: opt-in (variant 2) only.
-  if (op->variant == 2) {
+  // The marching kernel applies the same epilogue in its Z warps (pressure_apply_fast_fused).  For even n the update vectors
+  // reach them through bulk copies one plane ahead; for odd n they would be plain loads on the producer warps' critical
+  // path (2.1 ms per fused step against 1.0 ms here, 128^3 Q3 fp32 before the staging): there it stays opt-in (variant 2).
+  if (op->variant == 2 || (op->variant == 0 && op->degree == 3 && !getenv("DGX_NO_FUSED_MARCH"))) {
     rc = pressure_apply_fast_fused(op, dst, x, fu);
     if (rc != DGX_ERR_UNSUPPORTED) return rc;
   }

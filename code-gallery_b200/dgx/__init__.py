@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdgx.so")
+LIB_PATH = os.environ.get("DGX_LIB_PATH", os.path.join(_HERE, "libdgx.so"))   # override: kernel tuning experiments
 if not os.path.exists(LIB_PATH):
     raise ImportError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                       "(there is no CPU fallback)")

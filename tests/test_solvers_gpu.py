@@ -77,6 +77,38 @@ def test_chebyshev(dgx, gpu_ctx, np_dtype):
     assert rel_l2(vx.to_host(), och.step(x0, b)) < tol
 
 
+@pytest.mark.parametrize("np_dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("degree", [3, 4])
+def test_chebyshev_through_marching_kernel(dgx, gpu_ctx, degree, np_dtype):
+    """the smoother's fused operator + update launches on the marching kernel (variant 2 = marching kernel or fail):
+    even n stages the update vectors with bulk copies, odd n loads them in the Z warps"""
+    dim, cells0, nref, dt = 3, [1, 1, 1], 3, 5e-3
+    gm, om = make_meshes(dgx, dim, cells0, nref, [True] * dim, hi=[1.0, 1.0, 1.0])
+    dd = dgx.F64 if np_dtype == np.float64 else dgx.F32
+    tol = 1e-11 if np_dtype == np.float64 else 2e-5
+    mf = dgx.MatrixFree(gpu_ctx, gm, -1, dd)
+    op = dgx.NavierStokesProjectionOperator(mf, dgx.OP_PRESSURE, degree, 100.0, dt)
+    op.compute_diagonal()
+    op.set_variant(2)
+    oop = PressureOperator(om, degree, dt, np_dtype)
+    oop.compute_diagonal()
+    ch = dgx.PreconditionChebyshev(op, 3, 15.0, 10)
+    och = Chebyshev(oop.vmult, oop.inverse_diagonal, 3, 15.0, 10)
+    ch.estimate_eigenvalues()
+    och.estimate_eigenvalues(oop.n_dofs, np_dtype)
+    b = smooth_plus_noise(om, oop.sh.nodes, noise=0.2).astype(np_dtype)
+    x0 = np.random.default_rng(2).standard_normal(b.size).astype(np_dtype)
+    vb, vx = op.initialize_dof_vector(), op.initialize_dof_vector()
+    vb.from_host(b)
+    l0 = dgx.kernel_launch_count()
+    ch.vmult(vx, vb)
+    assert rel_l2(vx.to_host(), och.vmult(b)) < tol
+    vx.from_host(x0)
+    ch.step(vx, vb)
+    assert rel_l2(vx.to_host(), och.step(x0, b)) < tol
+    assert dgx.kernel_launch_count() - l0 <= 8      # 2 + 3 fused launches, first-iteration updates; no separate update passes
+
+
 def test_cg_on_mass_matrix(dgx, gpu_ctx):
     """project_grad's solver: unpreconditioned CG on the DG mass matrix, tol 1e-12 ||rhs|| (NS.cc:2574-2576)."""
     gm, om = make_meshes(dgx, 2, [3, 2], 2, [False, False])
