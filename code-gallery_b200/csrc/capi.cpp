@@ -1,5 +1,7 @@
 // extern "C" layer: context, operator handles (see include/dgx.h for the reference members replaced).
+#include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -28,6 +30,134 @@ int op_pool_vec(dgx_op *op, int i, dgx_vec **out) {
 }  // namespace dgx
 
 using namespace dgx;
+
+// ---- pipelined host entry point ----------------------------------------------------------------------------
+// y = A x with x and y in HOST memory is bound by the PCIe link, not by the kernel (2 x 2.1 GB against a 1.7 ms kernel at
+// 128^3 Q4).  The three legs are therefore overlapped inside ONE call: the owned cells are cut into chunks of the cell
+// order; chunk c is uploaded on its own stream, computed as soon as the last chunk holding one of its face neighbours has
+// arrived, and downloaded on a third stream while later chunks are still coming in (the link is full duplex).
+static bool host_pipeline_applies(dgx_op *op) {
+  dgx_mf *mf = op->mf;
+  static const bool off = getenv("DGX_NO_HOST_PIPELINE") != nullptr;
+  if (off || op->kind != DGX_OP_PRESSURE || mf->ctx->nranks != 1) return false;
+  if (op->hp_lg == 0) {
+    // chunk = 2^(dim k + dim - 1) cells and at least 8 MiB: every copy costs the DMA engines 15-20 us of set-up, measured
+    // 128^3 Q4 fp64 (2 x 2.1 GB): 2 MB chunks 69 ms, 16 MB chunks 54 ms, unpipelined 77 ms.  Fewer than 16 chunks: not worth it
+    const char *env = getenv("DGX_HOST_CHUNK_LOG2");
+    const size_t cell_bytes = (size_t)op->h_src->dofs_per_cell * op->h_src->elem();
+    int lg = mf->dim - 1;
+    if (env) lg = atoi(env);
+    else while (((size_t)cell_bytes << lg) < (8u << 20)) lg += mf->dim;
+    op->hp_lg = (mf->n_owned >> lg) >= 16 ? lg : -1;
+  }
+  return op->hp_lg > 0;
+}
+
+static int vmult_host_pipelined(dgx_op *op, void *dst_host, const void *src_host) {
+  dgx_mf *mf = op->mf;
+  dgx_ctx *ctx = mf->ctx;
+  const int nf = 2 * mf->dim, dim = mf->dim;
+  if (op->hp_up.empty()) {
+    // Chunks are aligned runs of 2^(dim k + dim - 1) cells of the hierarchical order: bricks that are 2^(k+1) cells wide in
+    // all directions but the last, 2^k there.  They are uploaded slab by slab along the last direction (for a periodic
+    // direction alternating between the two ends, so that no slab waits for the far end of the upload): a chunk is
+    // computable about two slabs after it arrived, and the download trails the upload by about three slabs.  Chunks that
+    // are neighbours in memory and in the schedule are merged into one copy / one launch.
+    const long long nc = mf->n_owned;
+    const long long G = 1LL << op->hp_lg;
+    const int C = (int)((nc + G - 1) / G);
+    auto cb = [&](int c) { return std::min<long long>(nc, (long long)c * G); };
+    std::vector<int> key(C);
+    for (int c = 0; c < C; ++c) {
+      int cc[3] = {0, 0, 0};
+      mf->mesh->m.coords_of(mf->level, mf->first_cell + cb(c), cc);
+      key[c] = cc[dim - 1];
+    }
+    std::vector<int> keys(key);
+    std::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    const int S = (int)keys.size();
+    std::vector<int> slab_rank(C);
+    for (int c = 0; c < C; ++c) slab_rank[c] = (int)(std::lower_bound(keys.begin(), keys.end(), key[c]) - keys.begin());
+    bool wraps = false;   // does the first slab see the last one (periodic last direction)?
+    for (int c = 0; c < C && !wraps; ++c)
+      if (slab_rank[c] == 0)
+        for (long long i = cb(c); i < cb(c + 1) && !wraps; ++i) {
+          const int nb = mf->nbr_host[(size_t)(2 * (dim - 1)) * nc + i];
+          if (nb >= 0 && nb < nc && slab_rank[nb / G] == S - 1 && S > 2) wraps = true;
+        }
+    std::vector<int> slab_pos(S);   // upload position of every slab
+    for (int r = 0; r < S; ++r) slab_pos[r] = !wraps ? r : (r < (S + 1) / 2 ? 2 * r : 2 * (S - 1 - r) + 1);
+    std::vector<int> upload(C);
+    for (int c = 0; c < C; ++c) upload[c] = c;
+    std::stable_sort(upload.begin(), upload.end(), [&](int a, int b) { return slab_pos[slab_rank[a]] < slab_pos[slab_rank[b]]; });
+    std::vector<int> seg_of(C);     // upload segment of every chunk
+    for (int k = 0; k < C; ++k) {
+      const int c = upload[k];
+      if (k > 0 && upload[k - 1] == c - 1 && slab_rank[c - 1] == slab_rank[c]) op->hp_up.back().e = cb(c + 1);
+      else op->hp_up.push_back({cb(c), cb(c + 1), 0});
+      seg_of[c] = (int)op->hp_up.size() - 1;
+    }
+    std::vector<int> need(C);       // upload segment after which chunk c is computable
+    for (int c = 0; c < C; ++c) {
+      int nd = seg_of[c];
+      for (int f = 0; f < nf; ++f)
+        for (long long i = cb(c); i < cb(c + 1); ++i) {
+          const int nb = mf->nbr_host[(size_t)f * nc + i];
+          if (nb >= 0 && nb < nc) nd = std::max(nd, seg_of[nb / G]);
+        }
+      need[c] = nd;
+    }
+    std::vector<int> order(C);
+    for (int c = 0; c < C; ++c) order[c] = c;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return need[a] < need[b]; });
+    for (int k = 0; k < C; ++k) {
+      const int c = order[k];
+      if (k > 0 && order[k - 1] == c - 1 && need[c - 1] == need[c]) op->hp_grp.back().e = cb(c + 1);
+      else op->hp_grp.push_back({cb(c), cb(c + 1), need[c]});
+    }
+    if (getenv("DGX_HOST_PIPELINE_DEBUG")) {
+      long long lag = 0;
+      for (const auto &g : op->hp_grp) lag = std::max<long long>(lag, g.need);
+      fprintf(stderr, "[dgx] host pipeline: %d chunks of %lld cells, %d slabs (%s), %zu upload segments, %zu compute groups\n", C, G, S,
+              wraps ? "periodic: alternating ends" : "in order", op->hp_up.size(), op->hp_grp.size());
+      for (size_t k = 0; k < op->hp_grp.size(); k += std::max<size_t>(1, op->hp_grp.size() / 16))
+        fprintf(stderr, "[dgx]   group %zu: cells [%lld, %lld) after upload segment %d\n", k, op->hp_grp[k].b, op->hp_grp[k].e, op->hp_grp[k].need);
+    }
+    op->hp_in.resize(op->hp_up.size()); op->hp_done.resize(op->hp_grp.size());
+    for (cudaEvent_t &e : op->hp_in) DGX_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (cudaEvent_t &e : op->hp_done) DGX_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    DGX_CUDA_CHECK(cudaStreamCreateWithFlags(&op->hp_s_in, cudaStreamNonBlocking));
+    DGX_CUDA_CHECK(cudaStreamCreateWithFlags(&op->hp_s_out, cudaStreamNonBlocking));
+  }
+  const size_t cell_bytes = (size_t)op->h_src->dofs_per_cell * op->h_src->elem();
+  cudaStream_t st = ctx->stream;
+  // uploads start once earlier work of the context's stream is done (it may still read the staging vectors)
+  DGX_CUDA_CHECK(cudaEventRecord(ctx->ev_src_ready, st));
+  DGX_CUDA_CHECK(cudaStreamWaitEvent(op->hp_s_in, ctx->ev_src_ready, 0));
+  for (size_t k = 0; k < op->hp_up.size(); ++k) {
+    const size_t off = (size_t)op->hp_up[k].b * cell_bytes, len = (size_t)(op->hp_up[k].e - op->hp_up[k].b) * cell_bytes;
+    DGX_CUDA_CHECK(cudaMemcpyAsync((char *)op->h_src->d + off, (const char *)src_host + off, len, cudaMemcpyHostToDevice, op->hp_s_in));
+    DGX_CUDA_CHECK(cudaEventRecord(op->hp_in[k], op->hp_s_in));   // event k = "the first k + 1 upload segments are in"
+  }
+  int waited = -1;
+  for (size_t k = 0; k < op->hp_grp.size(); ++k) {
+    const dgx_op::HostSeg &g = op->hp_grp[k];
+    if (g.need > waited) {   // the upload stream is in order, the compute stream too: one wait per new position
+      DGX_CUDA_CHECK(cudaStreamWaitEvent(st, op->hp_in[g.need], 0));
+      waited = g.need;
+    }
+    int rc = dgx::pressure_apply_range(op, op->h_dst, op->h_src, g.b, g.e, st);
+    if (rc) return rc;
+    DGX_CUDA_CHECK(cudaEventRecord(op->hp_done[k], st));
+    DGX_CUDA_CHECK(cudaStreamWaitEvent(op->hp_s_out, op->hp_done[k], 0));
+    const size_t off = (size_t)g.b * cell_bytes, len = (size_t)(g.e - g.b) * cell_bytes;
+    DGX_CUDA_CHECK(cudaMemcpyAsync((char *)dst_host + off, (const char *)op->h_dst->d + off, len, cudaMemcpyDeviceToHost, op->hp_s_out));
+  }
+  DGX_CUDA_CHECK(cudaStreamSynchronize(op->hp_s_out));
+  DGX_CUDA_CHECK(cudaStreamSynchronize(st));
+  return DGX_OK;
+}
 
 extern "C" {
 
@@ -139,6 +269,10 @@ int dgx_op_destroy(dgx_op *op) {
     if (v) { v->borrowed = false; dgx_vec_destroy(v); }
   for (dgx_vec *v : {op->u_extr, op->inv_diag, op->h_src, op->h_dst, op->work[0], op->work[1], op->work[2], op->work[3]})
     if (v) { v->borrowed = false; dgx_vec_destroy(v); }
+  for (cudaEvent_t e : op->hp_in) cudaEventDestroy(e);
+  for (cudaEvent_t e : op->hp_done) cudaEventDestroy(e);
+  if (op->hp_s_in) cudaStreamDestroy(op->hp_s_in);
+  if (op->hp_s_out) cudaStreamDestroy(op->hp_s_out);
   delete op;
   return DGX_OK;
 }
@@ -260,6 +394,7 @@ int dgx_op_vmult_host(dgx_op *op, void *dst_host, const void *src_host, long lon
   DGX_REQUIRE(n == op->h_src->n_owned, "host buffer size must equal the locally owned size");
   cudaStream_t st = op->mf->ctx->stream;
   const size_t bytes = (size_t)n * op->h_src->elem();
+  if (host_pipeline_applies(op)) return vmult_host_pipelined(op, dst_host, src_host);
   DGX_CUDA_CHECK(cudaMemcpyAsync(op->h_src->d, src_host, bytes, cudaMemcpyHostToDevice, st));
   int rc = apply(op, op->h_dst, op->h_src, false);
   if (rc) return rc;

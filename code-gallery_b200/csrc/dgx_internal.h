@@ -139,6 +139,13 @@ struct dgx_op {
   dgx_vec *u_extr = nullptr;
   dgx_vec *inv_diag = nullptr;
   dgx_vec *h_src = nullptr, *h_dst = nullptr;   // staging vectors of the host entry point
+  // pipelined host entry point: upload segments (cells [b, e), in upload order) and compute groups (cells [b, e), computable
+  // once upload segment `need` is in; in the order they become computable)
+  struct HostSeg { long long b, e; int need; };
+  std::vector<HostSeg> hp_up, hp_grp;
+  int hp_lg = 0;                                // log2(cells per chunk); 0 = not decided yet, -1 = pipeline not used
+  std::vector<cudaEvent_t> hp_in, hp_done;
+  cudaStream_t hp_s_in = nullptr, hp_s_out = nullptr;
   dgx_vec *work[4] = {nullptr, nullptr, nullptr, nullptr};   // Krylov work vectors, allocated on first use and kept
   std::vector<dgx_vec *> pool;                                // further work vectors (GMRES basis, diagonal probes), kept
 };
@@ -168,6 +175,8 @@ int ghost_exchange(dgx_vec *v);
 // same exchange on the context's communication stream: starts when the work already queued on the compute stream is
 // done; ghost_exchange_wait makes the compute stream wait for the ghosts
 int ghost_exchange_start(dgx_vec *v);
+// pressure operator on the owned cells [cell_begin, cell_end) only, on `stream` (single rank)
+int pressure_apply_range(dgx_op *op, dgx_vec *dst, const dgx_vec *src, long long cell_begin, long long cell_end, cudaStream_t stream);
 int ghost_exchange_wait(dgx_ctx *ctx);
 int allreduce_sum(dgx_ctx *ctx, double *vals, int n);
 int allreduce_max(dgx_ctx *ctx, double *vals, int n);

@@ -78,12 +78,12 @@ __host__ __device__ constexpr int cells_per_block() {
 // single-CTA coarse-grid CG kernel (loops over the batches of a tiny level).
 template <int dim, int n, typename T>
 __device__ __forceinline__ void pressure_cell_batch(const PresParams<T, n> &P, const int *nbr, int n_owned, const T *src, T *dst, int add,
-                                                    int cell0, T *su, T *sa, const Epilogue<T> &E = Epilogue<T>()) {
+                                                    int cell0, T *su, T *sa, const Epilogue<T> &E = Epilogue<T>(), int cell_end = -1) {
   constexpr int NL = ipow(n, dim - 1), ND = NL * n, CPB = cells_per_block<dim, n>(), NT = CPB * NL;
   constexpr int RS = row_stride<n>(), NBX = RS * NL;
   auto pidx = [](int idx) { return idx + (RS - n) * (idx / n); };   // block-linear dof index -> padded shared-memory index
   const int tid = threadIdx.x;
-  const int nblk = min(CPB, n_owned - cell0);
+  const int nblk = min(CPB, (cell_end < 0 ? n_owned : cell_end) - cell0);
   for (int idx = tid; idx < nblk * ND; idx += NT) su[pidx(idx)] = src[(size_t)cell0 * ND + idx];
   __syncthreads();
   const int c = tid / NL, l = tid % NL;
@@ -187,11 +187,12 @@ __device__ __forceinline__ void pressure_cell_batch(const PresParams<T, n> &P, c
 template <int dim, int n, typename T>
 __global__ void __launch_bounds__(cells_per_block<dim, n>() * ipow(n, dim - 1))
 pressure_generic_kernel(const __grid_constant__ PresParams<T, n> P, const int *__restrict__ nbr, int n_owned,
-                        const T *__restrict__ src, T *__restrict__ dst, int add, const __grid_constant__ Epilogue<T> E) {
+                        const T *__restrict__ src, T *__restrict__ dst, int add, const __grid_constant__ Epilogue<T> E, int cell_begin,
+                        int cell_end) {
   constexpr int NBX = row_stride<n>() * ipow(n, dim - 1), CPB = cells_per_block<dim, n>();
   __shared__ T su[CPB * NBX];
   __shared__ T sa[CPB * NBX];
-  pressure_cell_batch<dim, n, T>(P, nbr, n_owned, src, dst, add, blockIdx.x * CPB, su, sa, E);
+  pressure_cell_batch<dim, n, T>(P, nbr, n_owned, src, dst, add, cell_begin + blockIdx.x * CPB, su, sa, E, cell_end);
 }
 
 // MGCoarseGridIterativeSolver<SolverCG, PreconditionIdentity> (NS.cc:2519-2529) for a level of a few cells, entirely inside
@@ -302,15 +303,20 @@ __global__ void pressure_diag_kernel(const __grid_constant__ DiagParams<T, n> P,
   }
 }
 
+struct CellRange { long long begin = 0, end = -1; cudaStream_t stream = nullptr; };
+
 template <int dim, int n, typename T>
-int launch_generic(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const FusedUpdate *fu = nullptr) {
+int launch_generic(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const FusedUpdate *fu = nullptr, const CellRange *range = nullptr) {
   dgx_mf *mf = op->mf;
   PresParams<T, n> P;
   fill_pres_params<T, n>(P, op, pressure_kappa(op));
   constexpr int CPB = cells_per_block<dim, n>(), NT = CPB * ipow(n, dim - 1);
   const int n_owned = (int)mf->n_owned;
   if (n_owned == 0) return DGX_OK;
-  const int grid = (n_owned + CPB - 1) / CPB;
+  const int cb = range ? (int)range->begin : 0, ce = range ? (int)range->end : n_owned;
+  if (ce <= cb) return DGX_OK;
+  const int grid = (ce - cb + CPB - 1) / CPB;
+  cudaStream_t stream = range && range->stream ? range->stream : mf->ctx->stream;
   Epilogue<T> E;
   if (fu) {
     E.on = 1;
@@ -319,7 +325,7 @@ int launch_generic(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const
     E.rhs = (const T *)fu->rhs->d;
     E.a = (T)fu->a; E.b = (T)fu->b; E.c = (T)fu->c;
   }
-  pressure_generic_kernel<dim, n, T><<<grid, NT, 0, mf->ctx->stream>>>(P, mf->d_nbr, n_owned, (const T *)src->d, (T *)dst->d, add ? 1 : 0, E);
+  pressure_generic_kernel<dim, n, T><<<grid, NT, 0, stream>>>(P, mf->d_nbr, n_owned, (const T *)src->d, (T *)dst->d, add ? 1 : 0, E, cb, ce);
   count_launch();
   DGX_CUDA_CHECK(cudaGetLastError());
   return DGX_OK;
@@ -375,8 +381,8 @@ int launch_diag(dgx_op *op, dgx_vec *out) {
   }
 
 template <int dim, typename T>
-int generic_by_degree(int degree, dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const FusedUpdate *fu = nullptr) {
-#define CALL(N) launch_generic<dim, N, T>(op, dst, src, add, fu)
+int generic_by_degree(int degree, dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const FusedUpdate *fu = nullptr, const CellRange *range = nullptr) {
+#define CALL(N) launch_generic<dim, N, T>(op, dst, src, add, fu, range)
   DGX_DEGREE_SWITCH(CALL)
 #undef CALL
 }
@@ -432,6 +438,17 @@ int pressure_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) {
                                                  : generic_by_degree<2, float>(op->degree, op, dst, src, add);
   return mf->dtype == DGX_F64 ? generic_by_degree<3, double>(op->degree, op, dst, src, add)
                               : generic_by_degree<3, float>(op->degree, op, dst, src, add);
+}
+
+int pressure_apply_range(dgx_op *op, dgx_vec *dst, const dgx_vec *src, long long cell_begin, long long cell_end, cudaStream_t stream) {
+  dgx_mf *mf = op->mf;
+  if (op->kind != DGX_OP_PRESSURE || mf->ctx->nranks != 1) return DGX_ERR_UNSUPPORTED;
+  CellRange r;
+  r.begin = cell_begin; r.end = cell_end; r.stream = stream;
+  if (mf->dim == 2) return mf->dtype == DGX_F64 ? generic_by_degree<2, double>(op->degree, op, dst, src, false, nullptr, &r)
+                                                 : generic_by_degree<2, float>(op->degree, op, dst, src, false, nullptr, &r);
+  return mf->dtype == DGX_F64 ? generic_by_degree<3, double>(op->degree, op, dst, src, false, nullptr, &r)
+                              : generic_by_degree<3, float>(op->degree, op, dst, src, false, nullptr, &r);
 }
 
 // dst = a x + b xold + c d .* (rhs - A x) in ONE kernel (generic path).  dst must differ from x (neighbour cells read x).

@@ -60,6 +60,10 @@ struct Epilogue {
 double pressure_kappa(const dgx_op *op);
 int pressure_apply_fast_fused(dgx_op *op, dgx_vec *dst, const dgx_vec *x, const FusedUpdate &fu);
 
+// dst[cells] = A src for the owned cells [cell_begin, cell_end) only, on `stream` (generic kernel; the pipelined host entry
+// point computes chunk by chunk while later chunks are still in flight over PCIe)
+int pressure_apply_range(dgx_op *op, dgx_vec *dst, const dgx_vec *src, long long cell_begin, long long cell_end, cudaStream_t stream);
+
 // blocked fast path (pressure_fast.cu): returns DGX_ERR_UNSUPPORTED when the shape does not qualify
 int pressure_apply_fast(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add);
 // multi-rank form: starts the ghost import of src itself, runs the tile columns that need no ghosts meanwhile
