@@ -169,6 +169,7 @@ int pressure_coarse_cg(dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_vec *r, dgx
 int mass_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add);
 int mass_apply_any(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, bool inverse);
 int mass_inverse_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src);
+int mass_cg_front(dgx_op *op, dgx_vec *p, const dgx_vec *r, double beta, bool first, dgx_vec *v, double *pv);
 int velocity_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add);
 int velocity_diagonal(dgx_op *op, dgx_vec *diag_inv);
 int ghost_exchange(dgx_vec *v);

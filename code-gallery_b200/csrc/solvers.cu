@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -280,23 +281,33 @@ int cg_core(dgx_op *A, dgx_vec *x, dgx_vec *b, const Precond &pc, int max_it, do
   RC(dgx_vec_l2_norm(r, &res));
   int it = 0;
   bool converged = res <= tol;
+  bool mass_front = A->kind == DGX_OP_MASS && pc.kind == 0 && A->mf->ctx->nranks >= 1 && !getenv("DGX_NO_MASS_CG_FUSION");
   while (!converged && it < max_it && std::isfinite(res)) {
     ++it;
     prev_alpha = alpha;
     dgx_vec *zz = z;
     if (pc.kind == 0) zz = r; else RC(apply_precond(pc, z, r));
+    bool fused_front = false;
     if (it > 1) {
       prev_rz = r_dot_z;
       if (pc.kind == 0) r_dot_z = rr;           // z == r: r.z is the r.r the previous update already reduced
       else RC(dgx_vec_dot(r, zz, &r_dot_z));
       beta = r_dot_z / prev_rz;
-      RC(dgx_vec_sadd(p, beta, 1.0, zz));     // p = beta p + z
     } else {
-      RC(dgx_vec_copy(p, zz));
       RC(dgx_vec_dot(r, zz, &r_dot_z));
     }
-    RC(dgx_op_vmult(A, v, p));
-    RC(dgx_vec_dot(p, v, &pv));
+    if (mass_front) {   // mass matrix, identity preconditioner: p update + M p + p.v in one kernel
+      const int frc = mass_cg_front(A, p, r, beta, it == 1, v, &pv);
+      if (frc == DGX_OK) fused_front = true;
+      else if (frc != DGX_ERR_UNSUPPORTED) return frc;
+      else mass_front = false;
+    }
+    if (!fused_front) {
+      if (it > 1) RC(dgx_vec_sadd(p, beta, 1.0, zz));     // p = beta p + z
+      else RC(dgx_vec_copy(p, zz));
+      RC(dgx_op_vmult(A, v, p));
+      RC(dgx_vec_dot(p, v, &pv));
+    }
     alpha = r_dot_z / pv;
     RC(dgx_vec_cg_update(x, alpha, p, r, -alpha, v, &rr));   // x += alpha p ; r -= alpha v ; rr = r.r  (one pass)
     res = std::sqrt(rr);
