@@ -139,6 +139,7 @@ struct dgx_op {
   dgx_vec *u_extr = nullptr;
   dgx_vec *inv_diag = nullptr;
   dgx_vec *h_src = nullptr, *h_dst = nullptr;   // staging vectors of the host entry point
+  const dgx_vec *post_scale = nullptr;          // velocity operator only, set around one vmult: dst = post_scale .* (A src)
   // pipelined host entry point: upload segments (cells [b, e), in upload order) and compute groups (cells [b, e), computable
   // once upload segment `need` is in; in the order they become computable)
   struct HostSeg { long long b, e; int need; };

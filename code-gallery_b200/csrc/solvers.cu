@@ -670,8 +670,16 @@ int dgx_solve_gmres(dgx_op *A, dgx_vec *x, dgx_vec *b, int precond_kind, void *p
     g[0] = rho;
     int k_used = 0;
     for (int k = 0; k < kdim; ++k) {
-      RCG(dgx_op_vmult(A, tmp, V[k]));
-      RCG(apply_precond(pc, w, tmp));
+      const dgx_vec *jac = pc.kind == 1 ? pc.op->inv_diag : (pc.kind == 3 ? pc.diag : nullptr);
+      if (A->kind == DGX_OP_VELOCITY && jac && jac->dtype == w->dtype && A->variant == 0) {
+        A->post_scale = jac;                      // w = D^-1 (A v_k): the Jacobi scaling rides on the operator's store
+        const int vrc = dgx_op_vmult(A, w, V[k]);
+        A->post_scale = nullptr;
+        RCG(vrc);
+      } else {
+        RCG(dgx_op_vmult(A, tmp, V[k]));
+        RCG(apply_precond(pc, w, tmp));
+      }
       for (int pass = 0; pass < 2; ++pass) {   // classical Gram-Schmidt + one re-orthogonalisation, each sweep fused
         std::vector<double> h(k + 1);
         RCG(dgx_vec_orthogonalize(w, V.data(), k + 1, h.data()));

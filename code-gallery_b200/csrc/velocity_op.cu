@@ -132,7 +132,7 @@ __device__ __forceinline__ void group_sync(int g) {
 template <int dim, int n, typename T>
 __global__ void __launch_bounds__(kVelThreads, 3)
 velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict__ nbr, int n_owned, const T *__restrict__ src,
-                const T *__restrict__ ue, T *__restrict__ dst, int add) {
+                const T *__restrict__ ue, T *__restrict__ dst, int add, const T *__restrict__ post_scale) {
   using Cfg = VelCfg<dim, n, T>;
   constexpr int NL = Cfg::NL, ND = Cfg::ND, NF = Cfg::NF, RS = Cfg::RS, NB = Cfg::NB, PER_CELL = Cfg::PER_CELL;
   constexpr int NR = Cfg::NR, NLF = Cfg::NLF;
@@ -384,6 +384,12 @@ velocity_kernel(const __grid_constant__ VelParams<T, n> P, const int *__restrict
 #pragma unroll
       for (int q = 0; q < n; ++q) acc += P.S[q * n + i] * u[q];
       v[i] = acc;
+    }
+    if (post_scale) {   // Jacobi preconditioner of the GMRES loop riding on the store: dst = D^-1 (A src)
+      T sc[n];
+      load_row<T, n>(post_scale + ((size_t)(cell0 + ci) * dim + c) * ND + row * n, sc);
+#pragma unroll
+      for (int i = 0; i < n; ++i) v[i] *= sc[i];
     }
     store_row<T, n>(dst + ((size_t)(cell0 + ci) * dim + c) * ND + row * n, v, add);
   }
@@ -666,7 +672,8 @@ int launch_velocity(dgx_op *op, T *dst, const T *src, bool add) {
   const int n_owned = (int)mf->n_owned;
   if (n_owned == 0) return DGX_OK;
   const int grid = (n_owned + CPB - 1) / CPB;
-  velocity_kernel<dim, n, T><<<grid, NT, smem, mf->ctx->stream>>>(P, mf->d_nbr, n_owned, src, (const T *)op->u_extr->d, dst, add ? 1 : 0);
+  velocity_kernel<dim, n, T><<<grid, NT, smem, mf->ctx->stream>>>(P, mf->d_nbr, n_owned, src, (const T *)op->u_extr->d, dst, add ? 1 : 0,
+                                                                  op->post_scale && !add ? (const T *)op->post_scale->d : nullptr);
   count_launch();
   DGX_CUDA_CHECK(cudaGetLastError());
   return DGX_OK;
