@@ -165,6 +165,13 @@ const char *dgx_last_error(void) { return g_error.c_str(); }
 const char *dgx_version(void) { return "dgx 0.1 (sm_100a, CUDA " DGX_STR(CUDART_VERSION) ")"; }
 long long dgx_kernel_launch_count(void) { return g_launch_count; }
 
+int dgx_fe_unit_support_points(int degree, double *out) {
+  DGX_REQUIRE(out && degree >= 1 && degree <= 8, "degree must be in 1..8");
+  const Shape1D &s = get_shape(degree, degree + 1);
+  for (int i = 0; i <= degree; ++i) out[i] = s.nodes[i];
+  return DGX_OK;
+}
+
 int dgx_nccl_unique_id(void *out_id) {
   DGX_REQUIRE(out_id, "null argument");
   return comm_unique_id(out_id);

@@ -43,10 +43,13 @@ class NavierStokesProjection:
         self.mg.set_TR_BDF2_stage(stage)
 
     def interpolate_velocity(self):                                                       # NS.cc:2403-2418
+        g = GAMMA
         if self.TR_BDF2_stage == 1:
             interpolate_velocity(self.u_extr, 1, self.u_n, self.u_n_minus_1)
-        else:
+            self.u_tmp.equ(g / (2.0 * (1.0 - g)), self.u_n_minus_1)      # side effect of NS.cc:2409: u_tmp is the initial guess of
+        else:                                                             # the next project_grad solve (NS.cc:2576)
             interpolate_velocity(self.u_extr, 2, self.u_n_gamma, self.u_n)
+            self.u_tmp.equ((1.0 - g) / g, self.u_n)
 
     def diffusion_step(self):                                                             # NS.cc:2424-2464
         op = self.vel_op

@@ -8,7 +8,7 @@
  * solver objects wired around it in diffusion_step / projection_step / project_grad
  * (NS.cc:2424-2577).  The reference has no FFI: its "plugin API" is C++ duck typing against
  * deal.II class templates.  Each entry point below therefore cites the deal.II/NS.cc member it
- * replaces; `code-gallery_b200/include/dgx/dealii_shim.h` re-exposes them under the reference's
+ * replaces; `include/dgx_dealii_shim.h` (header-only C++) re-exposes them under the reference's
  * own class and method names so that drivers written like NS.cc:2424-2577 compile unchanged.
  *
  * Conventions
@@ -99,6 +99,10 @@ int dgx_mf_ghost_cells(const dgx_mf *mf, long long *out);
 int dgx_mf_n_peers(const dgx_mf *mf);
 int dgx_mf_peer_info(const dgx_mf *mf, int i, int *rank, long long *n_send, long long *recv_first, long long *recv_count);
 int dgx_mf_peer_send_cells(const dgx_mf *mf, int i, int *out_local_cells);
+
+/* unit support points of FE_DGQ(degree) in 1-D (Gauss-Lobatto nodes in [0,1], FE_DGQ NS.cc:2158-2159): out[degree+1];
+ * dof (i,j,k) of a cell sits at the tensor product of these (VectorTools::interpolate, NS.cc:2393-2396) */
+int dgx_fe_unit_support_points(int degree, double *out);
 
 /* ---- LinearAlgebra::distributed::Vector<Number> (NS.cc:2102-2115, 2330-2341) ---------------- */
 /* MatrixFree::initialize_dof_vector for FESystem(FE_DGQ(degree), ncomp); zero-initialised */

@@ -24,10 +24,14 @@ class OracleProjection:
 
     def interpolate_velocity(self):
         g = GAMMA
+        # equ / equ / -= as NS.cc:2408-2416: u_tmp keeps the scaled second operand and is the initial guess of the next
+        # project_grad solve (NS.cc:2576)
         if self.stage == 1:
-            self.u_extr = (1.0 + g / (2.0 * (1.0 - g))) * self.u_n - (g / (2.0 * (1.0 - g))) * self.u_n_minus_1
+            self.u_tmp = (g / (2.0 * (1.0 - g))) * self.u_n_minus_1
+            self.u_extr = (1.0 + g / (2.0 * (1.0 - g))) * self.u_n - self.u_tmp
         else:
-            self.u_extr = (1.0 + (1.0 - g) / g) * self.u_n_gamma - ((1.0 - g) / g) * self.u_n
+            self.u_tmp = ((1.0 - g) / g) * self.u_n
+            self.u_extr = (1.0 + (1.0 - g) / g) * self.u_n_gamma - self.u_tmp
 
     def diffusion_step(self):
         self.vel.set_TR_BDF2_stage(self.stage)

@@ -86,3 +86,25 @@ def test_partition_and_ghost_plan(dgx, nranks):
         assert np.array_equal(glob.T, nb)
         ctx.close()
     assert covered == om.n_cells
+
+
+def test_dealii_shim_header_and_driver_build(dgx):
+    """include/dgx_dealii_shim.h (the C++ mirror of the deal.II surface) compiles with plain g++, every dgx_* function it
+    or the example driver calls is declared in dgx.h, and the driver -- built by build() next to the library -- fails
+    loudly (exit code 1 like NS.cc:3055-3077) when there is no device instead of falling back to a CPU path."""
+    import subprocess
+    import torch
+    inc = os.path.join(ROOT, "include")
+    src = "#include \"dgx_dealii_shim.h\"\nint main() { dgxshim::SolverControl c(10, 1e-8); return (int)c.max_steps() - 10; }\n"
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", inc, "-x", "c++", "-"], input=src, text=True,
+                       capture_output=True)
+    assert r.returncode == 0, r.stderr
+    declared = set(declared_symbols())
+    for f in (os.path.join(inc, "dgx_dealii_shim.h"), os.path.join(ROOT, "examples", "trbdf2_tgv.cpp")):
+        used = set(re.findall(r"\b(dgx_[a-z0-9_]+)\s*\(", open(f).read()))
+        assert used and used <= declared, sorted(used - declared)
+    exe = os.path.join(os.path.dirname(dgx.LIB_PATH), "trbdf2_tgv")
+    assert os.path.exists(exe)
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "2", "1"], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 1 and "no CUDA device" in r.stderr

@@ -46,3 +46,38 @@ def test_trbdf2_step_matches_oracle(dgx, gpu_ctx, dim, nref, periodic):
         assert name == oname and abs(its - oits) <= 1, (name, its, oits)
     assert rel_l2(ns.u_n.to_host(), orc.u_n) < 1e-6
     assert rel_l2(ns.pres_n.to_host(), orc.pres_n) < 1e-4
+
+
+def test_cpp_driver_on_dealii_shim_matches_python_path(dgx, gpu_ctx):
+    """examples/trbdf2_tgv.cpp -- NavierStokesProjection's diffusion_step / projection_step / project_grad / run written in
+    C++ against include/dgx_dealii_shim.h like the reference is written against deal.II -- must take exactly the Krylov
+    iterations of the Python mirror on the same problem (periodic 3-D Taylor-Green vortex, 8^3 cells, velocity Q3 /
+    pressure Q2) and end with the same maximal velocity."""
+    import json
+    import os
+    import subprocess
+    from dgx.navier_stokes import NavierStokesProjection
+    exe = os.path.join(os.path.dirname(dgx.LIB_PATH), "trbdf2_tgv")
+    assert os.path.exists(exe), "build() compiles the driver next to libdgx.so"
+    R, dp, steps = 3, 2, 2
+    out = subprocess.run([exe, str(R), str(steps), str(dp)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    cpp = json.loads(out.stdout.strip().splitlines()[-1])
+    L = 2 * np.pi
+    mesh = dgx.Mesh(3, [1, 1, 1], R, [0, 0, 0], [L, L, L], [True] * 3)
+    om = CartesianMesh(3, [1, 1, 1], R, [0, 0, 0], [1.0, 1.0, 1.0], [True] * 3)
+    dt = 0.2 * (L / 2 ** R) / (dp + 2)
+    assert abs(cpp["dt"] - dt) < 1e-15
+    ns = NavierStokesProjection(gpu_ctx, mesh, dp, 1600.0, dt)
+    u0 = _taylor_green(om, shape(dp + 1, dp + 2).nodes, 3)
+    ppts = om.dof_points(shape(dp, dp + 1).nodes) * 2 * np.pi
+    p0 = ((np.cos(2 * ppts[..., 0]) + np.cos(2 * ppts[..., 1])) * (np.cos(2 * ppts[..., 2]) + 2.0) / 16.0).reshape(-1)
+    for v, h in ((ns.u_n, u0), (ns.u_n_minus_1, u0), (ns.pres_n, p0)):
+        v.from_host(h)
+    for s in range(steps):
+        ns.iterations.clear()
+        vmax = ns.advance()
+        got = cpp["steps"][s]
+        assert [list(x) for x in ns.iterations] == got["iterations"], (s, ns.iterations, got["iterations"])
+        assert abs(vmax - got["max_velocity"]) < 1e-7
+        assert got["launches"] > 100
