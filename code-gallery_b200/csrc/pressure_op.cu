@@ -51,24 +51,6 @@ __device__ __forceinline__ void padded_base_stride(int d, int l, int &base, int 
   }
 }
 
-// n contiguous values, in 16-byte pieces when the row length allows it
-template <typename T, int n>
-__device__ __forceinline__ void load_row(const T *__restrict__ p, T (&u)[n]) {
-  if constexpr (sizeof(T) == 8 && n % 2 == 0) {
-#pragma unroll
-    for (int k = 0; k < n / 2; ++k) { const double2 t = __ldg(reinterpret_cast<const double2 *>(p) + k); u[2 * k] = t.x; u[2 * k + 1] = t.y; }
-  } else if constexpr (sizeof(T) == 4 && n % 4 == 0) {
-#pragma unroll
-    for (int k = 0; k < n / 4; ++k) {
-      const float4 t = __ldg(reinterpret_cast<const float4 *>(p) + k);
-      u[4 * k] = t.x; u[4 * k + 1] = t.y; u[4 * k + 2] = t.z; u[4 * k + 3] = t.w;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < n; ++i) u[i] = p[i];
-  }
-}
-
 template <int dim, int n>
 __host__ __device__ constexpr int cells_per_block() {
   return (192 / ipow(n, dim - 1)) > 0 ? (192 / ipow(n, dim - 1)) : 1;

@@ -118,256 +118,393 @@ struct VelRhsConst { double alpha, a1, a2, a1Re, a2Re, ab, abRe, C, theta; int s
 template <int dim, int n>
 __host__ __device__ constexpr int rhs_cpb() { return (64 / ipow(n, dim - 1)) > 0 ? (64 / ipow(n, dim - 1)) : 1; }
 
+// Work decomposition as in velocity_op.cu: a 256-thread block is cut into independent groups of WPG warps that own CPG
+// cells and all their shared memory, run every phase as a group-wide loop over work items and synchronise only with
+// themselves.  Shared-memory boxes pad every x-row to n + 1 entries.
+constexpr int kRhsThreads = 256;
+constexpr int kRhsSmemBudget = 75 * 1024;
+
 template <int dim, int n, typename T>
-__global__ void __launch_bounds__(rhs_cpb<dim, n>() * ipow(n, dim - 1))
+struct VelRhsCfg {
+  static constexpr int NL = ipow(n, dim - 1), ND = NL * n;
+  static constexpr int NFLD = 3 * dim + 1;               // u_n, second velocity, p, u_e (stage-2 boundaries)
+  static constexpr int NF = 4 * dim + 1;                 // neighbour face fields: V0, G0, V1, G1 (dim each), Vp
+  static constexpr int RS = n + 1, NB = RS * NL, NR = NL / n, NLF = RS * NR;
+  static constexpr int PER_CELL = (NFLD + dim) * NB + 2 * NF * NLF;
+  static constexpr int fit = kRhsSmemBudget / (PER_CELL * (int)sizeof(T));
+  static constexpr int CPBraw = fit < 1 ? 1 : (fit > 16 ? 16 : fit);
+  static constexpr int WPG = CPBraw >= 8 ? 1 : (CPBraw >= 4 ? 2 : (CPBraw >= 2 ? 4 : 8));
+  static constexpr int NG = (kRhsThreads / 32) / WPG;
+  static constexpr int CPG = CPBraw >= 8 ? CPBraw / 8 : 1;
+  static constexpr int CPB = NG * CPG;
+  static constexpr size_t smem = sizeof(T) * (size_t)CPB * PER_CELL;
+};
+
+template <int dim, int n>
+__device__ __forceinline__ void rline(int d, int l, int &base, int &stride) {   // line `l` along d in a padded box
+  constexpr int RS = n + 1;
+  if (dim == 3) {
+    if (d == 0) { base = l * RS; stride = 1; }
+    else if (d == 1) { base = (l % n) + RS * n * (l / n); stride = RS; }
+    else { base = (l % n) + RS * (l / n); stride = RS * n; }
+  } else {
+    if (d == 0) { base = l * RS; stride = 1; }
+    else { base = l; stride = RS; }
+  }
+}
+
+template <int WPG>
+__device__ __forceinline__ void rhs_group_sync(int g) {
+  if (WPG == 1) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(WPG * 32) : "memory");
+}
+
+template <int dim, int n, typename T>
+__global__ void __launch_bounds__(kRhsThreads, 3)
 rhs_velocity_kernel(const __grid_constant__ FormTables<T, n> F, const __grid_constant__ VelRhsConst K, const __grid_constant__ CellGeom CG,
                     const int *__restrict__ nbr, int n_owned, const T *__restrict__ s0, const T *__restrict__ s1, const T *__restrict__ sp,
                     const T *__restrict__ s3, T *__restrict__ dst) {
-  constexpr int NL = ipow(n, dim - 1), ND = NL * n, CPB = rhs_cpb<dim, n>();
+  using Cfg = VelRhsCfg<dim, n, T>;
+  constexpr int NL = Cfg::NL, ND = Cfg::ND, NFLD = Cfg::NFLD, NF = Cfg::NF, RS = Cfg::RS, NB = Cfg::NB, NR = Cfg::NR, NLF = Cfg::NLF;
+  constexpr int PER_CELL = Cfg::PER_CELL, WPG = Cfg::WPG, CPG = Cfg::CPG, GT = WPG * 32;
   constexpr int np = n - 1, NDP = ipow(np, dim), NLP = ipow(np, dim - 1);
-  constexpr int NFLD = 3 * dim + 1;       // u_n, second velocity, p, u_e (stage-2 boundaries)
-  constexpr int NF = 5 * dim + 1;         // neighbour face fields: V0, G0, V1, G1 (dim each), Vp, then (unused pad) -> index helpers below
   extern __shared__ __align__(16) unsigned char rsm[];
-  T *sm = reinterpret_cast<T *>(rsm);
-  const int tid = threadIdx.x, ci = tid / NL, l = tid % NL;
-  const int cell = blockIdx.x * CPB + ci;
-  const bool active = cell < n_owned;
-  T *A = sm + (size_t)ci * ((NFLD + dim) * ND + 4 * NF * NL);
-  T *R = A + NFLD * ND;
-  T *NTa = R + dim * ND, *NTb = NTa + 2 * NF * NL;
+  const int g = threadIdx.x / GT, tid = threadIdx.x - g * GT;
+  const int cell0 = (blockIdx.x * Cfg::NG + g) * CPG;
+  const int ncell = min(CPG, n_owned - cell0);
+  if (ncell <= 0) return;
+  T *sm = reinterpret_cast<T *>(rsm) + (size_t)g * CPG * PER_CELL;
+  auto Ac = [&](int ci) { return sm + (size_t)ci * PER_CELL; };                  // [NFLD][NB]
+  auto Rc = [&](int ci) { return sm + (size_t)ci * PER_CELL + NFLD * NB; };      // [dim][NB]
+  auto Na = [&](int ci) { return sm + (size_t)ci * PER_CELL + (NFLD + dim) * NB; };   // [2 sides][NF][NLF]
   const int stage = K.stage;
-  const T *fsrc[4] = {s0, s1, sp, s3};
-  // field slots: [0,dim) u_n ; [dim,2dim) second velocity ; 2dim: p ; [2dim+1, 3dim+1) u_e of stage 2
-  if (active) {
-    for (int f = 0; f < NFLD; ++f) {
-      const bool isp = (f == 2 * dim);
-      if (f > 2 * dim && stage == 1) break;
-      const int grp = f < dim ? 0 : (f < 2 * dim ? 1 : (isp ? 2 : 3));
-      const int comp = f < dim ? f : (f < 2 * dim ? f - dim : (isp ? 0 : f - 2 * dim - 1));
-      if (isp) {
-        const T *g = fsrc[2] + (size_t)cell * NDP;
-        for (int i = l; i < NDP; i += NL) {
-          int r = i, o = 0, st = 1;
-          for (int d = 0; d < dim; ++d) { o += (r % np) * st; r /= np; st *= n; }
-          A[f * ND + o] = g[i];
-        }
-      } else {
-        const T *g = fsrc[grp] + ((size_t)cell * dim + comp) * ND;
-        for (int i = l; i < ND; i += NL) A[f * ND + i] = g[i];
-      }
-    }
-  }
-  __syncthreads();
-  // basis change to the Gauss points of QGauss(n)
-  {
-    int extp[3] = {np, np, np};
-    const int extv[3] = {n, n, n};
-#pragma unroll
-    for (int d = 0; d < dim; ++d) {
-      if (active)
-        for (int f = 0; f < NFLD; ++f) {
-          if (f > 2 * dim && stage == 1) break;
-          if (f == 2 * dim) sweep_box<dim, n, T>(A + f * ND, d, F.Sx, np, n, extp, l);
-          else sweep_box<dim, n, T>(A + f * ND, d, F.S, n, n, extv, l);
-        }
-      extp[d] = n;
-      __syncthreads();
-    }
-  }
-  T vol = 1;
-#pragma unroll
-  for (int d = 0; d < dim; ++d) vol *= F.h[d];
-  // mass part: alpha * JxW * (u_n | u_n_gamma)
-  if (active)
-    for (int i = l; i < ND; i += NL) {
-      int r = i;
-      T jxw = vol;
-#pragma unroll
-      for (int d = 0; d < dim; ++d) { jxw *= F.w[r % n]; r /= n; }
-      for (int c = 0; c < dim; ++c) R[c * ND + i] = (T)K.alpha * jxw * A[((stage == 1 ? 0 : dim) + c) * ND + i];
-    }
-  __syncthreads();
-  const int t0 = l % n, t1 = l / n;
-  const T wt = dim == 3 ? F.w[t0] * F.w[t1] : F.w[t0];
+  const int nfld = stage == 1 ? 2 * dim + 1 : NFLD;   // field slots: [0,dim) u_n ; [dim,2dim) second velocity ; 2dim: p ; then u_e (stage 2)
   // neighbour face-field slots
   auto iV0 = [](int c) { return c; };
   auto iG0 = [](int c) { return dim + c; };
   auto iV1 = [](int c) { return 2 * dim + c; };
   auto iG1 = [](int c) { return 3 * dim + c; };
-  const int iVp = 4 * dim;
+  constexpr int iVp = 4 * dim;
+  // 1. load one x-row per item and move it to the Gauss points of QGauss(n) on the way in (pressure: np nodes -> n points)
+  for (int it = tid; it < ncell * nfld * NL; it += GT) {
+    const int ci = CPG == 1 ? 0 : it / (nfld * NL), r = it - ci * (nfld * NL), f = r / NL, row = r - f * NL;
+    const int cell = cell0 + ci;
+    T *A = Ac(ci) + f * NB + row * RS;
+    if (f == 2 * dim) {
+      const int j = row % n, k = row / n;
+      if (j >= np || (dim == 3 && k >= np)) continue;
+      const T *gp = sp + (size_t)cell * NDP + (dim == 3 ? (j + np * k) * np : j * np);
+      T u[np > 0 ? np : 1];
+#pragma unroll
+      for (int i = 0; i < np; ++i) u[i] = gp[i];
+#pragma unroll
+      for (int q = 0; q < n; ++q) {
+        T acc = 0;
+#pragma unroll
+        for (int i = 0; i < np; ++i) acc += F.Sx[q * np + i] * u[i];
+        A[q] = acc;
+      }
+    } else {
+      const T *src = f < dim ? s0 : (f < 2 * dim ? s1 : s3);
+      const int comp = f < dim ? f : (f < 2 * dim ? f - dim : f - 2 * dim - 1);
+      T u[n];
+      load_row<T, n>(src + ((size_t)cell * dim + comp) * ND + row * n, u);
+#pragma unroll
+      for (int q = 0; q < n; ++q) {
+        T acc = 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) acc += F.S[q * n + i] * u[i];
+        A[q] = acc;
+      }
+    }
+  }
+  rhs_group_sync<WPG>(g);
+  // 2. remaining directions of the basis change (the pressure box grows from np to n entries along d)
+#pragma unroll
+  for (int d = 1; d < dim; ++d) {
+    for (int it = tid; it < ncell * nfld * NL; it += GT) {
+      const int ci = CPG == 1 ? 0 : it / (nfld * NL), r = it - ci * (nfld * NL), f = r / NL, l = r - f * NL;
+      int base, stride;
+      rline<dim, n>(d, l, base, stride);
+      T *A = Ac(ci) + f * NB;
+      if (f == 2 * dim) {
+        // lines along d: the directions below d are complete (n entries), the ones above still hold np
+        const int a2 = l % n, b2 = l / n;
+        if (dim == 3 && d == 1 && b2 >= np) continue;   // y pass: z still has np layers
+        (void)a2;
+        T u[np > 0 ? np : 1];
+#pragma unroll
+        for (int i = 0; i < np; ++i) u[i] = A[base + stride * i];
+#pragma unroll
+        for (int q = 0; q < n; ++q) {
+          T acc = 0;
+#pragma unroll
+          for (int i = 0; i < np; ++i) acc += F.Sx[q * np + i] * u[i];
+          A[base + stride * q] = acc;
+        }
+      } else {
+        T u[n];
+#pragma unroll
+        for (int i = 0; i < n; ++i) u[i] = A[base + stride * i];
+#pragma unroll
+        for (int q = 0; q < n; ++q) {
+          T acc = 0;
+#pragma unroll
+          for (int i = 0; i < n; ++i) acc += F.S[q * n + i] * u[i];
+          A[base + stride * q] = acc;
+        }
+      }
+    }
+    rhs_group_sync<WPG>(g);
+  }
+  T vol = 1;
+#pragma unroll
+  for (int d = 0; d < dim; ++d) vol *= F.h[d];
+  // 3. per direction: cell term (mass part with d == 0) and the two faces normal to d
 #pragma unroll
   for (int d = 0; d < dim; ++d) {
-    int base, stride;
-    bline<dim, n>(d, l, base, stride);
-    int nb[2] = {-1, -1};
-    if (active) {
+    // 3a. nodal traces of both neighbours: item = (cell, component, nodal tangential point); component 0 also fetches the
+    //     pressure layer on the np^(dim-1) tangential grid
+    for (int it = tid; it < ncell * dim * NL; it += GT) {
+      const int ci = CPG == 1 ? 0 : it / (dim * NL), r = it - ci * (dim * NL), c = r / NL, l = r - c * NL;
+      const int cell = cell0 + ci;
+      int base, stride;
+      bline<dim, n>(d, l, base, stride);
+      const int t0 = l % n, t1 = l / n, lf = t1 * RS + t0;
+      T *NTa = Na(ci);
+      int nb[2];
+      T x0[2][n], x1[2][n], xp[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) nb[s] = nbr[(size_t)(2 * d + s) * n_owned + cell];
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
-        nb[s] = nbr[(size_t)(2 * d + s) * n_owned + cell];
-        if (nb[s] < 0) continue;
-        const int e = (1 - s) * (n - 1);
-        for (int c = 0; c < dim; ++c) {
-          const T *g0 = s0 + ((size_t)nb[s] * dim + c) * ND + base;
-          const T *g1 = s1 + ((size_t)nb[s] * dim + c) * ND + base;
-          T d0 = 0, d1 = 0;
+        const size_t off = ((size_t)max(nb[s], 0) * dim + c) * ND + base;   // boundary sides read cell 0 and drop it
+        if (d == 0) { load_row<T, n>(s0 + off, x0[s]); load_row<T, n>(s1 + off, x1[s]); }
+        else {
 #pragma unroll
-          for (int i = 0; i < n; ++i) { d0 += F.gN[1 - s][i] * g0[stride * i]; d1 += F.gN[1 - s][i] * g1[stride * i]; }
-          NTa[(s * NF + iV0(c)) * NL + l] = g0[stride * e];
-          NTa[(s * NF + iG0(c)) * NL + l] = F.ih[d] * d0;
-          NTa[(s * NF + iV1(c)) * NL + l] = g1[stride * e];
-          NTa[(s * NF + iG1(c)) * NL + l] = F.ih[d] * d1;
+          for (int i = 0; i < n; ++i) { x0[s][i] = s0[off + stride * i]; x1[s][i] = s1[off + stride * i]; }
         }
-        // pressure: nodal face layer on the np^(dim-1) tangential grid
-        if (t0 < np && (dim == 2 || t1 < np)) {
+        xp[s] = 0;
+        if (c == 0 && t0 < np && (dim == 2 || t1 < np)) {
           int pb, ps;
           bline<dim, np>(d, dim == 3 ? t0 + np * t1 : t0, pb, ps);
-          NTa[(s * NF + iVp) * NL + l] = sp[(size_t)nb[s] * NDP + pb + ps * ((1 - s) * (np - 1))];
+          xp[s] = sp[(size_t)max(nb[s], 0) * NDP + pb + ps * ((1 - s) * (np - 1))];
         }
       }
-    }
-    __syncthreads();
-    if (active) {
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         if (nb[s] < 0) continue;
-        for (int f = 0; f <= iVp; ++f) {
+        T d0 = 0, d1 = 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) { d0 += F.gN[1 - s][i] * x0[s][i]; d1 += F.gN[1 - s][i] * x1[s][i]; }
+        const int e = (1 - s) * (n - 1);
+        NTa[(s * NF + iV0(c)) * NLF + lf] = x0[s][e];
+        NTa[(s * NF + iG0(c)) * NLF + lf] = F.ih[d] * d0;
+        NTa[(s * NF + iV1(c)) * NLF + lf] = x1[s][e];
+        NTa[(s * NF + iG1(c)) * NLF + lf] = F.ih[d] * d1;
+        if (c == 0 && t0 < np && (dim == 2 || t1 < np)) NTa[(s * NF + iVp) * NLF + lf] = xp[s];
+      }
+    }
+    rhs_group_sync<WPG>(g);
+    // tangential interpolation to the face Gauss points, in place: rows, then (3-D) columns
+    for (int it = tid; it < ncell * 2 * NF * NR; it += GT) {
+      const int ci = CPG == 1 ? 0 : it / (2 * NF * NR), r = it - ci * (2 * NF * NR), sf = r / NR, t1 = r - sf * NR;
+      const int f = sf % NF;
+      T *io = Na(ci) + sf * NLF + RS * t1;
+      if (f == iVp) {
+        if (dim == 3 && t1 >= np) continue;
+        T x[np > 0 ? np : 1];
+#pragma unroll
+        for (int a2 = 0; a2 < np; ++a2) x[a2] = io[a2];
+#pragma unroll
+        for (int t0 = 0; t0 < n; ++t0) {
           T acc = 0;
-          if (f == iVp) {
 #pragma unroll
-            for (int a2 = 0; a2 < np; ++a2) acc += F.Sx[t0 * np + a2] * NTa[(s * NF + f) * NL + a2 + n * t1];
-          } else {
+          for (int a2 = 0; a2 < np; ++a2) acc += F.Sx[t0 * np + a2] * x[a2];
+          io[t0] = acc;
+        }
+      } else {
+        T x[n];
 #pragma unroll
-            for (int a2 = 0; a2 < n; ++a2) acc += F.S[t0 * n + a2] * NTa[(s * NF + f) * NL + a2 + n * t1];
-          }
-          NTb[(s * NF + f) * NL + l] = acc;
+        for (int a2 = 0; a2 < n; ++a2) x[a2] = io[a2];
+#pragma unroll
+        for (int t0 = 0; t0 < n; ++t0) {
+          T acc = 0;
+#pragma unroll
+          for (int a2 = 0; a2 < n; ++a2) acc += F.S[t0 * n + a2] * x[a2];
+          io[t0] = acc;
         }
       }
     }
-    __syncthreads();
+    rhs_group_sync<WPG>(g);
     if (dim == 3) {
-      if (active) {
+      for (int it = tid; it < ncell * 2 * NF * n; it += GT) {
+        const int ci = CPG == 1 ? 0 : it / (2 * NF * n), r = it - ci * (2 * NF * n), sf = r / n, t0 = r - sf * n;
+        const int f = sf % NF;
+        T *io = Na(ci) + sf * NLF + t0;
+        if (f == iVp) {
+          T x[np > 0 ? np : 1];
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          if (nb[s] < 0) continue;
-          for (int f = 0; f <= iVp; ++f) {
+          for (int b2 = 0; b2 < np; ++b2) x[b2] = io[RS * b2];
+#pragma unroll
+          for (int t1 = 0; t1 < n; ++t1) {
             T acc = 0;
-            if (f == iVp) {
 #pragma unroll
-              for (int b2 = 0; b2 < np; ++b2) acc += F.Sx[t1 * np + b2] * NTb[(s * NF + f) * NL + t0 + n * b2];
-            } else {
+            for (int b2 = 0; b2 < np; ++b2) acc += F.Sx[t1 * np + b2] * x[b2];
+            io[RS * t1] = acc;
+          }
+        } else {
+          T x[n];
 #pragma unroll
-              for (int b2 = 0; b2 < n; ++b2) acc += F.S[t1 * n + b2] * NTb[(s * NF + f) * NL + t0 + n * b2];
-            }
-            NTa[(s * NF + f) * NL + l] = acc;
+          for (int b2 = 0; b2 < n; ++b2) x[b2] = io[RS * b2];
+#pragma unroll
+          for (int t1 = 0; t1 < n; ++t1) {
+            T acc = 0;
+#pragma unroll
+            for (int b2 = 0; b2 < n; ++b2) acc += F.S[t1 * n + b2] * x[b2];
+            io[RS * t1] = acc;
           }
         }
       }
-      __syncthreads();
+      rhs_group_sync<WPG>(g);
     }
-    const T *NTf = dim == 3 ? NTa : NTb;
-    if (active) {
+    // 3b. item = (cell, component, line along d)
+    for (int it = tid; it < ncell * dim * NL; it += GT) {
+      const int ci = CPG == 1 ? 0 : it / (dim * NL), r = it - ci * (dim * NL), c = r / NL, l = r - c * NL;
+      const int cell = cell0 + ci;
+      const T *A = Ac(ci);
+      T *R = Rc(ci);
+      const T *NTf = Na(ci);
+      int base, stride;
+      rline<dim, n>(d, l, base, stride);
+      const int t0 = l % n, t1 = l / n, lf = t1 * RS + t0;
+      const T wt = dim == 3 ? F.w[t0] * F.w[t1] : F.w[t0];
       T area = 1;
 #pragma unroll
       for (int e2 = 0; e2 < dim; ++e2) if (e2 != d) area *= F.h[e2];
       const T wf = area * wt;
-      // traces of the advecting components normal to the faces and of the pressure
+      // this line of the d-components (advecting velocities), of the pressure and of the own component
+      T a0d[n], a1d[n], apd[n], u0[n], u1[n];
       T W0[2] = {0, 0}, W1[2] = {0, 0}, W3[2] = {0, 0}, Pv[2] = {0, 0};
 #pragma unroll
       for (int q = 0; q < n; ++q) {
-        const T x0 = A[d * ND + base + stride * q], x1 = A[(dim + d) * ND + base + stride * q], xp = A[2 * dim * ND + base + stride * q];
-        const T x3 = stage == 1 ? T(0) : A[(2 * dim + 1 + d) * ND + base + stride * q];
+        a0d[q] = A[d * NB + base + stride * q]; a1d[q] = A[(dim + d) * NB + base + stride * q]; apd[q] = A[2 * dim * NB + base + stride * q];
+        const T x3 = stage == 1 ? T(0) : A[(2 * dim + 1 + d) * NB + base + stride * q];
+        u0[q] = A[c * NB + base + stride * q]; u1[q] = A[(dim + c) * NB + base + stride * q];
 #pragma unroll
-        for (int s = 0; s < 2; ++s) { W0[s] += F.fh[s][q] * x0; W1[s] += F.fh[s][q] * x1; W3[s] += F.fh[s][q] * x3; Pv[s] += F.fh[s][q] * xp; }
+        for (int s = 0; s < 2; ++s) { W0[s] += F.fh[s][q] * a0d[q]; W1[s] += F.fh[s][q] * a1d[q]; W3[s] += F.fh[s][q] * x3; Pv[s] += F.fh[s][q] * apd[q]; }
       }
-      for (int c = 0; c < dim; ++c) {
-        T u0[n], u1[n], r[n];
+      // cell term, direction d
+      T fl[n], rl[n];
 #pragma unroll
-        for (int q = 0; q < n; ++q) { u0[q] = A[c * ND + base + stride * q]; u1[q] = A[(dim + c) * ND + base + stride * q]; }
-        // cell term, direction d
-        T fl[n];
+      for (int q = 0; q < n; ++q) {
+        T d0 = 0, d1 = 0;
 #pragma unroll
-        for (int q = 0; q < n; ++q) {
-          T d0 = 0, d1 = 0;
+        for (int q2 = 0; q2 < n; ++q2) { d0 += F.Dh[q * n + q2] * u0[q2]; d1 += F.Dh[q * n + q2] * u1[q2]; }
+        d0 *= F.ih[d]; d1 *= F.ih[d];
+        T f;
+        if (stage == 1) f = -(T)K.a1Re * d0 + (T)K.a1 * u0[q] * a1d[q];                                           // NS.cc:497-507
+        else f = (T)K.a2 * u1[q] * a1d[q] + (T)K.a1 * u0[q] * a0d[q] - (T)K.a2Re * d1 - (T)K.a1Re * d0;             // NS.cc:538-546
+        if (c == d) f += apd[q];
+        fl[q] = vol * wt * F.w[q] * f;
+      }
 #pragma unroll
-          for (int q2 = 0; q2 < n; ++q2) { d0 += F.Dh[q * n + q2] * u0[q2]; d1 += F.Dh[q * n + q2] * u1[q2]; }
-          d0 *= F.ih[d]; d1 *= F.ih[d];
-          const T a0d = A[d * ND + base + stride * q], a1d = A[(dim + d) * ND + base + stride * q];
-          T f;
-          if (stage == 1) f = -(T)K.a1Re * d0 + (T)K.a1 * u0[q] * a1d;                                           // NS.cc:497-507
-          else f = (T)K.a2 * u1[q] * a1d + (T)K.a1 * u0[q] * a0d - (T)K.a2Re * d1 - (T)K.a1Re * d0;                // NS.cc:538-546
-          if (c == d) f += A[2 * dim * ND + base + stride * q];
-          fl[q] = vol * wt * F.w[q] * f;
-        }
+      for (int i = 0; i < n; ++i) {
+        T acc = 0;
 #pragma unroll
-        for (int i = 0; i < n; ++i) {
-          T acc = 0;
+        for (int q = 0; q < n; ++q) acc += F.Dh[q * n + i] * fl[q];
+        rl[i] = F.ih[d] * acc;
+        if (d == 0) rl[i] += (T)K.alpha * vol * wt * F.w[i] * (stage == 1 ? u0[i] : u1[i]);   // mass part: alpha JxW (u_n | u_n_gamma)
+      }
 #pragma unroll
-          for (int q = 0; q < n; ++q) acc += F.Dh[q * n + i] * fl[q];
-          r[i] = F.ih[d] * acc;
-        }
+      for (int s = 0; s < 2; ++s) {
+        const int nbs = nbr[(size_t)(2 * d + s) * n_owned + cell];
+        const T ns = s ? T(1) : T(-1);
+        T V0 = 0, G0 = 0, V1 = 0, G1 = 0;
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          const T ns = s ? T(1) : T(-1);
-          T V0 = 0, G0 = 0, V1 = 0, G1 = 0;
-#pragma unroll
-          for (int q = 0; q < n; ++q) { V0 += F.fh[s][q] * u0[q]; G0 += F.gh[s][q] * u0[q]; V1 += F.fh[s][q] * u1[q]; G1 += F.gh[s][q] * u1[q]; }
-          G0 *= F.ih[d]; G1 *= F.ih[d];
-          T val, nd = 0;
-          if (nb[s] >= 0) {
-            const T V0n = NTf[(s * NF + iV0(c)) * NL + l], G0n = NTf[(s * NF + iG0(c)) * NL + l];
-            const T V1n = NTf[(s * NF + iV1(c)) * NL + l], G1n = NTf[(s * NF + iG1(c)) * NL + l];
-            const T W0n = NTf[(s * NF + iV0(d)) * NL + l], W1n = NTf[(s * NF + iV1(d)) * NL + l], Pn = NTf[(s * NF + iVp) * NL + l];
-            if (stage == 1)   // NS.cc:593-603 in outward-normal form
-              val = (T)K.a1Re * T(0.5) * ns * (G0 + G0n) - (T)K.a1 * T(0.5) * ns * (V0 * W1[s] + V0n * W1n);
-            else              // NS.cc:640-652
-              val = (T)K.a1Re * T(0.5) * ns * (G0 + G0n) + (T)K.a2Re * T(0.5) * ns * (G1 + G1n)
-                    - (T)K.a1 * T(0.5) * ns * (V0 * W0[s] + V0n * W0n) - (T)K.a2 * T(0.5) * ns * (V1 * W1[s] + V1n * W1n);
-            if (c == d) val -= T(0.5) * (Pv[s] + Pn) * ns;
-          } else {            // boundary faces, NS.cc:671-724 / 725-780
-            const int bid = -1 - nb[s];
-            const T coef_jump = bid == 1 ? T(0) : (T)K.C * F.ih[d], aux = bid == 1 ? T(0) : T(1);
-            const T ext = ns * (stage == 1 ? W1[s] : W3[s]);       // u_extr . n
-            const T lam = bid == 1 ? T(0) : fabs(ext);
-            T uD = 0;
-            if (bid == 0 && c == 0) {   // inflow profile depends on y only
-              T y;
-              if (dim == 1 || d == 1) y = (T)(CG.lo[1] + (cell_coord(CG, cell, 1) + s) * CG.h[1]);
-              else {
-                const int ty = (dim == 2) ? t0 : (d == 0 ? t0 : t1);    // tangential index that runs along y
-                y = (T)(CG.lo[1] + (cell_coord(CG, cell, 1) + (double)F.xq[ty]) * CG.h[1]);
-              }
-              uD = inflow_u0<T>(y);
+        for (int q = 0; q < n; ++q) { V0 += F.fh[s][q] * u0[q]; G0 += F.gh[s][q] * u0[q]; V1 += F.fh[s][q] * u1[q]; G1 += F.gh[s][q] * u1[q]; }
+        G0 *= F.ih[d]; G1 *= F.ih[d];
+        T val, nd = 0;
+        if (nbs >= 0) {
+          const T V0n = NTf[(s * NF + iV0(c)) * NLF + lf], G0n = NTf[(s * NF + iG0(c)) * NLF + lf];
+          const T V1n = NTf[(s * NF + iV1(c)) * NLF + lf], G1n = NTf[(s * NF + iG1(c)) * NLF + lf];
+          const T W0n = NTf[(s * NF + iV0(d)) * NLF + lf], W1n = NTf[(s * NF + iV1(d)) * NLF + lf], Pn = NTf[(s * NF + iVp) * NLF + lf];
+          if (stage == 1)   // NS.cc:593-603 in outward-normal form
+            val = (T)K.a1Re * T(0.5) * ns * (G0 + G0n) - (T)K.a1 * T(0.5) * ns * (V0 * W1[s] + V0n * W1n);
+          else              // NS.cc:640-652
+            val = (T)K.a1Re * T(0.5) * ns * (G0 + G0n) + (T)K.a2Re * T(0.5) * ns * (G1 + G1n)
+                  - (T)K.a1 * T(0.5) * ns * (V0 * W0[s] + V0n * W0n) - (T)K.a2 * T(0.5) * ns * (V1 * W1[s] + V1n * W1n);
+          if (c == d) val -= T(0.5) * (Pv[s] + Pn) * ns;
+        } else {            // boundary faces, NS.cc:671-724 / 725-780
+          const int bid = -1 - nbs;
+          const T coef_jump = bid == 1 ? T(0) : (T)K.C * F.ih[d], aux = bid == 1 ? T(0) : T(1);
+          const T ext = ns * (stage == 1 ? W1[s] : W3[s]);       // u_extr . n
+          const T lam = bid == 1 ? T(0) : fabs(ext);
+          T uD = 0;
+          if (bid == 0 && c == 0) {   // inflow profile depends on y only
+            T y;
+            if (dim == 1 || d == 1) y = (T)(CG.lo[1] + (cell_coord(CG, cell, 1) + s) * CG.h[1]);
+            else {
+              const int ty = (dim == 2) ? t0 : (d == 0 ? t0 : t1);    // tangential index that runs along y
+              y = (T)(CG.lo[1] + (cell_coord(CG, cell, 1) + (double)F.xq[ty]) * CG.h[1]);
             }
-            if (stage == 1) val = ((T)K.a1Re * G0 - (T)K.a1 * V0 * W1[s]) * ns;
-            else val = ((T)K.a1Re * G0 + (T)K.a2Re * G1 - (T)K.a1 * V0 * W0[s] - (T)K.a2 * V1 * W1[s]) * ns;
-            if (c == d) val -= Pv[s] * ns;
-            val += (T)K.abRe * T(2) * coef_jump * uD - aux * (T)K.ab * uD * ext + (T)K.ab * lam * uD;
-            nd = -aux * (T)K.theta * (T)K.abRe * uD;
+            uD = inflow_u0<T>(y);
           }
-#pragma unroll
-          for (int q = 0; q < n; ++q) r[q] += wf * (F.fh[s][q] * val + ns * F.ih[d] * F.gh[s][q] * nd);
+          if (stage == 1) val = ((T)K.a1Re * G0 - (T)K.a1 * V0 * W1[s]) * ns;
+          else val = ((T)K.a1Re * G0 + (T)K.a2Re * G1 - (T)K.a1 * V0 * W0[s] - (T)K.a2 * V1 * W1[s]) * ns;
+          if (c == d) val -= Pv[s] * ns;
+          val += (T)K.abRe * T(2) * coef_jump * uD - aux * (T)K.ab * uD * ext + (T)K.ab * lam * uD;
+          nd = -aux * (T)K.theta * (T)K.abRe * uD;
         }
 #pragma unroll
-        for (int q = 0; q < n; ++q) R[c * ND + base + stride * q] += r[q];
+        for (int q = 0; q < n; ++q) rl[q] += wf * (F.fh[s][q] * val + ns * F.ih[d] * F.gh[s][q] * nd);
+      }
+      if (d == 0) {
+#pragma unroll
+        for (int q = 0; q < n; ++q) R[c * NB + base + stride * q] = rl[q];
+      } else {
+#pragma unroll
+        for (int q = 0; q < n; ++q) R[c * NB + base + stride * q] += rl[q];
       }
     }
-    __syncthreads();
+    rhs_group_sync<WPG>(g);
   }
-  // back to the nodal basis
-  {
-    const int extv[3] = {n, n, n};
+  // 4. back to the nodal basis (transposed basis change): y, z in shared memory, x on the way out
 #pragma unroll
-    for (int d = 0; d < dim; ++d) {
-      if (active)
-        for (int c = 0; c < dim; ++c) sweep_box<dim, n, T, true>(R + c * ND, d, F.S, n, n, extv, l);
-      __syncthreads();
+  for (int d = dim - 1; d >= 1; --d) {
+    for (int it = tid; it < ncell * dim * NL; it += GT) {
+      const int ci = CPG == 1 ? 0 : it / (dim * NL), r = it - ci * (dim * NL), c = r / NL, l = r - c * NL;
+      int base, stride;
+      rline<dim, n>(d, l, base, stride);
+      T *R = Rc(ci) + c * NB;
+      T u[n];
+#pragma unroll
+      for (int q = 0; q < n; ++q) u[q] = R[base + stride * q];
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        T acc = 0;
+#pragma unroll
+        for (int q = 0; q < n; ++q) acc += F.S[q * n + i] * u[q];
+        R[base + stride * i] = acc;
+      }
     }
+    rhs_group_sync<WPG>(g);
   }
-  if (active)
-    for (int c = 0; c < dim; ++c) {
-      T *o = dst + ((size_t)cell * dim + c) * ND;
-      for (int i = l; i < ND; i += NL) o[i] = R[c * ND + i];
+  for (int it = tid; it < ncell * dim * NL; it += GT) {
+    const int ci = CPG == 1 ? 0 : it / (dim * NL), r = it - ci * (dim * NL), c = r / NL, row = r - c * NL;
+    const T *R = Rc(ci) + c * NB + row * RS;
+    T u[n], v[n];
+#pragma unroll
+    for (int q = 0; q < n; ++q) u[q] = R[q];
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      T acc = 0;
+#pragma unroll
+      for (int q = 0; q < n; ++q) acc += F.S[q * n + i] * u[q];
+      v[i] = acc;
     }
+    store_row<T, n>(dst + ((size_t)(cell0 + ci) * dim + c) * ND + row * n, v, 0);
+  }
 }
 
 
@@ -609,14 +746,15 @@ int launch_rhs_velocity(dgx_op *op, dgx_vec *dst, dgx_vec *const *srcs) {
   else { K.alpha = 1.0 / ((1.0 - gamma) * op->dt); K.a1 = a31; K.a2 = a32; K.ab = a33; }
   K.a1Re = K.a1 / op->Re; K.a2Re = K.a2 / op->Re; K.abRe = K.ab / op->Re;
   K.C = (double)n * n; K.theta = 1.0;
-  constexpr int NL = ipow(n, dim - 1), ND = NL * n, CPB = rhs_cpb<dim, n>(), NF = 5 * dim + 1, NFLD = 3 * dim + 1;
-  const size_t smem = sizeof(T) * (size_t)CPB * ((NFLD + dim) * ND + 4 * NF * NL);
+  using Cfg = VelRhsCfg<dim, n, T>;
+  constexpr int CPB = Cfg::CPB;
+  const size_t smem = Cfg::smem;
   int rc = set_smem(rhs_velocity_kernel<dim, n, T>, smem);
   if (rc) return rc;
   const int n_owned = (int)mf->n_owned;
   if (n_owned == 0) return DGX_OK;
   const T *s3 = op->stage == 2 ? (const T *)srcs[3]->d : (const T *)srcs[1]->d;
-  rhs_velocity_kernel<dim, n, T><<<(n_owned + CPB - 1) / CPB, CPB * NL, smem, mf->ctx->stream>>>(
+  rhs_velocity_kernel<dim, n, T><<<(n_owned + CPB - 1) / CPB, kRhsThreads, smem, mf->ctx->stream>>>(
       F, K, make_geom(mf), mf->d_nbr, n_owned, (const T *)srcs[0]->d, (const T *)srcs[1]->d, (const T *)srcs[2]->d, s3, (T *)dst->d);
   count_launch();
   DGX_CUDA_CHECK(cudaGetLastError());

@@ -84,45 +84,6 @@ __device__ __forceinline__ void pline(int d, int l, int &base, int &stride) {
   }
 }
 
-// one x-row of a cell (n contiguous values) from / to global memory, in 16-byte pieces when the row length allows it
-template <typename T, int n>
-__device__ __forceinline__ void load_row(const T *__restrict__ p, T (&u)[n]) {
-  if constexpr (sizeof(T) == 8 && n % 2 == 0) {
-#pragma unroll
-    for (int k = 0; k < n / 2; ++k) { const double2 t = __ldg(reinterpret_cast<const double2 *>(p) + k); u[2 * k] = t.x; u[2 * k + 1] = t.y; }
-  } else if constexpr (sizeof(T) == 4 && n % 4 == 0) {
-#pragma unroll
-    for (int k = 0; k < n / 4; ++k) {
-      const float4 t = __ldg(reinterpret_cast<const float4 *>(p) + k);
-      u[4 * k] = t.x; u[4 * k + 1] = t.y; u[4 * k + 2] = t.z; u[4 * k + 3] = t.w;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < n; ++i) u[i] = p[i];
-  }
-}
-template <typename T, int n>
-__device__ __forceinline__ void store_row(T *p, const T (&u)[n], int add) {
-  if constexpr (sizeof(T) == 8 && n % 2 == 0) {
-#pragma unroll
-    for (int k = 0; k < n / 2; ++k) {
-      double2 t = make_double2(u[2 * k], u[2 * k + 1]);
-      if (add) { const double2 o = reinterpret_cast<double2 *>(p)[k]; t.x += o.x; t.y += o.y; }
-      reinterpret_cast<double2 *>(p)[k] = t;
-    }
-  } else if constexpr (sizeof(T) == 4 && n % 4 == 0) {
-#pragma unroll
-    for (int k = 0; k < n / 4; ++k) {
-      float4 t = make_float4(u[4 * k], u[4 * k + 1], u[4 * k + 2], u[4 * k + 3]);
-      if (add) { const float4 o = reinterpret_cast<float4 *>(p)[k]; t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w; }
-      reinterpret_cast<float4 *>(p)[k] = t;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < n; ++i) p[i] = add ? p[i] + u[i] : u[i];
-  }
-}
-
 template <int WPG>
 __device__ __forceinline__ void group_sync(int g) {
   if (WPG == 1) __syncwarp();
