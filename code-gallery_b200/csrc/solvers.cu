@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <vector>
 
 #include "pressure_op.cuh"
@@ -680,13 +681,23 @@ int dgx_solve_gmres(dgx_op *A, dgx_vec *x, dgx_vec *b, int precond_kind, void *p
         RCG(dgx_op_vmult(A, tmp, V[k]));
         RCG(apply_precond(pc, w, tmp));
       }
-      for (int pass = 0; pass < 2; ++pass) {   // classical Gram-Schmidt + one re-orthogonalisation, each sweep fused
+      // classical Gram-Schmidt, each sweep fused (2 passes whatever k); a second sweep only when the first one lost
+      // orthogonality: norm after < 10 sqrt(eps) * norm before (Kelley's test, as in deal.II's SolverGMRES).
+      // DGX_GMRES_REORTH=1 restores the unconditional second sweep.
+      static const bool always_reorth = getenv("DGX_GMRES_REORTH") != nullptr;
+      double hn = 0, ww = 0;
+      {
+        std::vector<double> h(k + 1);
+        RCG(dgx_vec_orthogonalize_checked(w, V.data(), k + 1, h.data(), &ww));
+        for (int j = 0; j <= k; ++j) H[(size_t)j * kdim + k] += h[j];
+      }
+      RCG(dgx_vec_l2_norm(w, &hn));
+      if (always_reorth || hn <= 10.0 * std::sqrt(std::numeric_limits<double>::epsilon()) * std::sqrt(ww)) {
         std::vector<double> h(k + 1);
         RCG(dgx_vec_orthogonalize(w, V.data(), k + 1, h.data()));
         for (int j = 0; j <= k; ++j) H[(size_t)j * kdim + k] += h[j];
+        RCG(dgx_vec_l2_norm(w, &hn));
       }
-      double hn = 0;
-      RCG(dgx_vec_l2_norm(w, &hn));
       H[(size_t)(k + 1) * kdim + k] = hn;
       for (int j = 0; j < k; ++j) {
         const double a = H[(size_t)j * kdim + k], c = H[(size_t)(j + 1) * kdim + k];

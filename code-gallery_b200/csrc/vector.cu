@@ -475,8 +475,12 @@ int dgx_vec_compress_add(dgx_vec *v) {
 
 // One Gram-Schmidt sweep of SolverGMRES: h_j = w . V_j for j < k (one pass over w, one all-reduce, one host read-back),
 // then w -= sum_j h_j V_j (one pass).  k <= 32.
-int dgx_vec_orthogonalize(dgx_vec *w, dgx_vec *const *V, int k, double *h) {
-  DGX_REQUIRE(w && V && h && k >= 1 && k <= kMaxMulti, "orthogonalize: 1 <= k <= 32");
+int dgx_vec_orthogonalize(dgx_vec *w, dgx_vec *const *V, int k, double *h) { return dgx_vec_orthogonalize_checked(w, V, k, h, nullptr); }
+
+// same sweep; *w_dot_w (if not NULL) receives w . w BEFORE the sweep, reduced in the same pass (the reference's loss-of-
+// orthogonality test compares the norms before and after, Kelley 1995 as used by deal.II's SolverGMRES)
+int dgx_vec_orthogonalize_checked(dgx_vec *w, dgx_vec *const *V, int k, double *h, double *w_dot_w) {
+  DGX_REQUIRE(w && V && h && k >= 1 && k + (w_dot_w ? 1 : 0) <= kMaxMulti, "orthogonalize: 1 <= k <= 32 (31 with the norm)");
   dgx_ctx *ctx = w->mf->ctx;
   const long long n = w->n_owned;
   const int grid = grid_for(n, 8);
@@ -491,16 +495,19 @@ int dgx_vec_orthogonalize(dgx_vec *w, dgx_vec *const *V, int k, double *h) {
       tab.v[j] = (const T *)V[j]->d;
       tab.h[j] = 0;
     }
-    for (int k0 = 0; k0 < k; k0 += KB) {
-      multi_dot_kernel<T, KB><<<grid, kThreads, 0, ctx->stream>>>((const T *)w->d, tab, k0, k, n, partial, result);
+    const int kd = k + (w_dot_w ? 1 : 0);   // dot products of this pass: the basis, then w itself
+    if (w_dot_w) { tab.v[k] = (const T *)w->d; tab.h[k] = 0; }
+    for (int k0 = 0; k0 < kd; k0 += KB) {
+      multi_dot_kernel<T, KB><<<grid, kThreads, 0, ctx->stream>>>((const T *)w->d, tab, k0, kd, n, partial, result);
       count_launch();
     }
     DGX_CUDA_CHECK(cudaGetLastError());
-    int rc = allreduce_sum(ctx, result, k);
+    int rc = allreduce_sum(ctx, result, kd);
     if (rc) return rc;
-    DGX_CUDA_CHECK(cudaMemcpyAsync(ctx->h_scratch, result, k * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DGX_CUDA_CHECK(cudaMemcpyAsync(ctx->h_scratch, result, kd * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     DGX_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     for (int j = 0; j < k; ++j) { h[j] = ctx->h_scratch[j]; tab.h[j] = h[j]; }
+    if (w_dot_w) *w_dot_w = ctx->h_scratch[k];
     if (n) { multi_axpy_kernel<T><<<grid_for(n), kThreads, 0, ctx->stream>>>((T *)w->d, tab, k, n); count_launch(); }
     DGX_CUDA_CHECK(cudaGetLastError());
     return DGX_OK;

@@ -133,6 +133,9 @@ int dgx_vec_cg_update(dgx_vec *x, double a, const dgx_vec *p, dgx_vec *r, double
 int dgx_vec_interpolate(dgx_vec *dst, double a, const dgx_vec *x, double b, const dgx_vec *y);
 /* one (classical) Gram-Schmidt sweep: h[j] = w . V[j] (j < k <= 32, one pass + one all-reduce), then w -= sum_j h[j] V[j] */
 int dgx_vec_orthogonalize(dgx_vec *w, dgx_vec *const *V, int k, double *h);
+/* same sweep (k <= 31); *w_dot_w = w . w BEFORE the sweep, reduced in the same pass: SolverGMRES re-orthogonalises only when the
+ * norm after the sweep is below 10 sqrt(eps) times the norm before (Kelley 1995, the test deal.II's SolverGMRES applies) */
+int dgx_vec_orthogonalize_checked(dgx_vec *w, dgx_vec *const *V, int k, double *h, double *w_dot_w);
 int dgx_vec_update_ghost_values(dgx_vec *v);
 int dgx_vec_zero_out_ghost_values(dgx_vec *v);
 /* compress(VectorOperation::add): a no-op by construction (cell-centric kernels never write ghosts) */
