@@ -173,7 +173,7 @@ FAST_CASES = [
 
 
 @pytest.mark.parametrize("np_dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("degree", [3, 4])
+@pytest.mark.parametrize("degree", [2, 3, 4])
 @pytest.mark.parametrize("case", FAST_CASES, ids=lambda c: f"{c[0]}-r{c[1]}")
 def test_marching_kernel_matches_oracle(dgx, gpu_ctx, case, degree, np_dtype):
     cells0, nref = case
