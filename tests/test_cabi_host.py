@@ -108,3 +108,18 @@ def test_dealii_shim_header_and_driver_build(dgx):
     if not torch.cuda.is_available():
         r = subprocess.run([exe, "2", "1"], capture_output=True, text=True, timeout=120)
         assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the CUDA arm) prints one JSON line with the contract's
+    keys; it times the oracle's C port on a bounded sample and needs no GPU."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-refine", "3"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "DoF/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0 and line["gpu_launches"] == 0
