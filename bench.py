@@ -8,7 +8,8 @@ FE_DGQ(4), periodic, fp64 (262,144,000 DoFs, 2.1 GB per vector => inputs exceed 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--refine R] [--degree P] [--impl reference]
 
 Prints ONE JSON line (rank 0).  `value` = DoFs processed per second with src/dst resident in HBM;
-`e2e` = the same through dgx_op_vmult_host (pinned host buffers, H2D + vmult + D2H timed);
+`e2e` = the same through dgx_op_vmult_host (pinned host buffers, H2D + vmult + D2H timed; on one rank the three legs
+  of a call are pipelined brick by brick, see DESIGN.md "Host entry point");
 `roofline` = algorithmic bytes (16 B/DoF) / kernel time vs MEASURED_PEAKS.json;
 `cpu_baseline` = the oracle's C port timed on the host cores on a bounded sample.
 """
