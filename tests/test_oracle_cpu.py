@@ -187,3 +187,31 @@ def test_cpu_kronecker_port_matches_oracle():
         got = cpu_port.kron_vmult(m, degree, 5e-3, u)
         ref = op.vmult(u)
         assert np.linalg.norm(got - ref) <= 1e-12 * np.linalg.norm(ref)
+
+
+def test_time_step_converges_to_the_analytic_taylor_green_vortex():
+    """Physics pin of the whole restatement (both RHS forms, the three operators, GMRES / MG-CG / mass CG, the TR-BDF2
+    projection sequence of NS.cc:2934-2986): on [0, 2 pi]^2 periodic the Navier-Stokes equations have the exact solution
+    u = (sin x cos y, -cos x sin y) exp(-2 t / Re), p = (cos 2x + cos 2y)/4 exp(-4 t / Re).  With the reference's degrees
+    (velocity Q2 / pressure Q1) the oracle's velocity error at t = 0.2 must fall under mesh refinement and be below 1 % on
+    16^2 cells."""
+    from oracle.timestep import OracleProjection
+    Re, L, T = 10.0, 2 * np.pi, 0.2
+    errs, perrs = [], []
+    for nref, nsteps in ((2, 4), (3, 4), (4, 8)):
+        om = CartesianMesh(2, [1, 1], nref, [0.0, 0.0], [L, L], [True, True])
+        orc = OracleProjection(om, 1, Re, T / nsteps)
+        pts = om.dof_points(np.asarray(shape(2, 3).nodes))
+        x, y = pts[..., 0], pts[..., 1]
+        exact = lambda t: np.stack([np.sin(x) * np.cos(y), -np.cos(x) * np.sin(y)], axis=1).reshape(-1) * np.exp(-2 * t / Re)
+        pp = om.dof_points(np.asarray(shape(1, 2).nodes))
+        pex = lambda t: (0.25 * (np.cos(2 * pp[..., 0]) + np.cos(2 * pp[..., 1]))).reshape(-1) * np.exp(-4 * t / Re)
+        orc.u_n, orc.u_n_minus_1, orc.pres_n = exact(0.0).copy(), exact(0.0).copy(), pex(0.0).copy()
+        for _ in range(nsteps):
+            orc.advance()
+        errs.append(np.linalg.norm(orc.u_n - exact(T)) / np.linalg.norm(exact(T)))
+        pe = pex(T)
+        perrs.append(np.linalg.norm((orc.pres_n - orc.pres_n.mean()) - (pe - pe.mean())) / np.linalg.norm(pe - pe.mean()))
+    assert errs[1] < 0.6 * errs[0] and errs[2] < 0.25 * errs[1], errs
+    assert errs[2] < 1e-2, errs
+    assert perrs[2] < 0.1 and perrs[2] < perrs[1], perrs
