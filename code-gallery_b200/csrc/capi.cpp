@@ -36,35 +36,18 @@ using namespace dgx;
 // 128^3 Q4).  The three legs are therefore overlapped inside ONE call: the owned cells are cut into chunks of the cell
 // order; chunk c is uploaded on its own stream, computed as soon as the last chunk holding one of its face neighbours has
 // arrived, and downloaded on a third stream while later chunks are still coming in (the link is full duplex).
-static bool host_pipeline_applies(dgx_op *op) {
-  dgx_mf *mf = op->mf;
-  static const bool off = getenv("DGX_NO_HOST_PIPELINE") != nullptr;
-  if (off || op->kind != DGX_OP_PRESSURE || mf->ctx->nranks != 1) return false;
-  if (op->hp_lg == 0) {
-    // chunk = 2^(dim k + dim - 1) cells and at least 8 MiB: every copy costs the DMA engines 15-20 us of set-up, measured
-    // 128^3 Q4 fp64 (2 x 2.1 GB): 2 MB chunks 69 ms, 16 MB chunks 54 ms, unpipelined 77 ms.  Fewer than 16 chunks: not worth it
-    const char *env = getenv("DGX_HOST_CHUNK_LOG2");
-    const size_t cell_bytes = (size_t)op->h_src->dofs_per_cell * op->h_src->elem();
-    int lg = mf->dim - 1;
-    if (env) lg = atoi(env);
-    else while (((size_t)cell_bytes << lg) < (8u << 20)) lg += mf->dim;
-    op->hp_lg = (mf->n_owned >> lg) >= 16 ? lg : -1;
-  }
-  return op->hp_lg > 0;
-}
-
-static int vmult_host_pipelined(dgx_op *op, void *dst_host, const void *src_host) {
-  dgx_mf *mf = op->mf;
-  dgx_ctx *ctx = mf->ctx;
+// Schedule of the pipelined host entry point (pure host logic; also reachable through dgx_mf_host_pipeline_plan for tests).
+static void build_host_plan(const dgx_mf *mf, int lg, std::vector<dgx_op::HostSeg> &up, std::vector<dgx_op::HostSeg> &grp) {
   const int nf = 2 * mf->dim, dim = mf->dim;
-  if (op->hp_up.empty()) {
+  up.clear(); grp.clear();
+  {
     // Chunks are aligned runs of 2^(dim k + dim - 1) cells of the hierarchical order: bricks that are 2^(k+1) cells wide in
     // all directions but the last, 2^k there.  They are uploaded slab by slab along the last direction (for a periodic
     // direction alternating between the two ends, so that no slab waits for the far end of the upload): a chunk is
     // computable about two slabs after it arrived, and the download trails the upload by about three slabs.  Chunks that
     // are neighbours in memory and in the schedule are merged into one copy / one launch.
     const long long nc = mf->n_owned;
-    const long long G = 1LL << op->hp_lg;
+    const long long G = 1LL << lg;
     const int C = (int)((nc + G - 1) / G);
     auto cb = [&](int c) { return std::min<long long>(nc, (long long)c * G); };
     std::vector<int> key(C);
@@ -94,9 +77,9 @@ static int vmult_host_pipelined(dgx_op *op, void *dst_host, const void *src_host
     std::vector<int> seg_of(C);     // upload segment of every chunk
     for (int k = 0; k < C; ++k) {
       const int c = upload[k];
-      if (k > 0 && upload[k - 1] == c - 1 && slab_rank[c - 1] == slab_rank[c]) op->hp_up.back().e = cb(c + 1);
-      else op->hp_up.push_back({cb(c), cb(c + 1), 0});
-      seg_of[c] = (int)op->hp_up.size() - 1;
+      if (k > 0 && upload[k - 1] == c - 1 && slab_rank[c - 1] == slab_rank[c]) up.back().e = cb(c + 1);
+      else up.push_back({cb(c), cb(c + 1), 0});
+      seg_of[c] = (int)up.size() - 1;
     }
     std::vector<int> need(C);       // upload segment after which chunk c is computable
     for (int c = 0; c < C; ++c) {
@@ -113,17 +96,43 @@ static int vmult_host_pipelined(dgx_op *op, void *dst_host, const void *src_host
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return need[a] < need[b]; });
     for (int k = 0; k < C; ++k) {
       const int c = order[k];
-      if (k > 0 && order[k - 1] == c - 1 && need[c - 1] == need[c]) op->hp_grp.back().e = cb(c + 1);
-      else op->hp_grp.push_back({cb(c), cb(c + 1), need[c]});
+      if (k > 0 && order[k - 1] == c - 1 && need[c - 1] == need[c]) grp.back().e = cb(c + 1);
+      else grp.push_back({cb(c), cb(c + 1), need[c]});
     }
     if (getenv("DGX_HOST_PIPELINE_DEBUG")) {
       long long lag = 0;
-      for (const auto &g : op->hp_grp) lag = std::max<long long>(lag, g.need);
+      for (const auto &g : grp) lag = std::max<long long>(lag, g.need);
       fprintf(stderr, "[dgx] host pipeline: %d chunks of %lld cells, %d slabs (%s), %zu upload segments, %zu compute groups\n", C, G, S,
-              wraps ? "periodic: alternating ends" : "in order", op->hp_up.size(), op->hp_grp.size());
-      for (size_t k = 0; k < op->hp_grp.size(); k += std::max<size_t>(1, op->hp_grp.size() / 16))
-        fprintf(stderr, "[dgx]   group %zu: cells [%lld, %lld) after upload segment %d\n", k, op->hp_grp[k].b, op->hp_grp[k].e, op->hp_grp[k].need);
+              wraps ? "periodic: alternating ends" : "in order", up.size(), grp.size());
+      for (size_t k = 0; k < grp.size(); k += std::max<size_t>(1, grp.size() / 16))
+        fprintf(stderr, "[dgx]   group %zu: cells [%lld, %lld) after upload segment %d\n", k, grp[k].b, grp[k].e, grp[k].need);
     }
+  }
+}
+
+// chunk = 2^(dim k + dim - 1) cells and at least 8 MiB: every copy costs the DMA engines 15-20 us of set-up, measured
+// 128^3 Q4 fp64 (2 x 2.1 GB): 2 MB chunks 69 ms, 16 MB chunks 54 ms, unpipelined 77 ms.  Fewer than 16 chunks: not worth it (-1)
+static int host_plan_chunk_log2(const dgx_mf *mf, size_t cell_bytes) {
+  const char *env = getenv("DGX_HOST_CHUNK_LOG2");
+  int lg = mf->dim - 1;
+  if (env) lg = atoi(env);
+  else while (((size_t)cell_bytes << lg) < (8u << 20)) lg += mf->dim;
+  return (mf->n_owned >> lg) >= 16 ? lg : -1;
+}
+
+static bool host_pipeline_applies(dgx_op *op) {
+  dgx_mf *mf = op->mf;
+  static const bool off = getenv("DGX_NO_HOST_PIPELINE") != nullptr;
+  if (off || op->kind != DGX_OP_PRESSURE || mf->ctx->nranks != 1) return false;
+  if (op->hp_lg == 0) op->hp_lg = host_plan_chunk_log2(mf, (size_t)op->h_src->dofs_per_cell * op->h_src->elem());
+  return op->hp_lg > 0;
+}
+
+static int vmult_host_pipelined(dgx_op *op, void *dst_host, const void *src_host) {
+  dgx_mf *mf = op->mf;
+  dgx_ctx *ctx = mf->ctx;
+  if (op->hp_up.empty()) {
+    build_host_plan(mf, op->hp_lg, op->hp_up, op->hp_grp);
     op->hp_in.resize(op->hp_up.size()); op->hp_done.resize(op->hp_grp.size());
     for (cudaEvent_t &e : op->hp_in) DGX_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (cudaEvent_t &e : op->hp_done) DGX_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -387,6 +396,24 @@ int dgx_op_precondition_Jacobi(dgx_op *op, dgx_vec *dst, const dgx_vec *src, dou
   int rc = dgx_vec_equ(dst, omega, src);
   if (rc) return rc;
   return dgx_vec_scale_by(dst, op->inv_diag);
+}
+
+int dgx_mf_host_pipeline_plan(const dgx_mf *mf, long long bytes_per_cell, int chunk_log2, int capacity, long long *up_begin, long long *up_end,
+                              long long *grp_begin, long long *grp_end, int *grp_need, int *n_up, int *n_grp) {
+  DGX_REQUIRE(mf && n_up && n_grp && bytes_per_cell > 0, "null argument");
+  const int lg = chunk_log2 > 0 ? chunk_log2 : host_plan_chunk_log2(mf, (size_t)bytes_per_cell);
+  *n_up = 0; *n_grp = 0;
+  if (lg <= 0 || mf->ctx->nranks != 1) return DGX_OK;   // the call is not pipelined
+  std::vector<dgx_op::HostSeg> up, grp;
+  build_host_plan(mf, lg, up, grp);
+  *n_up = (int)up.size(); *n_grp = (int)grp.size();
+  for (int i = 0; i < (int)up.size() && i < capacity; ++i) { if (up_begin) up_begin[i] = up[i].b; if (up_end) up_end[i] = up[i].e; }
+  for (int i = 0; i < (int)grp.size() && i < capacity; ++i) {
+    if (grp_begin) grp_begin[i] = grp[i].b;
+    if (grp_end) grp_end[i] = grp[i].e;
+    if (grp_need) grp_need[i] = grp[i].need;
+  }
+  return DGX_OK;
 }
 
 int dgx_op_vmult_host(dgx_op *op, void *dst_host, const void *src_host, long long n) {

@@ -151,6 +151,21 @@ class MatrixFree:
         _check(lib.dgx_mf_local_neighbors(self.h, out.ctypes.data_as(c_vp)))
         return out
 
+    def host_pipeline_plan(self, bytes_per_cell, chunk_log2=0):
+        """schedule of the pipelined host entry point (dgx_op_vmult_host): (uploads [n,2], groups [m,3] = begin, end, need);
+        empty arrays when the call would not be pipelined"""
+        n_up, n_grp = c_int(), c_int()
+        _check(lib.dgx_mf_host_pipeline_plan(self.h, c_ll(bytes_per_cell), c_int(chunk_log2), c_int(0), None, None, None, None, None,
+                                             C.byref(n_up), C.byref(n_grp)))
+        cap = max(n_up.value, n_grp.value, 1)
+        ub, ue, gb, ge = (np.zeros(cap, dtype=np.int64) for _ in range(4))
+        gn = np.zeros(cap, dtype=np.int32)
+        _check(lib.dgx_mf_host_pipeline_plan(self.h, c_ll(bytes_per_cell), c_int(chunk_log2), c_int(cap), ub.ctypes.data_as(c_vp), ue.ctypes.data_as(c_vp),
+                                             gb.ctypes.data_as(c_vp), ge.ctypes.data_as(c_vp), gn.ctypes.data_as(c_vp), C.byref(n_up), C.byref(n_grp)))
+        ups = np.stack([ub[:n_up.value], ue[:n_up.value]], axis=1)
+        grps = np.stack([gb[:n_grp.value], ge[:n_grp.value], gn[:n_grp.value].astype(np.int64)], axis=1)
+        return ups, grps
+
     def ghost_cells(self):
         out = np.empty(self.n_ghost_cells(), dtype=np.int64)
         _check(lib.dgx_mf_ghost_cells(self.h, out.ctypes.data_as(c_vp)))

@@ -123,3 +123,47 @@ def test_bench_reference_arm_contract():
     assert line["impl"] == "reference" and line["unit"] == "DoF/s" and line["higher_is_better"] is True
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0 and line["gpu_launches"] == 0
+
+
+@pytest.mark.parametrize("dim,cells0,nref,periodic,lg", [
+    (3, [1, 1, 1], 4, [True, True, True], 5),      # 4096 cells, 128 bricks of 32 cells, periodic: slabs uploaded from both ends
+    (3, [2, 1, 1], 4, [False, True, False], 8),    # boundaries, 2 coarse cells
+    (3, [1, 1, 1], 6, [True, True, True], 11),     # the production brick shape (16 x 16 x 8 cells) on 64^3: 8 slabs
+    (2, [1, 1], 6, [True, False], 5),              # 2-D: bricks 8 x 4 cells
+    (2, [3, 1], 5, [False, False], 3),
+])
+def test_host_pipeline_schedule_is_valid(dgx, dim, cells0, nref, periodic, lg):
+    """The schedule of the pipelined host entry point (pure host logic): uploads and compute groups each tile the owned cells
+    exactly once, and no group is computed before the upload segments holding its cells and all their face neighbours are
+    in.  With the slab-ordered upload most groups are computable long before the upload ends."""
+    mesh = dgx.Mesh(dim, cells0, nref, [0.0] * dim, [1.0] * dim, periodic)
+    ctx = dgx.Context(0, 0, 1)                         # host-only context: table queries only
+    mf = dgx.MatrixFree(ctx, mesh)
+    nc = mf.n_owned_cells()
+    ups, grps = mf.host_pipeline_plan(1000, lg)
+    assert len(ups) >= 16 and len(grps) >= 8
+    for segs in (ups, grps):
+        order = np.argsort(segs[:, 0])
+        assert segs[order[0], 0] == 0 and segs[order[-1], 1] == nc
+        assert np.array_equal(segs[order[1:], 0], segs[order[:-1], 1])       # disjoint and gap-free
+    seg_of = np.empty(nc, dtype=np.int64)              # upload position of every cell
+    for k, (b, e) in enumerate(ups):
+        seg_of[b:e] = k
+    nbr = mf.local_neighbors()
+    assert np.all(np.diff(grps[:, 2]) >= 0)            # computed in the order they become ready
+    for b, e, need in grps:
+        assert seg_of[b:e].max() <= need
+        nb = nbr[:, b:e]
+        nb = nb[(nb >= 0) & (nb < nc)]
+        assert seg_of[nb].max() <= need
+    # effectiveness: half of the cells are computable when 80 % of the upload is in (unpipelined: none before 100 %)
+    ready_at = np.empty(nc, dtype=np.int64)
+    for b, e, need in grps:
+        ready_at[b:e] = need
+    n_slabs = (cells0[dim - 1] << nref) >> ((lg - (dim - 1)) // dim)      # bricks are 2^k cells thick in the last direction
+    if n_slabs >= 8:
+        assert np.median(ready_at) <= 0.8 * len(ups)
+    # automatic brick size: small meshes are not pipelined
+    ups0, grps0 = mf.host_pipeline_plan(1000, 0)
+    if nc < (1 << 18):
+        assert len(ups0) == 0 and len(grps0) == 0
