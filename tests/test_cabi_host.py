@@ -167,3 +167,20 @@ def test_host_pipeline_schedule_is_valid(dgx, dim, cells0, nref, periodic, lg):
     ups0, grps0 = mf.host_pipeline_plan(1000, 0)
     if nc < (1 << 18):
         assert len(ups0) == 0 and len(grps0) == 0
+
+
+def test_compute_entry_points_fail_loudly_without_a_device(dgx):
+    """no CPU fallback anywhere on the product path: on a machine without a GPU operators, multigrid and vectors refuse to be
+    created (the oracle is test infrastructure and is never routed to)"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a CUDA device")
+    ctx = dgx.Context(0, 0, 1)
+    mesh = dgx.Mesh(3, [1, 1, 1], 1, [0, 0, 0], [1, 1, 1], [True] * 3)
+    mf = dgx.MatrixFree(ctx, mesh)
+    with pytest.raises(dgx.DgxError, match="no CUDA device"):
+        dgx.NavierStokesProjectionOperator(mf, dgx.OP_PRESSURE, 2, 100.0, 5e-3)
+    with pytest.raises(dgx.DgxError, match="no CUDA device"):
+        dgx.Multigrid(ctx, mesh, 2, 100.0, 5e-3)
+    with pytest.raises(dgx.DgxError):
+        mf.initialize_dof_vector(2)
