@@ -184,3 +184,12 @@ def test_compute_entry_points_fail_loudly_without_a_device(dgx):
         dgx.Multigrid(ctx, mesh, 2, 100.0, 5e-3)
     with pytest.raises(dgx.DgxError):
         mf.initialize_dof_vector(2)
+
+
+def test_header_is_plain_c():
+    """include/dgx.h is a C header (opaque handles, plain pointers and sizes): it compiles as C11 with -Werror"""
+    import subprocess
+    src = '#include "dgx.h"\nint main(void) { return dgx_version() == 0; }\n'
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), "-x", "c", "-"],
+                       input=src, text=True, capture_output=True)
+    assert r.returncode == 0, r.stderr
