@@ -32,7 +32,9 @@
 #include <utility>
 #include <vector>
 
+#include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "pressure_op.cuh"
 
@@ -690,9 +692,60 @@ void fill_fast_params(FastParams<T, n> &F, const dgx_op *op) {
   F.kappa = (T)pressure_kappa(op);
 }
 
+#include "pressure_march_v2.cuh"
+
+// which marching kernel runs the plain (no add, no fused update) Q4 fp64 operator: DGX_MARCH = v1 | v2 | v2eo (default)
+inline int march_generation() {   // read on every call (tests and the bench switch it inside one process)
+  const char *e = getenv("DGX_MARCH");
+  if (!e) return 2;
+  if (!strcmp(e, "v1")) return 0;
+  if (!strcmp(e, "v2")) return 1;
+  if (!strcmp(e, "v2r")) return 3;
+  if (!strcmp(e, "v2eor")) return 4;
+  return 2;
+}
+
+template <int n, typename T, bool EO, int XYV>
+int launch_march2(dgx_op *op, dgx_vec *dst, const dgx_vec *src, const FastGeom &G, const int *d_jobs, int n_jobs, cudaStream_t stream) {
+  using R = Roles2<n>;
+  constexpr int NL = n * n, ND = NL * n;
+  FastParams<T, n> F;
+  fill_fast_params<T, n>(F, op);
+  EOParams<T, n> Q;
+  {
+    FastParams<double, n> Fd;
+    fill_fast_params<double, n>(Fd, op);
+    if (EO && eo_asymmetry<n>(Fd) > 1e-13) { set_error("marching kernel: 1-D tables are not centro-symmetric"); return DGX_ERR_INVALID; }
+    fill_eo_params<T, n>(Q, Fd);
+  }
+  constexpr size_t smem = sizeof(T) * (size_t)((R::NSTAGE + 3) * TC * ND + 2 * (2 * TYC + 2 * TXC) * NL * 2) + 8 * (R::NSTAGE + 6) + 4 * R::NSTAGE + 16;
+  int dev = 0;
+  DGX_CUDA_CHECK(cudaGetDevice(&dev));
+  static bool configured[64] = {};
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    DGX_CUDA_CHECK(cudaFuncSetAttribute(pressure_march2_kernel<n, T, EO, XYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[dev] = true;
+  }
+  const int grid = d_jobs ? n_jobs : G.ntx * G.nty * G.nsz;
+  if (grid == 0) return DGX_OK;
+  pressure_march2_kernel<n, T, EO, XYV><<<grid, R::NW * 32, smem, stream>>>(F, Q, G, op->mf->d_nbr, (const T *)src->d, (T *)dst->d, d_jobs);
+  count_launch();
+  DGX_CUDA_CHECK(cudaGetLastError());
+  return DGX_OK;
+}
+
 template <int n, typename T>
 int launch_march(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const FastGeom &G, const int *d_jobs, int n_jobs, cudaStream_t stream,
                  const FusedUpdate *fu) {
+  if constexpr (n == 5 && std::is_same<T, double>::value) {
+    if (!add && !fu && march_generation() > 0)
+      switch (march_generation()) {
+        case 1: return launch_march2<n, T, false, 0>(op, dst, src, G, d_jobs, n_jobs, stream);
+        case 3: return launch_march2<n, T, false, 1>(op, dst, src, G, d_jobs, n_jobs, stream);
+        case 4: return launch_march2<n, T, true, 1>(op, dst, src, G, d_jobs, n_jobs, stream);
+        default: return launch_march2<n, T, true, 0>(op, dst, src, G, d_jobs, n_jobs, stream);
+      }
+  }
   using R = Roles<n>;
   constexpr int NL = n * n, ND = NL * n;
   FastParams<T, n> F;
@@ -701,11 +754,13 @@ int launch_march(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const F
   const size_t smem_plain = sizeof(T) * (size_t)(R::NSTAGE * TC * ND + (n % 2 == 0 ? 4 : 2) * TC * NDP + 4 * NL * TC + 2 * 2 * TYC * NL * 2 + 2 * 2 * TXC * NL * 2) + 8 * R::NSTAGE + 8 * ((4 * R::NSTAGE + 7) / 8) + 16;
   const size_t smem_fused = smem_plain + (n % 2 == 0 ? sizeof(T) * (size_t)(3 * TC * ND) : 0);   // + AUX planes of the fused update
   const size_t smem = fu ? smem_fused : smem_plain;
-  static bool configured = false;
-  if (!configured) {
+  int dev = 0;
+  DGX_CUDA_CHECK(cudaGetDevice(&dev));
+  static bool configured[64] = {};   // per device: the attribute belongs to the device's copy of the function
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
     DGX_CUDA_CHECK(cudaFuncSetAttribute(pressure_march_kernel<n, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused));
     DGX_CUDA_CHECK(cudaFuncSetAttribute(pressure_march_kernel<n, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plain));
-    configured = true;
+    configured[dev] = true;
   }
   const int grid = d_jobs ? n_jobs : G.ntx * G.nty * G.nsz;
   if (grid == 0) return DGX_OK;

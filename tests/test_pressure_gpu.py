@@ -188,3 +188,38 @@ def test_marching_kernel_matches_oracle(dgx, gpu_ctx, case, degree, np_dtype):
     op.set_variant(1)
     op.vmult(dst, src)
     assert rel_l2(dst.to_host(), ref) < TOL[np_dtype]
+
+
+@pytest.mark.parametrize("gen", ["v1", "v2", "v2eo"])
+@pytest.mark.parametrize("case", FAST_CASES + [([1, 2, 1], 4)], ids=lambda c: f"{c[0]}-r{c[1]}")
+def test_marching_generations_match_oracle(dgx, gpu_ctx, case, gen, monkeypatch):
+    """Q4 fp64 through every generation of the marching kernel (DGX_MARCH): v1 = round-1 kernel (named barriers), v2 =
+    mbarrier hand-offs + shuffled traces + bulk stores, v2eo = v2 with even-odd 1-D contractions (the default)."""
+    monkeypatch.setenv("DGX_MARCH", gen)
+    cells0, nref = case
+    for stage in (1, 2):
+        got, ref, op, oop, src, dst, u = _run(dgx, gpu_ctx, 3, cells0, nref, [True] * 3, 4, np.float64, stage, variant=2)
+        err = rel_l2(got, ref)
+        assert err < 1e-12, (gen, stage, err)
+    for _ in range(3):      # repeated launches on the same buffers: no state is left behind in shared / global memory
+        op.vmult(dst, src)
+    assert rel_l2(dst.to_host(), ref) < 1e-12
+
+
+def test_marching_generations_agree_at_scale(dgx, gpu_ctx, monkeypatch):
+    """64^3 Q4 fp64 (32.8 M dofs, 2048 tile columns of 16 planes = several waves of CTAs): every marching generation against the generic kernel"""
+    gm = dgx.Mesh(3, [1, 1, 1], 6, [0, 0, 0], [1.0, 1.5, 0.75], [True] * 3)
+    mf = dgx.MatrixFree(gpu_ctx, gm)
+    op = dgx.NavierStokesProjectionOperator(mf, dgx.OP_PRESSURE, 4, 100.0, 5e-3)
+    src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+    n = src.locally_owned_size()
+    src.from_host(np.random.default_rng(11).standard_normal(n))
+    op.set_variant(1)
+    op.vmult(dst, src)
+    ref = dst.to_host()
+    op.set_variant(2)
+    for gen in ("v1", "v2", "v2eo"):
+        monkeypatch.setenv("DGX_MARCH", gen)
+        dst.set(0.0)
+        op.vmult(dst, src)
+        assert rel_l2(dst.to_host(), ref) < 1e-13, gen
