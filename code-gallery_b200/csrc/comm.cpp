@@ -20,6 +20,7 @@ struct NcclApi {
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -43,11 +44,12 @@ NcclApi &api() {
     LOAD(Send, "ncclSend");
     LOAD(Recv, "ncclRecv");
     LOAD(AllReduce, "ncclAllReduce");
+    LOAD(AllGather, "ncclAllGather");
     LOAD(GroupStart, "ncclGroupStart");
     LOAD(GroupEnd, "ncclGroupEnd");
     LOAD(GetErrorString, "ncclGetErrorString");
 #undef LOAD
-    a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.Send && a.Recv && a.AllReduce && a.GroupStart && a.GroupEnd;
+    a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.Send && a.Recv && a.AllReduce && a.AllGather && a.GroupStart && a.GroupEnd;
   });
   return a;
 }
@@ -102,17 +104,26 @@ int allreduce_max(dgx_ctx *ctx, double *dvals, int n) {
   return DGX_OK;
 }
 
+int allgather_inplace(dgx_ctx *ctx, void *buf, size_t bytes_per_rank) {
+  if (ctx->nranks == 1 || bytes_per_rank == 0) return DGX_OK;
+  DGX_NCCL_CHECK(api().AllGather((const char *)buf + (size_t)ctx->rank * bytes_per_rank, buf, bytes_per_rank, ncclChar, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+  return DGX_OK;
+}
+
 // grouped point-to-point: send[i] -> peers, recv[i] <- peers (bytes)
 int comm_exchange(dgx_ctx *ctx, cudaStream_t stream, int npeers, const int *ranks, const void *const *sendbuf, const size_t *sendbytes,
                   void *const *recvbuf, const size_t *recvbytes) {
   if (ctx->nranks == 1 || npeers == 0) return DGX_OK;
   ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
   DGX_NCCL_CHECK(api().GroupStart());
-  for (int i = 0; i < npeers; ++i) {
-    if (sendbytes[i]) DGX_NCCL_CHECK(api().Send(sendbuf[i], sendbytes[i], ncclChar, ranks[i], comm, stream));
-    if (recvbytes[i]) DGX_NCCL_CHECK(api().Recv(recvbuf[i], recvbytes[i], ncclChar, ranks[i], comm, stream));
+  ncclResult_t bad = ncclSuccess;   // never return between GroupStart and GroupEnd: the group would stay open
+  for (int i = 0; i < npeers && bad == ncclSuccess; ++i) {
+    if (sendbytes[i]) bad = api().Send(sendbuf[i], sendbytes[i], ncclChar, ranks[i], comm, stream);
+    if (bad == ncclSuccess && recvbytes[i]) bad = api().Recv(recvbuf[i], recvbytes[i], ncclChar, ranks[i], comm, stream);
   }
-  DGX_NCCL_CHECK(api().GroupEnd());
+  const ncclResult_t end = api().GroupEnd();
+  DGX_NCCL_CHECK(bad);
+  DGX_NCCL_CHECK(end);
   return DGX_OK;
 }
 

@@ -102,6 +102,9 @@ struct dgx_mf {
   std::vector<long long> ghost_global;  // [n_ghost]
   int *d_nbr = nullptr;
   bool all_interior = false;            // no boundary faces at all (periodic everywhere)
+  // Replicated level (multigrid levels too small to be worth distributing): every rank holds ALL cells, computes the same
+  // numbers redundantly and never communicates on this level (no ghosts, reductions stay local).
+  bool replicated = false;
   // owned cells == the box [box_lo, box_lo + box_ext) of cell coordinates (true for Morton-aligned partitions)
   bool box_ok = false;
   int box_lo[dgx::MAX_DIM] = {0, 0, 0}, box_ext[dgx::MAX_DIM] = {1, 1, 1};
@@ -166,7 +169,8 @@ struct FusedUpdate {
 int pressure_apply_fused(dgx_op *op, dgx_vec *dst, dgx_vec *x, const FusedUpdate &fu);
 // i-th pooled work vector of the operator's space (created on first use, lives as long as the operator)
 int op_pool_vec(dgx_op *op, int i, dgx_vec **out);
-int pressure_coarse_cg(dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_vec *r, dgx_vec *p, dgx_vec *v, double tol, int max_it, int *d_info, double *d_res);
+int pressure_coarse_cg(dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_vec *r, dgx_vec *p, dgx_vec *v, const double *d_tol, int max_it, int *d_info, double *d_res,
+                       int *d_count, int log_cap);
 int mass_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add);
 int mass_apply_any(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, bool inverse);
 int mass_inverse_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src);
@@ -180,6 +184,10 @@ int ghost_exchange_start(dgx_vec *v);
 // pressure operator on the owned cells [cell_begin, cell_end) only, on `stream` (single rank)
 int pressure_apply_range(dgx_op *op, dgx_vec *dst, const dgx_vec *src, long long cell_begin, long long cell_end, cudaStream_t stream);
 int ghost_exchange_wait(dgx_ctx *ctx);
+// internal form of dgx_mf_create: replicated = every rank owns the whole level
+int mf_create(dgx_ctx *ctx, dgx_mesh *mesh, int level, int dtype, bool replicated, dgx_mf **out);
+// in-place all-gather of equal per-rank pieces: rank r's piece sits at buf + r * bytes_per_rank already
+int allgather_inplace(dgx_ctx *ctx, void *buf, size_t bytes_per_rank);
 int allreduce_sum(dgx_ctx *ctx, double *vals, int n);
 int allreduce_max(dgx_ctx *ctx, double *vals, int n);
 int comm_init(dgx_ctx *ctx, const void *id);

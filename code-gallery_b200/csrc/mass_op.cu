@@ -4,6 +4,7 @@
 #include <algorithm>
 
 #include "pressure_op.cuh"
+#include "reduce.cuh"
 
 namespace dgx {
 namespace {
@@ -124,7 +125,7 @@ mass_cg_front_kernel(const __grid_constant__ MassParams<T, n> P, long long n_ite
     }
     __syncthreads();
   }
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  acc = warp_sum_existing(acc);   // NT is not a multiple of 32 for most degrees
   if ((tid & 31) == 0) red[tid >> 5] = acc;
   __syncthreads();
   if (tid == 0) {

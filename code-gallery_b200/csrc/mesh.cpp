@@ -116,7 +116,11 @@ int dgx_mesh_neighbors(const dgx_mesh *mesh, int level, long long first, long lo
 }
 
 // ---- MatrixFree-style setup ------------------------------------------------------------------
-int dgx_mf_create(dgx_ctx *ctx, dgx_mesh *mesh, int level, int dtype, dgx_mf **out) {
+int dgx_mf_create(dgx_ctx *ctx, dgx_mesh *mesh, int level, int dtype, dgx_mf **out) { return dgx::mf_create(ctx, mesh, level, dtype, false, out); }
+
+}  // extern "C"
+
+int dgx::mf_create(dgx_ctx *ctx, dgx_mesh *mesh, int level, int dtype, bool replicated, dgx_mf **out) {
   DGX_REQUIRE(ctx && mesh && out, "null argument");
   DGX_REQUIRE(dtype == DGX_F64 || dtype == DGX_F32, "dtype");
   if (level < 0) level = mesh->m.n_refine;
@@ -126,7 +130,8 @@ int dgx_mf_create(dgx_ctx *ctx, dgx_mesh *mesh, int level, int dtype, dgx_mf **o
   mf->ctx = ctx; mf->mesh = mesh; mf->level = level; mf->dtype = dtype; mf->dim = m.dim;
   const long long N = m.n_cells(level);
   DGX_REQUIRE(N < (1LL << 31), "too many cells");
-  const int R = ctx->nranks, r = ctx->rank;
+  mf->replicated = replicated && ctx->nranks > 1;
+  const int R = mf->replicated ? 1 : ctx->nranks, r = mf->replicated ? 0 : ctx->rank;
   auto bound = [&](int k) { return (N * k) / R; };
   mf->n_global = N;
   mf->first_cell = bound(r);
@@ -231,6 +236,8 @@ int dgx_mf_create(dgx_ctx *ctx, dgx_mesh *mesh, int level, int dtype, dgx_mf **o
   *out = mf.release();
   return DGX_OK;
 }
+
+extern "C" {
 
 int dgx_mf_destroy(dgx_mf *mf) {
   if (!mf) return DGX_OK;

@@ -702,6 +702,7 @@ inline int march_generation() {   // read on every call (tests and the bench swi
   if (!strcmp(e, "v2")) return 1;
   if (!strcmp(e, "v2r")) return 3;
   if (!strcmp(e, "v2eor")) return 4;
+  if (!strcmp(e, "v2eol")) return 5;
   return 2;
 }
 
@@ -743,6 +744,7 @@ int launch_march(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const F
         case 1: return launch_march2<n, T, false, 0>(op, dst, src, G, d_jobs, n_jobs, stream);
         case 3: return launch_march2<n, T, false, 1>(op, dst, src, G, d_jobs, n_jobs, stream);
         case 4: return launch_march2<n, T, true, 1>(op, dst, src, G, d_jobs, n_jobs, stream);
+        case 5: return launch_march2<n, T, true, 2>(op, dst, src, G, d_jobs, n_jobs, stream);
         default: return launch_march2<n, T, true, 0>(op, dst, src, G, d_jobs, n_jobs, stream);
       }
   }

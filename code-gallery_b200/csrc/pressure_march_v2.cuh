@@ -163,6 +163,127 @@ __device__ __forceinline__ void line_traces(const FastParams<T, n> &P, const EOP
   }
 }
 
+// ---- NB lines in lockstep (coefficient-stationary): every table entry is fetched once and feeds NB independent FMAs, so a
+// thread always has NB FP64 chains in flight (DFMA latency is ~9 cycles at one issue per ~2.3 cycles, tools/fp64_issue.cu)
+// and the constant-bank loads (Blackwell FP64 instructions take no c[] operand: LDC + register) are amortised over NB lines.
+template <int n, typename T, int NB>
+__device__ __forceinline__ void traces_eo_nb(const EOParams<T, n> &Q, const T (&u)[NB][n], T (&G0)[NB], T (&G1)[NB]) {
+  constexpr int NE = (n + 1) / 2, NO = n / 2;
+  T gs[NB], gd[NB];
+  {
+    const T c = Q.gE[NE - 1];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) gs[b] = c * ((n & 1) ? u[b][NE - 1] : (u[b][NE - 1] + u[b][n - NE]));
+  }
+#pragma unroll
+  for (int l = 0; l < NE - 1; ++l) {
+    const T c = Q.gE[l];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) gs[b] = fma(c, u[b][l] + u[b][n - 1 - l], gs[b]);
+  }
+#pragma unroll
+  for (int l = 0; l < NO; ++l) {
+    const T c = Q.gO[l];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) gd[b] = l == 0 ? c * (u[b][l] - u[b][n - 1 - l]) : fma(c, u[b][l] - u[b][n - 1 - l], gd[b]);
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) { G0[b] = gs[b] + gd[b]; G1[b] = gs[b] - gd[b]; }
+}
+// out[b] += K' [u[b]; V0', G0', V1', G1'] for NB lines of direction d (nv[b] = V0', G0', V1', G1')
+template <int n, typename T, int NB>
+__device__ __forceinline__ void lines_eo_nb(const EOParams<T, n> &Q, const int d, const T (&u)[NB][n], const T (&nv)[NB][4], T (&out)[NB][n]) {
+  constexpr int NE = (n + 1) / 2, NO = n / 2;
+  T e[NB][NE], o[NB][NO > 0 ? NO : 1], ve[NB], vo[NB], ge[NB], go[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+#pragma unroll
+    for (int l = 0; l < NO; ++l) { e[b][l] = u[b][l] + u[b][n - 1 - l]; o[b][l] = u[b][l] - u[b][n - 1 - l]; }
+    if (n & 1) e[b][NE - 1] = u[b][NE - 1];
+    ve[b] = nv[b][0] + nv[b][2]; vo[b] = nv[b][0] - nv[b][2]; ge[b] = nv[b][1] + nv[b][3]; go[b] = nv[b][1] - nv[b][3];
+  }
+#pragma unroll
+  for (int i = 0; i < NE; ++i) {
+    const bool mid = (n & 1) && i == NE - 1;
+    T s[NB], dd[NB];
+    {
+      const T c = Q.KEv[d][i];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) s[b] = mid ? fma(c, ve[b], out[b][i]) : c * ve[b];
+    }
+    {
+      const T c = Q.KEg[d][i];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) s[b] = fma(c, ge[b], s[b]);
+    }
+#pragma unroll
+    for (int l = 0; l < NE; ++l) {
+      const T c = Q.KE[d][i][l];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) s[b] = fma(c, e[b][l], s[b]);
+    }
+    if (mid) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b) out[b][i] = s[b];
+      continue;
+    }
+    {
+      const T c = Q.KOv[d][i];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) dd[b] = c * vo[b];
+    }
+    {
+      const T c = Q.KOg[d][i];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) dd[b] = fma(c, go[b], dd[b]);
+    }
+#pragma unroll
+    for (int l = 0; l < NO; ++l) {
+      const T c = Q.KO[d][i][l];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) dd[b] = fma(c, o[b][l], dd[b]);
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) { out[b][i] = (out[b][i] + s[b]) + dd[b]; out[b][n - 1 - i] = (out[b][n - 1 - i] + s[b]) - dd[b]; }
+  }
+}
+// out[b] = (h M) q[b] for NB lines of direction d
+template <int n, typename T, int NB>
+__device__ __forceinline__ void mass_eo_nb(const EOParams<T, n> &Q, const int d, const T (&q)[NB][n], T (&out)[NB][n]) {
+  constexpr int NE = (n + 1) / 2, NO = n / 2;
+  T e[NB][NE], o[NB][NO > 0 ? NO : 1];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+#pragma unroll
+    for (int l = 0; l < NO; ++l) { e[b][l] = q[b][l] + q[b][n - 1 - l]; o[b][l] = q[b][l] - q[b][n - 1 - l]; }
+    if (n & 1) e[b][NE - 1] = q[b][NE - 1];
+  }
+#pragma unroll
+  for (int i = 0; i < NE; ++i) {
+    const bool mid = (n & 1) && i == NE - 1;
+    T s[NB], dd[NB];
+#pragma unroll
+    for (int l = 0; l < NE; ++l) {
+      const T c = Q.ME[d][i][l];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) s[b] = l == 0 ? c * e[b][l] : fma(c, e[b][l], s[b]);
+    }
+    if (mid) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b) out[b][i] = s[b];
+      continue;
+    }
+#pragma unroll
+    for (int l = 0; l < NO; ++l) {
+      const T c = Q.MO[d][i][l];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) dd[b] = l == 0 ? c * o[b][l] : fma(c, o[b][l], dd[b]);
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) { out[b][i] = s[b] + dd[b]; out[b][n - 1 - i] = s[b] - dd[b]; }
+  }
+}
+
 template <int n, typename T, bool EO, int XYV>
 __global__ void __launch_bounds__(Roles2<n>::NW * 32, 1)
 pressure_march2_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_constant__ EOParams<T, n> Q, const __grid_constant__ FastGeom G,
@@ -325,50 +446,141 @@ pressure_march2_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_
       const T *Up = U + (size_t)(p % NS) * TC * ND + c * ND + k * NL;
       const T *hb = HXY + (size_t)st * HBUF;
       mbar_wait_sleep(&ubar[p % NS], (unsigned)((p / NS) & 1));
-      if constexpr (XYV == 1) {
-        // streaming form: only the x results stay in registers; u rows / columns are read from the stage when needed
+      if constexpr (XYV == 2) {
+        // Lockstep form (even-odd only): the n rows, then the n columns of the layer go through the batched line operators
+        // in groups of 3 + 2 lines; only the x results (xr) stay in registers between the two passes.
+        static_assert(XYV != 2 || EO, "the lockstep form is written for the even-odd tables");
         mbar_wait_sleep(&full[st], (unsigned)((p >> 1) & 1));
         T xr[n][n];
+        auto batch = [&](auto isrow_c, auto a0_c, auto nb_c) {
+          constexpr bool isrow = decltype(isrow_c)::value;
+          constexpr int a0 = decltype(a0_c)::value, NB = decltype(nb_c)::value;
+          T u[NB][n], out[NB][n], g0[NB], g1[NB], nv[NB][4];
+          P2 h0[NB], h1[NB];
 #pragma unroll
-        for (int jj = 0; jj < n; ++jj) {   // x lines: row jj = face point jj
-          T row[n], g0, g1;
+          for (int b = 0; b < NB; ++b) {
 #pragma unroll
-          for (int i = 0; i < n; ++i) { row[i] = Up[jj * n + i]; xr[jj][i] = Wp[jj * n + i]; }
-          line_traces<n, T, EO>(P, Q, row, g0, g1);
-          T v0 = __shfl_sync(0xffffffffu, row[n - 1], lxm), w0 = __shfl_sync(0xffffffffu, g1, lxm);
-          T v1 = __shfl_sync(0xffffffffu, row[0], lxp), w1 = __shfl_sync(0xffffffffu, g0, lxp);
-          { const P2 t = *reinterpret_cast<const P2 *>(hb + hx0 + 2 * jj); v0 = ex0 ? t.x : v0; w0 = ex0 ? t.y : w0; }
-          { const P2 t = *reinterpret_cast<const P2 *>(hb + hx1 + 2 * jj); v1 = ex1 ? t.x : v1; w1 = ex1 ? t.y : w1; }
-          if constexpr (EO) line_eo<n, T, true>(Q, 0, row, v0, w0, v1, w1, xr[jj]);
-          else line_plain<n, T, true>(P.Kt[0], P.cV[0][0], P.cG[0][0], P.cV[0][1], P.cG[0][1], row, v0, w0, v1, w1, xr[jj]);
+            for (int l = 0; l < n; ++l) u[b][l] = isrow ? Up[(a0 + b) * n + l] : Up[l * n + a0 + b];
+#pragma unroll
+            for (int l = 0; l < n; ++l) out[b][l] = isrow ? Wp[(a0 + b) * n + l] : xr[l][a0 + b];
+            h0[b] = *reinterpret_cast<const P2 *>(hb + (isrow ? hx0 : hy0) + 2 * (a0 + b));
+            h1[b] = *reinterpret_cast<const P2 *>(hb + (isrow ? hx1 : hy1) + 2 * (a0 + b));
+          }
+          traces_eo_nb<n, T, NB>(Q, u, g0, g1);
+          const int lm = isrow ? lxm : lym, lp = isrow ? lxp : lyp;
+          const bool e0 = isrow ? ex0 : ey0, e1 = isrow ? ex1 : ey1;
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            const T v0 = __shfl_sync(0xffffffffu, u[b][n - 1], lm), w0 = __shfl_sync(0xffffffffu, g1[b], lm);
+            const T v1 = __shfl_sync(0xffffffffu, u[b][0], lp), w1 = __shfl_sync(0xffffffffu, g0[b], lp);
+            nv[b][0] = e0 ? h0[b].x : v0; nv[b][1] = e0 ? h0[b].y : w0;
+            nv[b][2] = e1 ? h1[b].x : v1; nv[b][3] = e1 ? h1[b].y : w1;
+          }
+          lines_eo_nb<n, T, NB>(Q, isrow ? 0 : 1, u, nv, out);
+          if constexpr (isrow) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+#pragma unroll
+              for (int l = 0; l < n; ++l) xr[a0 + b][l] = out[b][l];
+          } else {
+            T res[NB][n];
+            mass_eo_nb<n, T, NB>(Q, 1, out, res);   // mass in y (the Z warps apply Mx and Mz)
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+#pragma unroll
+              for (int l = 0; l < n; ++l) Wp[l * n + a0 + b] = res[b][l];
+          }
+        };
+        constexpr int NB1 = (n + 1) / 2, NB2 = n - NB1;
+        batch(std::true_type{}, std::integral_constant<int, 0>{}, std::integral_constant<int, NB1>{});
+        batch(std::true_type{}, std::integral_constant<int, NB1>{}, std::integral_constant<int, NB2>{});
+        batch(std::false_type{}, std::integral_constant<int, 0>{}, std::integral_constant<int, NB1>{});
+        batch(std::false_type{}, std::integral_constant<int, NB1>{}, std::integral_constant<int, NB2>{});
+        // all reads of the stage are done (the W stores above depend on them): the last XY warp refills it
+        {
+          __syncwarp();
+          int last = 0;
+          if (lane == 0) {
+            const int old = atomicAdd(&ucnt[p % NS], 1);
+            if (old == R::NXY - 1) { ucnt[p % NS] = 0; last = 1; }
+          }
+          last = __shfl_sync(0xffffffffu, last, 0);
+          if (last && p + NS < NZ) issue_plane(p + NS);
         }
+      } else if constexpr (XYV == 1) {
+        // Streaming form: only the x results stay in registers (xr); the 2 n lines of the layer (n rows, then n columns) are
+        // read from the stage when needed and go through an explicit 3-stage software pipeline, so that the loads of line
+        // t + 2 and the trace exchange of line t + 1 are in flight while line t is in the FP64 pipe:
+        //   A(t + 2): u line, W row (rows only), halo pairs        B(t + 1): own traces, shuffles, tile-edge select
+        //   C(t):     line operator (+ mass in y and the store for columns)
+        mbar_wait_sleep(&full[st], (unsigned)((p >> 1) & 1));
+        T xr[n][n];
+        T ln[3][n], wr[3][n];       // u line / W row of the lines in flight
+        P2 hp[3][2];                // halo pairs (V', G') of the two sides
+        T nv[2][4];                 // neighbour traces v0, w0, v1, w1 of the lines in stages B / C
+        auto stageA = [&](int t, int s) {
+          const bool isrow = t < n;
+          const int a = isrow ? t : t - n;
 #pragma unroll
-        for (int i = 0; i < n; ++i) {      // y lines: column i = face point i
-          T out[n], col[n], g0, g1;
+          for (int l = 0; l < n; ++l) ln[s][l] = isrow ? Up[a * n + l] : Up[l * n + a];
+          if (isrow) {
 #pragma unroll
-          for (int l = 0; l < n; ++l) { out[l] = xr[l][i]; col[l] = Up[l * n + i]; }
-          line_traces<n, T, EO>(P, Q, col, g0, g1);
-          T v0 = __shfl_sync(0xffffffffu, col[n - 1], lym), w0 = __shfl_sync(0xffffffffu, g1, lym);
-          T v1 = __shfl_sync(0xffffffffu, col[0], lyp), w1 = __shfl_sync(0xffffffffu, g0, lyp);
-          { const P2 t = *reinterpret_cast<const P2 *>(hb + hy0 + 2 * i); v0 = ey0 ? t.x : v0; w0 = ey0 ? t.y : w0; }
-          { const P2 t = *reinterpret_cast<const P2 *>(hb + hy1 + 2 * i); v1 = ey1 ? t.x : v1; w1 = ey1 ? t.y : w1; }
-          if constexpr (EO) line_eo<n, T, true>(Q, 1, col, v0, w0, v1, w1, out);
-          else line_plain<n, T, true>(P.Kt[1], P.cV[1][0], P.cG[1][0], P.cV[1][1], P.cG[1][1], col, v0, w0, v1, w1, out);
-          T res[n];
-          line_mass<n, T, EO>(P, Q, 1, out, res);   // mass in y (the Z warps apply Mx and Mz)
+            for (int l = 0; l < n; ++l) wr[s][l] = Wp[a * n + l];
+          }
+          hp[s][0] = *reinterpret_cast<const P2 *>(hb + (isrow ? hx0 : hy0) + 2 * a);
+          hp[s][1] = *reinterpret_cast<const P2 *>(hb + (isrow ? hx1 : hy1) + 2 * a);
+        };
+        auto stageB = [&](int t, int s, int s2) {
+          const bool isrow = t < n;
+          T g0, g1;
+          line_traces<n, T, EO>(P, Q, ln[s], g0, g1);
+          const int lm = isrow ? lxm : lym, lp = isrow ? lxp : lyp;
+          const bool e0 = isrow ? ex0 : ey0, e1 = isrow ? ex1 : ey1;
+          const T v0 = __shfl_sync(0xffffffffu, ln[s][n - 1], lm), w0 = __shfl_sync(0xffffffffu, g1, lm);
+          const T v1 = __shfl_sync(0xffffffffu, ln[s][0], lp), w1 = __shfl_sync(0xffffffffu, g0, lp);
+          nv[s2][0] = e0 ? hp[s][0].x : v0; nv[s2][1] = e0 ? hp[s][0].y : w0;
+          nv[s2][2] = e1 ? hp[s][1].x : v1; nv[s2][3] = e1 ? hp[s][1].y : w1;
+        };
+        auto stageC = [&](int t, int s, int s2) {
+          const bool isrow = t < n;
+          const int a = isrow ? t : t - n;
+          T out[n];
 #pragma unroll
-          for (int l = 0; l < n; ++l) Wp[l * n + i] = res[l];
+          for (int l = 0; l < n; ++l) out[l] = isrow ? wr[s][l] : xr[l][a];
+          if constexpr (EO) line_eo<n, T, true>(Q, isrow ? 0 : 1, ln[s], nv[s2][0], nv[s2][1], nv[s2][2], nv[s2][3], out);
+          else {
+            const int d = isrow ? 0 : 1;
+            line_plain<n, T, true>(P.Kt[d], P.cV[d][0], P.cG[d][0], P.cV[d][1], P.cG[d][1], ln[s], nv[s2][0], nv[s2][1], nv[s2][2], nv[s2][3], out);
+          }
+          if (isrow) {
+#pragma unroll
+            for (int l = 0; l < n; ++l) xr[a][l] = out[l];
+          } else {
+            T res[n];
+            line_mass<n, T, EO>(P, Q, 1, out, res);   // mass in y (the Z warps apply Mx and Mz)
+#pragma unroll
+            for (int l = 0; l < n; ++l) Wp[l * n + a] = res[l];
+          }
+        };
+        stageA(0, 0);
+        stageA(1, 1);
+        stageB(0, 0, 0);
+#pragma unroll
+        for (int t = 0; t < 2 * n; ++t) {
+          if (t + 2 < 2 * n) stageA(t + 2, (t + 2) % 3);
+          if (t + 1 < 2 * n) stageB(t + 1, (t + 1) % 3, (t + 1) & 1);
+          stageC(t, t % 3, t & 1);
         }
         // all reads of the stage are done (the W stores above depend on them): the last XY warp refills it
         {
-        __syncwarp();
-        int last = 0;
-        if (lane == 0) {
-          const int old = atomicAdd(&ucnt[p % NS], 1);
-          if (old == R::NXY - 1) { ucnt[p % NS] = 0; last = 1; }
-        }
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (last && p + NS < NZ) issue_plane(p + NS);
+          __syncwarp();
+          int last = 0;
+          if (lane == 0) {
+            const int old = atomicAdd(&ucnt[p % NS], 1);
+            if (old == R::NXY - 1) { ucnt[p % NS] = 0; last = 1; }
+          }
+          last = __shfl_sync(0xffffffffu, last, 0);
+          if (last && p + NS < NZ) issue_plane(p + NS);
         }
       } else {
       T u[n][n];

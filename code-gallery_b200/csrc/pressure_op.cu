@@ -11,6 +11,7 @@
 #include <cstdlib>
 
 #include "pressure_op.cuh"
+#include "reduce.cuh"
 
 namespace dgx {
 
@@ -183,7 +184,9 @@ pressure_generic_kernel(const __grid_constant__ PresParams<T, n> P, const int *_
 template <int dim, int n, typename T>
 __global__ void __launch_bounds__(cells_per_block<dim, n>() * ipow(n, dim - 1))
 pressure_coarse_cg_kernel(const __grid_constant__ PresParams<T, n> P, const int *nbr, int n_cells, const T *b, T *x, T *r, T *p, T *v,
-                          double tol, int max_it, int *info, double *res_out) {
+                          const double *tol_ptr, int max_it, int *info, double *res_out, int *log_count, int log_cap) {
+  // tolerance and log slot come from device memory: the launch is identical from solve to solve (CUDA-graph replay)
+  const double tol = *tol_ptr;
   constexpr int NL = ipow(n, dim - 1), ND = NL * n, CPB = cells_per_block<dim, n>(), NT = CPB * NL;
   __shared__ T su[CPB * row_stride<n>() * NL];
   __shared__ T sa[CPB * row_stride<n>() * NL];
@@ -191,7 +194,7 @@ pressure_coarse_cg_kernel(const __grid_constant__ PresParams<T, n> P, const int 
   __shared__ double bc;
   const int tid = threadIdx.x, N = n_cells * ND;
   auto block_sum = [&](double val) -> double {
-    for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(0xffffffffu, val, o);
+    val = warp_sum_existing(val);   // NT is not a multiple of 32 for most degrees
     __syncthreads();
     if ((tid & 31) == 0) red[tid >> 5] = val;
     __syncthreads();
@@ -237,7 +240,10 @@ pressure_coarse_cg_kernel(const __grid_constant__ PresParams<T, n> P, const int 
     res = sqrt(rr);
     conv = res <= tol;
   }
-  if (tid == 0) { info[0] = it; info[1] = conv ? 1 : 0; res_out[0] = res; }
+  if (tid == 0) {   // append to the device-side log: (iterations, converged), residual
+    const int slot = atomicAdd(log_count, 1) % log_cap;
+    info[2 * slot] = it; info[2 * slot + 1] = conv ? 1 : 0; res_out[slot] = res;
+  }
 }
 
 // Inverse "diagonal" exactly as the reference probes it (NS.cc:1857-2008): the interior-face probe sets
@@ -379,34 +385,35 @@ int diag_by_degree(int degree, dgx_op *op, dgx_vec *out) {
 }  // namespace
 
 template <int dim, int n, typename T>
-int launch_coarse_cg(dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_vec *r, dgx_vec *p, dgx_vec *v, double tol, int max_it, int *d_info, double *d_res) {
+int launch_coarse_cg(dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_vec *r, dgx_vec *p, dgx_vec *v, const double *d_tol, int max_it, int *d_info, double *d_res, int *d_count, int log_cap) {
   dgx_mf *mf = op->mf;
   PresParams<T, n> P;
   fill_pres_params<T, n>(P, op, pressure_kappa(op));
   constexpr int CPB = cells_per_block<dim, n>(), NT = CPB * ipow(n, dim - 1);
   pressure_coarse_cg_kernel<dim, n, T><<<1, NT, 0, mf->ctx->stream>>>(P, mf->d_nbr, (int)mf->n_owned, (const T *)b->d, (T *)x->d, (T *)r->d, (T *)p->d,
-                                                                      (T *)v->d, tol, max_it, d_info, d_res);
+                                                                      (T *)v->d, d_tol, max_it, d_info, d_res, d_count, log_cap);
   count_launch();
   DGX_CUDA_CHECK(cudaGetLastError());
   return DGX_OK;
 }
 
 template <int dim, typename T>
-int coarse_by_degree(int degree, dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_vec *r, dgx_vec *p, dgx_vec *v, double tol, int max_it, int *d_info, double *d_res) {
-#define CALL(N) launch_coarse_cg<dim, N, T>(op, x, b, r, p, v, tol, max_it, d_info, d_res)
+int coarse_by_degree(int degree, dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_vec *r, dgx_vec *p, dgx_vec *v, const double *d_tol, int max_it, int *d_info, double *d_res, int *d_count, int log_cap) {
+#define CALL(N) launch_coarse_cg<dim, N, T>(op, x, b, r, p, v, d_tol, max_it, d_info, d_res, d_count, log_cap)
   DGX_DEGREE_SWITCH(CALL)
 #undef CALL
 }
 
-// single-CTA coarse solve; DGX_ERR_UNSUPPORTED when the level is not tiny / not on one rank (caller falls back to cg_core)
-int pressure_coarse_cg(dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_vec *r, dgx_vec *p, dgx_vec *v, double tol, int max_it, int *d_info, double *d_res) {
+// single-CTA coarse solve; DGX_ERR_UNSUPPORTED when the level is not tiny / neither on one rank nor replicated on all ranks
+// (caller falls back to cg_core)
+int pressure_coarse_cg(dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_vec *r, dgx_vec *p, dgx_vec *v, const double *d_tol, int max_it, int *d_info, double *d_res, int *d_count, int log_cap) {
   dgx_mf *mf = op->mf;
-  if (op->kind != DGX_OP_PRESSURE || mf->ctx->nranks != 1 || mf->n_ghost != 0 || mf->n_owned < 1 || mf->n_owned > 64) return DGX_ERR_UNSUPPORTED;
+  if (op->kind != DGX_OP_PRESSURE || (mf->ctx->nranks != 1 && !mf->replicated) || mf->n_ghost != 0 || mf->n_owned < 1 || mf->n_owned > 64) return DGX_ERR_UNSUPPORTED;
   const int degree = op->degree;
-  if (mf->dim == 2) return mf->dtype == DGX_F64 ? coarse_by_degree<2, double>(degree, op, x, b, r, p, v, tol, max_it, d_info, d_res)
-                                                 : coarse_by_degree<2, float>(degree, op, x, b, r, p, v, tol, max_it, d_info, d_res);
-  return mf->dtype == DGX_F64 ? coarse_by_degree<3, double>(degree, op, x, b, r, p, v, tol, max_it, d_info, d_res)
-                              : coarse_by_degree<3, float>(degree, op, x, b, r, p, v, tol, max_it, d_info, d_res);
+  if (mf->dim == 2) return mf->dtype == DGX_F64 ? coarse_by_degree<2, double>(degree, op, x, b, r, p, v, d_tol, max_it, d_info, d_res, d_count, log_cap)
+                                                 : coarse_by_degree<2, float>(degree, op, x, b, r, p, v, d_tol, max_it, d_info, d_res, d_count, log_cap);
+  return mf->dtype == DGX_F64 ? coarse_by_degree<3, double>(degree, op, x, b, r, p, v, d_tol, max_it, d_info, d_res, d_count, log_cap)
+                              : coarse_by_degree<3, float>(degree, op, x, b, r, p, v, d_tol, max_it, d_info, d_res, d_count, log_cap);
 }
 
 int pressure_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) {

@@ -46,11 +46,19 @@ struct dgx_mg {
   std::vector<int> coarse_its;               // iterations of every coarse solve of the last outer solve
   // coarse CG work vectors
   dgx_vec *cg_r = nullptr, *cg_p = nullptr, *cg_v = nullptr;
-  // device-side log of the single-CTA coarse solves since the last setup: (iterations, converged) pairs, residuals
+  // device-side log of the single-CTA coarse solves: ring of (iterations, converged) pairs and residuals, appended by the
+  // kernel itself through d_count (so that a replayed CUDA graph logs too); the tolerance is read from d_tol
   static constexpr int kLog = 8192;
-  int *d_info = nullptr;
-  double *d_res = nullptr;
-  int n_dev_solves = 0;
+  int *d_info = nullptr, *d_count = nullptr;
+  double *d_res = nullptr, *d_tol = nullptr;
+  long long log_seen = 0;                    // entries already checked for convergence
+  long long log_setup = 0;                   // log position at the last setup (dgx_mg_coarse_iterations reports from here)
+  // the V-cycle as a CUDA graph per (stage, dt, estimate generation): launch sequence and kernel arguments are identical from
+  // one application to the next (defect / solution / work vectors are owned by this object)
+  struct CycleGraph { int stage; double dt; unsigned long long gen; int warm = 0; cudaGraphExec_t exec = nullptr; long long launches = 0; };
+  std::vector<CycleGraph> graphs;
+  unsigned long long est_gen = 0;            // bumped whenever smoother estimates are recomputed (they are kernel arguments)
+  bool graphs_ok = true;
   // Chebyshev eigenvalue estimates per (TR_BDF2 stage, dt): they depend on nothing else (the level operators are fixed by the
   // mesh, kappa(stage, dt) and the degree), so a time loop pays the 10 CG iterations per level once per stage, not per solve
   struct EigKey { int stage; double dt; };
@@ -59,7 +67,12 @@ struct dgx_mg {
   int last_setup_cached = 0;
 };
 
+extern "C" int mg_check_coarse_log(dgx_mg *mg);
+extern "C" int mg_cycle(dgx_mg *mg);
+
 namespace {
+
+__global__ void set_scalar_kernel(double *p, double v) { *p = v; }
 
 constexpr int kThreads = 256;
 inline int grid_for(long long n, int per_thread = 4) {
@@ -183,16 +196,33 @@ int transfer(bool prolong, dgx_vec *dst, const dgx_vec *src) {
   DGX_REQUIRE(fine->mf->level == coarse->mf->level + 1 && fine->mf->mesh == coarse->mf->mesh, "vectors must live on consecutive levels of one mesh");
   DGX_REQUIRE(fine->degree == coarse->degree && fine->ncomp == 1 && coarse->ncomp == 1 && fine->dtype == coarse->dtype, "transfer: scalar spaces of equal degree and number type");
   const int dim = fine->mf->dim, nc = 1 << dim;
-  if (fine->mf->first_cell != coarse->mf->first_cell * nc || fine->mf->n_owned != coarse->mf->n_owned * nc) {
+  // the parents of this rank's fine cells: the coarse cells [par_first, par_first + np) in global numbering
+  if (fine->mf->first_cell % nc != 0 || fine->mf->n_owned % nc != 0) {
+    set_error("transfer: the owned fine cells must be whole families of children");
+    return DGX_ERR_UNSUPPORTED;
+  }
+  const long long par_first = fine->mf->first_cell / nc, np = fine->mf->n_owned / nc;
+  // coarse side: distributed with the same cut (parents owned here), or replicated (every rank holds all coarse cells)
+  const bool gather = coarse->mf->replicated && !fine->mf->replicated;
+  if (!gather && (coarse->mf->first_cell != par_first || coarse->mf->n_owned != np)) {
     set_error("transfer: children of an owned parent cell must be owned by the same rank");
     return DGX_ERR_UNSUPPORTED;
   }
   dgx_ctx *ctx = fine->mf->ctx;
-  const long long np = coarse->mf->n_owned;
-  if (dim == 2) return fine->dtype == DGX_F64 ? transfer_by_degree<2, double>(fine->degree, ctx, prolong, np, dst->d, src->d)
-                                              : transfer_by_degree<2, float>(fine->degree, ctx, prolong, np, dst->d, src->d);
-  return fine->dtype == DGX_F64 ? transfer_by_degree<3, double>(fine->degree, ctx, prolong, np, dst->d, src->d)
-                                : transfer_by_degree<3, float>(fine->degree, ctx, prolong, np, dst->d, src->d);
+  const long long coarse_off = (par_first - coarse->mf->first_cell) * coarse->dofs_per_cell;   // 0 unless the coarse level is replicated
+  const size_t es = coarse->elem();
+  void *dptr = prolong ? dst->d : (char *)dst->d + (size_t)coarse_off * es;
+  const void *sptr = prolong ? (const char *)src->d + (size_t)coarse_off * es : src->d;
+  int rc;
+  if (dim == 2) rc = fine->dtype == DGX_F64 ? transfer_by_degree<2, double>(fine->degree, ctx, prolong, np, dptr, sptr)
+                                            : transfer_by_degree<2, float>(fine->degree, ctx, prolong, np, dptr, sptr);
+  else rc = fine->dtype == DGX_F64 ? transfer_by_degree<3, double>(fine->degree, ctx, prolong, np, dptr, sptr)
+                                   : transfer_by_degree<3, float>(fine->degree, ctx, prolong, np, dptr, sptr);
+  if (rc || prolong || !gather) return rc;
+  // restriction into a replicated level: every rank has filled the piece of its own parents; one all-gather completes the
+  // vector on all ranks (equal pieces: the fine level is cut into equal chunks).  Nothing is sent on the way up.
+  DGX_REQUIRE(np * ctx->nranks == coarse->mf->n_owned && par_first == np * ctx->rank, "transfer: unequal pieces in the gather to a replicated level");
+  return allgather_inplace(ctx, dst->d, (size_t)np * coarse->dofs_per_cell * es);
 }
 
 int cheb_update(dgx_vec *out, const dgx_vec *x, const dgx_vec *xold, const dgx_vec *d, const dgx_vec *rhs, const dgx_vec *t, double a, double b, double c) {
@@ -466,9 +496,33 @@ int dgx_mg_create(dgx_ctx *ctx, dgx_mesh *mesh, int degree, int level_dtype, dou
   auto *mg = new dgx_mg();
   mg->ctx = ctx; mg->mesh = mesh; mg->degree = degree; mg->Re = Re; mg->dt = dt;
   mg->n_levels = mesh->m.n_refine + 1;
+  // Level distribution over the ranks.  A level is cut into equal contiguous chunks of the hierarchical order when every chunk
+  // is a set of whole families of children (so that restriction / prolongation stay on the rank) and the level is large enough
+  // to be worth a ghost exchange per operator application; all coarser levels are REPLICATED: every rank holds them entirely
+  // and computes them redundantly (one all-gather on the way down, no communication on these levels or on the way up).
+  // DGX_MG_REPLICATE_MAX = largest number of cells of a replicated level (default 32^3: an operator application on such a
+  // level costs less than the latency of one exchange).
+  std::vector<bool> replicated(mg->n_levels, false);
+  if (ctx->nranks > 1) {
+    const char *env = getenv("DGX_MG_REPLICATE_MAX");
+    const long long rep_max = env ? atoll(env) : 32768;
+    const long long nc = 1LL << mesh->m.dim, R = ctx->nranks;
+    bool coarser_distributed = false;
+    for (int l = 0; l < mg->n_levels; ++l) {
+      const long long N = mesh->m.n_cells(l);
+      // whole families per chunk; the coarsest distributed level only needs equal chunks of whole families towards its own children
+      const bool cut_ok = N % R == 0 && (l == 0 || (N / R) % nc == 0);
+      replicated[l] = !coarser_distributed && (!cut_ok || N <= rep_max);
+      if (!replicated[l]) {
+        if (!cut_ok) { delete mg; set_error("multigrid: level " + std::to_string(l) + " cannot be cut into whole families of children over " + std::to_string(R) + " ranks"); return DGX_ERR_UNSUPPORTED; }
+        coarser_distributed = true;
+      }
+    }
+    if (replicated[mg->n_levels - 1] && mesh->m.n_cells(mg->n_levels - 1) % R == 0) replicated[mg->n_levels - 1] = false;   // the caller's fine vectors are distributed
+  }
   for (int l = 0; l < mg->n_levels; ++l) {
     dgx_mf *mf = nullptr; dgx_op *op = nullptr; dgx_vec *a = nullptr, *b = nullptr, *c = nullptr; dgx_cheb *sm = nullptr;
-    int rc = dgx_mf_create(ctx, mesh, l, level_dtype, &mf);                       // NS.cc:2353-2375
+    int rc = mf_create(ctx, mesh, l, level_dtype, replicated[l], &mf);            // NS.cc:2353-2375
     if (!rc) rc = dgx_op_create(mf, DGX_OP_PRESSURE, degree, Re, dt, &op);        // NS.cc:2376-2379
     if (!rc) rc = dgx_vec_create(mf, degree, 1, &a);
     if (!rc) rc = dgx_vec_create(mf, degree, 1, &b);
@@ -481,16 +535,22 @@ int dgx_mg_create(dgx_ctx *ctx, dgx_mesh *mesh, int degree, int level_dtype, dou
   if (!rc) rc = dgx_vec_create(mg->mf[0], degree, 1, &mg->cg_p);
   if (!rc) rc = dgx_vec_create(mg->mf[0], degree, 1, &mg->cg_v);
   if (rc) { delete mg; return rc; }
-  if (cudaMalloc(&mg->d_info, 2 * dgx_mg::kLog * sizeof(int)) != cudaSuccess || cudaMalloc(&mg->d_res, dgx_mg::kLog * sizeof(double)) != cudaSuccess) {
+  if (cudaMalloc(&mg->d_info, (2 * dgx_mg::kLog + 1) * sizeof(int)) != cudaSuccess || cudaMalloc(&mg->d_res, (dgx_mg::kLog + 1) * sizeof(double)) != cudaSuccess) {
     cudaGetLastError();
     mg->d_info = nullptr;   // fall back to the host-sequenced coarse solve
+  } else {
+    mg->d_count = mg->d_info + 2 * dgx_mg::kLog;
+    mg->d_tol = mg->d_res + dgx_mg::kLog;
+    cudaMemsetAsync(mg->d_count, 0, sizeof(int), ctx->stream);
   }
+  mg->graphs_ok = getenv("DGX_NO_MG_GRAPH") == nullptr;
   *out = mg;
   return DGX_OK;
 }
 
 int dgx_mg_destroy(dgx_mg *mg) {
   if (!mg) return DGX_OK;
+  for (auto &g : mg->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (mg->d_info) cudaFree(mg->d_info);
   if (mg->d_res) cudaFree(mg->d_res);
   for (dgx_vec *v : {mg->cg_r, mg->cg_p, mg->cg_v}) dgx_vec_destroy(v);
@@ -523,10 +583,16 @@ int dgx_mg_set_TR_BDF2_stage(dgx_mg *mg, int stage) {   // NS.cc:2941-2943, 2967
 // what projection_step rebuilds before every solve (NS.cc:2490-2517): level diagonals, smoother eigenvalue estimates
 int dgx_mg_setup(dgx_mg *mg, double coarse_abs_tol, int coarse_max_it) {
   DGX_REQUIRE(mg, "null argument");
+  if (coarse_max_it != mg->coarse_max_it) ++mg->est_gen;   // a kernel argument of the captured cycle
   mg->coarse_tol = coarse_abs_tol;
   mg->coarse_max_it = coarse_max_it;
   mg->coarse_its.clear();
-  mg->n_dev_solves = 0;
+  if (mg->d_info) {
+    RC(mg_check_coarse_log(mg));   // also brings log_seen up to date
+    mg->log_setup = mg->log_seen;
+    set_scalar_kernel<<<1, 1, 0, mg->ctx->stream>>>(mg->d_tol, coarse_abs_tol);
+    count_launch();
+  }
   const std::vector<std::array<double, 4>> *hit = nullptr;
   if (mg->cache_estimates)
     for (auto &e : mg->eig_cache)
@@ -546,6 +612,7 @@ int dgx_mg_setup(dgx_mg *mg, double coarse_abs_tol, int coarse_max_it) {
       fresh[l] = {c->min_eig_est, c->max_eig_est, c->theta, c->delta};
     }
   }
+  if (!hit) ++mg->est_gen;
   if (!hit && mg->cache_estimates) mg->eig_cache.push_back({{mg->stage, mg->dt}, fresh});
   return DGX_OK;
 }
@@ -563,12 +630,12 @@ static int mg_level(dgx_mg *mg, int l) {
   // input: defect[l]; output: sol[l]        (Multigrid::level_v_step)
   if (l == 0) {
     if (mg->d_info) {   // tiny level: the whole CG runs inside one CTA (no host round trips)
-      const int slot = mg->n_dev_solves % dgx_mg::kLog;
-      int rc = pressure_coarse_cg(mg->op[0], mg->sol[0], mg->defect[0], mg->cg_r, mg->cg_p, mg->cg_v, mg->coarse_tol, mg->coarse_max_it,
-                                  mg->d_info + 2 * slot, mg->d_res + slot);
-      if (rc == DGX_OK) { ++mg->n_dev_solves; return DGX_OK; }
+      int rc = pressure_coarse_cg(mg->op[0], mg->sol[0], mg->defect[0], mg->cg_r, mg->cg_p, mg->cg_v, mg->d_tol, mg->coarse_max_it, mg->d_info, mg->d_res,
+                                  mg->d_count, dgx_mg::kLog);
+      if (rc == DGX_OK) return DGX_OK;
       if (rc != DGX_ERR_UNSUPPORTED) return rc;
     }
+    mg->graphs_ok = false;   // the host-sequenced coarse solve synchronises: the cycle cannot be captured
     RC(dgx_vec_set(mg->sol[0], 0.0));
     Precond pc;   // identity
     int its = 0; double res = 0;
@@ -593,26 +660,96 @@ static int mg_level(dgx_mg *mg, int l) {
   return dgx_cheb_step(mg->smoother[l], mg->sol[l], mg->defect[l]);                 // post-smoothing
 }
 
+// One V-cycle defect[L] -> sol[L].  The first application of a (stage, dt, estimates) combination runs eagerly (it allocates
+// pooled work vectors and send buffers), the second one is captured into a CUDA graph, all later ones replay it: one graph
+// launch instead of ~60 kernel launches, NCCL ghost exchanges and the all-gather included.  DGX_NO_MG_GRAPH=1 disables it.
+int mg_cycle(dgx_mg *mg) {
+  const int L = mg->n_levels - 1;
+  if (!mg->graphs_ok) return mg_level(mg, L);
+  dgx_mg::CycleGraph *g = nullptr;
+  for (auto &e : mg->graphs)
+    if (e.stage == mg->stage && e.dt == mg->dt && e.gen == mg->est_gen) g = &e;
+  if (!g) {
+    if (mg->graphs.size() > 16) {   // stale entries (estimates recomputed on every setup): keep the table short
+      for (auto &e : mg->graphs) if (e.exec) cudaGraphExecDestroy(e.exec);
+      mg->graphs.clear();
+    }
+    dgx_mg::CycleGraph e;
+    e.stage = mg->stage; e.dt = mg->dt; e.gen = mg->est_gen;
+    mg->graphs.push_back(e);
+    g = &mg->graphs.back();
+  }
+  cudaStream_t st = mg->ctx->stream;
+  if (g->warm == 0) { g->warm = 1; return mg_level(mg, L); }
+  if (!g->exec) {
+    const long long l0 = g_launch_count;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); mg->graphs_ok = false; return mg_level(mg, L); }
+    const int rc = mg_level(mg, L);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc || ce != cudaSuccess || !graph || !mg->graphs_ok) {   // not capturable: run eagerly from now on
+      cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      mg->graphs_ok = false;
+      if (rc) return rc;
+      return mg_level(mg, L);
+    }
+    g->launches = g_launch_count - l0;
+    g_launch_count = l0;
+    const cudaError_t ie = cudaGraphInstantiate(&g->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { cudaGetLastError(); g->exec = nullptr; mg->graphs_ok = false; return mg_level(mg, L); }
+  }
+  DGX_CUDA_CHECK(cudaGraphLaunch(g->exec, st));
+  count_launch((int)g->launches);
+  return DGX_OK;
+}
+
 // PreconditionMG::vmult: copy_to_mg (double -> float), V-cycle, copy_from_mg
 int dgx_mg_vmult(dgx_mg *mg, dgx_vec *dst, dgx_vec *src) {
   DGX_REQUIRE(mg && dst && src, "null argument");
   const int L = mg->n_levels - 1;
   RC(dgx_vec_copy(mg->defect[L], src));
-  RC(mg_level(mg, L));
+  RC(mg_cycle(mg));
   return dgx_vec_copy(dst, mg->sol[L]);
 }
 
-int dgx_mg_coarse_iterations(const dgx_mg *mg, int *out, int capacity, int *count) {
-  DGX_REQUIRE(mg && count, "null argument");
-  if (mg->n_dev_solves > 0) {   // read the device-side log (also the place where a failed coarse solve surfaces)
-    const int nlog = std::min(mg->n_dev_solves, (int)dgx_mg::kLog);
-    std::vector<int> info(2 * nlog);
+// Reads the device-side log of the single-CTA coarse solves appended since the last check; a solve that did not converge
+// surfaces here as DGX_ERR_NO_CONVERGENCE (MGCoarseGridIterativeSolver throws SolverControl::NoConvergence, NS.cc:2519-2529).
+// Called at every setup and at the end of every multigrid-preconditioned dgx_solve_cg.
+int mg_check_coarse_log(dgx_mg *mg) {
+  if (!mg->d_info) return DGX_OK;
+  int count = 0;
+  DGX_CUDA_CHECK(cudaMemcpyAsync(&count, mg->d_count, sizeof(int), cudaMemcpyDeviceToHost, mg->ctx->stream));
+  DGX_CUDA_CHECK(cudaStreamSynchronize(mg->ctx->stream));
+  const long long seen = mg->log_seen, total = count;
+  mg->log_seen = total;
+  const long long fresh = std::min<long long>(total - seen, dgx_mg::kLog);
+  if (fresh <= 0) return DGX_OK;
+  std::vector<int> info(2 * dgx_mg::kLog);
+  DGX_CUDA_CHECK(cudaMemcpy(info.data(), mg->d_info, info.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  for (long long e = total - fresh; e < total; ++e) {
+    const int slot = (int)(e % dgx_mg::kLog);
+    if (!info[2 * slot + 1]) { set_error("coarse SolverCG: no convergence after " + std::to_string(info[2 * slot]) + " steps"); return DGX_ERR_NO_CONVERGENCE; }
+  }
+  return DGX_OK;
+}
+
+int dgx_mg_coarse_iterations(const dgx_mg *mg_, int *out, int capacity, int *count) {
+  DGX_REQUIRE(mg_ && count, "null argument");
+  dgx_mg *mg = const_cast<dgx_mg *>(mg_);
+  if (mg->d_info && mg->coarse_its.empty()) {   // device-side log: the solves since the last setup
+    int total = 0;
+    DGX_CUDA_CHECK(cudaMemcpyAsync(&total, mg->d_count, sizeof(int), cudaMemcpyDeviceToHost, mg->ctx->stream));
     DGX_CUDA_CHECK(cudaStreamSynchronize(mg->ctx->stream));
+    const long long first = std::max<long long>(mg->log_setup, (long long)total - dgx_mg::kLog);
+    std::vector<int> info(2 * dgx_mg::kLog);
     DGX_CUDA_CHECK(cudaMemcpy(info.data(), mg->d_info, info.size() * sizeof(int), cudaMemcpyDeviceToHost));
-    *count = nlog;
-    for (int i = 0; i < nlog; ++i) {
-      if (i < capacity) out[i] = info[2 * i];
-      if (!info[2 * i + 1]) { set_error("coarse SolverCG: no convergence after " + std::to_string(info[2 * i]) + " steps"); return DGX_ERR_NO_CONVERGENCE; }
+    *count = (int)std::max<long long>(0, total - first);
+    for (long long e = first; e < total; ++e) {
+      const int slot = (int)(e % dgx_mg::kLog), i = (int)(e - first);
+      if (i < capacity) out[i] = info[2 * slot];
+      if (!info[2 * slot + 1]) { set_error("coarse SolverCG: no convergence after " + std::to_string(info[2 * slot]) + " steps"); return DGX_ERR_NO_CONVERGENCE; }
     }
     return DGX_OK;
   }
@@ -637,7 +774,9 @@ int dgx_solve_cg(dgx_op *A, dgx_vec *x, dgx_vec *b, int precond_kind, void *prec
   else DGX_REQUIRE(precond_kind == 0, "precond_kind: 0 identity, 1 Jacobi, 2 multigrid");
   dgx_vec *w[4];
   RC(op_work(A, w, 4));
-  return cg_core(A, x, b, pc, max_it, abs_tol, w[0], w[1], w[2], w[3], iters, final_res, nullptr, nullptr, true);
+  const int rc = cg_core(A, x, b, pc, max_it, abs_tol, w[0], w[1], w[2], w[3], iters, final_res, nullptr, nullptr, true);
+  if (rc == DGX_OK && pc.kind == 2) return mg_check_coarse_log(pc.mg);   // a failed coarse solve must not pass silently
+  return rc;
 }
 
 // SolverGMRES, deal.II defaults: left preconditioning, restart length max_basis - 2, the monitored

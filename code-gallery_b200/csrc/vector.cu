@@ -171,8 +171,9 @@ __global__ void __launch_bounds__(kThreads) multi_axpy_kernel(T *__restrict__ w,
 }
 
 template <int OP, bool FUSED>
-int reduce_dispatch(dgx_ctx *ctx, int dtype, const void *a, const void *b, void *upd, const void *v, double alpha, long long n,
+int reduce_dispatch(const dgx_mf *mf, int dtype, const void *a, const void *b, void *upd, const void *v, double alpha, long long n,
                     double *out, bool is_max, void *upd2 = nullptr, const void *v2 = nullptr, double alpha2 = 0.0) {
+  dgx_ctx *ctx = mf->ctx;
   const int grid = grid_for(n, 8);
   double *partial = ctx->d_scratch + 8, *result = ctx->d_scratch;
   if (dtype == DGX_F64)
@@ -185,8 +186,10 @@ int reduce_dispatch(dgx_ctx *ctx, int dtype, const void *a, const void *b, void 
                                                                        (const float *)v2, (float)alpha2);
   count_launch();
   DGX_CUDA_CHECK(cudaGetLastError());
-  int rc = is_max ? allreduce_max(ctx, result, 1) : allreduce_sum(ctx, result, 1);
-  if (rc) return rc;
+  if (!mf->replicated) {   // a replicated level holds the whole vector on every rank
+    int rc = is_max ? allreduce_max(ctx, result, 1) : allreduce_sum(ctx, result, 1);
+    if (rc) return rc;
+  }
   DGX_CUDA_CHECK(cudaMemcpyAsync(ctx->h_scratch, result, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   DGX_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   *out = ctx->h_scratch[0];
@@ -398,7 +401,7 @@ int dgx_vec_scale_by(dgx_vec *dst, const dgx_vec *factors) {
 
 int dgx_vec_dot(const dgx_vec *a, const dgx_vec *b, double *out) {
   DGX_REQUIRE(same_shape(a, b) && a->dtype == b->dtype && out, "vector shape / dtype mismatch");
-  return reduce_dispatch<0, false>(a->mf->ctx, a->dtype, a->d, b->d, nullptr, nullptr, 0.0, a->n_owned, out, false);
+  return reduce_dispatch<0, false>(a->mf, a->dtype, a->d, b->d, nullptr, nullptr, 0.0, a->n_owned, out, false);
 }
 
 int dgx_vec_l2_norm(const dgx_vec *a, double *out) {
@@ -411,13 +414,13 @@ int dgx_vec_l2_norm(const dgx_vec *a, double *out) {
 
 int dgx_vec_linfty_norm(const dgx_vec *a, double *out) {
   DGX_REQUIRE(a && out, "null argument");
-  return reduce_dispatch<1, false>(a->mf->ctx, a->dtype, a->d, nullptr, nullptr, nullptr, 0.0, a->n_owned, out, true);
+  return reduce_dispatch<1, false>(a->mf, a->dtype, a->d, nullptr, nullptr, nullptr, 0.0, a->n_owned, out, true);
 }
 
 int dgx_vec_mean_value(const dgx_vec *a, double *out) {
   DGX_REQUIRE(a && out, "null argument");
   double s = 0;
-  int rc = reduce_dispatch<2, false>(a->mf->ctx, a->dtype, a->d, nullptr, nullptr, nullptr, 0.0, a->n_owned, &s, false);
+  int rc = reduce_dispatch<2, false>(a->mf, a->dtype, a->d, nullptr, nullptr, nullptr, 0.0, a->n_owned, &s, false);
   if (rc) return rc;
   *out = s / (double)a->n_global;
   return DGX_OK;
@@ -425,14 +428,14 @@ int dgx_vec_mean_value(const dgx_vec *a, double *out) {
 
 int dgx_vec_add_and_dot(dgx_vec *dst, double a, const dgx_vec *v, const dgx_vec *w, double *out) {
   DGX_REQUIRE(same_shape(dst, v) && same_shape(dst, w) && dst->dtype == v->dtype && dst->dtype == w->dtype && out, "vector mismatch");
-  return reduce_dispatch<0, true>(dst->mf->ctx, dst->dtype, nullptr, w->d, dst->d, v->d, a, dst->n_owned, out, false);
+  return reduce_dispatch<0, true>(dst->mf, dst->dtype, nullptr, w->d, dst->d, v->d, a, dst->n_owned, out, false);
 }
 
 // x += a p ; r += b v ; *out = r . r  -- the two vector updates and the residual norm of one SolverCG iteration, one pass
 int dgx_vec_cg_update(dgx_vec *x, double a, const dgx_vec *p, dgx_vec *r, double b, const dgx_vec *v, double *out) {
   DGX_REQUIRE(same_shape(x, p) && same_shape(x, r) && same_shape(x, v) && x->dtype == p->dtype && x->dtype == r->dtype && x->dtype == v->dtype && out,
               "vector mismatch");
-  return reduce_dispatch<0, true>(x->mf->ctx, x->dtype, nullptr, r->d, r->d, v->d, b, x->n_owned, out, false, x->d, p->d, a);
+  return reduce_dispatch<0, true>(x->mf, x->dtype, nullptr, r->d, r->d, v->d, b, x->n_owned, out, false, x->d, p->d, a);
 }
 
 // interpolate_velocity (NS.cc:2403-2418) fused into one pass: dst = a * x - (b * y), with the reference's rounding
@@ -502,8 +505,10 @@ int dgx_vec_orthogonalize_checked(dgx_vec *w, dgx_vec *const *V, int k, double *
       count_launch();
     }
     DGX_CUDA_CHECK(cudaGetLastError());
-    int rc = allreduce_sum(ctx, result, kd);
-    if (rc) return rc;
+    if (!w->mf->replicated) {
+      int rc = allreduce_sum(ctx, result, kd);
+      if (rc) return rc;
+    }
     DGX_CUDA_CHECK(cudaMemcpyAsync(ctx->h_scratch, result, kd * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     DGX_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     for (int j = 0; j < k; ++j) { h[j] = ctx->h_scratch[j]; tab.h[j] = h[j]; }

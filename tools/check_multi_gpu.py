@@ -54,7 +54,71 @@ for name, cells0, nref, periodic, kind, degree in [
         dist.all_reduce(e[:2])
         errs.append({"dtype": "f64" if dt == dgx.F64 else "f32", "rel_l2": float(torch.sqrt(e[0] / e[1])), "dot_abs_err": float(e[2])})
     report[name] = errs
-# MG-preconditioned pressure solve across ranks (projection_step's solver): same iteration count and solution as on one GPU
+# MG-preconditioned pressure solve across ranks (projection_step's solver): same iteration count and solution as on one GPU.
+# Two layouts: one coarse cube per rank, and ONE cube cut into contiguous Morton chunks (p4est-style; the coarse levels are
+# replicated on all ranks, DGX_MG_REPLICATE_MAX=64 forces two distributed levels + the gather).
+mg_report = {}
+for layout, cells0, nref, hi in (("row_of_cubes", [world, 1, 1], 3, [float(world), 1, 1]), ("one_cube_morton_chunks", [1, 1, 1], 4, [1.0, 1.0, 1.0])):
+  for rep_max in ("default", "64"):
+    if rep_max == "64":
+        os.environ["DGX_MG_REPLICATE_MAX"] = "64"
+    else:
+        os.environ.pop("DGX_MG_REPLICATE_MAX", None)
+    degree = 3
+    mesh = dgx.Mesh(3, cells0, nref, [0, 0, 0], hi, [True] * 3)
+    res = {}
+    sols = {}
+    for tag, c in (("multi", ctx), ("solo", solo)):
+        mf = dgx.MatrixFree(c, mesh)
+        op = dgx.NavierStokesProjectionOperator(mf, dgx.OP_PRESSURE, degree, 100.0, 5e-3)
+        mg = dgx.Multigrid(c, mesh, degree, 100.0, 5e-3)
+        dpc = (degree + 1) ** 3
+        N = mesh.n_cells() * dpc
+        g = np.sin(np.arange(N) * 3e-3) + 0.1 * np.random.default_rng(1).standard_normal(N)
+        g -= g.mean()
+        lo, n = mf.first_owned_cell() * dpc, mf.n_owned_cells() * dpc
+        x, b = op.initialize_dof_vector(), op.initialize_dof_vector()
+        b.from_host(g[lo:lo + n])
+        tol = 1e-8 * float(np.linalg.norm(g))
+        its_all = []
+        for rep in range(3):          # 3 solves: eager cycle, captured cycle, replayed graph
+            mg.setup(tol, 10000)
+            x.set(0.0)
+            its, r = dgx.solve_cg(op, x, b, mg, 10000, tol)
+            its_all.append(its)
+        res[tag] = its_all
+        sols[tag] = (x.to_host(), lo, n)
+    xm, lo, n = sols["multi"]
+    xs = sols["solo"][0][lo:lo + n]
+    e = torch.tensor([float(np.sum((xm - xs) ** 2)), float(np.sum(xs ** 2))], dtype=torch.float64, device="cuda")
+    dist.all_reduce(e)
+    mg_report[f"{layout}/replicate_max={rep_max}"] = {"iterations_multi": res["multi"], "iterations_solo": res["solo"], "solution_rel_l2": float(torch.sqrt(e[0] / e[1]))}
+os.environ.pop("DGX_MG_REPLICATE_MAX", None)
+
+# one TR-BDF2 step of the Taylor-Green vortex across ranks: Krylov iteration counts and velocity equal to the single-GPU run
+from dgx.navier_stokes import NavierStokesProjection
+L, R, dp = 2 * np.pi, 3, 2
+mesh = dgx.Mesh(3, [1, 1, 1], R, [0, 0, 0], [L, L, L], [True] * 3)
+h = L / 2 ** R
+step = {}
+for tag, c in (("multi", ctx), ("solo", solo)):
+    ns = NavierStokesProjection(c, mesh, dp, 1600.0, 0.2 * h / (dp + 2))
+    nv, npn = (dp + 2) ** 3 * 3, (dp + 1) ** 3
+    rng = np.random.default_rng(9)
+    ug = np.sin(np.arange(mesh.n_cells() * nv) * 1e-2) + 0.05 * rng.standard_normal(mesh.n_cells() * nv)
+    pg = np.cos(np.arange(mesh.n_cells() * npn) * 2e-2)
+    fc, nc = ns.mf.first_owned_cell(), ns.mf.n_owned_cells()
+    ns.u_n.from_host(ug[fc * nv:(fc + nc) * nv]); ns.u_n_minus_1.from_host(ug[fc * nv:(fc + nc) * nv]); ns.pres_n.from_host(pg[fc * npn:(fc + nc) * npn])
+    for _ in range(2):
+        vmax = ns.advance()
+    step[tag] = (list(ns.iterations), ns.u_n.to_host(), fc * nv, nc * nv, vmax)
+um, lo, n = step["multi"][1], step["multi"][2], step["multi"][3]
+us = step["solo"][1][lo:lo + n]
+e = torch.tensor([float(np.sum((um - us) ** 2)), float(np.sum(us ** 2))], dtype=torch.float64, device="cuda")
+dist.all_reduce(e)
+step_report = {"iterations_multi": step["multi"][0], "iterations_solo": step["solo"][0], "u_rel_l2": float(torch.sqrt(e[0] / e[1])),
+               "max_velocity": [step["multi"][4], step["solo"][4]]}
+
 cells0, nref, degree = [world, 1, 1], 3, 3
 mesh = dgx.Mesh(3, cells0, nref, [0, 0, 0], [float(world), 1, 1], [True] * 3)
 res = {}
@@ -81,9 +145,15 @@ e = torch.tensor([float(np.sum((xm - xs) ** 2)), float(np.sum(xs ** 2))], dtype=
 dist.all_reduce(e)
 mg_rel = float(torch.sqrt(e[0] / e[1]))
 if rank == 0:
-    print(json.dumps({"world": world, "checks": report, "mg_cg": {"iterations_multi": res["multi"], "iterations_solo": res["solo"], "solution_rel_l2": mg_rel}}))
+    print(json.dumps({"world": world, "checks": report, "mg_cg": {"iterations_multi": res["multi"], "iterations_solo": res["solo"], "solution_rel_l2": mg_rel},
+                      "mg_cg_layouts": mg_report, "trbdf2_step": step_report}))
     if abs(res["multi"] - res["solo"]) > 1 or mg_rel > 1e-5:
         report["mg_cg"] = [{"dtype": "f64", "rel_l2": 1.0}]
+    for k, v in mg_report.items():
+        if max(abs(a - b) for a, b in zip(v["iterations_multi"], v["iterations_solo"])) > 1 or v["solution_rel_l2"] > 1e-5:
+            report["mg_cg " + k] = [{"dtype": "f64", "rel_l2": 1.0}]
+    if any(abs(a[1] - b[1]) > 1 for a, b in zip(step_report["iterations_multi"], step_report["iterations_solo"])) or step_report["u_rel_l2"] > 1e-8:
+        report["trbdf2_step"] = [{"dtype": "f64", "rel_l2": 1.0}]
     bad = [k for k, v in report.items() for x in v if x["rel_l2"] > (1e-12 if x["dtype"] == "f64" else 1e-5)]
     print("MULTI-GPU CHECK", "FAILED " + str(bad) if bad else "PASSED")
 dist.destroy_process_group()
