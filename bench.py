@@ -11,7 +11,9 @@ Prints ONE JSON line (rank 0).  `value` = DoFs processed per second with src/dst
 `e2e` = the same through dgx_op_vmult_host (pinned host buffers, H2D + vmult + D2H timed; on one rank the three legs
   of a call are pipelined brick by brick, see DESIGN.md "Host entry point");
 `roofline` = algorithmic bytes (16 B/DoF) / kernel time vs MEASURED_PEAKS.json;
-`cpu_baseline` = the oracle's C port timed on the host cores on a bounded sample.
+`cpu_baseline` = the reference algorithm as deal.II executes it (SIMD over cells, even-odd, compile-time degree), restated in C
+  (oracle/cpu_simd.c), timed on all host cores on the SAME 128^3 workload (3 applications).
+`--impl reference` times that CPU implementation alone on the arm's config (rank 0 only, all host threads).
 """
 import argparse
 import json
@@ -44,7 +46,8 @@ def parse():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-refine", type=int, default=5)
+    ap.add_argument("--cpu-refine", type=int, default=-1, help="refinement of the CPU baseline's cube (default: the workload's own, 128^3)")
+    ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-solve", action="store_true", help="skip the (untimed-region) MG-CG pressure solve report")
     ap.add_argument("--solve-refine", type=int, default=6)
     ap.add_argument("--solve-degree", type=int, default=3)
@@ -98,16 +101,38 @@ def measured_peaks():
 
 
 def cpu_baseline(degree, refine, dtype, steps=3):
-    """Oracle C port (oracle/cpu_vmult.c) on all host cores; falls back to the numpy oracle."""
+    """The reference algorithm vectorised the way deal.II does it (oracle/cpu_simd.c: AVX2 / AVX-512 over cells, even-odd,
+    compile-time degree, face-centric) on ALL host threads, whatever OMP_NUM_THREADS says (torchrun sets it to 1); other
+    degrees than Q4 fall back to the scalar port (oracle/cpu_vmult.c)."""
     from oracle import cpu_port
-    return cpu_port.time_vmult(degree, refine, dtype, steps)
+    if degree == 4 and dtype == "f64":
+        return cpu_port.time_simd(degree, refine, steps)
+    os.environ["OMP_NUM_THREADS"] = str(cpu_port.host_threads())
+    return cpu_port.time_vmult(degree, min(refine, 5), dtype, steps)
+
+
+def layout_for(world, refine):
+    """weak scaling with (2^refine)^3 cells per GPU on ONE periodic box cut into contiguous chunks of the hierarchical (p4est /
+    Morton) order: 2 -> two cubes side by side, 4 -> 2 x 2 x 1 cubes, 8 -> one cube refined once more (octants, 6 face neighbours)"""
+    table = {1: ([1, 1, 1], refine), 2: ([2, 1, 1], refine), 4: ([2, 2, 1], refine), 8: ([1, 1, 1], refine + 1)}
+    if world in table:
+        return table[world]
+    return [world, 1, 1], refine
+
+
+def workload_string(degree, world, refine, n_global, dtype):
+    cells0, r = layout_for(world, refine)
+    n = [c << r for c in cells0]
+    return (f"3D DG SIPG pressure-operator vmult, Q{degree}, {n[0]}x{n[1]}x{n[2]} cells ({2**refine}^3 per GPU) periodic Cartesian, "
+            f"{n_global} DoFs {dtype}")
 
 
 def pressure_solve_report(dgx, ctx, args, world=1):
     """one CG solve preconditioned by the fp32 Chebyshev/V-cycle on a periodic box of `world` cubes, one per rank (weak
     scaling; not part of the timed region)"""
-    R, p = args.solve_refine, args.solve_degree
-    mesh = dgx.Mesh(3, [world, 1, 1], R, [0, 0, 0], [float(world), 1, 1], [True, True, True])
+    p = args.solve_degree
+    cells0, R = layout_for(world, args.solve_refine)
+    mesh = dgx.Mesh(3, cells0, R, [0, 0, 0], [float(c) for c in cells0], [True, True, True])
     mf = dgx.MatrixFree(ctx, mesh)
     op = dgx.NavierStokesProjectionOperator(mf, dgx.OP_PRESSURE, p, 100.0, 5e-3)
     mg = dgx.Multigrid(ctx, mesh, p, 100.0, 5e-3)
@@ -130,7 +155,9 @@ def pressure_solve_report(dgx, ctx, args, world=1):
         mg.setup(tol, 10000)        # the reference rebuilds diagonals / eigenvalue estimates per solve (NS.cc:2490-2517)
         its, res = dgx.solve_cg(op, x, b, mg, 10000, tol)
         ms = ctx.timer_stop()
-        out = {"workload": f"pressure MG-CG, 3D Q{p}, {world}x{2**R}^3 cells periodic, {n * world} DoFs on {world} GPU(s), fp64 outer / fp32 V-cycle, tol 1e-8*||rhs||",
+        nc = [c << R for c in cells0]
+        out = {"workload": f"pressure MG-CG, 3D Q{p}, {nc[0]}x{nc[1]}x{nc[2]} cells periodic ({2**args.solve_refine}^3 per GPU), {n * world} DoFs on {world} GPU(s), "
+                           f"fp64 outer / fp32 V-cycle, tol 1e-8*||rhs||",
                "ms_per_solve": ms, "cg_iterations": its, "levels": mg.n_levels(), "final_residual": res,
                "gpu_launches": dgx.kernel_launch_count() - l0, "includes": "level diagonals + Chebyshev eigenvalue estimates + solve"}
         if rep == 1:
@@ -141,24 +168,29 @@ def pressure_solve_report(dgx, ctx, args, world=1):
     return out
 
 
-def trbdf2_step_report(dgx, ctx, args):
-    """time per TR-BDF2 step (NS.cc:2934-2986) of the 3-D periodic Taylor-Green vortex, velocity Q3 / pressure Q2"""
+def trbdf2_step_report(dgx, ctx, args, world=1):
+    """time per TR-BDF2 step (NS.cc:2934-2986) of the 3-D periodic Taylor-Green vortex, velocity Q3 / pressure Q2, on `world`
+    GPUs ((2^step_refine)^3 cells per GPU; box = one 2 pi cube per coarse cell, so h and dt do not change with `world`)"""
     from dgx.navier_stokes import NavierStokesProjection
-    R, dp = args.step_refine, 2
+    dp = 2
+    cells0, R = layout_for(world, args.step_refine)
     L = 2 * np.pi
-    mesh = dgx.Mesh(3, [1, 1, 1], R, [0, 0, 0], [L, L, L], [True, True, True])
-    h = L / 2 ** R
+    per = 2 ** (R - args.step_refine)          # 2 when the cube itself is refined once more (8 GPUs): keep h fixed
+    hi = [L * c * per for c in cells0]
+    mesh = dgx.Mesh(3, cells0, R, [0, 0, 0], hi, [True, True, True])
+    h = L / 2 ** args.step_refine
     dt = 0.2 * h / (dp + 2)
     ns = NavierStokesProjection(ctx, mesh, dp, 1600.0, dt)
     ns_direct = NavierStokesProjection(ctx, mesh, dp, 1600.0, dt, direct_mass_inverse=True)
-    # TGV initial state interpolated at the dof support points (Gauss-Lobatto nodes), cells in the library's order
+    # TGV initial state interpolated at the dof support points (Gauss-Lobatto nodes), owned cells in the library's order
     def nodes(n):
         from numpy.polynomial import legendre as leg
         if n == 2:
             return np.array([0.0, 1.0])
         c = np.zeros(n); c[-1] = 1.0
         return np.concatenate(([0.0], (np.sort(leg.legroots(leg.legder(c))) + 1) / 2, [1.0]))
-    coords = mesh.cell_coords().astype(np.float64)                       # [cells, 3]
+    first, count = ns.mf.first_owned_cell(), ns.mf.n_owned_cells()
+    coords = mesh.cell_coords(-1, first, count).astype(np.float64)       # [owned cells, 3]
     def field(n, f):
         x1 = nodes(n)
         X = (coords[:, None, None, None, 0] + x1[None, None, None, :]) * h
@@ -172,17 +204,19 @@ def trbdf2_step_report(dgx, ctx, args):
     for s_ in (ns, ns_direct):
         s_.u_n.from_host(u); s_.u_n_minus_1.from_host(u); s_.pres_n.from_host(p)
     out = {}
-    for rep in range(2):
+    nc = [c << R for c in cells0]
+    for rep in range(3):            # step 1 warms up (allocations, graph capture); steps 2 and 3 are reported (3 = steady state)
         ns.iterations.clear()
         ctx.synchronize()
         l0 = dgx.kernel_launch_count()
         ctx.timer_start()
         vmax = ns.advance()
         ms = ctx.timer_stop()
-        out = {"workload": f"TR-BDF2 step, 3D periodic Taylor-Green vortex, {2**R}^3 cells, velocity Q{dp+1} ({u.size} DoFs) / pressure Q{dp} ({p.size} DoFs), Re 1600, dt {dt:.3e}",
+        out = {"workload": f"TR-BDF2 step, 3D periodic Taylor-Green vortex, {nc[0]}x{nc[1]}x{nc[2]} cells ({2**args.step_refine}^3 per GPU) on {world} GPU(s), "
+                           f"velocity Q{dp+1} ({u.size * world} DoFs) / pressure Q{dp} ({p.size * world} DoFs), Re 1600, dt {dt:.3e}",
                "ms_per_step": ms, "max_velocity": vmax, "iterations": dict((k + f"#{i}", v) for i, (k, v) in enumerate(ns.iterations)),
                "gpu_launches": dgx.kernel_launch_count() - l0,
-               "note": "2 GMRES + 2 MG-CG + 3 mass CG solves (reference algorithm), tensorised velocity diagonals"}
+               "note": "2 GMRES + 2 MG-CG + 3 mass CG solves (reference algorithm), tensorised velocity diagonals; third step of the run"}
     for rep in range(2):
         ctx.synchronize()
         ctx.timer_start()
@@ -191,19 +225,71 @@ def trbdf2_step_report(dgx, ctx, args):
     return out
 
 
+def multi_gpu_parity(dgx, ctx, local_rank, world, dist, torch):
+    """N-rank results against the single-GPU ones on small problems, run at the start of every N > 1 bench: the distributed Q4
+    vmult (marching kernel with ghost planes / halo) and the MG-CG solve (replicated coarse levels, gather, CUDA graph)."""
+    solo = dgx.Context(local_rank)
+    out = {}
+    cells0, R = layout_for(world, 3)
+    hi = [float(c) for c in cells0]
+    mesh = dgx.Mesh(3, cells0, R, [0, 0, 0], hi, [True] * 3)
+    # operator
+    mfd, mfs = dgx.MatrixFree(ctx, mesh), dgx.MatrixFree(solo, mesh)
+    opd, ops = (dgx.NavierStokesProjectionOperator(m, dgx.OP_PRESSURE, 4, 100.0, 5e-3) for m in (mfd, mfs))
+    N = mesh.n_cells() * 125
+    g = np.random.default_rng(42).standard_normal(N)
+    lo, n = mfd.first_owned_cell() * 125, mfd.n_owned_cells() * 125
+    xs, ys, xd, yd = ops.initialize_dof_vector(), ops.initialize_dof_vector(), opd.initialize_dof_vector(), opd.initialize_dof_vector()
+    xs.from_host(g); xd.from_host(g[lo:lo + n])
+    ops.vmult(ys, xs); opd.vmult(yd, xd)
+    ref, got = ys.to_host()[lo:lo + n], yd.to_host()
+    e = torch.tensor([float(np.sum((ref - got) ** 2)), float(np.sum(ref ** 2))], dtype=torch.float64, device="cuda")
+    dist.all_reduce(e)
+    out["vmult_rel_l2"] = float(torch.sqrt(e[0] / e[1]))
+    # MG-CG
+    its, sols = {}, {}
+    for tag, c, mf in (("multi", ctx, mfd), ("solo", solo, mfs)):
+        op = dgx.NavierStokesProjectionOperator(mf, dgx.OP_PRESSURE, 3, 100.0, 5e-3)
+        mg = dgx.Multigrid(c, mesh, 3, 100.0, 5e-3)
+        Np = mesh.n_cells() * 64
+        gp = np.sin(np.arange(Np) * 3e-3) + 0.1 * np.random.default_rng(1).standard_normal(Np)
+        gp -= gp.mean()
+        lo2, n2 = mf.first_owned_cell() * 64, mf.n_owned_cells() * 64
+        x, b = op.initialize_dof_vector(), op.initialize_dof_vector()
+        b.from_host(gp[lo2:lo2 + n2])
+        tol = 1e-8 * float(np.linalg.norm(gp))
+        for rep in range(3):
+            mg.setup(tol, 10000)
+            x.set(0.0)
+            its[tag], _ = dgx.solve_cg(op, x, b, mg, 10000, tol)
+        sols[tag] = x.to_host() if tag == "multi" else x.to_host()[lo2:lo2 + n2]
+    e = torch.tensor([float(np.sum((sols["multi"] - sols["solo"]) ** 2)), float(np.sum(sols["solo"] ** 2))], dtype=torch.float64, device="cuda")
+    dist.all_reduce(e)
+    out.update({"mg_cg_its": its["multi"], "mg_cg_its_single_gpu": its["solo"], "mg_cg_solution_rel_l2": float(torch.sqrt(e[0] / e[1])),
+                "what": f"{cells0[0] << R}x{cells0[1] << R}x{cells0[2] << R} cells on {world} ranks vs the same problem on one GPU: Q4 fp64 vmult, Q3 MG-CG (3rd solve = replayed graph)"})
+    solo.close()
+    return out
+
+
 def run_reference(args):
+    """the reference's own CPU path for this operator on the arm's config, all host threads, rank 0 only"""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     if rank != 0:
         return
     t0 = time.time()
-    res = cpu_baseline(args.degree, args.cpu_refine, args.dtype, steps=max(1, args.steps))
+    refine = args.cpu_refine if args.cpu_refine >= 0 else args.refine
+    steps = max(1, min(args.steps, 20))          # one step = one vmult of the whole cube on the host: ~0.5 s at 128^3
+    res = cpu_baseline(args.degree, refine, args.dtype, steps=steps)
     ndofs = res["n_dofs"]
+    same = refine == args.refine and world == 1
     line = {
         "impl": "reference", "metric": METRIC, "value": res["dofs_per_s"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": f"3D SIPG pressure vmult Q{args.degree}, {2**args.cpu_refine}^3 cells periodic "
-                               f"(bounded sample of the 128^3 workload), {ndofs} DoFs", "timing": "inputs exceed host caches"},
+        "config": {"workload": workload_string(args.degree, 1, refine, ndofs, args.dtype) if same else
+                   workload_string(args.degree, 1, refine, ndofs, args.dtype) + f" (one GPU's share of the {world}-GPU workload: the host cores are not scaled with N)",
+                   "l2": "inputs (2 vectors) exceed the host caches", "partition": "one thread per host core, contiguous chunks of the cell order"},
         "cpu_baseline": {"value": res["dofs_per_s"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
         "e2e": {"value": res["dofs_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.time() - t0,
@@ -238,9 +324,15 @@ def main():
         nccl_id = bytes(idt.cpu().numpy().tobytes())
     ctx = dgx.Context(local_rank, rank, world, nccl_id)
 
-    # weak scaling: per-GPU work fixed at (2^refine)^3 cells; N GPUs => N times the cells along x
-    cells0 = [world, 1, 1]
-    mesh = dgx.Mesh(3, cells0, args.refine, [0, 0, 0], [float(world), 1, 1], [True, True, True])
+    parity = None
+    if world > 1:
+        try:
+            parity = multi_gpu_parity(dgx, ctx, local_rank, world, dist, torch)
+        except Exception as exc:  # noqa: BLE001
+            parity = {"error": str(exc)}
+    # weak scaling: per-GPU work fixed at (2^refine)^3 cells of ONE periodic box in contiguous Morton chunks (layout_for)
+    cells0, refine_g = layout_for(world, args.refine)
+    mesh = dgx.Mesh(3, cells0, refine_g, [0, 0, 0], [float(c) for c in cells0], [True, True, True])
     dt = dgx.F64 if args.dtype == "f64" else dgx.F32
     mf = dgx.MatrixFree(ctx, mesh, -1, dt)
     op = dgx.NavierStokesProjectionOperator(mf, dgx.OP_PRESSURE, args.degree, 100.0, 5e-3)
@@ -289,6 +381,21 @@ def main():
     ms_per_step = ms / args.steps
     value = n_global / (ms_per_step * 1e-3)
 
+    # the timed kernel's output on the full workload against the generic kernel (variant 1) on the same input
+    check = None
+    if args.variant == 0:
+        try:
+            ref_v = op.initialize_dof_vector()
+            op.set_variant(1)
+            op.vmult(ref_v, src)
+            op.set_variant(0)
+            nrm = ref_v.l2_norm()
+            ref_v.add(-1.0, dst)
+            check = ref_v.l2_norm() / nrm
+            del ref_v
+        except Exception as exc:  # noqa: BLE001
+            check = str(exc)
+
     # end to end through the host-buffer entry point (pinned host memory)
     e2e = None
     if not args.no_e2e:
@@ -316,7 +423,9 @@ def main():
     bytes_per_dof = 2 * host.element_size()
     achieved = (n_local * bytes_per_dof) / (ms_per_step * 1e-3) / 1e9
     marching = args.variant != 1 and args.degree == 4 and args.refine >= 3
-    kernel = "pressure_march_kernel" if marching else "pressure_generic_kernel"
+    gen = os.environ.get("DGX_MARCH", "v2eor")
+    kernel = ("pressure_march_kernel" if gen == "v1" else "pressure_march2_kernel") if marching and args.dtype == "f64" else \
+             ("pressure_march_kernel" if marching else "pressure_generic_kernel")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                 "traffic": None, "peak_source": which, "algorithmic_bytes_per_dof": bytes_per_dof,
                 "kernel": kernel + " (1 launch per step)"}
@@ -333,7 +442,7 @@ def main():
     # the operator is also bound by the FP64 pipe: report the executed-flop fraction beside the HBM one
     try:
         pk = json.load(open(os.path.join(ROOT, "profiles", "r1_peaks.json")))
-        flop_per_dof = {"pressure_march_kernel": 96.0, "pressure_generic_kernel": 112.0}[kernel]
+        flop_per_dof = {"pressure_march_kernel": 96.0, "pressure_march2_kernel": 84.0, "pressure_generic_kernel": 112.0}[kernel]
         key = "fp64_fma_tflops" if args.dtype == "f64" else "fp32_fma_tflops"
         tf = n_local * flop_per_dof / (ms_per_step * 1e-3) / 1e12
         roofline["fma_pipe"] = {"achieved_tflops": tf, "peak_tflops": pk[key], "frac": tf / pk[key], "flop_per_dof": flop_per_dof,
@@ -350,20 +459,21 @@ def main():
             mg_solve = {"error": str(exc)}
 
     step = None
-    if not args.no_step and world == 1:
+    if not args.no_step:
         try:
-            step = trbdf2_step_report(dgx, ctx, args)
+            step = trbdf2_step_report(dgx, ctx, args, world)
         except Exception as exc:  # noqa: BLE001
             step = {"error": str(exc)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
-            res = cpu_baseline(args.degree, args.cpu_refine, args.dtype)
+            res = cpu_baseline(args.degree, args.cpu_refine if args.cpu_refine >= 0 else args.refine, args.dtype, args.cpu_steps)
             cpu = {"value": res["dofs_per_s"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]}
             try:    # extra: the kernels' own (Kronecker-factored) algorithm on the host cores, so the ratio is not inflated by the port
                 from oracle import cpu_port
-                k = cpu_port.time_kron(args.degree, args.cpu_refine + 1)
+                os.environ["OMP_NUM_THREADS"] = str(cpu_port.host_threads())
+                k = cpu_port.time_kron(args.degree, 6)
                 cpu["kronecker_algorithm_on_cpu"] = {"value": k["dofs_per_s"], "unit": UNIT, "cores": k["cores"], "what": k["what"]}
             except Exception as exc:  # noqa: BLE001
                 cpu["kronecker_algorithm_on_cpu"] = {"error": str(exc)}
@@ -375,11 +485,12 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"3D DG SIPG pressure-operator vmult, Q{args.degree}, {world}x{2**args.refine}^3 cells periodic Cartesian, "
-                                   f"{n_global} DoFs {args.dtype}", "l2": "inputs (2 vectors) exceed the 126 MB L2; no flush needed",
-                       "partition": f"{world} contiguous Morton chunks" if world > 1 else "single GPU"},
+            "config": {"workload": workload_string(args.degree, world, args.refine, n_global, args.dtype),
+                       "l2": "inputs (2 vectors) exceed the 126 MB L2; no flush needed",
+                       "input": "sin(1e-3 i) + 1e-3 U(-1,1), seed 1234 + rank (smooth field + noise as SURVEY 8d C2, generated per dof index)",
+                       "partition": f"{world} contiguous chunks of the hierarchical (Morton) cell order of one box" if world > 1 else "single GPU"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(),
-            "mg_solve": mg_solve, "trbdf2_step": step,
+            "mg_solve": mg_solve, "trbdf2_step": step, "marching_vs_generic_rel_l2": check, "multi_gpu_parity": parity,
         }
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)

@@ -62,6 +62,7 @@ struct FastGeom {
   int NZ;                // planes per segment
   long long first_cell;  // first owned cell (hierarchical index)
   int n_owned;
+  int wait_mode;         // v2 kernel: bit 0 / 1 / 2 = XY / Z / H warps spin on their mbarriers instead of sleeping
 };
 
 template <int n>
@@ -694,22 +695,24 @@ void fill_fast_params(FastParams<T, n> &F, const dgx_op *op) {
 
 #include "pressure_march_v2.cuh"
 
-// which marching kernel runs the plain (no add, no fused update) Q4 fp64 operator: DGX_MARCH = v1 | v2 | v2eo (default)
+// which marching kernel runs the plain (no add, no fused update) Q4 fp64 operator: DGX_MARCH = v1 | v2 | v2eo | v2r | v2eor (default) | v2eol
 inline int march_generation() {   // read on every call (tests and the bench switch it inside one process)
   const char *e = getenv("DGX_MARCH");
-  if (!e) return 2;
-  if (!strcmp(e, "v1")) return 0;
-  if (!strcmp(e, "v2")) return 1;
-  if (!strcmp(e, "v2r")) return 3;
-  if (!strcmp(e, "v2eor")) return 4;
-  if (!strcmp(e, "v2eol")) return 5;
-  return 2;
+  if (!e) return 4;
+  if (!strcmp(e, "v1")) return 0;      // round-1 kernel (named barriers, register tiles, STG)
+  if (!strcmp(e, "v2")) return 1;      // mbarrier hand-offs, shuffled traces, bulk stores; plain contractions, layer tile in registers
+  if (!strcmp(e, "v2eo")) return 2;    // + even-odd contractions
+  if (!strcmp(e, "v2r")) return 3;     // plain contractions, streaming XY role
+  if (!strcmp(e, "v2eol")) return 5;   // even-odd, XY role in lockstep batches
+  return 4;                            // v2eor (default): even-odd, streaming XY role with a 3-stage software pipeline
 }
 
 template <int n, typename T, bool EO, int XYV>
-int launch_march2(dgx_op *op, dgx_vec *dst, const dgx_vec *src, const FastGeom &G, const int *d_jobs, int n_jobs, cudaStream_t stream) {
+int launch_march2(dgx_op *op, dgx_vec *dst, const dgx_vec *src, const FastGeom &G_, const int *d_jobs, int n_jobs, cudaStream_t stream) {
   using R = Roles2<n>;
   constexpr int NL = n * n, ND = NL * n;
+  FastGeom G = G_;
+  { const char *e = getenv("DGX_MARCH_WAIT"); G.wait_mode = e ? atoi(e) : 0; }
   FastParams<T, n> F;
   fill_fast_params<T, n>(F, op);
   EOParams<T, n> Q;
@@ -745,7 +748,8 @@ int launch_march(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const F
         case 3: return launch_march2<n, T, false, 1>(op, dst, src, G, d_jobs, n_jobs, stream);
         case 4: return launch_march2<n, T, true, 1>(op, dst, src, G, d_jobs, n_jobs, stream);
         case 5: return launch_march2<n, T, true, 2>(op, dst, src, G, d_jobs, n_jobs, stream);
-        default: return launch_march2<n, T, true, 0>(op, dst, src, G, d_jobs, n_jobs, stream);
+        case 2: return launch_march2<n, T, true, 0>(op, dst, src, G, d_jobs, n_jobs, stream);
+        default: return launch_march2<n, T, true, 1>(op, dst, src, G, d_jobs, n_jobs, stream);
       }
   }
   using R = Roles<n>;
@@ -814,6 +818,7 @@ bool march_geometry(const dgx_op *op, FastGeom &G) {
   G.NZ = NZ; G.nsz = EZ / NZ;
   G.first_cell = mf->first_cell;
   G.n_owned = (int)mf->n_owned;
+  G.wait_mode = 0;
   return true;
 }
 

@@ -26,6 +26,12 @@ struct Roles2 {
 // Wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or ~1 ms passed) instead of
 // polling -- the polling loops of the waiting roles were 32 % of all executed instructions of the first v2 capture and
 // competed with the XY warps for issue slots.
+// spin (mode != 0) or sleep (mode == 0): measured choice per role, see launch_march2
+__device__ __forceinline__ void mbar_wait_sleep(unsigned long long *bar, unsigned parity);
+__device__ __forceinline__ void mbar_wait_mode(unsigned long long *bar, unsigned parity, int spin) {
+  if (spin) mbar_wait(bar, parity);
+  else mbar_wait_sleep(bar, parity);
+}
 __device__ __forceinline__ void mbar_wait_sleep(unsigned long long *bar, unsigned parity) {
   const unsigned addr = smem_u32(bar);
   unsigned ok = 0;
@@ -362,8 +368,8 @@ pressure_march2_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_
       }
     }
     auto mz_store = [&](int p) {   // OUT(plane p) = Mz Mx q
-      mbar_wait_sleep(&qready[p & 1], (unsigned)((p >> 1) & 1));
-      mbar_wait_sleep(outfree, (unsigned)((p - 1) & 1));   // the stores of plane p - 1 have read OUT (passes at once for p = 0)
+      mbar_wait_mode(&qready[p & 1], (unsigned)((p >> 1) & 1), G.wait_mode & 2);
+      mbar_wait_mode(outfree, (unsigned)((p - 1) & 1), G.wait_mode & 2);   // the stores of plane p - 1 have read OUT (passes at once for p = 0)
       const T *Ws = W + (size_t)(p & 1) * TC * ND + so;
       T q[n][n];   // [k][i]: my row of every layer
 #pragma unroll
@@ -386,7 +392,7 @@ pressure_march2_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive(outfull);
     };
-    mbar_wait_sleep(&ubar[0], 0);
+    mbar_wait_mode(&ubar[0], 0, G.wait_mode & 2);
 #pragma unroll
     for (int i = 0; i < n; ++i) {
 #pragma unroll
@@ -397,7 +403,7 @@ pressure_march2_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_
     for (int q = 0; q < NZ; ++q) {
       T *Un = U + (size_t)((q + 1) % NS) * TC * ND + so;
       if (q + 1 < NZ) {
-        mbar_wait_sleep(&ubar[(q + 1) % NS], (unsigned)(((q + 1) / NS) & 1));
+        mbar_wait_mode(&ubar[(q + 1) % NS], (unsigned)(((q + 1) / NS) & 1), G.wait_mode & 2);
       } else {
         // ghost plane above the segment: stage (q + 1) % NS is free (plane q - 2 went through the XY warps before the last
         // mz_store); every thread parks its own columns there and reads them back through the common path
@@ -445,12 +451,12 @@ pressure_march2_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_
       T *Wp = W + (size_t)st * TC * ND + c * ND + k * NL;
       const T *Up = U + (size_t)(p % NS) * TC * ND + c * ND + k * NL;
       const T *hb = HXY + (size_t)st * HBUF;
-      mbar_wait_sleep(&ubar[p % NS], (unsigned)((p / NS) & 1));
+      mbar_wait_mode(&ubar[p % NS], (unsigned)((p / NS) & 1), G.wait_mode & 1);
       if constexpr (XYV == 2) {
         // Lockstep form (even-odd only): the n rows, then the n columns of the layer go through the batched line operators
         // in groups of 3 + 2 lines; only the x results (xr) stay in registers between the two passes.
         static_assert(XYV != 2 || EO, "the lockstep form is written for the even-odd tables");
-        mbar_wait_sleep(&full[st], (unsigned)((p >> 1) & 1));
+        mbar_wait_mode(&full[st], (unsigned)((p >> 1) & 1), G.wait_mode & 1);
         T xr[n][n];
         auto batch = [&](auto isrow_c, auto a0_c, auto nb_c) {
           constexpr bool isrow = decltype(isrow_c)::value;
@@ -513,7 +519,7 @@ pressure_march2_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_
         // t + 2 and the trace exchange of line t + 1 are in flight while line t is in the FP64 pipe:
         //   A(t + 2): u line, W row (rows only), halo pairs        B(t + 1): own traces, shuffles, tile-edge select
         //   C(t):     line operator (+ mass in y and the store for columns)
-        mbar_wait_sleep(&full[st], (unsigned)((p >> 1) & 1));
+        mbar_wait_mode(&full[st], (unsigned)((p >> 1) & 1), G.wait_mode & 1);
         T xr[n][n];
         T ln[3][n], wr[3][n];       // u line / W row of the lines in flight
         P2 hp[3][2];                // halo pairs (V', G') of the two sides
@@ -593,7 +599,7 @@ pressure_march2_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_
 #pragma unroll
         for (int i = 0; i < n; ++i) keep(u[jj][i]);
       // z-partial sums from the Z warps (and the halo traces from the H warps) are ready
-      mbar_wait_sleep(&full[st], (unsigned)((p >> 1) & 1));
+      mbar_wait_mode(&full[st], (unsigned)((p >> 1) & 1), G.wait_mode & 1);
       // The layer is in registers: the last XY warp to get here refills the stage with plane p + NS.  Only now, after full(p):
       // the Z warps read plane 0 in their prologue, concurrently with this role (every later plane p is read by the Z warps
       // one iteration ahead, before full(p - 1)); a refill before full(0) would also let ubar[0] run two phases ahead of them.
@@ -677,44 +683,53 @@ pressure_march2_kernel(const __grid_constant__ FastParams<T, n> P, const __grid_
       hcn[sl] = nbr[(size_t)(2 * dir + side) * no + hcell[sl]];
     });
     for (int p = 0; p < NZ + 2; ++p) {
-      mbar_wait_sleep(&qready[p & 1], (unsigned)(((p - 2) >> 1) & 1));   // plane p - 2 is through the XY warps: halo buffer p & 1 is free
+      mbar_wait_mode(&qready[p & 1], (unsigned)(((p - 2) >> 1) & 1), G.wait_mode & 4);   // plane p - 2 is through the XY warps: halo buffer p & 1 is free
       if (p < NZ) {
-        T x[NSLOT][n];
-        for_slots([&](auto slc) {
-          constexpr int sl = decltype(slc)::value;
-          constexpr int str = sl < 2 * SX ? 1 : n;
-          const T *ptr = src + (size_t)hcn[sl] * ND + hline[sl];
+        // two half batches: NSLOT lines of n values at once would be 120 registers (the first version spilled them)
+        T *hb = HXY + (size_t)(p & 1) * HBUF;
+        auto half = [&](auto lo_c, auto hi_c) {
+          constexpr int LO = decltype(lo_c)::value, HI = decltype(hi_c)::value;
+          T x[HI - LO][n];
+          auto for_half = [&](auto &&f) {
+            [&]<int... I>(std::integer_sequence<int, I...>) { (f(std::integral_constant<int, LO + I>{}), ...); }(std::make_integer_sequence<int, HI - LO>{});
+          };
+          for_half([&](auto slc) {
+            constexpr int sl = decltype(slc)::value;
+            constexpr int str = sl < 2 * SX ? 1 : n;
+            const T *ptr = src + (size_t)hcn[sl] * ND + hline[sl];
 #pragma unroll
-          for (int l = 0; l < n; ++l) x[sl][l] = __ldg(ptr + l * str);
-        });
+            for (int l = 0; l < n; ++l) x[sl - LO][l] = __ldg(ptr + l * str);
+          });
+          for_half([&](auto slc) {
+            constexpr int sl = decltype(slc)::value;
+            constexpr int dir = sl < 2 * SX ? 0 : 1, side = dir == 0 ? sl / SX : (sl - 2 * SX) / SY, rnd = dir == 0 ? sl % SX : (sl - 2 * SX) % SY;
+            constexpr int per_side = (dir == 0 ? TYC : TXC) * NL;
+            constexpr int base = (dir == 0 ? 0 : 2 * TYC * NL) + side * per_side;
+            T g0, g1;
+            line_traces<n, T, false>(P, Q, x[sl - LO], g0, g1);
+            const int e = t + rnd * NT;
+            if (e < per_side) {
+              P2 v;
+              v.x = side ? x[sl - LO][0] : x[sl - LO][n - 1];   // the halo cell's facing side is 1 - side
+              v.y = side ? g0 : g1;
+              *reinterpret_cast<P2 *>(hb + 2 * (base + e)) = v;
+            }
+          });
+        };
+        half(std::integral_constant<int, 0>{}, std::integral_constant<int, NSLOT / 2>{});
+        half(std::integral_constant<int, NSLOT / 2>{}, std::integral_constant<int, NSLOT>{});
         const long long sh = plane_term(G, z0 + (p + 1 < NZ ? p + 1 : p)) - pt0;
-        for_slots([&](auto slc) {
+        for_slots([&](auto slc) {   // halo cells of the next plane
           constexpr int sl = decltype(slc)::value;
           constexpr int dir = sl < 2 * SX ? 0 : 1, side = dir == 0 ? sl / SX : (sl - 2 * SX) / SY;
           hcn[sl] = nbr[(size_t)(2 * dir + side) * no + (hcell[sl] + sh)];
-        });
-        T *hb = HXY + (size_t)(p & 1) * HBUF;
-        for_slots([&](auto slc) {
-          constexpr int sl = decltype(slc)::value;
-          constexpr int dir = sl < 2 * SX ? 0 : 1, side = dir == 0 ? sl / SX : (sl - 2 * SX) / SY, rnd = dir == 0 ? sl % SX : (sl - 2 * SX) % SY;
-          constexpr int per_side = (dir == 0 ? TYC : TXC) * NL;
-          constexpr int base = (dir == 0 ? 0 : 2 * TYC * NL) + side * per_side;
-          T g0, g1;
-          line_traces<n, T, false>(P, Q, x[sl], g0, g1);
-          const int e = t + rnd * NT;
-          if (e < per_side) {
-            P2 v;
-            v.x = side ? x[sl][0] : x[sl][n - 1];   // the halo cell's facing side is 1 - side
-            v.y = side ? g0 : g1;
-            *reinterpret_cast<P2 *>(hb + 2 * (base + e)) = v;
-          }
         });
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[p & 1]);
       }
       if (ridx == 0 && p >= 2) {   // bulk-store plane p - 2
         const int ps = p - 2;
-        mbar_wait_sleep(outfull, (unsigned)(ps & 1));
+        mbar_wait_mode(outfull, (unsigned)(ps & 1), G.wait_mode & 4);
         if (lane < TC / 4) {
           const long long sh = plane_term(G, z0 + ps) - pt0;
           const int ci = cell_index(G, x0 + slot_cx(4 * lane), y0 + slot_cy(4 * lane), z0);

@@ -58,7 +58,7 @@ struct dgx_mg {
   struct CycleGraph { int stage; double dt; unsigned long long gen; int warm = 0; cudaGraphExec_t exec = nullptr; long long launches = 0; };
   std::vector<CycleGraph> graphs;
   unsigned long long est_gen = 0;            // bumped whenever smoother estimates are recomputed (they are kernel arguments)
-  bool graphs_ok = true;
+  bool graphs_ok = true, warmed = false;
   // Chebyshev eigenvalue estimates per (TR_BDF2 stage, dt): they depend on nothing else (the level operators are fixed by the
   // mesh, kappa(stage, dt) and the degree), so a time loop pays the 10 CG iterations per level once per stage, not per solve
   struct EigKey { int stage; double dt; };
@@ -680,7 +680,10 @@ int mg_cycle(dgx_mg *mg) {
     g = &mg->graphs.back();
   }
   cudaStream_t st = mg->ctx->stream;
-  if (g->warm == 0) { g->warm = 1; return mg_level(mg, L); }
+  if (g->warm == 0) {   // the very first cycle of this object runs eagerly: it allocates pooled work vectors and send buffers
+    g->warm = 1;
+    if (!mg->warmed) { mg->warmed = true; return mg_level(mg, L); }
+  }
   if (!g->exec) {
     const long long l0 = g_launch_count;
     if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); mg->graphs_ok = false; return mg_level(mg, L); }

@@ -190,11 +190,12 @@ def test_marching_kernel_matches_oracle(dgx, gpu_ctx, case, degree, np_dtype):
     assert rel_l2(dst.to_host(), ref) < TOL[np_dtype]
 
 
-@pytest.mark.parametrize("gen", ["v1", "v2", "v2eo"])
+@pytest.mark.parametrize("gen", ["v1", "v2", "v2eo", "v2r", "v2eor", "v2eol"])
 @pytest.mark.parametrize("case", FAST_CASES + [([1, 2, 1], 4)], ids=lambda c: f"{c[0]}-r{c[1]}")
 def test_marching_generations_match_oracle(dgx, gpu_ctx, case, gen, monkeypatch):
     """Q4 fp64 through every generation of the marching kernel (DGX_MARCH): v1 = round-1 kernel (named barriers), v2 =
-    mbarrier hand-offs + shuffled traces + bulk stores, v2eo = v2 with even-odd 1-D contractions (the default)."""
+    mbarrier hand-offs + shuffled traces + bulk stores, v2eo = v2 with even-odd 1-D contractions, v2r / v2eor = streaming XY
+    role (v2eor is the default), v2eol = XY role in lockstep batches."""
     monkeypatch.setenv("DGX_MARCH", gen)
     cells0, nref = case
     for stage in (1, 2):
@@ -218,7 +219,7 @@ def test_marching_generations_agree_at_scale(dgx, gpu_ctx, monkeypatch):
     op.vmult(dst, src)
     ref = dst.to_host()
     op.set_variant(2)
-    for gen in ("v1", "v2", "v2eo"):
+    for gen in ("v1", "v2", "v2eo", "v2r", "v2eor", "v2eol"):
         monkeypatch.setenv("DGX_MARCH", gen)
         dst.set(0.0)
         op.vmult(dst, src)
