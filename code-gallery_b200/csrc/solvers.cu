@@ -55,7 +55,10 @@ struct dgx_mg {
   long long log_setup = 0;                   // log position at the last setup (dgx_mg_coarse_iterations reports from here)
   // the V-cycle as a CUDA graph per (stage, dt, estimate generation): launch sequence and kernel arguments are identical from
   // one application to the next (defect / solution / work vectors are owned by this object)
-  struct CycleGraph { int stage; double dt; unsigned long long gen; int warm = 0; cudaGraphExec_t exec = nullptr; long long launches = 0; };
+  // A combination is captured only when it comes back in a LATER solve (capturing costs about one eager cycle on one GPU and
+  // several with NCCL nodes): with recomputed estimates every solve has its own generation and stays eager.
+  struct CycleGraph { int stage; double dt; unsigned long long gen; long long first_setup = 0; cudaGraphExec_t exec = nullptr; long long launches = 0; };
+  long long n_setups = 0;
   std::vector<CycleGraph> graphs;
   unsigned long long est_gen = 0;            // bumped whenever smoother estimates are recomputed (they are kernel arguments)
   bool graphs_ok = true, warmed = false;
@@ -584,6 +587,7 @@ int dgx_mg_set_TR_BDF2_stage(dgx_mg *mg, int stage) {   // NS.cc:2941-2943, 2967
 int dgx_mg_setup(dgx_mg *mg, double coarse_abs_tol, int coarse_max_it) {
   DGX_REQUIRE(mg, "null argument");
   if (coarse_max_it != mg->coarse_max_it) ++mg->est_gen;   // a kernel argument of the captured cycle
+  ++mg->n_setups;
   mg->coarse_tol = coarse_abs_tol;
   mg->coarse_max_it = coarse_max_it;
   mg->coarse_its.clear();
@@ -675,15 +679,12 @@ int mg_cycle(dgx_mg *mg) {
       mg->graphs.clear();
     }
     dgx_mg::CycleGraph e;
-    e.stage = mg->stage; e.dt = mg->dt; e.gen = mg->est_gen;
+    e.stage = mg->stage; e.dt = mg->dt; e.gen = mg->est_gen; e.first_setup = mg->n_setups;
     mg->graphs.push_back(e);
     g = &mg->graphs.back();
   }
   cudaStream_t st = mg->ctx->stream;
-  if (g->warm == 0) {   // the very first cycle of this object runs eagerly: it allocates pooled work vectors and send buffers
-    g->warm = 1;
-    if (!mg->warmed) { mg->warmed = true; return mg_level(mg, L); }
-  }
+  if (!g->exec && g->first_setup == mg->n_setups) { mg->warmed = true; return mg_level(mg, L); }   // first solve with this combination: eager
   if (!g->exec) {
     const long long l0 = g_launch_count;
     if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); mg->graphs_ok = false; return mg_level(mg, L); }
