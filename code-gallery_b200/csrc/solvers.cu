@@ -569,6 +569,22 @@ int dgx_mg_destroy(dgx_mg *mg) {
 
 int dgx_mg_n_levels(const dgx_mg *mg) { return mg ? mg->n_levels : 0; }
 
+// smoother_data[level] of NS.cc:2501-2516 (PreconditionChebyshev::AdditionalData).  Level 0 is solved by the coarse grid solver:
+// the data the reference stores there (NS.cc:2510-2512) is never used by Multigrid and is accepted and ignored here.
+int dgx_mg_set_smoother(dgx_mg *mg, int level, int degree, double smoothing_range, int eig_cg_n_iterations) {
+  DGX_REQUIRE(mg && level >= 0 && level < mg->n_levels, "level");
+  if (level == 0) return DGX_OK;
+  DGX_REQUIRE(degree >= 1 && eig_cg_n_iterations >= 0, "Chebyshev degree / eigenvalue iterations");
+  dgx_cheb *c = mg->smoother[level];
+  if (c->degree != degree || c->smoothing_range != smoothing_range || c->eig_cg_n_iterations != eig_cg_n_iterations) {
+    c->degree = degree; c->smoothing_range = smoothing_range; c->eig_cg_n_iterations = eig_cg_n_iterations;
+    c->initialized = false;
+    mg->eig_cache.clear();
+    ++mg->est_gen;
+  }
+  return DGX_OK;
+}
+
 int dgx_mg_set_dt(dgx_mg *mg, double dt) {
   DGX_REQUIRE(mg, "null argument");
   mg->dt = dt;

@@ -28,7 +28,9 @@ public:
     const double L = 2.0 * M_PI;
     triangulation.subdivided_hyper_rectangle({1, 1, 1}, {0.0, 0.0, 0.0}, {L, L, L}, {true, true, true}, n_refines);
     matrix_free_storage = std::make_unique<MatrixFree<dim>>(context, triangulation);                   // NS.cc:2329
-    preconditioner_mg = std::make_unique<PreconditionMG<dim>>(context, triangulation, degree_p, Re, dt);   // NS.cc:2351-2379
+    mg_matrices = std::make_unique<MGLevelOperators<dim>>(context, triangulation, degree_p, Re, dt);      // NS.cc:2351-2379
+    dof_handler_pressure.tria = &triangulation;
+    dof_handler_pressure.fe_degree = degree_p;                                                              // NS.cc:2282-2283
     for (Vec *v : {&u_star, &rhs_u, &u_n, &u_extr, &u_n_minus_1, &u_n_gamma, &u_tmp, &grad_pres_int})
       v->reinit(*matrix_free_storage, degree_p + 1, dim);                                               // NS.cc:2330-2337
     for (Vec *v : {&pres_int, &pres_n, &rhs_p}) v->reinit(*matrix_free_storage, degree_p, 1);            // NS.cc:2339-2341
@@ -82,16 +84,51 @@ public:
     navier_stokes_matrix.initialize(*matrix_free_storage, 2);
     if (TR_BDF2_stage == 1) navier_stokes_matrix.vmult_rhs_pressure(rhs_p, {&u_star, &pres_n});
     else navier_stokes_matrix.vmult_rhs_pressure(rhs_p, {&u_star, &pres_int});
+    /*--- Build the linear solver (NS.cc:2485-2487) ---*/
     SolverControl solver_control(max_its, eps * rhs_p.l2_norm());
     SolverCG<Vec> cg(solver_control);
-    // transfer, Chebyshev smoothers, coarse CG and the multigrid object (NS.cc:2490-2537) are rebuilt for this solve
-    preconditioner_mg->setup(solver_control);
+
+    /*--- Build the preconditioner (NS.cc:2489-2537, statement by statement) ---*/
+    MGTransferMatrixFree<dim, float> mg_transfer;
+    mg_transfer.build(dof_handler_pressure);
+
+    using SmootherType = PreconditionChebyshev<LevelOperator<dim>, Vector<float>>;
+    mg::SmootherRelaxation<SmootherType, Vector<float>> mg_smoother;
+    MGLevelObject<typename SmootherType::AdditionalData> smoother_data;
+    smoother_data.resize(0, triangulation.n_global_levels() - 1);
+    for (unsigned int level = 0; level < triangulation.n_global_levels(); ++level) {
+      auto level_matrix = (*mg_matrices)[level];
+      if (level > 0) {
+        smoother_data[level].smoothing_range = 15.0;
+        smoother_data[level].degree = 3;
+        smoother_data[level].eig_cg_n_iterations = 10;
+      } else {
+        smoother_data[0].smoothing_range = 2e-2;
+        smoother_data[0].degree = numbers::invalid_unsigned_int;
+        smoother_data[0].eig_cg_n_iterations = (unsigned int)level_matrix.m();
+      }
+      level_matrix.compute_diagonal();
+      smoother_data[level].preconditioner = level_matrix.get_matrix_diagonal_inverse();
+    }
+    mg_smoother.initialize(*mg_matrices, smoother_data);
+
+    PreconditionIdentity identity;
+    SolverCG<Vector<float>> cg_mg(solver_control);
+    MGCoarseGridIterativeSolver<Vector<float>, SolverCG<Vector<float>>, LevelOperator<dim>, PreconditionIdentity> mg_coarse(cg_mg, (*mg_matrices)[0], identity);
+
+    mg::Matrix<Vector<float>> mg_matrix(*mg_matrices);
+
+    Multigrid<Vector<float>> mg(mg_matrix, mg_coarse, mg_transfer, mg_smoother, mg_smoother);
+
+    PreconditionMG<dim, Vector<float>, MGTransferMatrixFree<dim, float>> preconditioner(dof_handler_pressure, mg, mg_transfer);
+
+    /*--- Solve the linear system (NS.cc:2539-2547) ---*/
     if (TR_BDF2_stage == 1) {
       pres_int = pres_n;
-      cg.solve(navier_stokes_matrix, pres_int, rhs_p, *preconditioner_mg);
+      cg.solve(navier_stokes_matrix, pres_int, rhs_p, preconditioner);
     } else {
       pres_n = pres_int;
-      cg.solve(navier_stokes_matrix, pres_n, rhs_p, *preconditioner_mg);
+      cg.solve(navier_stokes_matrix, pres_n, rhs_p, preconditioner);
     }
     iterations.emplace_back("cg_pressure_stage" + std::to_string(TR_BDF2_stage), solver_control.last_step());
   }
@@ -110,7 +147,7 @@ public:
   void set_stage(unsigned int s) {                                                                     // NS.cc:2940-2943, 2967-2969
     TR_BDF2_stage = s;
     navier_stokes_matrix.set_TR_BDF2_stage(s);
-    preconditioner_mg->set_TR_BDF2_stage(s);
+    mg_matrices->set_TR_BDF2_stage(s);
   }
 
   // one pass of the while loop of run(), NS.cc:2934-2986
@@ -149,7 +186,8 @@ public:
   unsigned int TR_BDF2_stage = 1;
   Triangulation<dim> triangulation;
   std::unique_ptr<MatrixFree<dim>> matrix_free_storage;
-  std::unique_ptr<PreconditionMG<dim>> preconditioner_mg;
+  std::unique_ptr<MGLevelOperators<dim>> mg_matrices;
+  DoFHandler<dim> dof_handler_pressure;
   NavierStokesProjectionOperator<dim> navier_stokes_matrix;
   Vec pres_int, pres_n, rhs_p, u_star, rhs_u, u_n, u_extr, u_n_minus_1, u_n_gamma, u_tmp, grad_pres_int;
   std::vector<std::pair<std::string, unsigned int>> iterations;

@@ -194,6 +194,9 @@ int dgx_cheb_step(dgx_cheb *c, dgx_vec *x, dgx_vec *b);        /* non-zero initi
 int dgx_mg_create(dgx_ctx *ctx, dgx_mesh *mesh, int degree, int level_dtype, double Re, double dt, dgx_mg **out);
 int dgx_mg_destroy(dgx_mg *mg);
 int dgx_mg_n_levels(const dgx_mg *mg);
+/* smoother_data[level] (PreconditionChebyshev::AdditionalData, NS.cc:2501-2516); defaults are the reference's 3 / 15.0 / 10.
+ * Level 0 is solved by the coarse solver: its data (NS.cc:2510-2512) is accepted and ignored, as Multigrid never uses it. */
+int dgx_mg_set_smoother(dgx_mg *mg, int level, int degree, double smoothing_range, int eig_cg_n_iterations);
 int dgx_mg_set_dt(dgx_mg *mg, double dt);
 int dgx_mg_set_TR_BDF2_stage(dgx_mg *mg, int stage);
 int dgx_mg_setup(dgx_mg *mg, double coarse_abs_tol, int coarse_max_it);   /* diagonals + eigenvalue estimates */

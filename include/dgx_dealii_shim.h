@@ -10,6 +10,7 @@
 #ifndef DGX_DEALII_SHIM_H
 #define DGX_DEALII_SHIM_H
 
+#include <algorithm>
 #include <array>
 #include <cmath>
 #include <cstddef>
@@ -233,31 +234,173 @@ struct PreconditionJacobi {                                                     
   const Op *op_ = nullptr;
 };
 
-// mg::Matrix + MGTransferMatrixFree + mg::SmootherRelaxation<PreconditionChebyshev> + MGCoarseGridIterativeSolver +
-// Multigrid + PreconditionMG (NS.cc:2490-2537) as one object: levels 0..n_global_levels-1, float level operators,
-// Chebyshev(degree 3, smoothing range 15, 10 eigenvalue CG iterations), coarse CG sharing the outer SolverControl
+// ---- multigrid wiring of projection_step, NS.cc:2490-2537, class by class ----------------------------------------------
+// The reference builds the preconditioner from separate deal.II objects every solve.  Here every object is a thin, typed
+// view on ONE device engine (dgx_mg: level MatrixFree / operators / vectors, transfer, smoothers, coarse solver) that
+// lives with mg_matrices; each class forwards exactly the piece of configuration its deal.II namesake holds, so
+// projection_step keeps its statements (examples/trbdf2_tgv.cpp).
+
+// DoFHandler<dim> of the pressure space as far as MGTransferMatrixFree::build and PreconditionMG look at it
 template <int dim>
-class PreconditionMG {
+struct DoFHandler {
+  Triangulation<dim> *tria = nullptr;
+  int fe_degree = 1;
+};
+
+template <int dim> class MGLevelOperators;
+
+// mg_matrices[level]: the float level operator (NS.cc:2376-2379) = a borrowed dgx_op of the engine
+template <int dim>
+class LevelOperator {
 public:
-  PreconditionMG(Context &ctx, Triangulation<dim> &tria, int fe_degree_p, double Reynolds, double dt) {
+  LevelOperator(dgx_mg *mg, int level) : mg_(mg), level_(level) { check(dgx_mg_level_op(mg, level, &h)); }
+  void compute_diagonal() { check(dgx_op_compute_diagonal(h)); }                                       // NS.cc:2514
+  dgx_vec *get_matrix_diagonal_inverse() const { dgx_vec *d = nullptr; check(dgx_op_get_matrix_diagonal_inverse(h, &d)); return d; }   // NS.cc:2515
+  std::size_t m() const { return (std::size_t)dgx_op_m(h); }                                           // NS.cc:2512
+  int level() const { return level_; }
+  dgx_op *h = nullptr;
+
+private:
+  dgx_mg *mg_;
+  int level_;
+};
+
+// MGLevelObject<NavierStokesProjectionOperator<..., Vector<float>>> mg_matrices (NS.cc:2351-2379): owns the engine
+template <int dim>
+class MGLevelOperators {
+public:
+  MGLevelOperators(Context &ctx, Triangulation<dim> &tria, int fe_degree_p, double Reynolds, double dt) : tria_(&tria) {
     check(dgx_mg_create(ctx.h, tria.h, fe_degree_p, DGX_F32, Reynolds, dt, &h));
   }
-  ~PreconditionMG() { if (h) dgx_mg_destroy(h); }
-  PreconditionMG(const PreconditionMG &) = delete;
-  void set_dt(double dt) { check(dgx_mg_set_dt(h, dt)); }
-  void set_TR_BDF2_stage(unsigned int s) { check(dgx_mg_set_TR_BDF2_stage(h, (int)s)); }
-  // the per-solve rebuild of NS.cc:2501-2529: level diagonals, eigenvalue estimates, coarse solver control
-  void setup(const SolverControl &coarse_control) { check(dgx_mg_setup(h, coarse_control.tolerance(), (int)coarse_control.max_steps())); }
+  ~MGLevelOperators() { if (h) dgx_mg_destroy(h); }
+  MGLevelOperators(const MGLevelOperators &) = delete;
+  LevelOperator<dim> operator[](unsigned int level) const { return LevelOperator<dim>(h, (int)level); }
+  unsigned int min_level() const { return 0; }
+  unsigned int max_level() const { return (unsigned)dgx_mg_n_levels(h) - 1; }
+  void set_dt(double dt) { check(dgx_mg_set_dt(h, dt)); }                                              // NS.cc:2945-2948 on every level
+  void set_TR_BDF2_stage(unsigned int s) { check(dgx_mg_set_TR_BDF2_stage(h, (int)s)); }               // NS.cc:2941-2943
+  dgx_mg *h = nullptr;
+
+private:
+  Triangulation<dim> *tria_;
+};
+
+// MGLevelObject<T>: resize(min, max), operator[]
+template <typename T>
+class MGLevelObject {
+public:
+  void resize(unsigned int min_level, unsigned int max_level) { min_ = min_level; v_.assign(max_level - min_level + 1, T()); }
+  T &operator[](unsigned int level) { return v_.at(level - min_); }
+  const T &operator[](unsigned int level) const { return v_.at(level - min_); }
+  unsigned int min_level() const { return min_; }
+  unsigned int max_level() const { return min_ + (unsigned)v_.size() - 1; }
+
+private:
+  unsigned int min_ = 0;
+  std::vector<T> v_;
+};
+
+namespace numbers { constexpr unsigned int invalid_unsigned_int = static_cast<unsigned int>(-1); }
+
+// MGTransferMatrixFree<dim, Number> (NS.cc:2490-2491).  For FE_DGQ on the globally refined hierarchy the transfer is the fixed
+// embedding of a parent's basis into its children (dgx_transfer_prolongate_and_add / restrict_and_add): build() has no tables
+// to fill, it only checks the space.
+template <int dim, typename Number>
+class MGTransferMatrixFree {
+public:
+  void build(const DoFHandler<dim> &dof_handler) {
+    if (!dof_handler.tria || dof_handler.fe_degree < 1) throw ExcDGX("MGTransferMatrixFree::build: DoFHandler without triangulation / element");
+    built_ = true;
+  }
+  bool built() const { return built_; }
+
+private:
+  bool built_ = false;
+};
+
+// PreconditionChebyshev<Operator, Vector> (NS.cc:2493-2499): only its AdditionalData appears in the driver
+template <typename Op, typename Vec>
+struct PreconditionChebyshev {
+  struct AdditionalData {
+    double smoothing_range = 0.0;
+    unsigned int degree = 1;
+    unsigned int eig_cg_n_iterations = 8;
+    dgx_vec *preconditioner = nullptr;      // the inverse diagonal of the level operator (NS.cc:2515)
+  };
+};
+
+namespace mg {
+// mg::SmootherRelaxation<SmootherType, Vec> (NS.cc:2500, 2517)
+template <typename SmootherType, typename Vec>
+class SmootherRelaxation {
+public:
+  template <int dim>
+  void initialize(const MGLevelOperators<dim> &mg_matrices, const MGLevelObject<typename SmootherType::AdditionalData> &data) {
+    for (unsigned int level = data.min_level(); level <= data.max_level(); ++level) {
+      const auto &d = data[level];
+      if (level > 0 && !d.preconditioner) throw ExcDGX("SmootherRelaxation::initialize: level without inverse diagonal (compute_diagonal first)");
+      check(dgx_mg_set_smoother(mg_matrices.h, (int)level, d.degree == numbers::invalid_unsigned_int ? 1 : (int)d.degree, d.smoothing_range,
+                                (int)std::min<unsigned int>(d.eig_cg_n_iterations, 1u << 30)));
+    }
+    engine = mg_matrices.h;
+  }
+  dgx_mg *engine = nullptr;
+};
+
+// mg::Matrix<Vec> (NS.cc:2531)
+template <typename Vec>
+class Matrix {
+public:
+  template <int dim> explicit Matrix(const MGLevelOperators<dim> &mg_matrices) : engine(mg_matrices.h) {}
+  dgx_mg *engine;
+};
+}  // namespace mg
+
+// MGCoarseGridIterativeSolver<Vec, SolverCG<Vec>, Operator, PreconditionIdentity> (NS.cc:2519-2529): CG on level 0 with
+// the SolverControl of the solver handed in (the reference shares the outer solver_control, NS.cc:2520)
+template <typename Vec> class SolverCG;
+template <typename Vec, typename Solver, typename Op, typename Pre>
+class MGCoarseGridIterativeSolver {
+public:
+  MGCoarseGridIterativeSolver(Solver &solver, const Op &coarse_matrix, const Pre &) : control(&solver.control()) {
+    if (coarse_matrix.level() != 0) throw ExcDGX("MGCoarseGridIterativeSolver: the coarse matrix must be level 0");
+  }
+  const SolverControl *control;
+};
+
+// Multigrid<Vec>(matrix, coarse, transfer, pre_smooth, post_smooth) (NS.cc:2533): V-cycle over all levels
+template <typename Vec>
+class Multigrid {
+public:
+  template <class Coarse, class Transfer, class Smoother>
+  Multigrid(const mg::Matrix<Vec> &matrix, const Coarse &coarse, const Transfer &transfer, const Smoother &pre, const Smoother &post)
+      : engine(matrix.engine), coarse_control(coarse.control) {
+    if (!transfer.built()) throw ExcDGX("Multigrid: transfer.build() has not been called");
+    if (pre.engine != engine || post.engine != engine) throw ExcDGX("Multigrid: smoother initialised on other level matrices");
+  }
+  dgx_mg *engine;
+  const SolverControl *coarse_control;
+};
+
+// PreconditionMG<dim, Vec, Transfer>(dof_handler, mg, transfer) (NS.cc:2535-2537): what SolverCG applies.  Construction
+// finishes the per-solve set-up of the engine (eigenvalue estimates of the smoothers, coarse solver control).
+template <int dim, typename Vec, typename Transfer>
+class PreconditionMG {
+public:
+  PreconditionMG(const DoFHandler<dim> &, Multigrid<Vec> &mg, const Transfer &) : h(mg.engine) {
+    check(dgx_mg_setup(h, mg.coarse_control->tolerance(), (int)mg.coarse_control->max_steps()));
+  }
   void vmult(Vector<double> &dst, Vector<double> &src) const { check(dgx_mg_vmult(h, dst.h, src.h)); }
   int kind() const { return 2; }
   void *handle() const { return (void *)h; }
-  dgx_mg *h = nullptr;
+  dgx_mg *h;
 };
 
 template <typename Vec>
 class SolverCG {                                                                                       // NS.cc:2487, 2542, 2546, 2575
 public:
   explicit SolverCG(SolverControl &c) : control_(c) {}
+  SolverControl &control() const { return control_; }
   template <class Op, class Pre>
   void solve(const Op &A, Vec &x, Vec &b, const Pre &P) {
     int its = 0;
