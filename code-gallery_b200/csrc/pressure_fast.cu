@@ -694,6 +694,7 @@ void fill_fast_params(FastParams<T, n> &F, const dgx_op *op) {
 }
 
 #include "pressure_march_v2.cuh"
+#include "pressure_march_v3.cuh"
 
 // which marching kernel runs the plain (no add, no fused update) Q4 fp64 operator: DGX_MARCH = v1 | v2 | v2eo | v2r | v2eor (default) | v2eol
 inline int march_generation() {   // read on every call (tests and the bench switch it inside one process)
@@ -704,6 +705,11 @@ inline int march_generation() {   // read on every call (tests and the bench swi
   if (!strcmp(e, "v2eo")) return 2;    // + even-odd contractions
   if (!strcmp(e, "v2r")) return 3;     // plain contractions, streaming XY role
   if (!strcmp(e, "v2eol")) return 5;   // even-odd, XY role in lockstep batches
+  if (!strcmp(e, "v3")) return 10;     // v3: single Z visit (Mz folded), XY tasks on 7 warps, halo traces by the Z warps, batches of 3 lines
+  if (!strcmp(e, "v3x5")) return 11;   // 5 XY + 5 Z warps
+  if (!strcmp(e, "v3x6")) return 12;   // 6 XY + 5 Z warps
+  if (!strcmp(e, "v3b2")) return 13;   // as v3, batches of 2 lines
+  if (!strcmp(e, "v3b32")) return 14;  // as v3, rows in batches of 3, columns in batches of 2
   return 4;                            // v2eor (default): even-odd, streaming XY role with a 3-stage software pipeline
 }
 
@@ -738,12 +744,45 @@ int launch_march2(dgx_op *op, dgx_vec *dst, const dgx_vec *src, const FastGeom &
   return DGX_OK;
 }
 
+
+template <int n, typename T, int NXY, int NBX, int NBY>
+int launch_march3(dgx_op *op, dgx_vec *dst, const dgx_vec *src, const FastGeom &G, const int *d_jobs, int n_jobs, cudaStream_t stream) {
+  using R = Roles3<n, NXY>;
+  constexpr int NL = n * n, ND = NL * n;
+  EOParams<T, n> Q;
+  {
+    FastParams<double, n> Fd;
+    fill_fast_params<double, n>(Fd, op);
+    if (eo_asymmetry<n>(Fd) > 1e-13) { set_error("marching kernel: 1-D tables are not centro-symmetric"); return DGX_ERR_INVALID; }
+    fill_eo_params_v3<T, n>(Q, Fd);
+  }
+  constexpr size_t smem = sizeof(T) * (size_t)((R::NSU + R::NSW) * TC * ND + R::NSH * (2 * TYC + 2 * TXC) * NL * 2) + 8 * (3 * R::NSU + 4) + 4 * R::NSU + 16;
+  int dev = 0;
+  DGX_CUDA_CHECK(cudaGetDevice(&dev));
+  static bool configured[64] = {};
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    DGX_CUDA_CHECK(cudaFuncSetAttribute(pressure_march3_kernel<n, T, NXY, NBX, NBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[dev] = true;
+  }
+  const int grid = d_jobs ? n_jobs : G.ntx * G.nty * G.nsz;
+  if (grid == 0) return DGX_OK;
+  pressure_march3_kernel<n, T, NXY, NBX, NBY><<<grid, R::NW * 32, smem, stream>>>(Q, G, op->mf->d_nbr, (const T *)src->d, (T *)dst->d, d_jobs);
+  count_launch();
+  DGX_CUDA_CHECK(cudaGetLastError());
+  return DGX_OK;
+}
+
 template <int n, typename T>
 int launch_march(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const FastGeom &G, const int *d_jobs, int n_jobs, cudaStream_t stream,
                  const FusedUpdate *fu) {
   if constexpr (n == 5 && std::is_same<T, double>::value) {
     if (!add && !fu && march_generation() > 0)
       switch (march_generation()) {
+        case 10: return launch_march3<n, T, 7, 3, 3>(op, dst, src, G, d_jobs, n_jobs, stream);
+        case 11: return launch_march3<n, T, 5, 3, 3>(op, dst, src, G, d_jobs, n_jobs, stream);
+        case 12: return launch_march3<n, T, 6, 3, 3>(op, dst, src, G, d_jobs, n_jobs, stream);
+        case 13: return launch_march3<n, T, 7, 2, 2>(op, dst, src, G, d_jobs, n_jobs, stream);
+        case 14: return launch_march3<n, T, 7, 3, 2>(op, dst, src, G, d_jobs, n_jobs, stream);
         case 1: return launch_march2<n, T, false, 0>(op, dst, src, G, d_jobs, n_jobs, stream);
         case 3: return launch_march2<n, T, false, 1>(op, dst, src, G, d_jobs, n_jobs, stream);
         case 4: return launch_march2<n, T, true, 1>(op, dst, src, G, d_jobs, n_jobs, stream);
