@@ -750,13 +750,14 @@ int launch_march3(dgx_op *op, dgx_vec *dst, const dgx_vec *src, const FastGeom &
   using R = Roles3<n, NXY>;
   constexpr int NL = n * n, ND = NL * n;
   EOParams<T, n> Q;
+  ZTop<T, n> ZT;
   {
     FastParams<double, n> Fd;
     fill_fast_params<double, n>(Fd, op);
     if (eo_asymmetry<n>(Fd) > 1e-13) { set_error("marching kernel: 1-D tables are not centro-symmetric"); return DGX_ERR_INVALID; }
-    fill_eo_params_v3<T, n>(Q, Fd);
+    fill_eo_params_v3<T, n>(Q, ZT, Fd);
   }
-  constexpr size_t smem = sizeof(T) * (size_t)((R::NSU + R::NSW) * TC * ND + R::NSH * (2 * TYC + 2 * TXC) * NL * 2) + 8 * (3 * R::NSU + 4) + 4 * R::NSU + 16;
+  constexpr size_t smem = sizeof(T) * (size_t)((R::NSU + R::NSW) * TC * ND + R::NSH * (2 * TYC + 2 * TXC) * NL * 2) + 8 * (4 * R::NSU + 4) + 4 * R::NSU + 16;
   int dev = 0;
   DGX_CUDA_CHECK(cudaGetDevice(&dev));
   static bool configured[64] = {};
@@ -766,7 +767,7 @@ int launch_march3(dgx_op *op, dgx_vec *dst, const dgx_vec *src, const FastGeom &
   }
   const int grid = d_jobs ? n_jobs : G.ntx * G.nty * G.nsz;
   if (grid == 0) return DGX_OK;
-  pressure_march3_kernel<n, T, NXY, NBX, NBY><<<grid, R::NW * 32, smem, stream>>>(Q, G, op->mf->d_nbr, (const T *)src->d, (T *)dst->d, d_jobs);
+  pressure_march3_kernel<n, T, NXY, NBX, NBY><<<grid, R::NW * 32, smem, stream>>>(Q, ZT, G, op->mf->d_nbr, (const T *)src->d, (T *)dst->d, d_jobs);
   count_launch();
   DGX_CUDA_CHECK(cudaGetLastError());
   return DGX_OK;

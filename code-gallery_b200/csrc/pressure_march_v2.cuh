@@ -197,7 +197,7 @@ __device__ __forceinline__ void traces_eo_nb(const EOParams<T, n> &Q, const T (&
   for (int b = 0; b < NB; ++b) { G0[b] = gs[b] + gd[b]; G1[b] = gs[b] - gd[b]; }
 }
 // out[b] += K' [u[b]; V0', G0', V1', G1'] for NB lines of direction d (nv[b] = V0', G0', V1', G1')
-template <int n, typename T, int NB>
+template <int n, typename T, int NB, bool ACC = true>
 __device__ __forceinline__ void lines_eo_nb(const EOParams<T, n> &Q, const int d, const T (&u)[NB][n], const T (&nv)[NB][4], T (&out)[NB][n]) {
   constexpr int NE = (n + 1) / 2, NO = n / 2;
   T e[NB][NE], o[NB][NO > 0 ? NO : 1], ve[NB], vo[NB], ge[NB], go[NB];
@@ -215,7 +215,7 @@ __device__ __forceinline__ void lines_eo_nb(const EOParams<T, n> &Q, const int d
     {
       const T c = Q.KEv[d][i];
 #pragma unroll
-      for (int b = 0; b < NB; ++b) s[b] = mid ? fma(c, ve[b], out[b][i]) : c * ve[b];
+      for (int b = 0; b < NB; ++b) s[b] = (mid && ACC) ? fma(c, ve[b], out[b][i]) : c * ve[b];
     }
     {
       const T c = Q.KEg[d][i];
@@ -250,7 +250,10 @@ __device__ __forceinline__ void lines_eo_nb(const EOParams<T, n> &Q, const int d
       for (int b = 0; b < NB; ++b) dd[b] = fma(c, o[b][l], dd[b]);
     }
 #pragma unroll
-    for (int b = 0; b < NB; ++b) { out[b][i] = (out[b][i] + s[b]) + dd[b]; out[b][n - 1 - i] = (out[b][n - 1 - i] + s[b]) - dd[b]; }
+    for (int b = 0; b < NB; ++b) {
+      if (ACC) { out[b][i] = (out[b][i] + s[b]) + dd[b]; out[b][n - 1 - i] = (out[b][n - 1 - i] + s[b]) - dd[b]; }
+      else { out[b][i] = s[b] + dd[b]; out[b][n - 1 - i] = s[b] - dd[b]; }
+    }
   }
 }
 // out[b] = (h M) q[b] for NB lines of direction d

@@ -90,9 +90,37 @@ __device__ __forceinline__ void mass1(const EOParams<T, n> &Q, int d, const T (&
   }
 }
 
+// top-face (side 1) coefficient vectors of the folded z operator, plain form: the Z warps add this part of Az u once the plane
+// above has landed, everything else before
+template <typename T, int n>
+struct ZTop { T cV[n], cG[n]; };
+
+// even-odd line operator with the side-1 traces absent: out = K' [u; V0', G0', 0, 0] (direction d of EOParams)
+template <int n, typename T>
+__device__ __forceinline__ void line_eo_side0(const EOParams<T, n> &Q, int d, const T (&u)[n], T V0, T G0, T (&out)[n]) {
+  constexpr int NE = (n + 1) / 2, NO = n / 2;
+  T e[NE], o[NO > 0 ? NO : 1];
+#pragma unroll
+  for (int l = 0; l < NO; ++l) { e[l] = u[l] + u[n - 1 - l]; o[l] = u[l] - u[n - 1 - l]; }
+  if (n & 1) e[NE - 1] = u[NE - 1];
+#pragma unroll
+  for (int i = 0; i < NE; ++i) {
+    T s = Q.KEv[d][i] * V0;
+    s = fma(Q.KEg[d][i], G0, s);
+#pragma unroll
+    for (int l = 0; l < NE; ++l) s = fma(Q.KE[d][i][l], e[l], s);
+    if ((n & 1) && i == NE - 1) { out[i] = s; continue; }
+    T dd = Q.KOv[d][i] * V0;
+    dd = fma(Q.KOg[d][i], G0, dd);
+#pragma unroll
+    for (int l = 0; l < NO; ++l) dd = fma(Q.KO[d][i][l], o[l], dd);
+    out[i] = s + dd; out[n - 1 - i] = s - dd;
+  }
+}
+
 // EO tables for v3: direction 2 carries the folded operator Az = (h_z M) [Kt'_z | cV cG]
 template <typename T, int n>
-void fill_eo_params_v3(EOParams<T, n> &Q, const FastParams<double, n> &F) {
+void fill_eo_params_v3(EOParams<T, n> &Q, ZTop<T, n> &ZT, const FastParams<double, n> &F) {
   FastParams<double, n> Fz = F;
   for (int i = 0; i < n; ++i) {
     for (int l = 0; l < n; ++l) {
@@ -107,11 +135,12 @@ void fill_eo_params_v3(EOParams<T, n> &Q, const FastParams<double, n> &F) {
     }
   }
   fill_eo_params<T, n>(Q, Fz);
+  for (int i = 0; i < n; ++i) { ZT.cV[i] = (T)Fz.cV[2][1][i]; ZT.cG[i] = (T)Fz.cG[2][1][i]; }
 }
 
 template <int n, typename T, int NXY, int NBX, int NBY>
 __global__ void __launch_bounds__(Roles3<n, NXY>::NW * 32, 1)
-pressure_march3_kernel(const __grid_constant__ EOParams<T, n> Q, const __grid_constant__ FastGeom G, const int *__restrict__ nbr,
+pressure_march3_kernel(const __grid_constant__ EOParams<T, n> Q, const __grid_constant__ ZTop<T, n> ZT, const __grid_constant__ FastGeom G, const int *__restrict__ nbr,
                        const T *__restrict__ src, T *__restrict__ dst, const int *__restrict__ jobs) {
   static_assert(n % 2 == 1, "odd n: the lane stride n^3 must be odd (bank-conflict free without padding)");
   static_assert(NXY >= 1 && NXY <= 2 * n, "a warp's next task lies at most two planes ahead (mbarrier parity waits)");
@@ -126,8 +155,9 @@ pressure_march3_kernel(const __grid_constant__ EOParams<T, n> Q, const __grid_co
   unsigned long long *ubar = reinterpret_cast<unsigned long long *>(HXY + NSH * HBUF);   // [NSU]
   unsigned long long *outfull = ubar + NSU;   // [NSU]
   unsigned long long *sfree = outfull + NSU;  // [NSU]
-  unsigned long long *full = sfree + NSU;     // [2]
-  unsigned long long *wfree = full + 2;       // [2]
+  unsigned long long *ufull = sfree + NSU;    // [NSU]
+  unsigned long long *wfull = ufull + NSU;    // [2]
+  unsigned long long *wfree = wfull + 2;      // [2]
   int *ucnt = reinterpret_cast<int *>(wfree + 2);   // [NSU] tasks done with the plane held by each stage
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -135,8 +165,8 @@ pressure_march3_kernel(const __grid_constant__ EOParams<T, n> Q, const __grid_co
   const int role = warp < R::NXY ? 0 : 1;
   const int ridx = warp < R::NXY ? warp : warp - R::NXY;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSU; ++s) { mbar_init(&ubar[s], 1); mbar_init(&outfull[s], n); mbar_init(&sfree[s], 1); ucnt[s] = 0; }
-    for (int s = 0; s < 2; ++s) { mbar_init(&full[s], R::NZW); mbar_init(&wfree[s], n); }
+    for (int s = 0; s < NSU; ++s) { mbar_init(&ubar[s], 1); mbar_init(&outfull[s], n); mbar_init(&sfree[s], 1); mbar_init(&ufull[s], R::NZW); ucnt[s] = 0; }
+    for (int s = 0; s < 2; ++s) { mbar_init(&wfull[s], R::NZW); mbar_init(&wfree[s], n); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -234,7 +264,24 @@ pressure_march3_kernel(const __grid_constant__ EOParams<T, n> Q, const __grid_co
       }
       halo_issue(hcn);            // lines of plane q + 1: in flight during the z work below
       hcn = halo_index(q + 2);
-      // b. the plane above
+      // b. u^(q) = Mz u over the plane in place (only this thread ever reads these raw columns) and the part of Az u that does
+      //    not need the plane above.  The columns of plane q are read back from the stage (not carried in registers: the
+      //    register file holds the halo lines in flight and the partial sums instead).
+      T acc[n][n];   // [i][k]
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        T uc[n], r[n];
+#pragma unroll
+        for (int k = 0; k < n; ++k) uc[k] = Us[k * NL + i];
+        mass1<n, T>(Q, 2, uc, r);
+        line_eo_side0<n, T>(Q, 2, uc, Vt[i], Gt[i], acc[i]);
+#pragma unroll
+        for (int k = 0; k < n; ++k) Us[k * NL + i] = r[k];
+        Gt[i] = Gown[i]; Vt[i] = uc[n - 1];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ufull[q % NSU]);   // u^(q) and the halo traces are ready: the tasks of plane q may start
+      // c. the plane above
       if (q + 1 < NZ) {
         mbar_wait_sleep(&ubar[(q + 1) % NSU], (unsigned)(((q + 1) / NSU) & 1));
       } else {
@@ -248,25 +295,21 @@ pressure_march3_kernel(const __grid_constant__ EOParams<T, n> Q, const __grid_co
 #pragma unroll
           for (int k = 0; k < n; ++k) Un[k * NL + i] = __ldg(p + k * NL + i);
       }
-      // c. u^(q) = Mz u over the plane in place (only this thread ever reads these raw columns) and W(q) = Az u, once the tasks
-      //    of plane q - 2 have read W.  The columns of plane q are read back from the stage (not carried in registers: the
-      //    register file holds the halo lines in flight instead).
+      // d. W(q) = Az u: add the top-face terms; the buffer is free once the tasks of plane q - 2 have read it
       if (q >= 2) mbar_wait_sleep(&wfree[q & 1], (unsigned)(((q >> 1) - 1) & 1));
       T *Ws = W + (size_t)(q & 1) * TC * ND + so;
 #pragma unroll
       for (int i = 0; i < n; ++i) {
-        T uc[n], nw[n], gb, g1n, acc[n], r[n];
+        T nw[n], gb, g1n;
 #pragma unroll
-        for (int k = 0; k < n; ++k) { uc[k] = Us[k * NL + i]; nw[k] = Un[k * NL + i]; }
-        mass1<n, T>(Q, 2, uc, r);
+        for (int k = 0; k < n; ++k) nw[k] = Un[k * NL + i];
         traces1<n, T>(Q, nw, gb, g1n);   // bottom-side derivative of the plane above; its top-side one for later
-        line_eo<n, T, false>(Q, 2, uc, Vt[i], Gt[i], nw[0], gb, acc);
 #pragma unroll
-        for (int k = 0; k < n; ++k) { Us[k * NL + i] = r[k]; Ws[k * NL + i] = acc[k]; }
-        Gt[i] = Gown[i]; Vt[i] = uc[n - 1]; Gown[i] = g1n;
+        for (int k = 0; k < n; ++k) Ws[k * NL + i] = fma(ZT.cG[k], gb, fma(ZT.cV[k], nw[0], acc[i][k]));
+        Gown[i] = g1n;
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full[q & 1]);
+      if (lane == 0) mbar_arrive(&wfull[q & 1]);
     }
   } else {
     // ------------------------------------------------------------------ XY warps: lane = cell, task = (plane p, layer k)
@@ -284,7 +327,7 @@ pressure_march3_kernel(const __grid_constant__ EOParams<T, n> Q, const __grid_co
       const T *Wp = W + (size_t)st * TC * ND + c * ND + k * NL;
       T *Up = U + (size_t)(p % NSU) * TC * ND + c * ND + k * NL;
       const T *hb = HXY + (size_t)(p % NSH) * HBUF;
-      mbar_wait_sleep(&full[st], (unsigned)((p >> 1) & 1));
+      mbar_wait_sleep(&ufull[p % NSU], (unsigned)((p / NSU) & 1));
       T tl[n][n];   // [row j][column i] of the layer: W + Lx u^, then + Ly u^, then My, then Mx
       auto kbatch = [&](auto isrow_c, auto a0_c, auto nb_c) {
         constexpr bool isrow = decltype(isrow_c)::value;
@@ -295,8 +338,10 @@ pressure_march3_kernel(const __grid_constant__ EOParams<T, n> Q, const __grid_co
         for (int b = 0; b < NB; ++b) {
 #pragma unroll
           for (int l = 0; l < n; ++l) u[b][l] = isrow ? Up[(a0 + b) * n + l] : Up[l * n + a0 + b];
+          if constexpr (!isrow) {
 #pragma unroll
-          for (int l = 0; l < n; ++l) out[b][l] = isrow ? Wp[(a0 + b) * n + l] : tl[l][a0 + b];
+            for (int l = 0; l < n; ++l) out[b][l] = tl[l][a0 + b];
+          }
           h0[b] = *reinterpret_cast<const P2 *>(hb + (isrow ? hx0 : hy0) + 2 * (a0 + b));
           h1[b] = *reinterpret_cast<const P2 *>(hb + (isrow ? hx1 : hy1) + 2 * (a0 + b));
         }
@@ -310,13 +355,19 @@ pressure_march3_kernel(const __grid_constant__ EOParams<T, n> Q, const __grid_co
           nv[b][0] = e0 ? h0[b].x : v0; nv[b][1] = e0 ? h0[b].y : w0;
           nv[b][2] = e1 ? h1[b].x : v1; nv[b][3] = e1 ? h1[b].y : w1;
         }
-        lines_eo_nb<n, T, NB>(Q, isrow ? 0 : 1, u, nv, out);
+        lines_eo_nb<n, T, NB, !isrow>(Q, isrow ? 0 : 1, u, nv, out);
         if constexpr (isrow) {
 #pragma unroll
           for (int b = 0; b < NB; ++b)
 #pragma unroll
             for (int l = 0; l < n; ++l) tl[a0 + b][l] = out[b][l];
         } else {
+          // Az u joins here: the only read of W, half way through the task (the Z warps finish W(p) after u^(p))
+          if constexpr (a0 == 0) mbar_wait_sleep(&wfull[st], (unsigned)((p >> 1) & 1));
+#pragma unroll
+          for (int b = 0; b < NB; ++b)
+#pragma unroll
+            for (int l = 0; l < n; ++l) out[b][l] += Wp[l * n + a0 + b];
           T res[NB][n];
           mass_eo_nb<n, T, NB>(Q, 1, out, res);   // My
 #pragma unroll
@@ -345,10 +396,10 @@ pressure_march3_kernel(const __grid_constant__ EOParams<T, n> Q, const __grid_co
         if constexpr (n % NB != 0) kbatch(isrow_c, std::integral_constant<int, (n / NB) * NB>{}, std::integral_constant<int, n % NB>{});
       };
       sweep(std::true_type{}, std::integral_constant<int, NBX>{});
+      sweep(std::false_type{}, std::integral_constant<int, NBY>{});
       // W(p) is read: the Z warps may overwrite it with plane p + 2
       __syncwarp();
       if (lane == 0) mbar_arrive(&wfree[st]);
-      sweep(std::false_type{}, std::integral_constant<int, NBY>{});
       {
         constexpr int NB = NBX;
         [&]<int... I>(std::integer_sequence<int, I...>) { (xmass(std::integral_constant<int, I * NB>{}, std::integral_constant<int, NB>{}), ...); }(std::make_integer_sequence<int, n / NB>{});
