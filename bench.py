@@ -428,9 +428,9 @@ def main():
     bytes_per_dof = 2 * host.element_size()
     achieved = (n_local * bytes_per_dof) / (ms_per_step * 1e-3) / 1e9
     marching = args.variant != 1 and args.degree == 4 and args.refine >= 3
-    gen = os.environ.get("DGX_MARCH", "v2eor")
-    kernel = ("pressure_march_kernel" if gen == "v1" else "pressure_march2_kernel") if marching and args.dtype == "f64" else \
-             ("pressure_march_kernel" if marching else "pressure_generic_kernel")
+    gen = os.environ.get("DGX_MARCH", "v3")
+    kernel = ("pressure_march_kernel" if gen == "v1" else "pressure_march2_kernel" if gen.startswith("v2") else "pressure_march3_kernel") \
+        if marching and args.dtype == "f64" else ("pressure_march_kernel" if marching else "pressure_generic_kernel")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                 "traffic": None, "peak_source": which, "algorithmic_bytes_per_dof": bytes_per_dof,
                 "kernel": kernel + " (1 launch per step)"}
@@ -447,7 +447,8 @@ def main():
     # the operator is also bound by the FP64 pipe: report the executed-flop fraction beside the HBM one
     try:
         pk = json.load(open(os.path.join(ROOT, "profiles", "r1_peaks.json")))
-        flop_per_dof = {"pressure_march_kernel": 96.0, "pressure_march2_kernel": 84.0, "pressure_generic_kernel": 112.0}[kernel]
+        # executed FP64 flops per dof (FMA = 2), counted from the SASS instruction mix of the ncu captures; v3: 44.6 FP64 instructions
+        flop_per_dof = {"pressure_march_kernel": 96.0, "pressure_march2_kernel": 84.0, "pressure_march3_kernel": 65.5, "pressure_generic_kernel": 112.0}[kernel]
         key = "fp64_fma_tflops" if args.dtype == "f64" else "fp32_fma_tflops"
         tf = n_local * flop_per_dof / (ms_per_step * 1e-3) / 1e12
         roofline["fma_pipe"] = {"achieved_tflops": tf, "peak_tflops": pk[key], "frac": tf / pk[key], "flop_per_dof": flop_per_dof,

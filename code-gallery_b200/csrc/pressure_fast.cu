@@ -696,10 +696,10 @@ void fill_fast_params(FastParams<T, n> &F, const dgx_op *op) {
 #include "pressure_march_v2.cuh"
 #include "pressure_march_v3.cuh"
 
-// which marching kernel runs the plain (no add, no fused update) Q4 fp64 operator: DGX_MARCH = v1 | v2 | v2eo | v2r | v2eor (default) | v2eol
+// which marching kernel runs the plain (no add, no fused update) Q4 fp64 operator: DGX_MARCH = v1 | v2 | v2eo | v2r | v2eor | v2eol | v3 (default) | v3x5 | v3x6 | v3b2 | v3b32
 inline int march_generation() {   // read on every call (tests and the bench switch it inside one process)
   const char *e = getenv("DGX_MARCH");
-  if (!e) return 4;
+  if (!e) return 10;
   if (!strcmp(e, "v1")) return 0;      // round-1 kernel (named barriers, register tiles, STG)
   if (!strcmp(e, "v2")) return 1;      // mbarrier hand-offs, shuffled traces, bulk stores; plain contractions, layer tile in registers
   if (!strcmp(e, "v2eo")) return 2;    // + even-odd contractions
@@ -710,7 +710,8 @@ inline int march_generation() {   // read on every call (tests and the bench swi
   if (!strcmp(e, "v3x6")) return 12;   // 6 XY + 5 Z warps
   if (!strcmp(e, "v3b2")) return 13;   // as v3, batches of 2 lines
   if (!strcmp(e, "v3b32")) return 14;  // as v3, rows in batches of 3, columns in batches of 2
-  return 4;                            // v2eor (default): even-odd, streaming XY role with a 3-stage software pipeline
+  if (!strcmp(e, "v2eor")) return 4;   // even-odd, streaming XY role with a 3-stage software pipeline (round-2 default before v3)
+  return 10;                           // v3 (default)
 }
 
 template <int n, typename T, bool EO, int XYV>
@@ -789,7 +790,7 @@ int launch_march(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const F
         case 4: return launch_march2<n, T, true, 1>(op, dst, src, G, d_jobs, n_jobs, stream);
         case 5: return launch_march2<n, T, true, 2>(op, dst, src, G, d_jobs, n_jobs, stream);
         case 2: return launch_march2<n, T, true, 0>(op, dst, src, G, d_jobs, n_jobs, stream);
-        default: return launch_march2<n, T, true, 1>(op, dst, src, G, d_jobs, n_jobs, stream);
+        default: return launch_march3<n, T, 7, 3, 3>(op, dst, src, G, d_jobs, n_jobs, stream);
       }
   }
   using R = Roles<n>;

@@ -17,17 +17,18 @@
 //   * no H warps: the Z warps also reduce the x / y halo cells to (V', G') traces of u^ (24 of the 120 halo tasks of a plane
 //     per warp; the global loads are issued at the top of the iteration and consumed at its end; Mz is applied to the traces
 //     in registers), and the XY warp that finishes the last task of a plane bulk-stores it and refills the stage.
-//   * four u stages, two W planes, three halo buffers.  W(q) is free again as soon as the tasks of plane q have READ it
-//     (after their row sweep), so the Z role runs a full plane ahead of the XY role and neither waits for the other.
+//   * four u stages, two W planes, four halo buffers.  W(q) is free again as soon as the tasks of plane q have READ it (they add
+//     Az u half way, after their column sweep), and the Z role hands u^(q) and the halo traces over (ufull) BEFORE it waits for
+//     the plane above and finishes W(q) (wfull): the tasks of a plane start without waiting for the next plane to land.
 //
-// Barriers (mbarrier, counts = producing warps / tasks): ubar[4] plane landed; full[2] u^, W and halo traces of plane p
-// ready (5 Z warps); wfree[2] the 5 tasks of plane p have read W; outfull[4] the 5 tasks of plane p are done;
-// sfree[4] the bulk store of plane p has read its stage.
+// Barriers (mbarrier, counts = producing warps / tasks): ubar[4] plane landed; ufull[4] u^ and halo traces of plane p ready,
+// wfull[2] W(p) ready (5 Z warps each); wfree[2] the 5 tasks of plane p have read W; outfull[4] the 5 tasks of plane p are
+// done; sfree[4] the bulk store of plane p has read its stage.
 #pragma once
 
 template <int n, int NXY_>
 struct Roles3 {
-  static constexpr int NXY = NXY_, NZW = n, NW = NXY + NZW, NSU = 4, NSW = 2, NSH = 3;
+  static constexpr int NXY = NXY_, NZW = n, NW = NXY + NZW, NSU = 4, NSW = 2, NSH = 4;
 };
 
 // One halo task = the n face points (a, k), k = 0..n-1, of one x-halo (a = j) or y-halo (a = i) face cell of the tile, so that Mz can
@@ -148,6 +149,7 @@ pressure_march3_kernel(const __grid_constant__ EOParams<T, n> Q, const __grid_co
   using P2 = typename Pair<T>::type;
   constexpr int NL = n * n, ND = NL * n, NSU = R::NSU, NSH = R::NSH;
   constexpr int HBUF = (2 * TYC + 2 * TXC) * NL * 2;
+  static_assert(NSH == NSU, "halo buffer p % NSH is recycled together with stage p % NSU");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T *U = reinterpret_cast<T *>(smem_raw);   // [NSU][TC][ND]  u planes (bulk-copied, memory order) -> u^ = Mz u (Z warps) -> result (XY tasks), all in place
   T *W = U + NSU * TC * ND;                 // [2][TC][ND]    Az u
@@ -240,8 +242,8 @@ pressure_march3_kernel(const __grid_constant__ EOParams<T, n> Q, const __grid_co
     for (int q = 0; q < NZ; ++q) {
       T *Us = U + (size_t)(q % NSU) * TC * ND + so;
       T *Un = U + (size_t)((q + 1) % NSU) * TC * ND + so;
-      // a. halo traces of u^ on the n face points (a, k) of my task; buffer q % NSH was last read by the tasks of plane q - NSH
-      if (q >= NSH) mbar_wait_sleep(&outfull[(q - NSH) % NSU], (unsigned)(((q - NSH) / NSU) & 1));
+      // a. halo traces of u^ on the n face points (a, k) of my task.  Buffer q % NSH was last read by the tasks of plane q - NSH,
+      //    which were done before the refill of stage q % NSU with plane q was issued (NSH == NSU): no wait.
       {
         T *hb = HXY + (size_t)(q % NSH) * HBUF;
         T V[n], Gd[n], Vh[n], Gh[n];
@@ -262,7 +264,9 @@ pressure_march3_kernel(const __grid_constant__ EOParams<T, n> Q, const __grid_co
           }
         }
       }
-      halo_issue(hcn);            // lines of plane q + 1: in flight during the z work below
+      // Halo lines of plane q + 1: in flight during step b.  ptxas drains the load scoreboards in front of every wait loop, so
+      // their latency is paid in front of the wait of step c -- behind the ufull arrival, off the critical path of the XY role.
+      halo_issue(hcn);
       hcn = halo_index(q + 2);
       // b. u^(q) = Mz u over the plane in place (only this thread ever reads these raw columns) and the part of Az u that does
       //    not need the plane above.  The columns of plane q are read back from the stage (not carried in registers: the
