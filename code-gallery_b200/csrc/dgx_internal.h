@@ -4,6 +4,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -88,7 +89,10 @@ struct dgx_ctx {
   double *d_scratch = nullptr;   // reduction scratch (device)
   double *h_scratch = nullptr;   // pinned
   size_t scratch_doubles = 0;
+  bool p2p_off = false;          // CUDA IPC / peer access not available: ghost imports go through NCCL
 };
+
+namespace dgx { struct P2PBox; }
 
 struct dgx_mf {
   dgx_ctx *ctx = nullptr;
@@ -119,6 +123,8 @@ struct dgx_mf {
   // marching kernel job lists (tile columns that need no ghost data / that do), built on first use for jobs_NZ
   int *d_jobs = nullptr;
   int n_jobs_interior = 0, n_jobs_boundary = 0, jobs_NZ = 0;
+  // ghost import over NVLink peer memory (p2p.cu): one mailbox per cell size in bytes, created at the first exchange
+  std::map<size_t, dgx::P2PBox *> p2p;
 };
 
 struct dgx_vec {
@@ -178,6 +184,9 @@ int mass_cg_front(dgx_op *op, dgx_vec *p, const dgx_vec *r, double beta, bool fi
 int velocity_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add);
 int velocity_diagonal(dgx_op *op, dgx_vec *diag_inv);
 int ghost_exchange(dgx_vec *v);
+// ghost import over peer memory: *done = 1 when it was enqueued on `stream`, 0 when the caller must use NCCL
+int p2p_ghost_exchange(dgx_vec *v, cudaStream_t stream, int *done);
+void p2p_destroy(dgx_mf *mf);
 // same exchange on the context's communication stream: starts when the work already queued on the compute stream is
 // done; ghost_exchange_wait makes the compute stream wait for the ghosts
 int ghost_exchange_start(dgx_vec *v);

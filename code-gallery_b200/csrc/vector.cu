@@ -203,6 +203,12 @@ static int ghost_exchange_on(dgx_vec *v, cudaStream_t stream) {
   dgx_mf *mf = v->mf;
   dgx_ctx *ctx = mf->ctx;
   if (ctx->nranks == 1 || mf->peers.empty()) return DGX_OK;
+  {
+    int done = 0;
+    int rc = p2p_ghost_exchange(v, stream, &done);
+    if (rc) return rc;
+    if (done) return DGX_OK;
+  }
   const int dpc = (int)v->dofs_per_cell;
   const size_t es = v->elem();
   size_t total_send = 0;
