@@ -87,22 +87,29 @@ int comm_init(dgx_ctx *ctx, const void *idbytes) {
 }
 
 int comm_destroy(dgx_ctx *ctx) {
+  p2p_scalar_destroy(ctx);
   if (ctx->nccl_comm) api().CommDestroy((ncclComm_t)ctx->nccl_comm);
   ctx->nccl_comm = nullptr;
   return DGX_OK;
 }
 
-int allreduce_sum(dgx_ctx *ctx, double *dvals, int n) {
+int nccl_allreduce(dgx_ctx *ctx, double *dvals, int n, bool is_max) {
   if (ctx->nranks == 1) return DGX_OK;
-  DGX_NCCL_CHECK(api().AllReduce(dvals, dvals, n, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+  DGX_NCCL_CHECK(api().AllReduce(dvals, dvals, n, ncclFloat64, is_max ? ncclMax : ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
   return DGX_OK;
 }
 
-int allreduce_max(dgx_ctx *ctx, double *dvals, int n) {
+// dot products / norms: over peer memory when the ranks can map each other (p2p.cu), else NCCL
+static int allreduce_any(dgx_ctx *ctx, double *dvals, int n, bool is_max) {
   if (ctx->nranks == 1) return DGX_OK;
-  DGX_NCCL_CHECK(api().AllReduce(dvals, dvals, n, ncclFloat64, ncclMax, (ncclComm_t)ctx->nccl_comm, ctx->stream));
-  return DGX_OK;
+  int done = 0;
+  int rc = p2p_allreduce(ctx, dvals, n, is_max, &done);
+  if (rc) return rc;
+  if (done) return DGX_OK;
+  return nccl_allreduce(ctx, dvals, n, is_max);
 }
+int allreduce_sum(dgx_ctx *ctx, double *dvals, int n) { return allreduce_any(ctx, dvals, n, false); }
+int allreduce_max(dgx_ctx *ctx, double *dvals, int n) { return allreduce_any(ctx, dvals, n, true); }
 
 int allgather_inplace(dgx_ctx *ctx, void *buf, size_t bytes_per_rank) {
   if (ctx->nranks == 1 || bytes_per_rank == 0) return DGX_OK;

@@ -78,6 +78,8 @@ struct dgx_mesh {
   dgx::Mesh m;
 };
 
+namespace dgx { struct P2PScalar; }
+
 struct dgx_ctx {
   int device = 0, rank = 0, nranks = 1;
   cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -90,6 +92,8 @@ struct dgx_ctx {
   double *h_scratch = nullptr;   // pinned
   size_t scratch_doubles = 0;
   bool p2p_off = false;          // CUDA IPC / peer access not available: ghost imports go through NCCL
+  dgx::P2PScalar *p2ps = nullptr;   // all-reduce of a few doubles over peer memory (p2p.cu)
+  bool p2ps_tried = false;
 };
 
 namespace dgx { struct P2PBox; }
@@ -187,6 +191,9 @@ int ghost_exchange(dgx_vec *v);
 // ghost import over peer memory: *done = 1 when it was enqueued on `stream`, 0 when the caller must use NCCL
 int p2p_ghost_exchange(dgx_vec *v, cudaStream_t stream, int *done);
 void p2p_destroy(dgx_mf *mf);
+int p2p_allreduce(dgx_ctx *ctx, double *dvals, int n, bool is_max, int *done);
+void p2p_scalar_destroy(dgx_ctx *ctx);
+int nccl_allreduce(dgx_ctx *ctx, double *dvals, int n, bool is_max);
 // same exchange on the context's communication stream: starts when the work already queued on the compute stream is
 // done; ghost_exchange_wait makes the compute stream wait for the ghosts
 int ghost_exchange_start(dgx_vec *v);

@@ -176,14 +176,16 @@ int create_box(dgx_mf *mf, size_t bpc, P2PBox **out) {
     }
   }
   {
-    double *d = ctx->d_scratch;
+    double *d = nullptr;
+    DGX_CUDA_CHECK(cudaMalloc(&d, 8));
     const double v = map_ok ? 0.0 : 1.0;
     DGX_CUDA_CHECK(cudaMemcpyAsync(d, &v, 8, cudaMemcpyHostToDevice, ctx->stream));
-    rc = allreduce_sum(ctx, d, 1);
-    if (rc) { free_box(b); return rc; }
+    rc = nccl_allreduce(ctx, d, 1, false);
+    if (rc) { cudaFree(d); free_box(b); return rc; }
     double bad = 0;
     DGX_CUDA_CHECK(cudaMemcpyAsync(&bad, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
     DGX_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
     if (bad != 0.0) { free_box(b); *out = nullptr; return DGX_OK; }   // every rank falls back to NCCL
   }
   // send tables: cell, destination ghost slot on the receiver, neighbour index
@@ -279,6 +281,160 @@ int p2p_ghost_exchange(dgx_vec *v, cudaStream_t stream, int *done) {
   else if (bpc % 8 == 0) rc = launch_exchange<unsigned long long>(v, b, stream);
   else rc = launch_exchange<unsigned int>(v, b, stream);
   if (rc) return rc;
+  *done = 1;
+  return DGX_OK;
+}
+
+// ---- all-reduce of a few doubles over peer memory (dot products, norms) --------------------------------------------------------
+// Replaces ncclAllReduce of 1 - 32 doubles (MPI_Allreduce in deal.II's vector dot / norm): every rank stores its values into its
+// own row of a small table in EVERY rank's HBM, then its sequence number; every rank waits for all rows and adds them up in rank
+// order, so all ranks get bit-identical sums.  One single-block kernel, no NCCL launch: a few microseconds instead of ~20.
+struct P2PScalar {
+  char *d_local = nullptr;            // [seq: R x 8 B, padded to 1 KiB][2 slots][R rows][32 doubles]
+  char **d_base = nullptr;            // [R] every rank's table (own entry = d_local)
+  unsigned long long *d_seq = nullptr;
+  int *d_err = nullptr;
+  std::vector<void *> opened;
+};
+
+namespace {
+constexpr int kScalarMax = 32;
+
+__global__ void p2p_allreduce_kernel(double *vals, int n, int is_max, char *const *__restrict__ base, unsigned long long *seq, int R, int me, int *err) {
+  const unsigned long long s = *seq + 1;
+  const int t = threadIdx.x;
+  // my row into every rank's table
+  for (int e = t; e < R * n; e += blockDim.x) {
+    const int r = e / n, i = e - r * n;
+    double *row = reinterpret_cast<double *>(base[r] + kFlagBytes) + ((size_t)(s & 1) * R + me) * kScalarMax;
+    row[i] = vals[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t < R) st_release_sys(reinterpret_cast<unsigned long long *>(base[t]) + me, s);
+  // all rows of my table
+  if (t < R) {
+    const unsigned long long *flag = reinterpret_cast<const unsigned long long *>(base[me]) + t;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < s) {
+      if (clock64() - t0 > 6000000000LL) { atomicExch(err, 1); break; }
+    }
+  }
+  __syncthreads();
+  if (t < n) {
+    const double *tab = reinterpret_cast<const double *>(base[me] + kFlagBytes) + (size_t)(s & 1) * R * kScalarMax;
+    double a = __ldcg(tab + t);
+    for (int r = 1; r < R; ++r) {
+      const double b = __ldcg(tab + (size_t)r * kScalarMax + t);
+      a = is_max ? fmax(a, b) : a + b;
+    }
+    vals[t] = a;
+  }
+  __syncthreads();
+  if (t == 0) *seq = s;
+}
+
+int create_scalar(dgx_ctx *ctx, P2PScalar **out) {
+  const int R = ctx->nranks;
+  auto *b = new P2PScalar();
+  const size_t bytes = kFlagBytes + 2 * (size_t)R * kScalarMax * 8;
+  int ok_local = R * 8 <= (int)kFlagBytes ? 1 : 0;
+  if (ok_local && cudaMalloc(&b->d_local, bytes) != cudaSuccess) { cudaGetLastError(); ok_local = 0; }
+  if (ok_local) { cudaMemset(b->d_local, 0, bytes); cudaDeviceSynchronize(); }
+  const size_t stride = 8 + sizeof(cudaIpcMemHandle_t);
+  std::vector<char> all(stride * R, 0);
+  {
+    cudaIpcMemHandle_t h;
+    std::memset(&h, 0, sizeof(h));
+    if (ok_local && cudaIpcGetMemHandle(&h, b->d_local) != cudaSuccess) { cudaGetLastError(); ok_local = 0; }
+    long long okv = ok_local;
+    std::memcpy(all.data() + stride * ctx->rank, &okv, 8);
+    std::memcpy(all.data() + stride * ctx->rank + 8, &h, sizeof(h));
+  }
+  char *d_all = nullptr;
+  DGX_CUDA_CHECK(cudaMalloc(&d_all, all.size()));
+  DGX_CUDA_CHECK(cudaMemcpyAsync(d_all, all.data(), all.size(), cudaMemcpyHostToDevice, ctx->stream));
+  int rc = allgather_inplace(ctx, d_all, stride);
+  if (rc) { cudaFree(d_all); return rc; }
+  DGX_CUDA_CHECK(cudaMemcpyAsync(all.data(), d_all, all.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  DGX_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_all);
+  int map_ok = 1;
+  for (int r = 0; r < R; ++r) { long long okv; std::memcpy(&okv, all.data() + stride * r, 8); if (okv != 1) map_ok = 0; }
+  std::vector<char *> base(R, nullptr);
+  for (int r = 0; r < R && map_ok; ++r) {
+    if (r == ctx->rank) { base[r] = b->d_local; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, all.data() + stride * r + 8, sizeof(h));
+    void *ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); map_ok = 0; break; }
+    b->opened.push_back(ptr);
+    base[r] = (char *)ptr;
+  }
+  {   // agree on the outcome with NCCL (the last time it is used for a scalar)
+    double *d = nullptr;   // not the context's scratch: the caller's partial sums live there
+    DGX_CUDA_CHECK(cudaMalloc(&d, 8));
+    const double v = map_ok ? 0.0 : 1.0;
+    DGX_CUDA_CHECK(cudaMemcpyAsync(d, &v, 8, cudaMemcpyHostToDevice, ctx->stream));
+    rc = nccl_allreduce(ctx, d, 1, false);
+    if (rc) { cudaFree(d); return rc; }
+    double bad = 0;
+    DGX_CUDA_CHECK(cudaMemcpyAsync(&bad, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    DGX_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+    if (bad != 0.0) {
+      for (void *p : b->opened) cudaIpcCloseMemHandle(p);
+      if (b->d_local) cudaFree(b->d_local);
+      delete b;
+      *out = nullptr;
+      return DGX_OK;
+    }
+  }
+  DGX_CUDA_CHECK(cudaMalloc(&b->d_base, R * sizeof(char *)));
+  DGX_CUDA_CHECK(cudaMemcpy(b->d_base, base.data(), R * sizeof(char *), cudaMemcpyHostToDevice));
+  DGX_CUDA_CHECK(cudaMalloc(&b->d_seq, 8));
+  DGX_CUDA_CHECK(cudaMemset(b->d_seq, 0, 8));
+  DGX_CUDA_CHECK(cudaMalloc(&b->d_err, 4));
+  DGX_CUDA_CHECK(cudaMemset(b->d_err, 0, 4));
+  DGX_CUDA_CHECK(cudaDeviceSynchronize());
+  *out = b;
+  return DGX_OK;
+}
+}  // namespace
+
+void p2p_scalar_destroy(dgx_ctx *ctx) {
+  P2PScalar *b = ctx->p2ps;
+  if (!b) return;
+  for (void *p : b->opened) cudaIpcCloseMemHandle(p);
+  if (b->d_local) cudaFree(b->d_local);
+  if (b->d_base) cudaFree(b->d_base);
+  if (b->d_seq) cudaFree(b->d_seq);
+  if (b->d_err) cudaFree(b->d_err);
+  delete b;
+  ctx->p2ps = nullptr;
+}
+
+// *done = 1 when the reduction was enqueued on the context's stream, 0 when the caller must use NCCL
+int p2p_allreduce(dgx_ctx *ctx, double *dvals, int n, bool is_max, int *done) {
+  *done = 0;
+  static const bool enabled = [] { const char *e = getenv("DGX_P2P"); return !(e && e[0] == '0'); }();
+  if (!enabled || ctx->p2p_off || n > kScalarMax || ctx->nranks > 64) return DGX_OK;
+  if (!ctx->p2ps) {
+    if (ctx->p2ps_tried) return DGX_OK;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(ctx->stream, &cs);
+    if (cs != cudaStreamCaptureStatusNone) return DGX_OK;
+    ctx->p2ps_tried = true;
+    P2PScalar *b = nullptr;
+    int rc = create_scalar(ctx, &b);
+    if (rc) return rc;
+    if (!b) return DGX_OK;
+    ctx->p2ps = b;
+  }
+  P2PScalar *b = ctx->p2ps;
+  p2p_allreduce_kernel<<<1, 128, 0, ctx->stream>>>(dvals, n, is_max ? 1 : 0, b->d_base, b->d_seq, ctx->nranks, ctx->rank, b->d_err);
+  count_launch();
+  DGX_CUDA_CHECK(cudaGetLastError());
   *done = 1;
   return DGX_OK;
 }
