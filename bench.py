@@ -319,6 +319,17 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
+    # host side of the end-to-end leg: run on (and first-touch the pinned buffers from) the cores next to this rank's GPU; the
+    # launcher does not pin ranks, and 8 ranks pulling 2 x 2.1 GB per call through the other socket's memory controller do not scale
+    numa = None
+    all_cores = os.sched_getaffinity(0)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        numa = len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        pass
     nccl_id = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -474,6 +485,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
+            os.sched_setaffinity(0, all_cores)   # the CPU leg uses every host core
             res = cpu_baseline(args.degree, args.cpu_refine if args.cpu_refine >= 0 else args.refine, args.dtype, args.cpu_steps)
             cpu = {"value": res["dofs_per_s"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]}
             try:    # extra: the kernels' own (Kronecker-factored) algorithm on the host cores, so the ratio is not inflated by the port

@@ -210,7 +210,7 @@ int dgx_ctx_create(int device, int rank, int nranks, const void *nccl_id, dgx_ct
   DGX_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_ghosts_done, cudaEventDisableTiming));
   DGX_CUDA_CHECK(cudaEventCreate(&ctx->ev0));
   DGX_CUDA_CHECK(cudaEventCreate(&ctx->ev1));
-  ctx->scratch_doubles = 8 + 32 + 148 * 8 * 8;   // result slots + per-block partials of the widest (8-way) reduction
+  ctx->scratch_doubles = kScratchPartial + 32 + 148 * 8 * 8;   // result slots, ticket, per-block partials of the widest (8-way) reduction
   DGX_CUDA_CHECK(cudaMalloc(&ctx->d_scratch, ctx->scratch_doubles * sizeof(double)));
   DGX_CUDA_CHECK(cudaMemset(ctx->d_scratch, 0, ctx->scratch_doubles * sizeof(double)));
   DGX_CUDA_CHECK(cudaMallocHost(&ctx->h_scratch, 64 * sizeof(double)));

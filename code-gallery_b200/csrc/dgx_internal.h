@@ -34,6 +34,14 @@ inline void count_launch(int n = 1) { g_launch_count += n; }
     }                                                                                         \
   } while (0)
 
+// Reduction scratch of a context (dgx_ctx::d_scratch, doubles): [0, 32) results (up to 32 dot products of one Gram-Schmidt
+// sweep), [32] last-block ticket of the two-level reductions (per context: two contexts on one device do not share it),
+// [kScratchPartial, ...) per-block partial sums.
+constexpr int kScratchPartial = 34;
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned int *scratch_ticket(double *partial) { return reinterpret_cast<unsigned int *>(partial - 2); }
+#endif
+
 constexpr int MAX_DIM = 3;
 constexpr int MAX_N = 9;  // degree <= 8
 

@@ -60,7 +60,6 @@ mass_kernel(const __grid_constant__ MassParams<T, n> P, long long n_items, const
 //   p = r + beta p   (first iteration: p = r),   v = M p,   *result = p . v
 // The search direction is built while the cell is loaded, the dot product while the result is stored; per-block partial
 // sums are combined in a fixed order by the last block (deterministic).  Persistent grid (<= 8 blocks per SM).
-__device__ unsigned int g_mass_ticket = 0;
 
 template <int dim, int n, typename T>
 __global__ void __launch_bounds__(mass_cpb<dim, n>() * ipow(n, dim - 1))
@@ -133,7 +132,7 @@ mass_cg_front_kernel(const __grid_constant__ MassParams<T, n> P, long long n_ite
     for (int w = 0; w < (NT + 31) / 32; ++w) s2 += red[w];
     partial[blockIdx.x] = s2;
     __threadfence();
-    last = (atomicInc(&g_mass_ticket, gridDim.x - 1) == gridDim.x - 1);
+    last = (atomicInc(scratch_ticket(partial), gridDim.x - 1) == gridDim.x - 1);
   }
   __syncthreads();
   if (last && tid < 32) {
@@ -158,7 +157,7 @@ int launch_mass_cg_front(dgx_op *op, dgx_vec *p, const dgx_vec *r, double beta, 
   const long long items = mf->n_owned * op->ncomp;
   constexpr int CPB = mass_cpb<dim, n>(), NT = CPB * ipow(n, dim - 1);
   const int grid = (int)std::max<long long>(1, std::min<long long>((items + CPB - 1) / CPB, 148 * 8));
-  double *partial = ctx->d_scratch + 8, *result = ctx->d_scratch;
+  double *partial = ctx->d_scratch + kScratchPartial, *result = ctx->d_scratch;
   mass_cg_front_kernel<dim, n, T><<<grid, NT, 0, ctx->stream>>>(P, items, (T *)p->d, (const T *)r->d, (T)beta, first ? 1 : 0, (T *)v->d, partial, result);
   count_launch();
   DGX_CUDA_CHECK(cudaGetLastError());

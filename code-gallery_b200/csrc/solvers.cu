@@ -799,7 +799,8 @@ int dgx_solve_cg(dgx_op *A, dgx_vec *x, dgx_vec *b, int precond_kind, void *prec
   return rc;
 }
 
-// SolverGMRES, deal.II defaults: left preconditioning, restart length max_basis - 2, the monitored
+// SolverGMRES, deal.II >= 9.6 defaults (the reference requires 9.6.0; AdditionalData::max_basis_size = 30 IS the basis size there,
+// the pre-9.6 max_n_tmp_vectors = 30 meant a basis of 28): left preconditioning, restart length max_basis, the monitored
 // residual is the preconditioned one from the Givens recurrence, classical Gram-Schmidt with one re-orthogonalisation.
 int dgx_solve_gmres(dgx_op *A, dgx_vec *x, dgx_vec *b, int precond_kind, void *precond, int max_it, double abs_tol, int max_basis, int *iters, double *final_res) {
   DGX_REQUIRE(A && x && b, "null argument");
@@ -807,7 +808,8 @@ int dgx_solve_gmres(dgx_op *A, dgx_vec *x, dgx_vec *b, int precond_kind, void *p
   pc.kind = precond_kind;
   if (precond_kind == 1) pc.op = precond ? (dgx_op *)precond : A;
   else if (precond_kind == 2) pc.mg = (dgx_mg *)precond;
-  const int kdim = std::max(1, max_basis - 2);
+  DGX_REQUIRE(max_basis >= 1 && max_basis <= 31, "max_basis (the Gram-Schmidt kernels hold at most 32 basis vectors)");
+  const int kdim = max_basis;
   std::vector<dgx_vec *> V(kdim + 1, nullptr);
   dgx_vec *w = nullptr, *tmp = nullptr;
   auto cleanup = [&]() {};   // all work vectors are pooled with the operator

@@ -36,7 +36,6 @@ __global__ void __launch_bounds__(kThreads) map2_kernel(T *__restrict__ dst, con
     dst[i] = f(dst[i], src[i]);
 }
 
-__device__ unsigned int g_ticket = 0;
 
 // op: 0 = sum a*b, 1 = max |a|, 2 = sum a ; optionally fused update dst += alpha*v before dot(dst, w)
 // (upd2 += alpha2 * v2 rides along in the same pass: the x and r updates of one CG iteration)
@@ -69,7 +68,7 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(const T *a, const T *b
     for (int w = 1; w < kThreads / 32; ++w) s = (OP == 1) ? fmax(s, sm[w]) : s + sm[w];
     partial[blockIdx.x] = s;
     __threadfence();
-    unsigned int t = atomicInc(&g_ticket, gridDim.x - 1);
+    unsigned int t = atomicInc(scratch_ticket(partial), gridDim.x - 1);
     last = (t == gridDim.x - 1);
   }
   __syncthreads();
@@ -146,7 +145,7 @@ __global__ void __launch_bounds__(kThreads) multi_dot_kernel(const T *__restrict
   }
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) last = (atomicInc(&g_ticket, gridDim.x - 1) == gridDim.x - 1);
+  if (threadIdx.x == 0) last = (atomicInc(scratch_ticket(partial), gridDim.x - 1) == gridDim.x - 1);
   __syncthreads();
   if (last) {   // fixed-order combination of the block partials: warp j sums column j
     __threadfence();
@@ -175,7 +174,7 @@ int reduce_dispatch(const dgx_mf *mf, int dtype, const void *a, const void *b, v
                     double *out, bool is_max, void *upd2 = nullptr, const void *v2 = nullptr, double alpha2 = 0.0) {
   dgx_ctx *ctx = mf->ctx;
   const int grid = grid_for(n, 8);
-  double *partial = ctx->d_scratch + 8, *result = ctx->d_scratch;
+  double *partial = ctx->d_scratch + kScratchPartial, *result = ctx->d_scratch;
   if (dtype == DGX_F64)
     reduce_kernel<double, OP, FUSED><<<grid, kThreads, 0, ctx->stream>>>((const double *)a, (const double *)b, (double *)upd,
                                                                         (const double *)v, alpha, n, partial, result, (double *)upd2,
@@ -494,8 +493,9 @@ int dgx_vec_orthogonalize_checked(dgx_vec *w, dgx_vec *const *V, int k, double *
   const long long n = w->n_owned;
   const int grid = grid_for(n, 8);
   constexpr int KB = 8;
-  DGX_REQUIRE((size_t)grid * KB + 8 + kMaxMulti <= ctx->scratch_doubles, "reduction scratch too small");
-  double *result = ctx->d_scratch, *partial = ctx->d_scratch + 8 + kMaxMulti;
+  DGX_REQUIRE((size_t)grid * KB + kScratchPartial <= ctx->scratch_doubles, "reduction scratch too small");
+  double *result = ctx->d_scratch, *partial = ctx->d_scratch + kScratchPartial;
+  static_assert(kMaxMulti <= 32, "result slots of the context scratch");
   auto run = [&](auto tag) -> int {
     using T = decltype(tag);
     PtrTable<T> tab;

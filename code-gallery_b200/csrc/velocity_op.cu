@@ -625,7 +625,8 @@ int launch_velocity(dgx_op *op, T *dst, const T *src, bool add) {
   for (int q = 0; q < n; ++q) P.aw[q] = (T)(s.wq[q] * (op->stage == 1 ? 1.0 / (gamma * op->dt) : 1.0 / ((1.0 - gamma) * op->dt)));
   constexpr int CPB = VelCfg<dim, n, T>::CPB, NT = kVelThreads;
   const size_t smem = VelCfg<dim, n, T>::smem;
-  static bool configured = false;
+  static bool configured_dev[64] = {};   // per device: the attribute belongs to the device's copy of the function
+  bool &configured = configured_dev[mf->ctx->device >= 0 && mf->ctx->device < 64 ? mf->ctx->device : 0];
   if (!configured) {
     DGX_CUDA_CHECK(cudaFuncSetAttribute(velocity_kernel<dim, n, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
@@ -679,7 +680,8 @@ int launch_velocity_diag(dgx_op *op, T *out) {
   P.a = (T)a; P.aRe = (T)(a / op->Re); P.C = (T)((double)n * n); P.theta = (T)1.0;
   constexpr int NL = ipow(n, dim - 1), ND = NL * n, CPB = veld_cpb<dim, n, T>();
   const size_t smem = sizeof(T) * (size_t)CPB * ((dim + 2) * ND + (2 * 3 + 2 * dim * 3) * NL);
-  static bool configured = false;
+  static bool configured_dev[64] = {};   // per device: the attribute belongs to the device's copy of the function
+  bool &configured = configured_dev[mf->ctx->device >= 0 && mf->ctx->device < 64 ? mf->ctx->device : 0];
   if (!configured) {
     DGX_CUDA_CHECK(cudaFuncSetAttribute(velocity_diag_kernel<dim, n, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;

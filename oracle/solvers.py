@@ -97,9 +97,10 @@ def lanczos_eigenvalues(diag, offdiag):
 
 def solver_gmres(A, x, b, precond, control, max_basis=30):
     """Left-preconditioned restarted GMRES monitoring the preconditioned residual (deal.II
-    SolverGMRES defaults, SURVEY 9.5: max_n_tmp_vectors = 30 => Krylov dimension 28)."""
+    SolverGMRES defaults of deal.II >= 9.6, which the reference requires: AdditionalData::max_basis_size = 30 is the Krylov
+    dimension itself; before 9.6 max_n_tmp_vectors = 30 meant 28)."""
     dt = x.dtype.type
-    kdim = max_basis - 2
+    kdim = max_basis
     it_total = 0
     while True:
         r = precond(b - A(x))
