@@ -49,7 +49,8 @@ def parse():
     ap.add_argument("--cpu-refine", type=int, default=-1, help="refinement of the CPU baseline's cube (default: the workload's own, 128^3)")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-solve", action="store_true", help="skip the (untimed-region) MG-CG pressure solve report")
-    ap.add_argument("--solve-refine", type=int, default=6)
+    ap.add_argument("--solve-refine", type=int, default=7, help="cells per GPU of the MG-CG report: (2^r)^3 (7: 8 GPUs = 256^3 Q3, 9 levels = BASELINE config 4)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the (untimed-region) Q1..Q8 x fp64/fp32 sweep (BASELINE config 3)")
     ap.add_argument("--solve-degree", type=int, default=3)
     ap.add_argument("--no-step", action="store_true", help="skip the (untimed-region) TR-BDF2 step report")
     ap.add_argument("--step-refine", type=int, default=5)
@@ -167,6 +168,34 @@ def pressure_solve_report(dgx, ctx, args, world=1):
     out["ms_per_solve_cached_estimates"] = ms
     out["note"] = ("ms_per_solve recomputes the eigenvalue estimates like NS.cc:2501-2517; the cached variant reuses them for an unchanged (stage, dt) "
                    "and replays the V-cycle as one CUDA graph")
+    return out
+
+
+def degree_sweep_report(dgx, ctx, hbm_gbs, steps=5):
+    """BASELINE config 3: the pressure-operator vmult for Q1..Q8 in fp64 and fp32 on the periodic cubes of SURVEY 8d C3
+    (not part of the timed region); which kernel ran is reported per entry."""
+    refine = {1: 8, 2: 8, 3: 7, 4: 7, 5: 7, 6: 7, 7: 6, 8: 6}
+    out = []
+    for p in range(1, 9):
+        mesh = dgx.Mesh(3, [1, 1, 1], refine[p], [0, 0, 0], [1, 1, 1], [True] * 3)
+        for dt, name, nb in ((dgx.F64, "f64", 8), (dgx.F32, "f32", 4)):
+            mf = dgx.MatrixFree(ctx, mesh, -1, dt)
+            op = dgx.NavierStokesProjectionOperator(mf, dgx.OP_PRESSURE, p, 100.0, 5e-3)
+            src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+            n = src.locally_owned_size()
+            src.from_host(np.sin(np.arange(n, dtype=np.float64) * 1e-3).astype(np.float64 if dt == dgx.F64 else np.float32))
+            for _ in range(3):
+                op.vmult(dst, src)
+            ctx.synchronize()
+            ctx.timer_start()
+            for _ in range(steps):
+                op.vmult(dst, src)
+            ms = ctx.timer_stop() / steps
+            gb = 2 * nb * n / (ms * 1e-3) / 1e9
+            out.append({"degree": p, "dtype": name, "cells": f"{2 ** refine[p]}^3", "dofs": n, "ms": round(ms, 4),
+                        "gdofs": round(n / (ms * 1e-3) / 1e9, 2), "hbm_frac": round(gb / hbm_gbs, 3),
+                        "kernel": "marching" if 2 <= p <= 4 else "generic"})
+            del src, dst, op, mf
     return out
 
 
@@ -482,6 +511,13 @@ def main():
         except Exception as exc:  # noqa: BLE001
             step = {"error": str(exc)}
 
+    sweep = None
+    if world == 1 and not args.no_sweep:
+        try:
+            sweep = degree_sweep_report(dgx, ctx, peaks["hbm_gbs"])
+        except Exception as exc:  # noqa: BLE001
+            sweep = {"error": str(exc)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
@@ -509,6 +545,7 @@ def main():
                        "partition": f"{world} contiguous chunks of the hierarchical (Morton) cell order of one box" if world > 1 else "single GPU"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(),
             "mg_solve": mg_solve, "trbdf2_step": step, "marching_vs_generic_rel_l2": check, "multi_gpu_parity": parity,
+            "degree_sweep": sweep,
         }
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
