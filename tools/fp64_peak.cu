@@ -39,6 +39,26 @@ __global__ void dmma_kernel(double *out, double a, double b, int iters) {
   if (s == 123456.789) out[0] = s;
 }
 
+// DMMA m16n8k16 (sm_90+ shape): D(16x8) += A(16x16) B(16x8); per thread 8 a, 4 b, 4 c -- 2048 FMAs per instruction, 8 x m8n8k4
+template <int ILP>
+__global__ void dmma16_kernel(double *out, double a, double b, int iters) {
+  double c[ILP][4];
+#pragma unroll
+  for (int i = 0; i < ILP; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[i][j] = threadIdx.x + i + j;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < ILP; ++i)
+      asm volatile("mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%4,%4,%4,%4,%4,%4,%4}, {%5,%5,%5,%5}, {%0,%1,%2,%3};"
+                   : "+d"(c[i][0]), "+d"(c[i][1]), "+d"(c[i][2]), "+d"(c[i][3]) : "d"(a), "d"(b));
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+  if (s == 123456.789) out[0] = s;
+}
+
 __global__ void lds_kernel(double *out, int iters) {
   __shared__ double sm[4096];
   for (int i = threadIdx.x; i < 4096; i += blockDim.x) sm[i] = i;
@@ -95,6 +115,10 @@ int main() {
   {
     float ms = time_ms([&] { dmma_kernel<8, false><<<blocks, threads>>>(out, 1.0000001, 1e-9, iters / 4); });
     printf(", \"fp64_dmma_tflops\": %.2f", 2.0 * 256.0 * blocks * (threads / 32) * 8.0 * (iters / 4) / ms * 1e-9);
+  }
+  {
+    float ms = time_ms([&] { dmma16_kernel<4><<<blocks, threads>>>(out, 1.0000001, 1e-9, iters / 16); });
+    printf(", \"fp64_dmma_m16n8k16_tflops\": %.2f", 2.0 * 2048.0 * blocks * (threads / 32) * 4.0 * (iters / 16) / ms * 1e-9);
   }
   {
     float ms = time_ms([&] { dmma_kernel<8, true><<<blocks, threads>>>(out, 1.0000001, 1e-9, iters / 4); });
