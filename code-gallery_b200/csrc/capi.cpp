@@ -246,6 +246,7 @@ void *dgx_ctx_get_stream(dgx_ctx *ctx) { return ctx ? (void *)ctx->stream : null
 int dgx_ctx_synchronize(dgx_ctx *ctx) {
   DGX_REQUIRE(ctx && ctx->device >= 0, "context has no device");
   DGX_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->comm_stream) DGX_CUDA_CHECK(cudaStreamSynchronize(ctx->comm_stream));   // outgoing ghost transfers
   return DGX_OK;
 }
 
@@ -348,6 +349,10 @@ static int apply(dgx_op *op, dgx_vec *dst, dgx_vec *src, bool add) {
   static const bool overlap = [] { const char *e = getenv("DGX_OVERLAP"); return e && e[0] == '1'; }();
   if (overlap && op->kind == DGX_OP_PRESSURE && op->variant != 1 && op->mf->ctx->nranks > 1) {
     rc = pressure_apply_fast_overlapped(op, dst, src, add);
+    if (rc != DGX_ERR_UNSUPPORTED) return rc;
+  }
+  if (op->kind == DGX_OP_PRESSURE && op->mf->ctx->nranks > 1) {   // ghost import in flight while the marching kernel runs
+    rc = pressure_apply_fast_async(op, dst, src, add);
     if (rc != DGX_ERR_UNSUPPORTED) return rc;
   }
   if (op->kind != DGX_OP_MASS) { rc = ghost_exchange(src); if (rc) return rc; }

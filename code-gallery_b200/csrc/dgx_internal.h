@@ -135,6 +135,8 @@ struct dgx_mf {
   // marching kernel job lists (tile columns that need no ghost data / that do), built on first use for jobs_NZ
   int *d_jobs = nullptr;
   int n_jobs_interior = 0, n_jobs_boundary = 0, jobs_NZ = 0;
+  int *d_jobs_async = nullptr;          // all tile columns, those that read ghost cells from their first plane on last
+  int jobs_async_NZ = 0;
   // ghost import over NVLink peer memory (p2p.cu): one mailbox per cell size in bytes, created at the first exchange
   std::map<size_t, dgx::P2PBox *> p2p;
 };
@@ -196,6 +198,19 @@ int mass_cg_front(dgx_op *op, dgx_vec *p, const dgx_vec *r, double beta, bool fi
 int velocity_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add);
 int velocity_diagonal(dgx_op *op, dgx_vec *diag_inv);
 int ghost_exchange(dgx_vec *v);
+// Ghost cells of an import that is still in flight (p2p.cu, asynchronous mode): the consumer kernel waits for the neighbours'
+// sequence numbers itself and reads the ghost cells straight from the mailbox slot.  base == nullptr: ghosts are in the vector tail.
+struct GhostSrc {
+  const char *base = nullptr;                  // ghost cells of this exchange in ghost-slot order
+  const unsigned long long *flags = nullptr;   // [nranks] arrival sequence numbers, written by the neighbours' copy engines
+  const int *peer_ranks = nullptr;             // [npeers]
+  int npeers = 0;
+  unsigned long long seq = 0;
+};
+// pack on the context's stream, then copy-engine transfers into the neighbours' mailboxes + sequence numbers on the communication
+// stream; *done = 0: not available (caller imports synchronously)
+int p2p_ghost_import_async(dgx_vec *v, GhostSrc *gs, int *done);
+int pressure_apply_fast_async(dgx_op *op, dgx_vec *dst, dgx_vec *src, bool add);
 // ghost import over peer memory: *done = 1 when it was enqueued on `stream`, 0 when the caller must use NCCL
 int p2p_ghost_exchange(dgx_vec *v, cudaStream_t stream, int *done);
 void p2p_destroy(dgx_mf *mf);

@@ -243,6 +243,7 @@ int dgx_mf_destroy(dgx_mf *mf) {
   if (!mf) return DGX_OK;
   if (mf->d_nbr) cudaFree(mf->d_nbr);
   if (mf->d_jobs) cudaFree(mf->d_jobs);
+  if (mf->d_jobs_async) cudaFree(mf->d_jobs_async);
   dgx::p2p_destroy(mf);
   for (auto &p : mf->peers) if (p.d_send_cells) cudaFree(p.d_send_cells);
   delete mf;

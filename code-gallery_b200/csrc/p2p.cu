@@ -20,6 +20,7 @@
 // waited for B's push of s + 1, which B enqueued after its unpack of s: B has read slot s & 1 before A overwrites it.
 // The sequence number lives in device memory and is advanced by the push kernel itself, so a captured CUDA graph (the V-cycle)
 // replays exchanges correctly.
+#include <algorithm>
 #include <cstring>
 #include <map>
 
@@ -42,6 +43,13 @@ struct P2PBox {
   unsigned int *d_ticket = nullptr;
   int *d_err = nullptr;
   std::vector<void *> opened;
+  // asynchronous mode (copy engines): packed send buffer, host-side sequence number, one contiguous range per neighbour
+  char *d_sendbuf = nullptr;
+  unsigned long long h_seq = 0;
+  unsigned long long *d_seqword = nullptr;   // [2]
+  std::vector<char *> h_peer_base;
+  std::vector<long long> send_off, send_cnt, dst_first;   // cells
+  cudaEvent_t ev_packed = nullptr, ev_sent = nullptr;
 };
 
 namespace {
@@ -120,6 +128,10 @@ void free_box(P2PBox *b) {
   if (b->d_seq) cudaFree(b->d_seq);
   if (b->d_ticket) cudaFree(b->d_ticket);
   if (b->d_err) cudaFree(b->d_err);
+  if (b->d_sendbuf) cudaFree(b->d_sendbuf);
+  if (b->d_seqword) cudaFree(b->d_seqword);
+  if (b->ev_packed) cudaEventDestroy(b->ev_packed);
+  if (b->ev_sent) cudaEventDestroy(b->ev_sent);
   delete b;
 }
 
@@ -196,6 +208,9 @@ int create_box(dgx_mf *mf, size_t bpc, P2PBox **out) {
     long long rf_on_peer;
     std::memcpy(&rf_on_peer, all.data() + stride * p.rank + 8 + sizeof(cudaIpcMemHandle_t) + 8 * (size_t)ctx->rank, 8);
     if (!p.send_cells.empty() && rf_on_peer < 0) { free_box(b); set_error("p2p ghost import: neighbour does not expect my cells"); return DGX_ERR_INVALID; }
+    b->send_off.push_back((long long)cells.size());
+    b->send_cnt.push_back((long long)p.send_cells.size());
+    b->dst_first.push_back(rf_on_peer);
     for (size_t i = 0; i < p.send_cells.size(); ++i) {
       cells.push_back(p.send_cells[i]);
       dst.push_back(rf_on_peer + (long long)i);
@@ -203,6 +218,7 @@ int create_box(dgx_mf *mf, size_t bpc, P2PBox **out) {
     }
   }
   b->n_send = (long long)cells.size();
+  b->h_peer_base = peer_base;
   auto up = [&](auto **dptr, const auto &vec) -> cudaError_t {
     using E = typename std::remove_reference<decltype(vec[0])>::type;
     if (vec.empty()) { *dptr = nullptr; return cudaSuccess; }
@@ -281,6 +297,83 @@ int p2p_ghost_exchange(dgx_vec *v, cudaStream_t stream, int *done) {
   else if (bpc % 8 == 0) rc = launch_exchange<unsigned long long>(v, b, stream);
   else rc = launch_exchange<unsigned int>(v, b, stream);
   if (rc) return rc;
+  *done = 1;
+  return DGX_OK;
+}
+
+namespace {
+template <typename Wd>
+__global__ void p2p_pack_kernel(Wd *__restrict__ out, const Wd *__restrict__ v, const int *__restrict__ cells, long long n_send, int wpc,
+                                unsigned long long *seqword, unsigned long long s) {
+  const long long total = n_send * wpc;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e / wpc;
+    out[e] = v[(long long)cells[i] * wpc + (int)(e - i * wpc)];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *seqword = s;
+}
+}  // namespace
+
+// Asynchronous ghost import: the boundary cells are packed on the context's stream, the COPY ENGINES carry them into the neighbours'
+// mailboxes (and then this rank's sequence number) on the communication stream while the consumer kernel already runs; it waits
+// for the neighbours' sequence numbers only where it first touches a ghost cell (GhostSrc).  Own mailbox (host-side sequence
+// numbers), separate from the push / unpack one.
+int p2p_ghost_import_async(dgx_vec *v, GhostSrc *gs, int *done) {
+  *done = 0;
+  dgx_mf *mf = v->mf;
+  dgx_ctx *ctx = mf->ctx;
+  static const bool enabled = [] { const char *e = getenv("DGX_P2P"); const char *a = getenv("DGX_P2P_ASYNC"); return !(e && e[0] == '0') && !(a && a[0] == '0'); }();
+  if (!enabled || ctx->p2p_off || ctx->nranks == 1 || mf->peers.empty() || mf->peers.size() > 32) return DGX_OK;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(ctx->stream, &cs);
+  if (cs != cudaStreamCaptureStatusNone) return DGX_OK;
+  const size_t bpc = (size_t)v->dofs_per_cell * v->elem();
+  const size_t key = bpc | ((size_t)1 << 62);
+  auto it = mf->p2p.find(key);
+  if (it == mf->p2p.end()) {
+    P2PBox *b = nullptr;
+    int rc = create_box(mf, bpc, &b);
+    if (rc) return rc;
+    if (!b) { ctx->p2p_off = true; return DGX_OK; }
+    DGX_CUDA_CHECK(cudaMalloc(&b->d_sendbuf, (size_t)std::max<long long>(1, b->n_send) * bpc));
+    DGX_CUDA_CHECK(cudaMalloc(&b->d_seqword, 16));
+    DGX_CUDA_CHECK(cudaMemset(b->d_seqword, 0, 16));
+    DGX_CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_packed, cudaEventDisableTiming));
+    DGX_CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_sent, cudaEventDisableTiming));
+    it = mf->p2p.emplace(key, b).first;
+  }
+  P2PBox *b = it->second;
+  const unsigned long long s = ++b->h_seq;
+  const size_t slot_off = b->data_off + (size_t)(s & 1) * b->slot_bytes;
+  cudaStream_t A = ctx->stream, B = ctx->comm_stream;
+  if (s > 1) DGX_CUDA_CHECK(cudaStreamWaitEvent(A, b->ev_sent, 0));   // the previous transfer has read the send buffer
+  {
+    const int threads = 256;
+    if (bpc % 16 == 0) {
+      const int wpc = (int)(bpc / 16);
+      p2p_pack_kernel<uint4><<<grid_for_words(b->n_send * wpc, threads), threads, 0, A>>>((uint4 *)b->d_sendbuf, (const uint4 *)v->d, b->d_send_cells, b->n_send, wpc, b->d_seqword + (s & 1), s);
+    } else {
+      const int wpc = (int)(bpc / 8);
+      if (bpc % 8) return DGX_OK;
+      p2p_pack_kernel<unsigned long long><<<grid_for_words(b->n_send * wpc, threads), threads, 0, A>>>((unsigned long long *)b->d_sendbuf, (const unsigned long long *)v->d, b->d_send_cells, b->n_send, wpc, b->d_seqword + (s & 1), s);
+    }
+    count_launch();
+    DGX_CUDA_CHECK(cudaGetLastError());
+  }
+  DGX_CUDA_CHECK(cudaEventRecord(b->ev_packed, A));
+  DGX_CUDA_CHECK(cudaStreamWaitEvent(B, b->ev_packed, 0));
+  for (size_t p = 0; p < b->h_peer_base.size(); ++p)
+    if (b->send_cnt[p])
+      DGX_CUDA_CHECK(cudaMemcpyAsync(b->h_peer_base[p] + slot_off + (size_t)b->dst_first[p] * bpc, b->d_sendbuf + (size_t)b->send_off[p] * bpc,
+                                     (size_t)b->send_cnt[p] * bpc, cudaMemcpyDefault, B));
+  for (size_t p = 0; p < b->h_peer_base.size(); ++p)   // stream order: the sequence number lands behind the data
+    DGX_CUDA_CHECK(cudaMemcpyAsync(b->h_peer_base[p] + (size_t)ctx->rank * 8, b->d_seqword + (s & 1), 8, cudaMemcpyDefault, B));
+  DGX_CUDA_CHECK(cudaEventRecord(b->ev_sent, B));
+  gs->base = b->d_local + slot_off;
+  gs->flags = reinterpret_cast<const unsigned long long *>(b->d_local);
+  gs->peer_ranks = b->d_peer_ranks;
+  gs->npeers = b->npeers;
+  gs->seq = s;
   *done = 1;
   return DGX_OK;
 }

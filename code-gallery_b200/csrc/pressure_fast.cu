@@ -747,7 +747,8 @@ int launch_march2(dgx_op *op, dgx_vec *dst, const dgx_vec *src, const FastGeom &
 
 
 template <int n, typename T, int NXY, int NBX, int NBY>
-int launch_march3(dgx_op *op, dgx_vec *dst, const dgx_vec *src, const FastGeom &G, const int *d_jobs, int n_jobs, cudaStream_t stream) {
+int launch_march3(dgx_op *op, dgx_vec *dst, const dgx_vec *src, const FastGeom &G, const int *d_jobs, int n_jobs, cudaStream_t stream,
+                  const GhostSrc *gsrc = nullptr) {
   using R = Roles3<n, NXY>;
   constexpr int NL = n * n, ND = NL * n;
   EOParams<T, n> Q;
@@ -768,7 +769,7 @@ int launch_march3(dgx_op *op, dgx_vec *dst, const dgx_vec *src, const FastGeom &
   }
   const int grid = d_jobs ? n_jobs : G.ntx * G.nty * G.nsz;
   if (grid == 0) return DGX_OK;
-  pressure_march3_kernel<n, T, NXY, NBX, NBY><<<grid, R::NW * 32, smem, stream>>>(Q, ZT, G, op->mf->d_nbr, (const T *)src->d, (T *)dst->d, d_jobs);
+  pressure_march3_kernel<n, T, NXY, NBX, NBY><<<grid, R::NW * 32, smem, stream>>>(Q, ZT, G, op->mf->d_nbr, (const T *)src->d, (T *)dst->d, d_jobs, gsrc ? *gsrc : GhostSrc{});
   count_launch();
   DGX_CUDA_CHECK(cudaGetLastError());
   return DGX_OK;
@@ -870,6 +871,48 @@ int pressure_apply_fast_fused(dgx_op *op, dgx_vec *dst, const dgx_vec *x, const 
   FastGeom G;
   if (op->variant == 1 || !march_geometry(op, G)) return DGX_ERR_UNSUPPORTED;
   return march_dispatch(op, dst, x, false, G, nullptr, 0, nullptr, &fu);
+}
+
+
+// Multi-rank vmult with the ghost import in flight (v3 kernel, Q4 fp64): the boundary cells are packed, the copy engines carry them to
+// the neighbours over NVLink, and the marching kernel starts at once -- tile columns that read ghost cells from their first plane on
+// (rank-boundary faces in x / y, the ghost plane below) are scheduled last, the others touch a ghost plane only at the end of their
+// march; each warp waits for the neighbours' sequence numbers where it first needs a ghost cell and reads it from the mailbox.
+int pressure_apply_fast_async(dgx_op *op, dgx_vec *dst, dgx_vec *src, bool add) {
+  FastGeom G;
+  dgx_mf *mf = op->mf;
+  if (add || op->variant == 1 || mf->dtype != DGX_F64 || op->degree != 4 || march_generation() != 10 || !march_geometry(op, G)) return DGX_ERR_UNSUPPORTED;
+  GhostSrc gs;
+  int done = 0;
+  int rc = p2p_ghost_import_async(src, &gs, &done);
+  if (rc) return rc;
+  if (!done) return DGX_ERR_UNSUPPORTED;
+  if (!mf->d_jobs_async || mf->jobs_async_NZ != G.NZ) {
+    const Mesh &m = mf->mesh->m;
+    bool ghost_face[6];
+    for (int f = 0; f < 6; ++f) {
+      int c[3] = {mf->box_lo[0], mf->box_lo[1], mf->box_lo[2]};
+      if (f & 1) c[f / 2] += mf->box_ext[f / 2] - 1;
+      const long long local = m.index_of(mf->level, c) - mf->first_cell;
+      ghost_face[f] = mf->nbr_host[(size_t)f * mf->n_owned + local] >= mf->n_owned;
+    }
+    std::vector<int> order[3];   // no ghost at all / ghost plane above only (read at the end) / ghosts from the first plane on
+    for (int sz = 0; sz < G.nsz; ++sz)
+      for (int ty = 0; ty < G.nty; ++ty)
+        for (int tx = 0; tx < G.ntx; ++tx) {
+          const bool early = (tx == 0 && ghost_face[0]) || (tx == G.ntx - 1 && ghost_face[1]) || (ty == 0 && ghost_face[2]) ||
+                             (ty == G.nty - 1 && ghost_face[3]) || (sz == 0 && ghost_face[4]);
+          const bool late = sz == G.nsz - 1 && ghost_face[5];
+          order[early ? 2 : (late ? 1 : 0)].push_back(tx + G.ntx * (ty + G.nty * sz));
+        }
+    std::vector<int> all;
+    for (auto &o : order) all.insert(all.end(), o.begin(), o.end());
+    if (mf->d_jobs_async) cudaFree(mf->d_jobs_async);
+    DGX_CUDA_CHECK(cudaMalloc(&mf->d_jobs_async, all.size() * sizeof(int)));
+    DGX_CUDA_CHECK(cudaMemcpy(mf->d_jobs_async, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice));
+    mf->jobs_async_NZ = G.NZ;
+  }
+  return launch_march3<5, double, 7, 3, 3>(op, dst, src, G, mf->d_jobs_async, G.ntx * G.nty * G.nsz, mf->ctx->stream, &gs);
 }
 
 // The marching kernel applies when every face is interior (fully periodic mesh) and the owned cells form a

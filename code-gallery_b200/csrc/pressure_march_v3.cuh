@@ -142,7 +142,7 @@ void fill_eo_params_v3(EOParams<T, n> &Q, ZTop<T, n> &ZT, const FastParams<doubl
 template <int n, typename T, int NXY, int NBX, int NBY>
 __global__ void __launch_bounds__(Roles3<n, NXY>::NW * 32, 1)
 pressure_march3_kernel(const __grid_constant__ EOParams<T, n> Q, const __grid_constant__ ZTop<T, n> ZT, const __grid_constant__ FastGeom G, const int *__restrict__ nbr,
-                       const T *__restrict__ src, T *__restrict__ dst, const int *__restrict__ jobs) {
+                       const T *__restrict__ src, T *__restrict__ dst, const int *__restrict__ jobs, const __grid_constant__ GhostSrc GS) {
   static_assert(n % 2 == 1, "odd n: the lane stride n^3 must be odd (bank-conflict free without padding)");
   static_assert(NXY >= 1 && NXY <= 2 * n, "a warp's next task lies at most two planes ahead (mbarrier parity waits)");
   using R = Roles3<n, NXY>;
@@ -179,6 +179,26 @@ pressure_march3_kernel(const __grid_constant__ EOParams<T, n> Q, const __grid_co
   const int NZ = G.NZ;
   const size_t no = (size_t)G.n_owned;
   const long long pt0 = plane_term(G, z0);
+  // Ghost cells: in the vector tail, or (import still in flight, GS.base != nullptr) in the mailbox slot of this exchange, which is
+  // complete once every neighbour's sequence number has arrived.  ghost_wait is called by whole warps.
+  bool ghost_ready = GS.base == nullptr;
+  auto ghost_wait = [&]() {
+    if (ghost_ready) return;
+    if (lane < GS.npeers) {
+      const unsigned long long *flag = GS.flags + GS.peer_ranks[lane];
+      const long long t0 = clock64();
+      unsigned long long f;
+      do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(flag) : "memory");
+        if (clock64() - t0 > 20000000000LL) __trap();   // ~10 s: a lost neighbour must not hang the device
+      } while (f < GS.seq);
+    }
+    __syncwarp();
+    ghost_ready = true;
+  };
+  auto cell_ptr = [&](int idx) -> const T * {
+    return (idx < (int)no || GS.base == nullptr) ? src + (size_t)idx * ND : reinterpret_cast<const T *>(GS.base) + (size_t)(idx - (int)no) * ND;
+  };
 
   // called by a whole warp: lane 0 arms the barrier, lanes 0..7 issue one bulk copy of 4 consecutive cells each
   auto issue_plane = [&](int p) {
@@ -200,7 +220,9 @@ pressure_march3_kernel(const __grid_constant__ EOParams<T, n> Q, const __grid_co
     // per column i: (V', G') of the plane below on the shared face; own top-side derivative of plane q
     T Gt[n], Vt[n], Gown[n];
     {   // ghost plane below the segment: only its top traces are needed
-      const T *p = src + (size_t)nbr[4 * no + cell0] * ND + j * n;
+      const int below = nbr[4 * no + cell0];
+      if (__any_sync(0xffffffffu, below >= (int)no)) ghost_wait();
+      const T *p = cell_ptr(below) + j * n;
 #pragma unroll
       for (int i = 0; i < n; ++i) {
         T col[n];
@@ -219,7 +241,8 @@ pressure_march3_kernel(const __grid_constant__ EOParams<T, n> Q, const __grid_co
     // role runs a plane ahead of the XY role only if no HBM / L2 latency sits on its critical path.
     T xh[n][n];   // [k][l] halo lines of the plane about to be processed
     auto halo_issue = [&](int hcn) {
-      const T *ptr = src + (size_t)hcn * ND + ht.off;
+      if (__any_sync(0xffffffffu, hcn >= (int)no)) ghost_wait();
+      const T *ptr = cell_ptr(hcn) + ht.off;
 #pragma unroll
       for (int k = 0; k < n; ++k)
 #pragma unroll
@@ -293,7 +316,9 @@ pressure_march3_kernel(const __grid_constant__ EOParams<T, n> Q, const __grid_co
         // parks its own columns there and reads them back below
         if (q >= 3) mbar_wait_sleep(&sfree[(q + 1) % NSU], (unsigned)(((q - 3) / NSU) & 1));
         const long long shl = plane_term(G, z0 + NZ - 1) - pt0;
-        const T *p = src + (size_t)nbr[5 * no + (cell0 + shl)] * ND + j * n;
+        const int above = nbr[5 * no + (cell0 + shl)];
+        if (__any_sync(0xffffffffu, above >= (int)no)) ghost_wait();
+        const T *p = cell_ptr(above) + j * n;
 #pragma unroll
         for (int i = 0; i < n; ++i)
 #pragma unroll
