@@ -246,7 +246,7 @@ void *dgx_ctx_get_stream(dgx_ctx *ctx) { return ctx ? (void *)ctx->stream : null
 int dgx_ctx_synchronize(dgx_ctx *ctx) {
   DGX_REQUIRE(ctx && ctx->device >= 0, "context has no device");
   DGX_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  if (ctx->comm_stream) DGX_CUDA_CHECK(cudaStreamSynchronize(ctx->comm_stream));   // outgoing ghost transfers
+  if (ctx->comm_stream) DGX_CUDA_CHECK(cudaStreamSynchronize(ctx->comm_stream));
   return DGX_OK;
 }
 

@@ -49,7 +49,9 @@ struct P2PBox {
   unsigned long long *d_seqword = nullptr;   // [2]
   std::vector<char *> h_peer_base;
   std::vector<long long> send_off, send_cnt, dst_first;   // cells
-  cudaEvent_t ev_packed = nullptr, ev_sent = nullptr;
+  cudaEvent_t ev_packed = nullptr;
+  std::vector<cudaStream_t> peer_stream;   // one per neighbour: the transfers run on separate copy engines
+  std::vector<cudaEvent_t> ev_sent;
 };
 
 namespace {
@@ -118,6 +120,7 @@ int grid_for_words(long long n, int threads) {
 
 void free_box(P2PBox *b) {
   if (!b) return;
+  for (cudaStream_t st : b->peer_stream) cudaStreamSynchronize(st);   // outgoing transfers
   for (void *p : b->opened) cudaIpcCloseMemHandle(p);
   if (b->d_local) cudaFree(b->d_local);
   if (b->d_send_cells) cudaFree(b->d_send_cells);
@@ -131,7 +134,8 @@ void free_box(P2PBox *b) {
   if (b->d_sendbuf) cudaFree(b->d_sendbuf);
   if (b->d_seqword) cudaFree(b->d_seqword);
   if (b->ev_packed) cudaEventDestroy(b->ev_packed);
-  if (b->ev_sent) cudaEventDestroy(b->ev_sent);
+  for (cudaEvent_t e : b->ev_sent) cudaEventDestroy(e);
+  for (cudaStream_t st : b->peer_stream) cudaStreamDestroy(st);
   delete b;
 }
 
@@ -339,14 +343,20 @@ int p2p_ghost_import_async(dgx_vec *v, GhostSrc *gs, int *done) {
     DGX_CUDA_CHECK(cudaMalloc(&b->d_seqword, 16));
     DGX_CUDA_CHECK(cudaMemset(b->d_seqword, 0, 16));
     DGX_CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_packed, cudaEventDisableTiming));
-    DGX_CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_sent, cudaEventDisableTiming));
+    b->peer_stream.resize(b->h_peer_base.size());
+    b->ev_sent.resize(b->h_peer_base.size());
+    for (size_t p = 0; p < b->h_peer_base.size(); ++p) {
+      DGX_CUDA_CHECK(cudaStreamCreateWithFlags(&b->peer_stream[p], cudaStreamNonBlocking));
+      DGX_CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_sent[p], cudaEventDisableTiming));
+    }
     it = mf->p2p.emplace(key, b).first;
   }
   P2PBox *b = it->second;
   const unsigned long long s = ++b->h_seq;
   const size_t slot_off = b->data_off + (size_t)(s & 1) * b->slot_bytes;
-  cudaStream_t A = ctx->stream, B = ctx->comm_stream;
-  if (s > 1) DGX_CUDA_CHECK(cudaStreamWaitEvent(A, b->ev_sent, 0));   // the previous transfer has read the send buffer
+  cudaStream_t A = ctx->stream;
+  if (s > 1)
+    for (cudaEvent_t e : b->ev_sent) DGX_CUDA_CHECK(cudaStreamWaitEvent(A, e, 0));   // the previous transfers have read the send buffer
   {
     const int threads = 256;
     if (bpc % 16 == 0) {
@@ -361,14 +371,16 @@ int p2p_ghost_import_async(dgx_vec *v, GhostSrc *gs, int *done) {
     DGX_CUDA_CHECK(cudaGetLastError());
   }
   DGX_CUDA_CHECK(cudaEventRecord(b->ev_packed, A));
-  DGX_CUDA_CHECK(cudaStreamWaitEvent(B, b->ev_packed, 0));
-  for (size_t p = 0; p < b->h_peer_base.size(); ++p)
+  for (size_t p = 0; p < b->h_peer_base.size(); ++p) {
+    cudaStream_t B = b->peer_stream[p];
+    DGX_CUDA_CHECK(cudaStreamWaitEvent(B, b->ev_packed, 0));
     if (b->send_cnt[p])
       DGX_CUDA_CHECK(cudaMemcpyAsync(b->h_peer_base[p] + slot_off + (size_t)b->dst_first[p] * bpc, b->d_sendbuf + (size_t)b->send_off[p] * bpc,
                                      (size_t)b->send_cnt[p] * bpc, cudaMemcpyDefault, B));
-  for (size_t p = 0; p < b->h_peer_base.size(); ++p)   // stream order: the sequence number lands behind the data
+    // stream order: the sequence number lands behind the data
     DGX_CUDA_CHECK(cudaMemcpyAsync(b->h_peer_base[p] + (size_t)ctx->rank * 8, b->d_seqword + (s & 1), 8, cudaMemcpyDefault, B));
-  DGX_CUDA_CHECK(cudaEventRecord(b->ev_sent, B));
+    DGX_CUDA_CHECK(cudaEventRecord(b->ev_sent[p], B));
+  }
   gs->base = b->d_local + slot_off;
   gs->flags = reinterpret_cast<const unsigned long long *>(b->d_local);
   gs->peer_ranks = b->d_peer_ranks;

@@ -35,10 +35,17 @@ __device__ __forceinline__ void mbar_wait_mode(unsigned long long *bar, unsigned
 __device__ __forceinline__ void mbar_wait_sleep(unsigned long long *bar, unsigned parity) {
   const unsigned addr = smem_u32(bar);
   unsigned ok = 0;
+  long long t0 = 0;
   for (int spin = 0; !ok; ++spin) {
     asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
                  : "=r"(ok) : "r"(addr), "r"(parity), "r"(1000000u) : "memory");
-    if (spin > (1 << 12)) __trap();   // ~4 s: never hang the device on a lost arrival
+    // never hang the device on a lost arrival -- but by the clock, not by the poll count: with the ghost import in flight a CTA
+    // may legitimately wait for a neighbour rank that is still busy (e.g. uploading its input over PCIe) for many milliseconds
+    if ((spin & 1023) == 1023) {
+      const long long t = clock64();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 40000000000LL) __trap();   // ~20 s
+    }
   }
 }
 // (V', G') pair from shared memory for the lanes with pred != 0, the others keep their values: one predicated LDS.128, no
