@@ -470,7 +470,7 @@ def main():
     marching = args.variant != 1 and args.degree == 4 and args.refine >= 3
     gen = os.environ.get("DGX_MARCH", "v3")
     kernel = ("pressure_march_kernel" if gen == "v1" else "pressure_march2_kernel" if gen.startswith("v2") else "pressure_march3_kernel") \
-        if marching and args.dtype == "f64" else ("pressure_march_kernel" if marching else "pressure_generic_kernel")
+        if marching and args.dtype == "f64" else ("pressure_march3_kernel" if marching else "pressure_generic_kernel")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                 "traffic": None, "peak_source": which, "algorithmic_bytes_per_dof": bytes_per_dof,
                 "kernel": kernel + " (1 launch per step)"}

@@ -710,6 +710,7 @@ inline int march_generation() {   // read on every call (tests and the bench swi
   if (!strcmp(e, "v3x6")) return 12;   // 6 XY + 5 Z warps
   if (!strcmp(e, "v3b2")) return 13;   // as v3, batches of 2 lines
   if (!strcmp(e, "v3b32")) return 14;  // as v3, rows in batches of 3, columns in batches of 2
+  if (!strcmp(e, "v3zf")) return 16;   // as v3, Z warps on the low warp ids
   if (!strcmp(e, "v2eor")) return 4;   // even-odd, streaming XY role with a 3-stage software pipeline (round-2 default before v3)
   return 10;                           // v3 (default)
 }
@@ -746,7 +747,7 @@ int launch_march2(dgx_op *op, dgx_vec *dst, const dgx_vec *src, const FastGeom &
 }
 
 
-template <int n, typename T, int NXY, int NBX, int NBY>
+template <int n, typename T, int NXY, int NBX, int NBY, bool ZFIRST = false, int MINB = 1>
 int launch_march3(dgx_op *op, dgx_vec *dst, const dgx_vec *src, const FastGeom &G, const int *d_jobs, int n_jobs, cudaStream_t stream,
                   const GhostSrc *gsrc = nullptr) {
   using R = Roles3<n, NXY>;
@@ -764,12 +765,12 @@ int launch_march3(dgx_op *op, dgx_vec *dst, const dgx_vec *src, const FastGeom &
   DGX_CUDA_CHECK(cudaGetDevice(&dev));
   static bool configured[64] = {};
   if (dev >= 0 && dev < 64 && !configured[dev]) {
-    DGX_CUDA_CHECK(cudaFuncSetAttribute(pressure_march3_kernel<n, T, NXY, NBX, NBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DGX_CUDA_CHECK(cudaFuncSetAttribute(pressure_march3_kernel<n, T, NXY, NBX, NBY, ZFIRST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[dev] = true;
   }
   const int grid = d_jobs ? n_jobs : G.ntx * G.nty * G.nsz;
   if (grid == 0) return DGX_OK;
-  pressure_march3_kernel<n, T, NXY, NBX, NBY><<<grid, R::NW * 32, smem, stream>>>(Q, ZT, G, op->mf->d_nbr, (const T *)src->d, (T *)dst->d, d_jobs, gsrc ? *gsrc : GhostSrc{});
+  pressure_march3_kernel<n, T, NXY, NBX, NBY, ZFIRST, MINB><<<grid, R::NW * 32, smem, stream>>>(Q, ZT, G, op->mf->d_nbr, (const T *)src->d, (T *)dst->d, d_jobs, gsrc ? *gsrc : GhostSrc{});
   count_launch();
   DGX_CUDA_CHECK(cudaGetLastError());
   return DGX_OK;
@@ -786,6 +787,7 @@ int launch_march(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const F
         case 12: return launch_march3<n, T, 6, 3, 3>(op, dst, src, G, d_jobs, n_jobs, stream);
         case 13: return launch_march3<n, T, 7, 2, 2>(op, dst, src, G, d_jobs, n_jobs, stream);
         case 14: return launch_march3<n, T, 7, 3, 2>(op, dst, src, G, d_jobs, n_jobs, stream);
+        case 16: return launch_march3<n, T, 7, 3, 3, true>(op, dst, src, G, d_jobs, n_jobs, stream);
         case 1: return launch_march2<n, T, false, 0>(op, dst, src, G, d_jobs, n_jobs, stream);
         case 3: return launch_march2<n, T, false, 1>(op, dst, src, G, d_jobs, n_jobs, stream);
         case 4: return launch_march2<n, T, true, 1>(op, dst, src, G, d_jobs, n_jobs, stream);
@@ -793,6 +795,20 @@ int launch_march(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const F
         case 2: return launch_march2<n, T, true, 0>(op, dst, src, G, d_jobs, n_jobs, stream);
         default: return launch_march3<n, T, 7, 3, 3>(op, dst, src, G, d_jobs, n_jobs, stream);
       }
+  }
+  if constexpr (n == 3) {
+    // Q2: the v3 design with 3 Z + 6 XY warps and 2 (fp64) / 3 (fp32) CTAs per SM: 134 -> 164 GDoF/s fp64, 155 -> 243 GDoF/s fp32 at
+    // 256^3 cells (DGX_MARCH3_Q2=0: round-1 kernel)
+    static const int q2 = [] { const char *e = getenv("DGX_MARCH3_Q2"); return e ? atoi(e) : 1; }();
+    if (!add && !fu && q2) {
+      if constexpr (std::is_same<T, double>::value) return launch_march3<n, T, 6, 3, 3, false, 2>(op, dst, src, G, d_jobs, n_jobs, stream);
+      else return launch_march3<n, T, 6, 3, 3, false, 3>(op, dst, src, G, d_jobs, n_jobs, stream);
+    }
+  }
+  if constexpr (n == 5 && std::is_same<T, float>::value) {
+    // Q4 fp32: the v3 kernel as for fp64 (one CTA per SM): 212 -> 282 GDoF/s at 128^3 cells (DGX_MARCH3_F32=0: round-1 kernel)
+    static const int f32 = [] { const char *e = getenv("DGX_MARCH3_F32"); return e ? atoi(e) : 1; }();
+    if (!add && !fu && f32) return launch_march3<n, T, 7, 3, 3>(op, dst, src, G, d_jobs, n_jobs, stream);
   }
   using R = Roles<n>;
   constexpr int NL = n * n, ND = NL * n;

@@ -139,8 +139,8 @@ void fill_eo_params_v3(EOParams<T, n> &Q, ZTop<T, n> &ZT, const FastParams<doubl
   for (int i = 0; i < n; ++i) { ZT.cV[i] = (T)Fz.cV[2][1][i]; ZT.cG[i] = (T)Fz.cG[2][1][i]; }
 }
 
-template <int n, typename T, int NXY, int NBX, int NBY>
-__global__ void __launch_bounds__(Roles3<n, NXY>::NW * 32, 1)
+template <int n, typename T, int NXY, int NBX, int NBY, bool ZFIRST = false, int MINB = 1>
+__global__ void __launch_bounds__(Roles3<n, NXY>::NW * 32, MINB)
 pressure_march3_kernel(const __grid_constant__ EOParams<T, n> Q, const __grid_constant__ ZTop<T, n> ZT, const __grid_constant__ FastGeom G, const int *__restrict__ nbr,
                        const T *__restrict__ src, T *__restrict__ dst, const int *__restrict__ jobs, const __grid_constant__ GhostSrc GS) {
   static_assert(n % 2 == 1, "odd n: the lane stride n^3 must be odd (bank-conflict free without padding)");
@@ -164,8 +164,9 @@ pressure_march3_kernel(const __grid_constant__ EOParams<T, n> Q, const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // warps 0 .. NXY-1: XY, then n Z warps; with warp % 4 = sub-partition this spreads both roles over all four
-  const int role = warp < R::NXY ? 0 : 1;
-  const int ridx = warp < R::NXY ? warp : warp - R::NXY;
+  // (ZFIRST: the Z warps take the low warp ids instead -- the scheduler favours high ids)
+  const int role = ZFIRST ? (warp < R::NZW ? 1 : 0) : (warp < R::NXY ? 0 : 1);
+  const int ridx = ZFIRST ? (warp < R::NZW ? warp : warp - R::NZW) : (warp < R::NXY ? warp : warp - R::NXY);
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSU; ++s) { mbar_init(&ubar[s], 1); mbar_init(&outfull[s], n); mbar_init(&sfree[s], 1); mbar_init(&ufull[s], R::NZW); ucnt[s] = 0; }
     for (int s = 0; s < 2; ++s) { mbar_init(&wfull[s], R::NZW); mbar_init(&wfree[s], n); }

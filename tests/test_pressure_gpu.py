@@ -190,7 +190,7 @@ def test_marching_kernel_matches_oracle(dgx, gpu_ctx, case, degree, np_dtype):
     assert rel_l2(dst.to_host(), ref) < TOL[np_dtype]
 
 
-@pytest.mark.parametrize("gen", ["v1", "v2", "v2eo", "v2r", "v2eor", "v2eol", "v3", "v3x5", "v3x6", "v3b2", "v3b32"])
+@pytest.mark.parametrize("gen", ["v1", "v2", "v2eo", "v2r", "v2eor", "v2eol", "v3", "v3x5", "v3x6", "v3b2", "v3b32", "v3zf"])
 @pytest.mark.parametrize("case", FAST_CASES + [([1, 2, 1], 4)], ids=lambda c: f"{c[0]}-r{c[1]}")
 def test_marching_generations_match_oracle(dgx, gpu_ctx, case, gen, monkeypatch):
     """Q4 fp64 through every generation of the marching kernel (DGX_MARCH): v1 = round-1 kernel (named barriers), v2 =
@@ -219,7 +219,7 @@ def test_marching_generations_agree_at_scale(dgx, gpu_ctx, monkeypatch):
     op.vmult(dst, src)
     ref = dst.to_host()
     op.set_variant(2)
-    for gen in ("v1", "v2", "v2eo", "v2r", "v2eor", "v2eol", "v3", "v3x5", "v3x6", "v3b2", "v3b32"):
+    for gen in ("v1", "v2", "v2eo", "v2r", "v2eor", "v2eol", "v3", "v3x5", "v3x6", "v3b2", "v3b32", "v3zf"):
         monkeypatch.setenv("DGX_MARCH", gen)
         dst.set(0.0)
         op.vmult(dst, src)
