@@ -139,6 +139,9 @@ struct dgx_mf {
   int jobs_async_NZ = 0;
   // ghost import over NVLink peer memory (p2p.cu): one mailbox per cell size in bytes, created at the first exchange
   std::map<size_t, dgx::P2PBox *> p2p;
+  // boundary faces (local cell, face number) per boundary id, built on first use (diagnostics.cu: lift and drag)
+  struct BFaces { int *d = nullptr; int n = 0; };
+  std::map<int, BFaces> bfaces;
 };
 
 struct dgx_vec {

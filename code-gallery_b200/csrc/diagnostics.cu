@@ -1,0 +1,358 @@
+// Output and diagnostics of the time loop, kept on the device:
+//   * compute_lift_and_drag (NS.cc:2642-2708): integral of (1/Re grad u - p I)(-n) over the boundary faces with one boundary id
+//     (the reference: 4, the cylinder), QGauss(degree_p + 2) face quadrature, FEFaceValues-style point evaluation;
+//   * output_results (NS.cc:2608-2633): DataOut::build_patches(MappingQ1, 1) = one patch per cell with the 2^dim cell vertices as
+//     points, data v, p, v_old and PostprocessorVorticity (NS.cc:115-160: curl of v from the velocity gradients) at these points,
+//     written as an UnstructuredGrid .vtu (one piece file per rank plus a .pvtu index when there are several ranks).
+// Neither is on the operator hot path: the kernels are plain point evaluations (one thread per face quadrature point / per
+// patch vertex, run-time degree); what matters is that u and p never leave the device except as the patch data to be written.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "dgx_internal.h"
+
+namespace dgx {
+namespace {
+
+constexpr int kMaxNq = MAX_N + 1;
+
+struct FaceEvalTables {
+  double Sv[kMaxNq * MAX_N];                        // velocity basis at the face quadrature points: [q][i]
+  double gv[2][MAX_N];                              // l_i'(s) of the velocity basis
+  double Sp[kMaxNq * MAX_N];                        // pressure basis at the face quadrature points
+  double w[kMaxNq];
+  double h[MAX_DIM];
+  int nv, np, nq, dim;
+  double inv_Re;
+};
+
+// item = (boundary face of the list, face quadrature point).  FE_DGQ is nodal at the cell boundary, so face values need the
+// face layer only; the normal derivative needs all layers of the line through the point.
+template <typename T>
+__global__ void __launch_bounds__(128) lift_drag_kernel(const __grid_constant__ FaceEvalTables P, const int *__restrict__ faces, int n_faces,
+                                                        const T *__restrict__ u, const T *__restrict__ p, double *partial, double *result) {
+  const int dim = P.dim, nv = P.nv, np = P.np, nq = P.nq;
+  const int nqf = dim == 3 ? nq * nq : nq;
+  int ndv = 1, ndp = 1;
+  for (int d = 0; d < dim; ++d) { ndv *= nv; ndp *= np; }
+  double drag = 0.0, lift = 0.0;
+  const long long items = (long long)n_faces * nqf;
+  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
+    const int fi = (int)(it / nqf), q = (int)(it - (long long)fi * nqf);
+    const int cell = faces[2 * fi], f = faces[2 * fi + 1], d = f >> 1, s = f & 1;
+    const int e1 = d == 0 ? 1 : 0, e2 = d == 2 ? 1 : 2;      // tangential directions, ascending (e2 unused in 2-D)
+    const int q1 = q % nq, q2 = q / nq;
+    int strv[3] = {1, nv, nv * nv}, strp[3] = {1, np, np * np};
+    // pressure value
+    double pv = 0.0;
+    {
+      const T *pc = p + (size_t)cell * ndp + (size_t)(s ? np - 1 : 0) * strp[d];
+      for (int b = 0; b < (dim == 3 ? np : 1); ++b)
+        for (int a = 0; a < np; ++a) {
+          const double wgt = P.Sp[q1 * np + a] * (dim == 3 ? P.Sp[q2 * np + b] : 1.0);
+          pv += wgt * (double)pc[a * strp[e1] + (dim == 3 ? b * strp[e2] : 0)];
+        }
+    }
+    // velocity gradients grad[c][k] = d u_c / d x_k
+    double force[3] = {0, 0, 0};
+    const double ns = s ? 1.0 : -1.0;
+    double JxW = P.w[q1] * P.h[e1];
+    if (dim == 3) JxW *= P.w[q2] * P.h[e2];
+    for (int c = 0; c < dim; ++c) {
+      const T *uc = u + ((size_t)cell * dim + c) * ndv;
+      double gn = 0.0;   // derivative along the face normal direction d
+      for (int b = 0; b < (dim == 3 ? nv : 1); ++b)
+        for (int a = 0; a < nv; ++a) {
+          const double wt = P.Sv[q1 * nv + a] * (dim == 3 ? P.Sv[q2 * nv + b] : 1.0);
+          const T *line = uc + a * strv[e1] + (dim == 3 ? b * strv[e2] : 0);
+          double acc = 0.0;
+          for (int i = 0; i < nv; ++i) acc += P.gv[s][i] * (double)line[(size_t)i * strv[d]];
+          gn += wt * acc;
+        }
+      gn /= P.h[d];
+      // forces = (1/Re grad u - p I) (-n_out) JxW,  n_out = ns e_d: only column d of the stress enters
+      force[c] = -ns * (P.inv_Re * gn - (c == d ? pv : 0.0)) * JxW;
+    }
+    drag += force[0];
+    lift += force[1];
+  }
+  __shared__ double sm[2][4];
+  __shared__ bool last;
+  for (int o = 16; o > 0; o >>= 1) { drag += __shfl_down_sync(0xffffffffu, drag, o); lift += __shfl_down_sync(0xffffffffu, lift, o); }
+  if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = drag; sm[1][threadIdx.x >> 5] = lift; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    partial[2 * blockIdx.x] = sm[0][0] + sm[0][1] + sm[0][2] + sm[0][3];
+    partial[2 * blockIdx.x + 1] = sm[1][0] + sm[1][1] + sm[1][2] + sm[1][3];
+    __threadfence();
+    const unsigned int t = atomicInc(scratch_ticket(partial), gridDim.x - 1);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x < 32) {   // fixed-order combination of the block partials
+    __threadfence();
+    double s0 = 0.0, s1 = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) { s0 += ((volatile double *)partial)[2 * i]; s1 += ((volatile double *)partial)[2 * i + 1]; }
+    for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_down_sync(0xffffffffu, s0, o); s1 += __shfl_down_sync(0xffffffffu, s1, o); }
+    if (threadIdx.x == 0) { result[0] = s0; result[1] = s1; }
+  }
+}
+
+struct PatchTables {
+  double gv[2][MAX_N];   // l_i'(0), l_i'(1) of the velocity basis
+  double ih[MAX_DIM];
+  int nv, np, dim;
+};
+
+// item = (cell, vertex); out[(cell * 2^dim + vertex) * nf + field], fields = v (dim), p, v_old (dim), vorticity (1 or 3)
+template <typename T>
+__global__ void __launch_bounds__(128) patch_kernel(const __grid_constant__ PatchTables P, long long n_cells, const T *__restrict__ u, const T *__restrict__ p,
+                                                    const T *__restrict__ uold, double *__restrict__ out) {
+  const int dim = P.dim, nv = P.nv, np = P.np, NV = 1 << dim, nvort = dim == 2 ? 1 : 3, nf = 2 * dim + 1 + nvort;
+  int ndv = 1, ndp = 1;
+  for (int d = 0; d < dim; ++d) { ndv *= nv; ndp *= np; }
+  const int strv[3] = {1, nv, nv * nv}, strp[3] = {1, np, np * np};
+  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < n_cells * NV; it += (long long)gridDim.x * blockDim.x) {
+    const long long cell = it / NV;
+    const int v = (int)(it - cell * NV);
+    int offv = 0, offp = 0;
+    for (int d = 0; d < dim; ++d) { const int s = (v >> d) & 1; offv += s * (nv - 1) * strv[d]; offp += s * (np - 1) * strp[d]; }
+    double *o = out + (size_t)it * nf;
+    double grad[3][3];
+    for (int c = 0; c < dim; ++c) {
+      const T *uc = u + ((size_t)cell * dim + c) * ndv;
+      o[c] = (double)uc[offv];
+      o[dim + 1 + c] = (double)uold[((size_t)cell * dim + c) * ndv + offv];
+      for (int d = 0; d < dim; ++d) {
+        const int s = (v >> d) & 1;
+        const T *line = uc + offv - s * (nv - 1) * strv[d];
+        double acc = 0.0;
+        for (int i = 0; i < nv; ++i) acc += P.gv[s][i] * (double)line[(size_t)i * strv[d]];
+        grad[c][d] = acc * P.ih[d];
+      }
+    }
+    o[dim] = (double)p[(size_t)cell * ndp + offp];
+    if (dim == 2) o[2 * dim + 1] = grad[1][0] - grad[0][1];                    // NS.cc:146-148
+    else {                                                                     // NS.cc:150-155
+      o[2 * dim + 1] = grad[2][1] - grad[1][2];
+      o[2 * dim + 2] = grad[0][2] - grad[2][0];
+      o[2 * dim + 3] = grad[1][0] - grad[0][1];
+    }
+  }
+}
+
+int check_pair(const dgx_vec *u, const dgx_vec *p) {
+  DGX_REQUIRE(u && p, "null argument");
+  DGX_REQUIRE(u->mf == p->mf, "velocity and pressure must live on the same MatrixFree");
+  DGX_REQUIRE(u->ncomp == u->mf->dim && p->ncomp == 1, "velocity (dim components) and pressure (scalar) expected");
+  DGX_REQUIRE(u->dtype == p->dtype, "dtype mismatch");
+  DGX_REQUIRE(u->degree >= 1 && p->degree >= 1, "degree >= 1");
+  return DGX_OK;
+}
+
+}  // namespace
+
+// boundary faces (local cell, face number) with the given boundary id, device copy cached per MatrixFree and id
+int boundary_face_list(dgx_mf *mf, int boundary_id, const int **d_faces, int *n_faces) {
+  auto it = mf->bfaces.find(boundary_id);
+  if (it == mf->bfaces.end()) {
+    std::vector<int> list;
+    const int nf = 2 * mf->dim;
+    for (long long c = 0; c < mf->n_owned; ++c)
+      for (int f = 0; f < nf; ++f)
+        if (mf->nbr_host[(size_t)f * mf->n_owned + c] == -1 - boundary_id) { list.push_back((int)c); list.push_back(f); }
+    dgx_mf::BFaces bf;
+    bf.n = (int)(list.size() / 2);
+    if (bf.n) {
+      DGX_CUDA_CHECK(cudaMalloc(&bf.d, list.size() * sizeof(int)));
+      DGX_CUDA_CHECK(cudaMemcpy(bf.d, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    it = mf->bfaces.emplace(boundary_id, bf).first;
+  }
+  *d_faces = it->second.d;
+  *n_faces = it->second.n;
+  return DGX_OK;
+}
+
+}  // namespace dgx
+
+using namespace dgx;
+
+extern "C" {
+
+int dgx_compute_lift_and_drag(const dgx_vec *u, const dgx_vec *p, double Re, int boundary_id, double *lift, double *drag) {
+  if (int rc = check_pair(u, p)) return rc;
+  DGX_REQUIRE(lift && drag, "null argument");
+  dgx_mf *mf = u->mf;
+  dgx_ctx *ctx = mf->ctx;
+  DGX_REQUIRE(ctx->d_scratch, "no device");
+  const int nq = p->degree + 2;   // QGauss<dim - 1>(EquationData::degree_p + 2), NS.cc:2643
+  DGX_REQUIRE(nq <= kMaxNq && u->degree + 1 <= MAX_N, "degree too large");
+  DGX_CUDA_CHECK(cudaSetDevice(ctx->device));
+  const int *d_faces = nullptr;
+  int n_faces = 0;
+  if (int rc = boundary_face_list(mf, boundary_id, &d_faces, &n_faces)) return rc;
+  FaceEvalTables P;
+  std::memset(&P, 0, sizeof(P));
+  const Shape1D &sv = get_shape(u->degree, nq), &sp = get_shape(p->degree, nq);
+  P.nv = u->degree + 1; P.np = p->degree + 1; P.nq = nq; P.dim = mf->dim; P.inv_Re = 1.0 / Re;
+  for (int q = 0; q < nq; ++q) {
+    for (int i = 0; i < P.nv; ++i) P.Sv[q * P.nv + i] = sv.S[q * P.nv + i];
+    for (int i = 0; i < P.np; ++i) P.Sp[q * P.np + i] = sp.S[q * P.np + i];
+    P.w[q] = sv.wq[q];
+  }
+  for (int s = 0; s < 2; ++s)
+    for (int i = 0; i < P.nv; ++i) P.gv[s][i] = sv.g[s][i];
+  for (int d = 0; d < MAX_DIM; ++d) P.h[d] = d < mf->dim ? mf->h[d] : 1.0;
+  double *partial = ctx->d_scratch + kScratchPartial, *result = ctx->d_scratch;
+  const long long items = (long long)n_faces * (mf->dim == 3 ? nq * nq : nq);
+  const int grid = (int)std::max<long long>(1, std::min<long long>((items + 127) / 128, 148 * 4));
+  if (u->dtype == DGX_F64)
+    lift_drag_kernel<double><<<grid, 128, 0, ctx->stream>>>(P, d_faces, n_faces, (const double *)u->d, (const double *)p->d, partial, result);
+  else
+    lift_drag_kernel<float><<<grid, 128, 0, ctx->stream>>>(P, d_faces, n_faces, (const float *)u->d, (const float *)p->d, partial, result);
+  count_launch();
+  DGX_CUDA_CHECK(cudaGetLastError());
+  if (!mf->replicated) {   // Utilities::MPI::sum, NS.cc:2698-2699
+    if (int rc = allreduce_sum(ctx, result, 2)) return rc;
+  }
+  DGX_CUDA_CHECK(cudaMemcpyAsync(ctx->h_scratch, result, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  DGX_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  *drag = ctx->h_scratch[0];
+  *lift = ctx->h_scratch[1];
+  return DGX_OK;
+}
+
+int dgx_output_n_fields(int dim) { return 2 * dim + 1 + (dim == 2 ? 1 : 3); }
+
+int dgx_output_patch_data(const dgx_vec *u_n, const dgx_vec *pres_n, const dgx_vec *u_n_minus_1, double *out_host, long long capacity) {
+  if (int rc = check_pair(u_n, pres_n)) return rc;
+  DGX_REQUIRE(u_n_minus_1 && u_n_minus_1->mf == u_n->mf && u_n_minus_1->degree == u_n->degree && u_n_minus_1->ncomp == u_n->ncomp &&
+                  u_n_minus_1->dtype == u_n->dtype,
+              "u_n_minus_1 must have the shape of u_n");
+  dgx_mf *mf = u_n->mf;
+  dgx_ctx *ctx = mf->ctx;
+  DGX_REQUIRE(ctx->d_scratch, "no device");
+  const int dim = mf->dim, NV = 1 << dim, nf = dgx_output_n_fields(dim);
+  const long long total = mf->n_owned * NV * nf;
+  DGX_REQUIRE(out_host && capacity >= total, "output buffer too small");
+  if (total == 0) return DGX_OK;
+  DGX_CUDA_CHECK(cudaSetDevice(ctx->device));
+  PatchTables P;
+  std::memset(&P, 0, sizeof(P));
+  const Shape1D &sv = get_shape(u_n->degree, u_n->degree + 1);
+  P.nv = u_n->degree + 1; P.np = pres_n->degree + 1; P.dim = dim;
+  for (int s = 0; s < 2; ++s)
+    for (int i = 0; i < P.nv; ++i) P.gv[s][i] = sv.g[s][i];
+  for (int d = 0; d < MAX_DIM; ++d) P.ih[d] = d < dim ? 1.0 / mf->h[d] : 1.0;
+  double *d_out = nullptr;
+  DGX_CUDA_CHECK(cudaMalloc(&d_out, (size_t)total * sizeof(double)));
+  const int grid = (int)std::max<long long>(1, std::min<long long>((mf->n_owned * NV + 127) / 128, 148 * 8));
+  if (u_n->dtype == DGX_F64)
+    patch_kernel<double><<<grid, 128, 0, ctx->stream>>>(P, mf->n_owned, (const double *)u_n->d, (const double *)pres_n->d, (const double *)u_n_minus_1->d, d_out);
+  else
+    patch_kernel<float><<<grid, 128, 0, ctx->stream>>>(P, mf->n_owned, (const float *)u_n->d, (const float *)pres_n->d, (const float *)u_n_minus_1->d, d_out);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, d_out, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_out);
+  if (e != cudaSuccess) { set_error(std::string("output patches: ") + cudaGetErrorString(e)); return DGX_ERR_CUDA; }
+  return DGX_OK;
+}
+
+// host side of output_results: pure format work (pieces in the layout DataOutBase::write_vtu uses: every patch owns its points)
+int dgx_write_vtu_piece(const char *path, int dim, long long n_cells, const double *points, const double *patch_data) {
+  DGX_REQUIRE(path && (dim == 2 || dim == 3) && n_cells >= 0 && (n_cells == 0 || (points && patch_data)), "arguments");
+  FILE *f = std::fopen(path, "w");
+  if (!f) { set_error(std::string("cannot open ") + path); return DGX_ERR_INVALID; }
+  const int NV = 1 << dim, nf = dgx_output_n_fields(dim), nvort = dim == 2 ? 1 : 3;
+  const long long np = n_cells * NV;
+  std::fprintf(f, "<?xml version=\"1.0\" ?>\n<!--\n# vtk DataFile Version 3.0\n# written by libdgx in the layout of deal.II's DataOut::write_vtu\n-->\n");
+  std::fprintf(f, "<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n<UnstructuredGrid>\n");
+  std::fprintf(f, "<Piece NumberOfPoints=\"%lld\" NumberOfCells=\"%lld\">\n", np, n_cells);
+  std::fprintf(f, "<Points>\n<DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"ascii\">\n");
+  for (long long i = 0; i < np; ++i)
+    std::fprintf(f, "%.17g %.17g %.17g\n", points[i * dim], points[i * dim + 1], dim == 3 ? points[i * dim + 2] : 0.0);
+  std::fprintf(f, "</DataArray>\n</Points>\n<Cells>\n<DataArray type=\"Int64\" Name=\"connectivity\" format=\"ascii\">\n");
+  static const int vtk2[4] = {0, 1, 3, 2}, vtk3[8] = {0, 1, 3, 2, 4, 5, 7, 6};   // deal.II vertex order -> VTK_QUAD / VTK_HEXAHEDRON
+  for (long long c = 0; c < n_cells; ++c) {
+    for (int v = 0; v < NV; ++v) std::fprintf(f, "%lld ", c * NV + (dim == 2 ? vtk2[v] : vtk3[v]));
+    std::fputc('\n', f);
+  }
+  std::fprintf(f, "</DataArray>\n<DataArray type=\"Int64\" Name=\"offsets\" format=\"ascii\">\n");
+  for (long long c = 0; c < n_cells; ++c) std::fprintf(f, "%lld\n", (c + 1) * NV);
+  std::fprintf(f, "</DataArray>\n<DataArray type=\"UInt8\" Name=\"types\" format=\"ascii\">\n");
+  for (long long c = 0; c < n_cells; ++c) std::fprintf(f, "%d\n", dim == 2 ? 9 : 12);
+  std::fprintf(f, "</DataArray>\n</Cells>\n<PointData Scalars=\"scalars\">\n");
+  auto vec3 = [&](const char *name, int first, int ncomp) {
+    std::fprintf(f, "<DataArray type=\"Float64\" Name=\"%s\" NumberOfComponents=\"3\" format=\"ascii\">\n", name);
+    for (long long i = 0; i < np; ++i) {
+      const double *o = patch_data + i * nf + first;
+      std::fprintf(f, "%.17g %.17g %.17g\n", o[0], ncomp > 1 ? o[1] : 0.0, ncomp > 2 ? o[2] : 0.0);
+    }
+    std::fprintf(f, "</DataArray>\n");
+  };
+  auto scalar = [&](const char *name, int first) {
+    std::fprintf(f, "<DataArray type=\"Float64\" Name=\"%s\" format=\"ascii\">\n", name);
+    for (long long i = 0; i < np; ++i) std::fprintf(f, "%.17g\n", patch_data[i * nf + first]);
+    std::fprintf(f, "</DataArray>\n");
+  };
+  vec3("v", 0, dim);                  // NS.cc:2612-2616
+  scalar("p", dim);                   // NS.cc:2617-2618
+  vec3("v_old", dim + 1, dim);        // NS.cc:2620-2622
+  if (nvort == 1) scalar("vorticity", 2 * dim + 1);   // NS.cc:2625-2626, component_is_scalar in 2-D
+  else vec3("vorticity", 2 * dim + 1, 3);
+  std::fprintf(f, "</PointData>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n");
+  const bool ok = std::fclose(f) == 0;
+  if (!ok) { set_error(std::string("write failed: ") + path); return DGX_ERR_INVALID; }
+  return DGX_OK;
+}
+
+int dgx_output_results(const dgx_vec *u_n, const dgx_vec *pres_n, const dgx_vec *u_n_minus_1, const char *path) {
+  if (int rc = check_pair(u_n, pres_n)) return rc;
+  DGX_REQUIRE(path, "null argument");
+  dgx_mf *mf = u_n->mf;
+  dgx_ctx *ctx = mf->ctx;
+  const Mesh &m = mf->mesh->m;
+  const int dim = mf->dim, NV = 1 << dim, nf = dgx_output_n_fields(dim);
+  std::vector<double> data((size_t)mf->n_owned * NV * nf), pts((size_t)mf->n_owned * NV * dim);
+  if (int rc = dgx_output_patch_data(u_n, pres_n, u_n_minus_1, data.data(), (long long)data.size())) return rc;
+  for (long long c = 0; c < mf->n_owned; ++c) {
+    int cc[MAX_DIM] = {0, 0, 0};
+    m.coords_of(mf->level, mf->first_cell + c, cc);
+    for (int v = 0; v < NV; ++v)
+      for (int d = 0; d < dim; ++d) pts[((size_t)c * NV + v) * dim + d] = m.lo[d] + (cc[d] + ((v >> d) & 1)) * mf->h[d];
+  }
+  const bool parallel = ctx->nranks > 1 && !mf->replicated;
+  if (mf->replicated && ctx->rank != 0) return DGX_OK;   // every rank holds the same cells: rank 0 writes
+  std::string base(path), piece = base;
+  if (parallel) {   // one piece per rank + an index written by rank 0 (the reference writes one file through MPI I/O, NS.cc:2632)
+    const size_t dot = base.rfind(".vtu");
+    const std::string stem = dot == std::string::npos ? base : base.substr(0, dot);
+    char suf[32];
+    std::snprintf(suf, sizeof(suf), ".%04d.vtu", ctx->rank);
+    piece = stem + suf;
+    if (ctx->rank == 0) {
+      FILE *f = std::fopen((stem + ".pvtu").c_str(), "w");
+      if (!f) { set_error("cannot open " + stem + ".pvtu"); return DGX_ERR_INVALID; }
+      std::fprintf(f, "<?xml version=\"1.0\" ?>\n<VTKFile type=\"PUnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n<PUnstructuredGrid GhostLevel=\"0\">\n");
+      std::fprintf(f, "<PPointData Scalars=\"scalars\">\n<PDataArray type=\"Float64\" Name=\"v\" NumberOfComponents=\"3\" format=\"ascii\"/>\n");
+      std::fprintf(f, "<PDataArray type=\"Float64\" Name=\"p\" format=\"ascii\"/>\n<PDataArray type=\"Float64\" Name=\"v_old\" NumberOfComponents=\"3\" format=\"ascii\"/>\n");
+      if (dim == 2) std::fprintf(f, "<PDataArray type=\"Float64\" Name=\"vorticity\" format=\"ascii\"/>\n");
+      else std::fprintf(f, "<PDataArray type=\"Float64\" Name=\"vorticity\" NumberOfComponents=\"3\" format=\"ascii\"/>\n");
+      std::fprintf(f, "</PPointData>\n<PPoints>\n<PDataArray type=\"Float64\" NumberOfComponents=\"3\"/>\n</PPoints>\n");
+      const size_t slash = stem.find_last_of('/');
+      const std::string leaf = slash == std::string::npos ? stem : stem.substr(slash + 1);
+      for (int r = 0; r < ctx->nranks; ++r) std::fprintf(f, "<Piece Source=\"%s.%04d.vtu\"/>\n", leaf.c_str(), r);
+      std::fprintf(f, "</PUnstructuredGrid>\n</VTKFile>\n");
+      std::fclose(f);
+    }
+  }
+  return dgx_write_vtu_piece(piece.c_str(), dim, mf->n_owned, pts.data(), data.data());
+}
+
+}  // extern "C"

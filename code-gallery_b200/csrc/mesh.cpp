@@ -245,6 +245,7 @@ int dgx_mf_destroy(dgx_mf *mf) {
   if (mf->d_jobs) cudaFree(mf->d_jobs);
   if (mf->d_jobs_async) cudaFree(mf->d_jobs_async);
   dgx::p2p_destroy(mf);
+  for (auto &kv : mf->bfaces) if (kv.second.d) cudaFree(kv.second.d);
   for (auto &p : mf->peers) if (p.d_send_cells) cudaFree(p.d_send_cells);
   delete mf;
   return DGX_OK;

@@ -491,6 +491,29 @@ def solve_gmres(op, x, b, precond=None, max_it=10000, abs_tol=0.0, max_basis=30)
     return _solve(lib.dgx_solve_gmres, op, x, b, precond, max_it, abs_tol, c_int(max_basis))
 
 
+# ---- diagnostics and output of the time loop (NS.cc:2608-2708), evaluated on the device --------------------
+def compute_lift_and_drag(u: Vector, p: Vector, Re, boundary_id=4):
+    """NavierStokesProjection::compute_lift_and_drag (NS.cc:2642-2708); returns (lift, drag) summed over all ranks"""
+    lift, drag = c_dbl(), c_dbl()
+    _check(lib.dgx_compute_lift_and_drag(u.h, p.h, c_dbl(Re), c_int(boundary_id), C.byref(lift), C.byref(drag)))
+    return lift.value, drag.value
+
+
+def output_patch_data(u_n: Vector, pres_n: Vector, u_n_minus_1: Vector):
+    """what DataOut::build_patches(MappingQ1, 1) collects in output_results (NS.cc:2608-2630):
+    [owned cells, 2^dim vertices, fields] with fields = v (dim), p, v_old (dim), vorticity (1 in 2-D, 3 in 3-D)"""
+    dim = u_n.mf.dim
+    nf = lib.dgx_output_n_fields(dim)
+    out = np.empty((u_n.mf.n_owned_cells(), 1 << dim, nf), dtype=np.float64)
+    _check(lib.dgx_output_patch_data(u_n.h, pres_n.h, u_n_minus_1.h, out.ctypes.data_as(c_vp), c_ll(out.size)))
+    return out
+
+
+def output_results(u_n: Vector, pres_n: Vector, u_n_minus_1: Vector, path):
+    """NavierStokesProjection::output_results (NS.cc:2608-2633): writes `path` (.vtu; one piece per rank + .pvtu on several ranks)"""
+    _check(lib.dgx_output_results(u_n.h, pres_n.h, u_n_minus_1.h, os.fsencode(path)))
+
+
 GAMMA = 2.0 - 2.0 ** 0.5      # NS.cc:396, 2210
 
 

@@ -5,8 +5,10 @@ reference only prints through deallog.
 """
 from __future__ import annotations
 
-from . import (GAMMA, OP_MASS, OP_PRESSURE, OP_VELOCITY, MatrixFree, Multigrid, NavierStokesProjectionOperator, interpolate_velocity,
-               solve_cg, solve_gmres)
+import os
+
+from . import (GAMMA, OP_MASS, OP_PRESSURE, OP_VELOCITY, MatrixFree, Multigrid, NavierStokesProjectionOperator, compute_lift_and_drag,
+               interpolate_velocity, output_results, solve_cg, solve_gmres)
 
 
 class NavierStokesProjection:
@@ -115,3 +117,30 @@ class NavierStokesProjection:
         self.u_tmp.equ((g - 1.0) * dt, self.u_tmp)
         self.u_n.add(1.0, self.u_tmp)
         return self.u_n.linfty_norm()                                                     # get_maximal_velocity, NS.cc:2988
+
+    def compute_lift_and_drag(self, boundary_id=4):                                       # NS.cc:2642-2708
+        """returns (lift, drag) of the faces with `boundary_id` (the reference appends them to lift.dat / drag.dat)"""
+        return compute_lift_and_drag(self.u_n, self.pres_n, self.Re, boundary_id)
+
+    def output_results(self, step, saving_dir="."):                                       # NS.cc:2608-2633
+        path = os.path.join(saving_dir, f"solution-{step:05d}.vtu")
+        output_results(self.u_n, self.pres_n, self.u_n_minus_1, path)
+        return path
+
+    def run(self, T, output_interval=0, saving_dir=".", verbose=False, boundary_id=4):
+        """NavierStokesProjection::run (NS.cc:2928-3010) without mesh refinement: returns the (lift, drag) history"""
+        forces = []
+        if output_interval:
+            self.output_results(1, saving_dir)
+        while abs(T - self.time) > 1e-10:
+            max_vel = self.advance()
+            if verbose and self.ctx.rank == 0:
+                print(f"Step = {self.n} Time = {self.time}\nMaximal velocity = {max_vel}")
+            forces.append(self.compute_lift_and_drag(boundary_id))
+            if output_interval and self.n % output_interval == 0:
+                self.output_results(self.n, saving_dir)
+            if T - self.time < self.dt and T - self.time > 1e-10:                         # NS.cc:2996-3002
+                self.set_dt(T - self.time)
+        if output_interval and self.n % output_interval != 0:
+            self.output_results(self.n, saving_dir)
+        return forces

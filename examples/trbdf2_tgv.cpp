@@ -178,6 +178,21 @@ public:
     return u_n.linfty_norm();                                                                          // get_maximal_velocity, NS.cc:2583-2587
   }
 
+  // compute_lift_and_drag, NS.cc:2642-2708: face integrals on the device, summed over the ranks (no face of the periodic box
+  // carries id 4: the call is here because run() makes it after every step, NS.cc:2991)
+  std::pair<double, double> compute_lift_and_drag() {
+    double lift = 0, drag = 0;
+    check(dgx_compute_lift_and_drag(u_n.h, pres_n.h, Re, 4, &lift, &drag));
+    return {lift, drag};
+  }
+
+  // output_results, NS.cc:2608-2633: v, p, v_old and the vorticity at the patch vertices, evaluated on the device
+  void output_results(const std::string &saving_dir, unsigned int step) {
+    char name[64];
+    std::snprintf(name, sizeof(name), "/solution-%05u.vtu", step);
+    check(dgx_output_results(u_n.h, pres_n.h, u_n_minus_1.h, (saving_dir + name).c_str()));
+  }
+
   Context context;
   int degree_p;
   double Re, gamma, dt;
@@ -197,6 +212,7 @@ int main(int argc, char **argv) {
   try {
     const int n_refines = argc > 1 ? std::atoi(argv[1]) : 4, n_steps = argc > 2 ? std::atoi(argv[2]) : 2, degree_p = argc > 3 ? std::atoi(argv[3]) : 2;
     const double Re = argc > 4 ? std::atof(argv[4]) : 1600.0;
+    const std::string saving_dir = argc > 5 ? argv[5] : "";   // output_results after the last step when given
     NavierStokesProjection<3> test(n_refines, degree_p, Re, 0.2);
     std::printf("{\"cells\": \"%d^3\", \"degree_p\": %d, \"dt\": %.17g, \"launches_setup\": %lld, \"steps\": [", 1 << n_refines, degree_p, test.dt,
                 dgx_kernel_launch_count());
@@ -208,8 +224,11 @@ int main(int argc, char **argv) {
       const double vmax = test.advance();
       double ms = 0;
       check(dgx_ctx_timer_stop(test.context.h, &ms));
-      std::printf("%s{\"step\": %d, \"ms\": %.3f, \"max_velocity\": %.17g, \"launches\": %lld, \"iterations\": [", s ? ", " : "", s, ms, vmax,
-                  dgx_kernel_launch_count() - l0);
+      const long long launches = dgx_kernel_launch_count() - l0;
+      const auto forces = test.compute_lift_and_drag();                                                 // NS.cc:2991
+      if (!saving_dir.empty() && s == n_steps - 1) test.output_results(saving_dir, (unsigned int)(s + 2));
+      std::printf("%s{\"step\": %d, \"ms\": %.3f, \"max_velocity\": %.17g, \"lift\": %.17g, \"drag\": %.17g, \"launches\": %lld, \"iterations\": [", s ? ", " : "",
+                  s, ms, vmax, forces.first, forces.second, launches);
       for (std::size_t i = 0; i < test.iterations.size(); ++i)
         std::printf("%s[\"%s\", %u]", i ? ", " : "", test.iterations[i].first.c_str(), test.iterations[i].second);
       std::printf("]}");

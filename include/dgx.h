@@ -214,6 +214,24 @@ int dgx_mg_level_op(dgx_mg *mg, int level, dgx_op **op);                  /* bor
 int dgx_solve_cg(dgx_op *A, dgx_vec *x, dgx_vec *b, int precond_kind, void *precond, int max_it, double abs_tol, int *iters, double *final_res);
 int dgx_solve_gmres(dgx_op *A, dgx_vec *x, dgx_vec *b, int precond_kind, void *precond, int max_it, double abs_tol, int max_basis, int *iters, double *final_res);
 
+/* ---- diagnostics and output of the time loop, evaluated on the device (NS.cc:2608-2708) ---------------------------------- */
+/* NavierStokesProjection::compute_lift_and_drag (NS.cc:2642-2708): sum over the boundary faces with id `boundary_id` (the
+ * reference: 4) of (1/Re grad u - p I) (-n) JxW at the points of QGauss<dim-1>(degree_p + 2); drag = component 0, lift = component 1,
+ * summed over all ranks (Utilities::MPI::sum).  u, p: vectors of one MatrixFree. */
+int dgx_compute_lift_and_drag(const dgx_vec *u, const dgx_vec *p, double Re, int boundary_id, double *lift, double *drag);
+/* fields per patch point of output_results: v (dim), p, v_old (dim), vorticity (1 in 2-D, 3 in 3-D) */
+int dgx_output_n_fields(int dim);
+/* the data DataOut::build_patches(MappingQ1, 1) collects for output_results (NS.cc:2608-2630): one patch per owned cell, its 2^dim
+ * vertices in deal.II vertex order (x fastest), out_host[(cell * 2^dim + vertex) * n_fields + field]; the vorticity is
+ * PostprocessorVorticity::evaluate_vector_field (NS.cc:131-158) on the velocity gradients at the vertex */
+int dgx_output_patch_data(const dgx_vec *u_n, const dgx_vec *pres_n, const dgx_vec *u_n_minus_1, double *out_host, long long capacity);
+/* one <Piece> as an UnstructuredGrid .vtu file (ascii arrays; every patch owns its points like DataOutBase::write_vtu):
+ * points[n_cells * 2^dim * dim], patch_data as above */
+int dgx_write_vtu_piece(const char *path, int dim, long long n_cells, const double *points, const double *patch_data);
+/* output_results (NS.cc:2608-2633): patch data from the device, written to `path` (.vtu); with several ranks every rank writes
+ * <stem>.<rank>.vtu and rank 0 the index <stem>.pvtu (the reference: one file through MPI I/O, write_vtu_in_parallel) */
+int dgx_output_results(const dgx_vec *u_n, const dgx_vec *pres_n, const dgx_vec *u_n_minus_1, const char *path);
+
 #ifdef __cplusplus
 }
 #endif

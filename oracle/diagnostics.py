@@ -1,0 +1,100 @@
+"""Lift / drag and output data of the reference's time loop (oracle; test infrastructure only).
+
+* ``lift_and_drag`` follows NavierStokesProjection::compute_lift_and_drag,
+  navier_stokes_TRBDF2_DG.cc:2642-2708: FEFaceValues with QGauss<dim-1>(degree_p + 2) on the faces with
+  boundary id 4, full velocity gradient and pressure value at every face quadrature point,
+  ``forces = (1/Re grad u - p I) * (-n) * JxW``, drag = forces[0], lift = forces[1].
+* ``patch_data`` follows output_results, NS.cc:2608-2633, with PostprocessorVorticity, NS.cc:131-158:
+  ``build_patches(MappingQ1, 1)`` evaluates every field at the 2^dim vertices of every cell (deal.II vertex order: x fastest);
+  the vorticity is formed from ``solution_gradients[q][component][derivative]``.
+
+Both are written with dense point evaluations (every basis function at every point), i.e. not the way the CUDA
+kernels index the face layer / the line through the vertex.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .dg1d import gauss_lobatto_nodes, lagrange_eval, shape
+from .feeval import FaceEval
+from .mesh import CartesianMesh
+
+
+def lift_and_drag(mesh: CartesianMesh, degree_v: int, degree_p: int, u, p, Re: float, boundary_id: int = 4):
+    dim = mesh.dim
+    nq = degree_p + 2                                                   # NS.cc:2643
+    shv, shp = shape(degree_v, nq), shape(degree_p, nq)
+    nv, npp = degree_v + 1, degree_p + 1
+    U = np.asarray(u, dtype=np.float64).reshape((mesh.n_cells, dim) + (nv,) * dim)
+    P = np.asarray(p, dtype=np.float64).reshape((mesh.n_cells, 1) + (npp,) * dim)
+    drag = lift = 0.0
+    for f in range(2 * dim):
+        d, s = f // 2, f % 2
+        cells = np.nonzero(mesh.nbr[:, f] == -1 - boundary_id)[0]       # NS.cc:2671
+        if len(cells) == 0:
+            continue
+        fv, fp = FaceEval(dim, mesh.h, shv, d, s), FaceEval(dim, mesh.h, shp, d, s)
+        grad = fv.gradients(U[cells])                                   # [N, c, k, face points]: d u_c / d x_k
+        pres = fp.values(P[cells])[:, 0]                                # [N, face points]
+        normal = np.zeros(dim)
+        normal[d] = -(2 * s - 1)                                        # NS.cc:2679: minus the outward normal
+        stress = grad / Re                                              # NS.cc:2684
+        for c in range(dim):
+            stress[:, c, c] -= pres                                     # NS.cc:2686
+        forces = np.einsum("nck...,k->nc...", stress, normal) * fv.JxW  # NS.cc:2688
+        drag += float(forces[:, 0].sum())
+        lift += float(forces[:, 1].sum())
+    return lift, drag
+
+
+def _point_tables(degree, pts):
+    nodes = gauss_lobatto_nodes(degree + 1)
+    L, D = lagrange_eval(nodes, np.asarray(pts, dtype=np.longdouble))
+    return np.asarray(L, dtype=np.float64), np.asarray(D, dtype=np.float64)
+
+
+def patch_data(mesh: CartesianMesh, degree_v: int, degree_p: int, u_n, pres_n, u_n_minus_1):
+    """[n_cells, 2^dim vertices, fields]: v (dim), p, v_old (dim), vorticity (1 in 2-D, 3 in 3-D)."""
+    dim = mesh.dim
+    nv, npp = degree_v + 1, degree_p + 1
+    Lv, Dv = _point_tables(degree_v, [0.0, 1.0])
+    Lp, _ = _point_tables(degree_p, [0.0, 1.0])
+    U = np.asarray(u_n, dtype=np.float64).reshape((mesh.n_cells, dim) + (nv,) * dim)
+    Uo = np.asarray(u_n_minus_1, dtype=np.float64).reshape((mesh.n_cells, dim) + (nv,) * dim)
+    P = np.asarray(pres_n, dtype=np.float64).reshape((mesh.n_cells,) + (npp,) * dim)
+    nvort = 1 if dim == 2 else 3
+    out = np.zeros((mesh.n_cells, 1 << dim, 2 * dim + 1 + nvort))
+
+    def at_vertex(T, tabs):
+        """contract the trailing spatial axes (slowest..fastest = z, y, x) of T with one 1-D row per direction"""
+        for d in range(dim - 1, -1, -1):        # first contraction removes the z (or y) axis = first spatial axis
+            T = np.tensordot(T, tabs[d], axes=([T.ndim - 1 - d], [0]))
+        return T
+
+    for v in range(1 << dim):
+        s = [(v >> d) & 1 for d in range(dim)]
+        val_rows = [Lv[s[d]] for d in range(dim)]
+        out[:, v, 0:dim] = at_vertex(U, val_rows)
+        out[:, v, dim] = at_vertex(P, [Lp[s[d]] for d in range(dim)])
+        out[:, v, dim + 1:2 * dim + 1] = at_vertex(Uo, val_rows)
+        grad = np.zeros((mesh.n_cells, dim, dim))
+        for k in range(dim):
+            rows = [Dv[s[d]] / mesh.h[d] if d == k else Lv[s[d]] for d in range(dim)]
+            grad[:, :, k] = at_vertex(U, rows)
+        if dim == 2:
+            out[:, v, 2 * dim + 1] = grad[:, 1, 0] - grad[:, 0, 1]      # NS.cc:146-148
+        else:
+            out[:, v, 2 * dim + 1] = grad[:, 2, 1] - grad[:, 1, 2]      # NS.cc:150-155
+            out[:, v, 2 * dim + 2] = grad[:, 0, 2] - grad[:, 2, 0]
+            out[:, v, 2 * dim + 3] = grad[:, 1, 0] - grad[:, 0, 1]
+    return out
+
+
+def patch_points(mesh: CartesianMesh):
+    """[n_cells, 2^dim, dim] vertex coordinates of every cell, deal.II vertex order"""
+    org = mesh.cell_origin()
+    out = np.zeros((mesh.n_cells, 1 << mesh.dim, mesh.dim))
+    for v in range(1 << mesh.dim):
+        for d in range(mesh.dim):
+            out[:, v, d] = org[:, d] + ((v >> d) & 1) * mesh.h[d]
+    return out

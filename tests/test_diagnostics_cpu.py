@@ -1,0 +1,101 @@
+"""CPU tests of the oracle's lift / drag and output data (oracle/diagnostics.py, following NS.cc:2608-2708) against closed
+forms, and of the host-only VTU writer behind the C ABI (dgx_write_vtu_piece: no device needed)."""
+import ctypes as C
+import xml.etree.ElementTree as ET
+
+import numpy as np
+
+from oracle.dg1d import gauss_lobatto_nodes
+from oracle.diagnostics import lift_and_drag, patch_data, patch_points
+from oracle.mesh import CartesianMesh
+
+
+def interp(om, degree, funcs):
+    nodes = np.asarray(gauss_lobatto_nodes(degree + 1), dtype=np.float64)
+    pts = om.dof_points(nodes)
+    x = [pts[..., d] for d in range(om.dim)]
+    return np.stack([f(*x) for f in funcs], axis=1).reshape(-1)
+
+
+def fields_2d(om, dv=2, dp=1):
+    u = interp(om, dv, [lambda x, y: y * y + x + x * y, lambda x, y: x * y + 2 * y])
+    p = interp(om, dp, [lambda x, y: 3 * x + y])
+    return u, p
+
+
+def fields_3d(om, dv=2, dp=1):
+    u = interp(om, dv, [lambda x, y, z: x * x + y * z, lambda x, y, z: x * y, lambda x, y, z: x * z * z])
+    p = interp(om, dp, [lambda x, y, z: x + y])
+    return u, p
+
+
+def test_lift_and_drag_closed_form_2d():
+    Re = 7.0
+    om = CartesianMesh(2, [2, 1], 2, [0, 0], [2, 1], [False, False], [0, 1, 4, 3])   # lower y face carries id 4
+    u, p = fields_2d(om)
+    lift, drag = lift_and_drag(om, 2, 1, u, p, Re)
+    # on y = 0 the reference's normal is (0, 1): forces = (1/Re du0/dy, 1/Re du1/dy - p) = (x / Re, (x + 2) / Re - 3 x)
+    assert abs(drag - 2.0 / Re) < 1e-13
+    assert abs(lift - (6.0 / Re - 6.0)) < 1e-13
+
+
+def test_lift_and_drag_closed_form_3d():
+    Re = 3.0
+    om = CartesianMesh(3, [1, 1, 1], 2, [0, 0, 0], [1, 1, 1], [False] * 3, [0, 4, 2, 3, 5, 5])   # upper x face carries id 4
+    u, p = fields_3d(om)
+    lift, drag = lift_and_drag(om, 2, 1, u, p, Re)
+    # on x = 1 the reference's normal is (-1, 0, 0): forces = -(1/Re du_c/dx - p delta_c0) = -(2/Re - 1 - y, y/Re, z^2/Re)
+    assert abs(drag + (2.0 / Re - 1.5)) < 1e-13
+    assert abs(lift + 0.5 / Re) < 1e-13
+
+
+def test_patch_data_closed_form():
+    om = CartesianMesh(3, [1, 2, 1], 1, [0, 0, 0], [1, 2, 1], [False] * 3)
+    u, p = fields_3d(om)
+    uo = 0.5 * u
+    out = patch_data(om, 2, 1, u, p, uo)
+    X = patch_points(om)
+    x, y, z = X[..., 0], X[..., 1], X[..., 2]
+    assert np.allclose(out[..., 0], x * x + y * z, atol=1e-13) and np.allclose(out[..., 3], x + y, atol=1e-13)
+    assert np.allclose(out[..., 4:7], 0.5 * out[..., 0:3], atol=1e-14)
+    # curl of (x^2 + y z, x y, x z^2) = (0 - 0, y - z^2, y - z)
+    assert np.allclose(out[..., 7], 0.0, atol=1e-12)
+    assert np.allclose(out[..., 8], y - z * z, atol=1e-12)
+    assert np.allclose(out[..., 9], y - z, atol=1e-12)
+    om2 = CartesianMesh(2, [2, 1], 1, [0, 0], [2, 1], [False, False])
+    u2, p2 = fields_2d(om2)
+    out2 = patch_data(om2, 2, 1, u2, p2, u2)
+    X2 = patch_points(om2)
+    # d u1/dx - d u0/dy = y - (2 y + x)
+    assert np.allclose(out2[..., 5], -X2[..., 1] - X2[..., 0], atol=1e-12)
+
+
+def read_vtu(path):
+    root = ET.parse(path).getroot()
+    piece = root.find("UnstructuredGrid/Piece")
+    arrays = {}
+    for da in piece.iter("DataArray"):
+        name = da.get("Name", "points")
+        arr = np.array(da.text.split(), dtype=np.float64)
+        nc = int(da.get("NumberOfComponents", "1"))
+        arrays[name] = arr.reshape(-1, nc) if nc > 1 else arr
+    return int(piece.get("NumberOfPoints")), int(piece.get("NumberOfCells")), arrays
+
+
+def test_vtu_writer_round_trip(dgx, tmp_path):
+    om = CartesianMesh(2, [2, 1], 1, [0, 0], [2, 1], [False, False])
+    u, p = fields_2d(om)
+    data = patch_data(om, 2, 1, u, p, 2 * u)
+    pts = patch_points(om)
+    path = str(tmp_path / "piece.vtu")
+    dgx.lib.dgx_write_vtu_piece.argtypes = [C.c_char_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]
+    rc = dgx.lib.dgx_write_vtu_piece(path.encode(), 2, om.n_cells, np.ascontiguousarray(pts).ctypes.data, np.ascontiguousarray(data).ctypes.data)
+    assert rc == 0
+    npnt, ncell, arr = read_vtu(path)
+    assert npnt == om.n_cells * 4 and ncell == om.n_cells
+    assert np.array_equal(arr["points"][:, :2], pts.reshape(-1, 2)) and np.all(arr["points"][:, 2] == 0)
+    flat = data.reshape(-1, data.shape[-1])
+    assert np.array_equal(arr["v"][:, :2], flat[:, 0:2]) and np.array_equal(arr["p"], flat[:, 2])
+    assert np.array_equal(arr["v_old"][:, :2], flat[:, 3:5]) and np.array_equal(arr["vorticity"], flat[:, 5])
+    assert np.array_equal(arr["connectivity"].reshape(-1, 4)[1], [4, 5, 7, 6]) and np.all(arr["types"] == 9)
+    assert np.array_equal(arr["offsets"], 4 * np.arange(1, om.n_cells + 1))
