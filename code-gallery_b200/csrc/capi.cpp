@@ -123,7 +123,7 @@ static int host_plan_chunk_log2(const dgx_mf *mf, size_t cell_bytes) {
 static bool host_pipeline_applies(dgx_op *op) {
   dgx_mf *mf = op->mf;
   static const bool off = getenv("DGX_NO_HOST_PIPELINE") != nullptr;
-  if (off || op->kind != DGX_OP_PRESSURE || mf->ctx->nranks != 1) return false;
+  if (off || op->kind != DGX_OP_PRESSURE || mf->ctx->nranks != 1 || mf->general) return false;
   if (op->hp_lg == 0) op->hp_lg = host_plan_chunk_log2(mf, (size_t)op->h_src->dofs_per_cell * op->h_src->elem());
   return op->hp_lg > 0;
 }
@@ -355,6 +355,10 @@ static int apply(dgx_op *op, dgx_vec *dst, dgx_vec *src, bool add) {
     rc = pressure_apply_fast_async(op, dst, src, add);
     if (rc != DGX_ERR_UNSUPPORTED) return rc;
   }
+  if (op->mf->general && op->kind != DGX_OP_PRESSURE) {
+    set_error("only the pressure operator (NS_stage 2) supports non-Cartesian levels");
+    return DGX_ERR_UNSUPPORTED;
+  }
   if (op->kind != DGX_OP_MASS) { rc = ghost_exchange(src); if (rc) return rc; }
   switch (op->kind) {
     case DGX_OP_PRESSURE: return pressure_apply(op, dst, src, add);
@@ -377,8 +381,11 @@ int dgx_op_mass_inverse(dgx_op *op, dgx_vec *dst, dgx_vec *src) {
   return mass_inverse_apply(op, dst, src);
 }
 
+long long dgx_mf_general_metric_bytes(dgx_mf *mf, int degree) { return mf ? general_metric_bytes(mf, degree + 1) : 0; }
+
 int dgx_op_compute_diagonal(dgx_op *op) {
   DGX_REQUIRE(op, "null argument");
+  if (op->mf->general && op->kind != DGX_OP_PRESSURE) { set_error("only the pressure operator (NS_stage 2) supports non-Cartesian levels"); return DGX_ERR_UNSUPPORTED; }
   DGX_REQUIRE(op->kind == DGX_OP_VELOCITY || op->kind == DGX_OP_PRESSURE, "compute_diagonal needs NS_stage 1 or 2");  // NS.cc:2019
   if (!op->inv_diag) {
     int rc = dgx_vec_create(op->mf, op->degree, op->ncomp, &op->inv_diag);

@@ -70,6 +70,10 @@ struct Mesh {
   double lo[MAX_DIM] = {0, 0, 0}, hi[MAX_DIM] = {1, 1, 1};
   bool periodic[MAX_DIM] = {false, false, false};
   int bids[2 * MAX_DIM] = {0, 1, 2, 3, 4, 5};
+  // vertex positions per level (dgx_mesh_set_vertices): lattice of (cells_dir + 1)^dim points, x fastest, dim doubles each; empty =
+  // the Cartesian box.  A level with vertices is a MappingQ1 mesh: operators use the per-quadrature-point metric path.
+  std::vector<std::vector<double>> vertices;
+  bool general(int level) const { return level >= 0 && level < (int)vertices.size() && !vertices[level].empty(); }
 
   long long n_cells(int level) const;
   int cells_dir(int level, int d) const { return cells0[d] << level; }
@@ -142,6 +146,10 @@ struct dgx_mf {
   // boundary faces (local cell, face number) per boundary id, built on first use (diagnostics.cu: lift and drag)
   struct BFaces { int *d = nullptr; int n = 0; };
   std::map<int, BFaces> bfaces;
+  // non-Cartesian level (Mesh::general): metric tables of the owned cells per number of 1-D quadrature points (pressure_general.cu)
+  bool general = false;
+  struct GeneralMetric { void *cellG = nullptr, *faceA = nullptr; size_t bytes = 0; };
+  std::map<int, GeneralMetric> gmetric;
 };
 
 struct dgx_vec {
@@ -190,6 +198,11 @@ struct FusedUpdate {
   double a = 0, b = 0, c = 0;
 };
 int pressure_apply_fused(dgx_op *op, dgx_vec *dst, dgx_vec *x, const FusedUpdate &fu);
+// pressure operator on a level with vertex positions (MappingQ1 metric at every quadrature point); bfac scales the boundary penalty
+int pressure_general_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const FusedUpdate *fu, double bfac);
+int pressure_general_diagonal(dgx_op *op, dgx_vec *diag_inv);
+void general_metric_destroy(dgx_mf *mf);
+long long general_metric_bytes(dgx_mf *mf, int n);
 // i-th pooled work vector of the operator's space (created on first use, lives as long as the operator)
 int op_pool_vec(dgx_op *op, int i, dgx_vec **out);
 int pressure_coarse_cg(dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_vec *r, dgx_vec *p, dgx_vec *v, const double *d_tol, int max_it, int *d_info, double *d_res,

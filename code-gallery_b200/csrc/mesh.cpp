@@ -89,6 +89,24 @@ int dgx_mesh_create_cartesian(int dim, const int *cells0, int n_refine, const do
 
 int dgx_mesh_destroy(dgx_mesh *mesh) { delete mesh; return DGX_OK; }
 
+int dgx_mesh_set_vertices(dgx_mesh *mesh, int level, const double *coords, long long n_values) {
+  DGX_REQUIRE(mesh && coords, "null argument");
+  Mesh &m = mesh->m;
+  if (level < 0) level = m.n_refine;
+  DGX_REQUIRE(level <= m.n_refine, "level");
+  long long nv = 1;
+  for (int d = 0; d < m.dim; ++d) nv *= m.cells_dir(level, d) + 1;
+  DGX_REQUIRE(n_values == nv * m.dim, "coords must hold (cells + 1)^dim vertices of dim doubles each");
+  if ((int)m.vertices.size() <= m.n_refine) m.vertices.resize(m.n_refine + 1);
+  m.vertices[level].assign(coords, coords + n_values);
+  return DGX_OK;
+}
+
+int dgx_mesh_is_general(const dgx_mesh *mesh, int level) {
+  if (!mesh) return 0;
+  return mesh->m.general(level < 0 ? mesh->m.n_refine : level) ? 1 : 0;
+}
+
 int dgx_mesh_n_levels(const dgx_mesh *mesh) { return mesh ? mesh->m.n_refine + 1 : 0; }
 
 long long dgx_mesh_n_cells(const dgx_mesh *mesh, int level) {
@@ -137,6 +155,7 @@ int dgx::mf_create(dgx_ctx *ctx, dgx_mesh *mesh, int level, int dtype, bool repl
   mf->first_cell = bound(r);
   mf->n_owned = bound(r + 1) - bound(r);
   for (int d = 0; d < m.dim; ++d) mf->h[d] = m.h(level, d);
+  mf->general = m.general(level);
   const int nf = 2 * m.dim;
   const long long no = mf->n_owned;
   auto owner_of = [&](long long g) {
@@ -246,6 +265,7 @@ int dgx_mf_destroy(dgx_mf *mf) {
   if (mf->d_jobs_async) cudaFree(mf->d_jobs_async);
   dgx::p2p_destroy(mf);
   for (auto &kv : mf->bfaces) if (kv.second.d) cudaFree(kv.second.d);
+  dgx::general_metric_destroy(mf);
   for (auto &p : mf->peers) if (p.d_send_cells) cudaFree(p.d_send_cells);
   delete mf;
   return DGX_OK;

@@ -858,7 +858,7 @@ int march_dispatch(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const
 // geometry of the march for this operator, or false when the marching kernel does not apply
 bool march_geometry(const dgx_op *op, FastGeom &G) {
   const dgx_mf *mf = op->mf;
-  if (mf->dim != 3 || !mf->all_interior || !mf->box_ok) return false;
+  if (mf->dim != 3 || !mf->all_interior || !mf->box_ok || mf->general) return false;
   if (op->degree < 2 || op->degree > 4) return false;   // Q2: 84 -> 125 GDoF/s fp64, 128 -> 145 fp32 against the generic kernel (128^3)
   const Mesh &m = mf->mesh->m;
   G.L = mf->level;

@@ -408,7 +408,7 @@ int coarse_by_degree(int degree, dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_v
 // (caller falls back to cg_core)
 int pressure_coarse_cg(dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_vec *r, dgx_vec *p, dgx_vec *v, const double *d_tol, int max_it, int *d_info, double *d_res, int *d_count, int log_cap) {
   dgx_mf *mf = op->mf;
-  if (op->kind != DGX_OP_PRESSURE || (mf->ctx->nranks != 1 && !mf->replicated) || mf->n_ghost != 0 || mf->n_owned < 1 || mf->n_owned > 64) return DGX_ERR_UNSUPPORTED;
+  if (op->kind != DGX_OP_PRESSURE || (mf->ctx->nranks != 1 && !mf->replicated) || mf->n_ghost != 0 || mf->n_owned < 1 || mf->n_owned > 64 || mf->general) return DGX_ERR_UNSUPPORTED;
   const int degree = op->degree;
   if (mf->dim == 2) return mf->dtype == DGX_F64 ? coarse_by_degree<2, double>(degree, op, x, b, r, p, v, d_tol, max_it, d_info, d_res, d_count, log_cap)
                                                  : coarse_by_degree<2, float>(degree, op, x, b, r, p, v, d_tol, max_it, d_info, d_res, d_count, log_cap);
@@ -418,6 +418,7 @@ int pressure_coarse_cg(dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_vec *r, dgx
 
 int pressure_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) {
   dgx_mf *mf = op->mf;
+  if (mf->general) return pressure_general_apply(op, dst, src, add, nullptr, 1.0);
   if (op->variant != 1) {
     int rc = pressure_apply_fast(op, dst, src, add);
     if (rc != DGX_ERR_UNSUPPORTED) return rc;
@@ -431,7 +432,7 @@ int pressure_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) {
 
 int pressure_apply_range(dgx_op *op, dgx_vec *dst, const dgx_vec *src, long long cell_begin, long long cell_end, cudaStream_t stream) {
   dgx_mf *mf = op->mf;
-  if (op->kind != DGX_OP_PRESSURE || mf->ctx->nranks != 1) return DGX_ERR_UNSUPPORTED;
+  if (op->kind != DGX_OP_PRESSURE || mf->ctx->nranks != 1 || mf->general) return DGX_ERR_UNSUPPORTED;
   CellRange r;
   r.begin = cell_begin; r.end = cell_end; r.stream = stream;
   if (mf->dim == 2) return mf->dtype == DGX_F64 ? generic_by_degree<2, double>(op->degree, op, dst, src, false, nullptr, &r)
@@ -446,6 +447,7 @@ int pressure_apply_fused(dgx_op *op, dgx_vec *dst, dgx_vec *x, const FusedUpdate
   if (op->kind != DGX_OP_PRESSURE || dst->d == x->d) return DGX_ERR_UNSUPPORTED;
   int rc = ghost_exchange(x);
   if (rc) return rc;
+  if (mf->general) return pressure_general_apply(op, dst, x, false, &fu, 1.0);
   // The marching kernel applies the same epilogue in its Z warps (pressure_apply_fast_fused).  For even n the update vectors
   // reach them through bulk copies one plane ahead; for odd n they would be plain loads on the producer warps' critical
   // path (2.1 ms per fused step against 1.0 ms here, 128^3 Q3 fp32 before the staging): there it stays opt-in (variant 2).
@@ -461,6 +463,7 @@ int pressure_apply_fused(dgx_op *op, dgx_vec *dst, dgx_vec *x, const FusedUpdate
 
 int pressure_diagonal(dgx_op *op, dgx_vec *out) {
   dgx_mf *mf = op->mf;
+  if (mf->general) return pressure_general_diagonal(op, out);
   if (mf->dim == 2) return mf->dtype == DGX_F64 ? diag_by_degree<2, double>(op->degree, op, out) : diag_by_degree<2, float>(op->degree, op, out);
   return mf->dtype == DGX_F64 ? diag_by_degree<3, double>(op->degree, op, out) : diag_by_degree<3, float>(op->degree, op, out);
 }

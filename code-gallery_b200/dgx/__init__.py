@@ -32,7 +32,7 @@ lib.dgx_version.restype = C.c_char_p
 lib.dgx_kernel_launch_count.restype = c_ll
 lib.dgx_ctx_get_stream.restype = c_vp
 lib.dgx_vec_data.restype = c_vp
-for _name in ("dgx_mesh_n_cells", "dgx_mf_n_owned_cells", "dgx_mf_n_ghost_cells", "dgx_mf_first_owned_cell",
+for _name in ("dgx_mf_general_metric_bytes", "dgx_mesh_n_cells", "dgx_mf_n_owned_cells", "dgx_mf_n_ghost_cells", "dgx_mf_first_owned_cell",
               "dgx_vec_size", "dgx_vec_ghost_size", "dgx_vec_global_size", "dgx_op_m"):
     getattr(lib, _name).restype = c_ll
 
@@ -111,6 +111,21 @@ class Mesh:
     def n_levels(self):
         return lib.dgx_mesh_n_levels(self.h)
 
+    def set_vertices(self, level, coords):
+        """vertex positions of `level` (lattice order, x fastest, dim doubles each): the level becomes a MappingQ1 mesh"""
+        arr = np.ascontiguousarray(coords, dtype=np.float64)
+        _check(lib.dgx_mesh_set_vertices(self.h, c_int(level), arr.ctypes.data_as(c_vp), c_ll(arr.size)))
+
+    def transform(self, fn, lo, hi, cells0):
+        """GridTools::transform on every level of the hierarchy: x = fn(X) for the Cartesian vertex lattice X[..., dim]"""
+        for level in range(self.n_refine + 1):
+            axes = [lo[d] + (hi[d] - lo[d]) / (cells0[d] << level) * np.arange((cells0[d] << level) + 1) for d in range(self.dim)]
+            grids = np.meshgrid(*axes[::-1], indexing="ij")
+            self.set_vertices(level, fn(np.stack(grids[::-1], axis=-1)))
+
+    def is_general(self, level=-1):
+        return bool(lib.dgx_mesh_is_general(self.h, c_int(level)))
+
     def n_cells(self, level=-1):
         return int(lib.dgx_mesh_n_cells(self.h, level))
 
@@ -185,6 +200,10 @@ class MatrixFree:
 
     def initialize_dof_vector(self, degree, ncomp=1):
         return Vector(self, degree, ncomp)
+
+    def general_metric_bytes(self, degree):
+        """bytes of per-quadrature-point metric data a degree-`degree` operator streams per application on a non-Cartesian level"""
+        return int(lib.dgx_mf_general_metric_bytes(self.h, c_int(degree)))
 
 
 class Vector:

@@ -76,6 +76,14 @@ int dgx_ctx_timer_stop(dgx_ctx *ctx, double *ms);
 int dgx_mesh_create_cartesian(int dim, const int *cells0, int n_refine, const double *lo, const double *hi,
                               int periodic_mask, const int *boundary_ids, dgx_mesh **out);
 int dgx_mesh_destroy(dgx_mesh *mesh);
+/* Non-Cartesian geometry on the same topology (what GridTools::transform / a manifold give the reference's triangulation before
+ * MatrixFree::reinit(MappingQ1, ...), NS.cc:2264, 2329): positions of the (cells + 1)^dim vertices of `level` (-1: finest), lattice
+ * order with x fastest, dim doubles per vertex.  Every cell of that level becomes the multilinear (MappingQ1) image of the unit
+ * cell; MatrixFree objects created afterwards carry the metric at every quadrature point (the pressure operator, its diagonal,
+ * Chebyshev / multigrid / CG on top of it; the other operators return DGX_ERR_UNSUPPORTED on such a level).  Periodic directions
+ * need vertex positions that are periodic up to a translation.  Set the vertices of every level a multigrid hierarchy uses. */
+int dgx_mesh_set_vertices(dgx_mesh *mesh, int level, const double *coords, long long n_values);
+int dgx_mesh_is_general(const dgx_mesh *mesh, int level);
 int dgx_mesh_n_levels(const dgx_mesh *mesh); /* Triangulation::n_global_levels, NS.cc:2351 */
 long long dgx_mesh_n_cells(const dgx_mesh *mesh, int level);
 /* integer coordinates (x,y,z) of cells [first, first+count) of `level` in deal.II cell order; out[count*dim] */
@@ -95,6 +103,9 @@ long long dgx_mf_first_owned_cell(const dgx_mf *mf);
 int dgx_mf_local_neighbors(const dgx_mf *mf, int *out);
 /* global cell index of every ghost slot, out[n_ghost] */
 int dgx_mf_ghost_cells(const dgx_mf *mf, long long *out);
+/* bytes of metric data in HBM (J^-1 J^-T JxW per cell point; J^-1 n JxW of both sides and the penalty per face point) that a
+ * degree-`degree` operator on a non-Cartesian level streams per application; 0 before its first application / on Cartesian levels */
+long long dgx_mf_general_metric_bytes(dgx_mf *mf, int degree);
 /* ghost-exchange plan (Utilities::MPI::Partitioner import / export lists): peers in ascending rank order */
 int dgx_mf_n_peers(const dgx_mf *mf);
 int dgx_mf_peer_info(const dgx_mf *mf, int i, int *rank, long long *n_send, long long *recv_first, long long *recv_count);

@@ -23,13 +23,15 @@ def build_hierarchy(mesh: CartesianMesh):
 
 
 class PressureMGSolver:
-    def __init__(self, mesh, degree, dt, stage=1, level_dtype=np.float32):
+    def __init__(self, mesh, degree, dt, stage=1, level_dtype=np.float32, op_class=PressureOperator):
+        """op_class(mesh, degree, dt, dtype): PressureOperator on a CartesianMesh, PressureOperatorGeneral on a GeneralMesh (the
+        hierarchy, smoothers, transfers and solvers do not depend on the geometry)"""
         self.levels = build_hierarchy(mesh)
-        self.op = PressureOperator(mesh, degree, dt, np.float64)
+        self.op = op_class(mesh, degree, dt, np.float64)
         self.op.set_TR_BDF2_stage(stage)
         self.level_ops = []
         for m in self.levels:
-            lop = PressureOperator(m, degree, dt, level_dtype)
+            lop = op_class(m, degree, dt, level_dtype)
             lop.set_TR_BDF2_stage(stage)
             self.level_ops.append(lop)
         self.level_dtype = np.dtype(level_dtype).type
@@ -42,7 +44,7 @@ class PressureMGSolver:
             if l > 0:
                 self.smoothers.append(Chebyshev(lop.vmult, lop.inverse_diagonal, degree=3,
                                                 smoothing_range=15.0, eig_cg_n_iterations=10))
-                self.transfers.append(Transfer(self.levels[l], self.degree, self.level_dtype))
+                self.transfers.append(Transfer(getattr(self.levels[l], "cart", self.levels[l]), self.degree, self.level_dtype))
 
     def solve(self, x, rhs, eps=1e-8, max_its=10000):
         self.setup()

@@ -1,0 +1,81 @@
+"""CPU pins of the oracle's MappingQ1 pressure operator (oracle/general.py, following NS.cc:1230-1326 with deal.II's general-mapping
+semantics): it must reduce to the Cartesian restatement (itself pinned by the exact-rational element matrices), be invariant under
+rigid motions, stay symmetric on a deformed mesh and reproduce linear fields."""
+import numpy as np
+import pytest
+
+from oracle.dg1d import gauss_lobatto_nodes
+from oracle.general import GeneralMesh, PressureOperatorGeneral
+from oracle.mesh import CartesianMesh
+from oracle.operators import PressureOperator
+
+
+def wavy(amp):
+    def fn(X):
+        x = np.array(X, dtype=np.float64)
+        out = x.copy()
+        out[..., 0] = x[..., 0] + amp * np.sin(2 * np.pi * x[..., 1]) * (1 + 0.5 * np.cos(2 * np.pi * x[..., 0]))
+        out[..., 1] = x[..., 1] + amp * np.sin(2 * np.pi * x[..., 0])
+        if x.shape[-1] == 3:
+            out[..., 1] += 0.5 * amp * np.sin(2 * np.pi * x[..., 2])
+            out[..., 2] = x[..., 2] + amp * np.sin(2 * np.pi * (x[..., 0] + x[..., 1]))
+        return out
+    return fn
+
+
+def rng_vec(n, seed=0):
+    return np.random.default_rng(seed).standard_normal(n)
+
+
+@pytest.mark.parametrize("dim,periodic,bids", [(2, [False, False], [1, 0, 1, 3]), (2, [True, True], None), (3, [False, True, False], [1, 1, 2, 3, 1, 5])])
+def test_identity_map_reduces_to_the_cartesian_operator(dim, periodic, bids):
+    cm = CartesianMesh(dim, [2, 1, 1][:dim], 1, [0.0] * dim, [1.0, 1.5, 0.75][:dim], periodic, bids)
+    for degree in (1, 2):
+        ref = PressureOperator(cm, degree, 5e-3)
+        gen = PressureOperatorGeneral(GeneralMesh(cm, lambda X: X), degree, 5e-3)
+        u = rng_vec(ref.n_dofs, degree)
+        a, b = gen.vmult(u), ref.vmult(u)
+        assert np.linalg.norm(a - b) < 1e-12 * np.linalg.norm(b)
+    dref = ref.compute_diagonal()
+    assert np.linalg.norm(gen.compute_diagonal() - dref) < 1e-12 * np.linalg.norm(dref)
+
+
+def test_rigid_motion_and_scaling():
+    cm = CartesianMesh(2, [2, 2], 1, [0.0, 0.0], [1.0, 1.0], [False, False], [1, 0, 1, 1])
+    th = 0.7
+    R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    base = PressureOperatorGeneral(GeneralMesh(cm, lambda X: X), 2, 5e-3)
+    rot = PressureOperatorGeneral(GeneralMesh(cm, lambda X: X @ R.T + np.array([3.0, -1.0])), 2, 5e-3)
+    u = rng_vec(base.n_dofs, 3)
+    assert np.linalg.norm(rot.vmult(u) - base.vmult(u)) < 1e-12 * np.linalg.norm(base.vmult(u))
+    cm2 = CartesianMesh(2, [2, 2], 1, [0.0, 0.0], [2.0, 2.0], [False, False], [1, 0, 1, 1])
+    scaled = PressureOperatorGeneral(GeneralMesh(cm, lambda X: 2.0 * X), 2, 5e-3)
+    ref2 = PressureOperator(cm2, 2, 5e-3)
+    assert np.linalg.norm(scaled.vmult(u) - ref2.vmult(u)) < 1e-12 * np.linalg.norm(ref2.vmult(u))
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_symmetric_and_reproduces_linear_fields_on_a_deformed_mesh(dim):
+    periodic = [False] * dim
+    cm = CartesianMesh(dim, [1] * dim, 2 if dim == 2 else 1, [0.0] * dim, [1.0] * dim, periodic, [1] * (2 * dim))
+    gm = GeneralMesh(cm, wavy(0.04))
+    degree = 2 if dim == 2 else 1
+    op = PressureOperatorGeneral(gm, degree, 5e-3)
+    N = op.n_dofs
+    A = np.stack([op.vmult(e) for e in np.eye(N)], axis=1)
+    assert np.max(np.abs(A - A.T)) < 1e-11 * np.max(np.abs(A))          # SIPG with theta_p = 1
+    assert np.min(np.linalg.eigvalsh(0.5 * (A + A.T))) > 0
+    if dim == 2:
+        # u = a . x is in the mapped Q_p space; on cells without boundary faces the Laplace part vanishes: (A u)_i = 1/coeff int phi_i u
+        nodes = np.asarray(gauss_lobatto_nodes(degree + 1), dtype=np.float64)
+        X = op.X                                                         # [c, 4, 2]
+        a, b = np.meshgrid(nodes, nodes, indexing="xy")                  # a: x (fastest), b: y
+        N0, N1, N2, N3 = (1 - a) * (1 - b), a * (1 - b), (1 - a) * b, a * b
+        pts = (N0[None, ..., None] * X[:, None, None, 0] + N1[None, ..., None] * X[:, None, None, 1] +
+               N2[None, ..., None] * X[:, None, None, 2] + N3[None, ..., None] * X[:, None, None, 3])          # [c, j, i, 2]
+        u = (0.3 + 1.7 * pts[..., 0] - 0.9 * pts[..., 1]).reshape(-1)
+        r = op.vmult(u).reshape(cm.n_cells, -1)
+        mass = (np.einsum("cq,qi,cq->ci", u.reshape(cm.n_cells, -1) @ op.B.T, op.B, op.JxW)) / op.coeff()
+        interior = np.all(cm.nbr >= 0, axis=1)
+        assert interior.sum() == 4
+        assert np.max(np.abs(r[interior] - mass[interior])) < 1e-11 * np.max(np.abs(r))
