@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--no-solve", action="store_true", help="skip the (untimed-region) MG-CG pressure solve report")
     ap.add_argument("--solve-refine", type=int, default=7, help="cells per GPU of the MG-CG report: (2^r)^3 (7: 8 GPUs = 256^3 Q3, 9 levels = BASELINE config 4)")
     ap.add_argument("--no-sweep", action="store_true", help="skip the (untimed-region) Q1..Q8 x fp64/fp32 sweep (BASELINE config 3)")
+    ap.add_argument("--no-general", action="store_true", help="skip the (untimed-region) non-Cartesian (MappingQ1) operator report")
     ap.add_argument("--solve-degree", type=int, default=3)
     ap.add_argument("--no-step", action="store_true", help="skip the (untimed-region) TR-BDF2 step report")
     ap.add_argument("--step-refine", type=int, default=5)
@@ -196,6 +197,56 @@ def degree_sweep_report(dgx, ctx, hbm_gbs, steps=5):
                         "gdofs": round(n / (ms * 1e-3) / 1e9, 2), "hbm_frac": round(gb / hbm_gbs, 3),
                         "kernel": "marching" if 2 <= p <= 4 else "generic"})
             del src, dst, op, mf
+    return out
+
+
+def general_mapping_report(dgx, ctx, hbm_gbs, refine=6, steps=10):
+    """SURVEY 8f rank 2, the regime with per-quadrature-point metric data: the pressure operator on a smoothly deformed periodic
+    cube (every cell a MappingQ1 image of the unit cell; csrc/pressure_general.cu), Q4 in fp64 and fp32.  Algorithmic bytes =
+    src + dst + the metric tables the kernel streams.  Not part of the timed region.  `identity_vs_cartesian_rel_l2`: the same
+    kernel on undeformed vertex positions against the Cartesian (Kronecker) kernels."""
+    def wavy(X):
+        x = np.array(X, dtype=np.float64)
+        out = x.copy()
+        a = 0.2 / (1 << refine) * 4
+        out[..., 0] = x[..., 0] + a * np.sin(2 * np.pi * x[..., 1]) * (1 + 0.5 * np.cos(2 * np.pi * x[..., 0]))
+        out[..., 1] = x[..., 1] + a * np.sin(2 * np.pi * x[..., 0]) + 0.5 * a * np.sin(2 * np.pi * x[..., 2])
+        out[..., 2] = x[..., 2] + a * np.sin(2 * np.pi * (x[..., 0] + x[..., 1]))
+        return out
+    degree, out = 4, {"workload": f"3D pressure operator Q4 on a deformed periodic cube, {1 << refine}^3 MappingQ1 cells", "entries": []}
+    lat = lambda r: np.stack(np.meshgrid(*[np.arange((1 << r) + 1) / (1 << r)] * 3, indexing="ij")[::-1], axis=-1)
+    for dt, name, es in ((dgx.F64, "f64", 8), (dgx.F32, "f32", 4)):
+        mesh = dgx.Mesh(3, [1, 1, 1], refine, [0, 0, 0], [1, 1, 1], [True] * 3)
+        mesh.set_vertices(refine, wavy(lat(refine)))
+        mf = dgx.MatrixFree(ctx, mesh, -1, dt)
+        op = dgx.NavierStokesProjectionOperator(mf, dgx.OP_PRESSURE, degree, 100.0, 5e-3)
+        src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+        n = src.locally_owned_size()
+        src.from_host(np.sin(np.arange(n, dtype=np.float64) * 1e-3))
+        for _ in range(3):
+            op.vmult(dst, src)
+        ctx.synchronize()
+        ctx.timer_start()
+        for _ in range(steps):
+            op.vmult(dst, src)
+        ms = ctx.timer_stop() / steps
+        bpd = 2 * es + mf.general_metric_bytes(degree) / n
+        out["entries"].append({"dtype": name, "dofs": n, "ms": round(ms, 4), "gdofs": round(n / ms * 1e-6, 2), "algorithmic_bytes_per_dof": round(bpd, 1),
+                               "GBs": round(bpd * n / ms * 1e-6, 1), "hbm_frac": round(bpd * n / ms * 1e-6 / hbm_gbs, 3), "kernel": "pressure_general_kernel"})
+        del src, dst, op, mf, mesh
+    r = 4
+    res = []
+    for general in (False, True):
+        mesh = dgx.Mesh(3, [1, 1, 1], r, [0, 0, 0], [1, 1, 1], [True] * 3)
+        if general:
+            mesh.set_vertices(r, lat(r))
+        mf = dgx.MatrixFree(ctx, mesh)
+        op = dgx.NavierStokesProjectionOperator(mf, dgx.OP_PRESSURE, degree, 100.0, 5e-3)
+        src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+        src.from_host(np.sin(np.arange(src.locally_owned_size(), dtype=np.float64) * 1e-2))
+        op.vmult(dst, src)
+        res.append(dst.to_host())
+    out["identity_vs_cartesian_rel_l2"] = float(np.linalg.norm(res[1] - res[0]) / np.linalg.norm(res[0]))
     return out
 
 
@@ -518,6 +569,13 @@ def main():
         except Exception as exc:  # noqa: BLE001
             sweep = {"error": str(exc)}
 
+    general = None
+    if world == 1 and not args.no_general:
+        try:
+            general = general_mapping_report(dgx, ctx, peaks["hbm_gbs"])
+        except Exception as exc:  # noqa: BLE001
+            general = {"error": str(exc)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
@@ -545,7 +603,7 @@ def main():
                        "partition": f"{world} contiguous chunks of the hierarchical (Morton) cell order of one box" if world > 1 else "single GPU"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(),
             "mg_solve": mg_solve, "trbdf2_step": step, "marching_vs_generic_rel_l2": check, "multi_gpu_parity": parity,
-            "degree_sweep": sweep,
+            "degree_sweep": sweep, "general_mapping": general,
         }
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)

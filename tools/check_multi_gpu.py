@@ -21,13 +21,23 @@ dist.broadcast(idt, 0)
 ctx = dgx.Context(local, rank, world, bytes(idt.cpu().numpy().tobytes()))
 solo = dgx.Context(local)
 report = {}
+def wavy(X):   # smooth deformation of the box, periodic up to a translation: the MappingQ1 metric path (pressure_general.cu)
+    x = np.array(X, dtype=np.float64); out = x.copy()
+    out[..., 0] = x[..., 0] + 0.03 * np.sin(2 * np.pi * x[..., 1]); out[..., 1] = x[..., 1] + 0.03 * np.sin(2 * np.pi * x[..., 2])
+    out[..., 2] = x[..., 2] + 0.03 * np.sin(2 * np.pi * x[..., 0])
+    return out
+
 for name, cells0, nref, periodic, kind, degree in [
         ("pressure Q4 periodic slab (marching kernel)", [world, 1, 1], 3, [True] * 3, dgx.OP_PRESSURE, 4),
         ("pressure Q3 periodic cube (Morton chunks)", [1, 1, 1], 3, [True] * 3, dgx.OP_PRESSURE, 3),
         ("pressure Q2 box with boundaries", [2, 1, 1], 2, [False] * 3, dgx.OP_PRESSURE, 2),
+        ("pressure Q3 deformed periodic cube (metric kernel)", [1, 1, 1], 2, [True] * 3, dgx.OP_PRESSURE, 3),
+        ("pressure Q2 deformed box with boundaries (metric kernel)", [2, 1, 1], 2, [False, True, False], dgx.OP_PRESSURE, 2),
         ("velocity Q3 periodic cube", [1, 1, 1], 2, [True] * 3, dgx.OP_VELOCITY, 3)]:
     hi = [float(c) for c in cells0]
-    mesh = dgx.Mesh(3, cells0, nref, [0, 0, 0], hi, periodic)
+    mesh = dgx.Mesh(3, cells0, nref, [0, 0, 0], hi, periodic, [1, 1, 2, 3, 1, 5] if "deformed box" in name else None)
+    if "deformed" in name:
+        mesh.transform(wavy, [0, 0, 0], hi, cells0)
     errs = []
     for dt in (dgx.F64, dgx.F32):
         if kind == dgx.OP_VELOCITY and dt == dgx.F32:
@@ -58,6 +68,20 @@ for name, cells0, nref, periodic, kind, degree in [
         dist.all_reduce(e[:2])
         errs.append({"dtype": "f64" if dt == dgx.F64 else "f32", "rel_l2": float(torch.sqrt(e[0] / e[1])), "dot_abs_err": float(e[2])})
     report[name] = errs
+# lift / drag face integrals (compute_lift_and_drag, NS.cc:2642-2708) summed over the ranks == the single-GPU value
+mesh = dgx.Mesh(3, [2, 1, 1], 2, [0, 0, 0], [2.0, 1.0, 1.0], [False] * 3)   # boundary id 4 = the lower z face
+rng = np.random.default_rng(5)
+ug, pg = rng.standard_normal(mesh.n_cells() * 3 * 64), rng.standard_normal(mesh.n_cells() * 27)
+forces = {}
+for tag, c in (("multi", ctx), ("solo", solo)):
+    mf = dgx.MatrixFree(c, mesh)
+    fc, nc = mf.first_owned_cell(), mf.n_owned_cells()
+    u, p = mf.initialize_dof_vector(3, 3), mf.initialize_dof_vector(2, 1)
+    u.from_host(ug[fc * 192:(fc + nc) * 192]); p.from_host(pg[fc * 27:(fc + nc) * 27])
+    forces[tag] = dgx.compute_lift_and_drag(u, p, 100.0, 4)
+report["lift_and_drag"] = [{"dtype": "f64", "multi": forces["multi"], "solo": forces["solo"],
+                            "rel_l2": max(abs(a - b) / max(abs(b), 1e-300) for a, b in zip(forces["multi"], forces["solo"]))}]
+
 # MG-preconditioned pressure solve across ranks (projection_step's solver): same iteration count and solution as on one GPU.
 # Two layouts: one coarse cube per rank, and ONE cube cut into contiguous Morton chunks (p4est-style; the coarse levels are
 # replicated on all ranks, DGX_MG_REPLICATE_MAX=64 forces two distributed levels + the gather).
