@@ -150,6 +150,8 @@ struct dgx_mf {
   bool general = false;
   struct GeneralMetric { void *cellG = nullptr, *faceA = nullptr; size_t bytes = 0; };
   std::map<int, GeneralMetric> gmetric;
+  double *d_cellX = nullptr;            // vertices of the owned cells [cell][2^dim][dim] (diagnostics.cu), built on first use
+  std::vector<double> h_cellX;
 };
 
 struct dgx_vec {

@@ -20,7 +20,8 @@ namespace {
 constexpr int kMaxNq = MAX_N + 1;
 
 struct FaceEvalTables {
-  double Sv[kMaxNq * MAX_N];                        // velocity basis at the face quadrature points: [q][i]
+  double Sv[kMaxNq * MAX_N], Dv[kMaxNq * MAX_N];   // velocity basis and its derivative at the face quadrature points: [q][i]
+  double xq[kMaxNq];                                // face quadrature points (non-Cartesian cells: the metric is evaluated there)
   double gv[2][MAX_N];                              // l_i'(s) of the velocity basis
   double Sp[kMaxNq * MAX_N];                        // pressure basis at the face quadrature points
   double w[kMaxNq];
@@ -29,11 +30,39 @@ struct FaceEvalTables {
   double inv_Re;
 };
 
+// inverse Jacobian inv[e][i] = d xi_e / d x_i and det J of the multilinear (MappingQ1) cell with vertices X[2^dim][dim] at xi
+__device__ __forceinline__ double q1_jacobian(int dim, const double *X, const double *xi, double inv[3][3]) {
+  double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int v = 0; v < (1 << dim); ++v)
+    for (int e = 0; e < dim; ++e) {
+      double dN = 1;
+      for (int d = 0; d < dim; ++d) {
+        const int b = (v >> d) & 1;
+        dN *= d == e ? (b ? 1.0 : -1.0) : (b ? xi[d] : 1.0 - xi[d]);
+      }
+      for (int i = 0; i < dim; ++i) J[i][e] += X[v * dim + i] * dN;
+    }
+  if (dim == 2) {
+    const double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    inv[0][0] = J[1][1] / det; inv[0][1] = -J[0][1] / det;
+    inv[1][0] = -J[1][0] / det; inv[1][1] = J[0][0] / det;
+    return det;
+  }
+  const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2], c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+  const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+  inv[0][0] = c00 / det; inv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det; inv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
+  inv[1][0] = c01 / det; inv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det; inv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
+  inv[2][0] = c02 / det; inv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det; inv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+  return det;
+}
+
 // item = (boundary face of the list, face quadrature point).  FE_DGQ is nodal at the cell boundary, so face values need the
-// face layer only; the normal derivative needs all layers of the line through the point.
+// face layer only; the normal derivative needs all layers of the line through the point.  cellX == nullptr: Cartesian cells;
+// otherwise cellX[cell][2^dim][dim] are the vertices of the MappingQ1 cells and normal, JxW and J^-1 are evaluated at the point.
 template <typename T>
 __global__ void __launch_bounds__(128) lift_drag_kernel(const __grid_constant__ FaceEvalTables P, const int *__restrict__ faces, int n_faces,
-                                                        const T *__restrict__ u, const T *__restrict__ p, double *partial, double *result) {
+                                                        const T *__restrict__ u, const T *__restrict__ p, const double *__restrict__ cellX,
+                                                        double *partial, double *result) {
   const int dim = P.dim, nv = P.nv, np = P.np, nq = P.nq;
   const int nqf = dim == 3 ? nq * nq : nq;
   int ndv = 1, ndp = 1;
@@ -56,25 +85,50 @@ __global__ void __launch_bounds__(128) lift_drag_kernel(const __grid_constant__ 
           pv += wgt * (double)pc[a * strp[e1] + (dim == 3 ? b * strp[e2] : 0)];
         }
     }
-    // velocity gradients grad[c][k] = d u_c / d x_k
-    double force[3] = {0, 0, 0};
+    // reference gradients of the velocity components at the face point: along the normal direction d from all layers of the line,
+    // along the tangential directions from the face layer
     const double ns = s ? 1.0 : -1.0;
-    double JxW = P.w[q1] * P.h[e1];
-    if (dim == 3) JxW *= P.w[q2] * P.h[e2];
+    double gref[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};   // [component][reference direction]
     for (int c = 0; c < dim; ++c) {
       const T *uc = u + ((size_t)cell * dim + c) * ndv;
-      double gn = 0.0;   // derivative along the face normal direction d
+      const T *layer = uc + (size_t)(s ? nv - 1 : 0) * strv[d];
       for (int b = 0; b < (dim == 3 ? nv : 1); ++b)
         for (int a = 0; a < nv; ++a) {
-          const double wt = P.Sv[q1 * nv + a] * (dim == 3 ? P.Sv[q2 * nv + b] : 1.0);
+          const double sa = P.Sv[q1 * nv + a], sb = dim == 3 ? P.Sv[q2 * nv + b] : 1.0;
           const T *line = uc + a * strv[e1] + (dim == 3 ? b * strv[e2] : 0);
           double acc = 0.0;
           for (int i = 0; i < nv; ++i) acc += P.gv[s][i] * (double)line[(size_t)i * strv[d]];
-          gn += wt * acc;
+          gref[c][d] += sa * sb * acc;
+          const double val = (double)layer[a * strv[e1] + (dim == 3 ? b * strv[e2] : 0)];
+          gref[c][e1] += P.Dv[q1 * nv + a] * sb * val;
+          if (dim == 3) gref[c][e2] += sa * P.Dv[q2 * nv + b] * val;
         }
-      gn /= P.h[d];
-      // forces = (1/Re grad u - p I) (-n_out) JxW,  n_out = ns e_d: only column d of the stress enters
-      force[c] = -ns * (P.inv_Re * gn - (c == d ? pv : 0.0)) * JxW;
+    }
+    // forces = (1/Re grad u - p I) (-n_out) JxW   (NS.cc:2679-2688)
+    double force[3] = {0, 0, 0};
+    if (cellX == nullptr) {   // Cartesian: n_out = ns e_d, grad = diag(1/h) grad_xi
+      double JxW = P.w[q1] * P.h[e1];
+      if (dim == 3) JxW *= P.w[q2] * P.h[e2];
+      for (int c = 0; c < dim; ++c) force[c] = -ns * (P.inv_Re * gref[c][d] / P.h[d] - (c == d ? pv : 0.0)) * JxW;
+    } else {
+      double xi[3] = {0, 0, 0}, inv[3][3], w = P.w[q1];
+      xi[d] = s; xi[e1] = P.xq[q1];
+      if (dim == 3) { xi[e2] = P.xq[q2]; w *= P.w[q2]; }
+      const double det = q1_jacobian(dim, cellX + (size_t)cell * (1 << dim) * dim, xi, inv);
+      double norm = 0;
+      for (int i = 0; i < dim; ++i) norm += inv[d][i] * inv[d][i];
+      norm = sqrt(norm);
+      const double JxW = det * norm * w;
+      for (int c = 0; c < dim; ++c) {
+        double f = 0;
+        for (int k = 0; k < dim; ++k) {
+          double g = 0;   // d u_c / d x_k = sum_e d u_c / d xi_e * d xi_e / d x_k
+          for (int e = 0; e < dim; ++e) g += gref[c][e] * inv[e][k];
+          const double nk = ns * inv[d][k] / norm;
+          f += (P.inv_Re * g - (c == k ? pv : 0.0)) * (-nk);
+        }
+        force[c] = f * JxW;
+      }
     }
     drag += force[0];
     lift += force[1];
@@ -110,7 +164,7 @@ struct PatchTables {
 // item = (cell, vertex); out[(cell * 2^dim + vertex) * nf + field], fields = v (dim), p, v_old (dim), vorticity (1 or 3)
 template <typename T>
 __global__ void __launch_bounds__(128) patch_kernel(const __grid_constant__ PatchTables P, long long n_cells, const T *__restrict__ u, const T *__restrict__ p,
-                                                    const T *__restrict__ uold, double *__restrict__ out) {
+                                                    const T *__restrict__ uold, const double *__restrict__ cellX, double *__restrict__ out) {
   const int dim = P.dim, nv = P.nv, np = P.np, NV = 1 << dim, nvort = dim == 2 ? 1 : 3, nf = 2 * dim + 1 + nvort;
   int ndv = 1, ndp = 1;
   for (int d = 0; d < dim; ++d) { ndv *= nv; ndp *= np; }
@@ -131,7 +185,18 @@ __global__ void __launch_bounds__(128) patch_kernel(const __grid_constant__ Patc
         const T *line = uc + offv - s * (nv - 1) * strv[d];
         double acc = 0.0;
         for (int i = 0; i < nv; ++i) acc += P.gv[s][i] * (double)line[(size_t)i * strv[d]];
-        grad[c][d] = acc * P.ih[d];
+        grad[c][d] = cellX ? acc : acc * P.ih[d];
+      }
+    }
+    if (cellX) {   // MappingQ1 cell: grad_x = J^-T grad_xi at the vertex
+      double xi[3] = {0, 0, 0}, inv[3][3];
+      for (int d = 0; d < dim; ++d) xi[d] = (v >> d) & 1;
+      q1_jacobian(dim, cellX + (size_t)cell * NV * dim, xi, inv);
+      for (int c = 0; c < dim; ++c) {
+        double g[3] = {0, 0, 0};
+        for (int k = 0; k < dim; ++k)
+          for (int e = 0; e < dim; ++e) g[k] += grad[c][e] * inv[e][k];
+        for (int k = 0; k < dim; ++k) grad[c][k] = g[k];
       }
     }
     o[dim] = (double)p[(size_t)cell * ndp + offp];
@@ -177,6 +242,33 @@ int boundary_face_list(dgx_mf *mf, int boundary_id, const int **d_faces, int *n_
   return DGX_OK;
 }
 
+// vertices of the owned cells of a non-Cartesian level on the device, [cell][2^dim][dim] (deal.II vertex order); nullptr on Cartesian levels
+int cell_vertex_table(dgx_mf *mf, const double **d_X) {
+  *d_X = nullptr;
+  if (!mf->general) return DGX_OK;
+  if (!mf->d_cellX && mf->n_owned) {
+    const Mesh &m = mf->mesh->m;
+    const int dim = mf->dim, NV = 1 << dim;
+    const std::vector<double> &V = m.vertices[mf->level];
+    const int nx = m.cells_dir(mf->level, 0) + 1, ny = m.cells_dir(mf->level, 1) + 1;
+    std::vector<double> X((size_t)mf->n_owned * NV * dim);
+    for (long long c = 0; c < mf->n_owned; ++c) {
+      int cc[MAX_DIM] = {0, 0, 0};
+      m.coords_of(mf->level, mf->first_cell + c, cc);
+      for (int v = 0; v < NV; ++v) {
+        const int ix = cc[0] + (v & 1), iy = cc[1] + ((v >> 1) & 1), iz = dim == 3 ? cc[2] + ((v >> 2) & 1) : 0;
+        const size_t idx = (size_t)ix + (size_t)nx * ((size_t)iy + (size_t)ny * iz);
+        for (int i = 0; i < dim; ++i) X[((size_t)c * NV + v) * dim + i] = V[idx * dim + i];
+      }
+    }
+    DGX_CUDA_CHECK(cudaMalloc(&mf->d_cellX, X.size() * sizeof(double)));
+    DGX_CUDA_CHECK(cudaMemcpy(mf->d_cellX, X.data(), X.size() * sizeof(double), cudaMemcpyHostToDevice));
+    mf->h_cellX = std::move(X);
+  }
+  *d_X = mf->d_cellX;
+  return DGX_OK;
+}
+
 }  // namespace dgx
 
 using namespace dgx;
@@ -200,10 +292,12 @@ int dgx_compute_lift_and_drag(const dgx_vec *u, const dgx_vec *p, double Re, int
   const Shape1D &sv = get_shape(u->degree, nq), &sp = get_shape(p->degree, nq);
   P.nv = u->degree + 1; P.np = p->degree + 1; P.nq = nq; P.dim = mf->dim; P.inv_Re = 1.0 / Re;
   for (int q = 0; q < nq; ++q) {
-    for (int i = 0; i < P.nv; ++i) P.Sv[q * P.nv + i] = sv.S[q * P.nv + i];
+    for (int i = 0; i < P.nv; ++i) { P.Sv[q * P.nv + i] = sv.S[q * P.nv + i]; P.Dv[q * P.nv + i] = sv.D[q * P.nv + i]; }
     for (int i = 0; i < P.np; ++i) P.Sp[q * P.np + i] = sp.S[q * P.np + i];
-    P.w[q] = sv.wq[q];
+    P.w[q] = sv.wq[q]; P.xq[q] = sv.xq[q];
   }
+  const double *d_X = nullptr;
+  if (int rc = cell_vertex_table(mf, &d_X)) return rc;
   for (int s = 0; s < 2; ++s)
     for (int i = 0; i < P.nv; ++i) P.gv[s][i] = sv.g[s][i];
   for (int d = 0; d < MAX_DIM; ++d) P.h[d] = d < mf->dim ? mf->h[d] : 1.0;
@@ -211,9 +305,9 @@ int dgx_compute_lift_and_drag(const dgx_vec *u, const dgx_vec *p, double Re, int
   const long long items = (long long)n_faces * (mf->dim == 3 ? nq * nq : nq);
   const int grid = (int)std::max<long long>(1, std::min<long long>((items + 127) / 128, 148 * 4));
   if (u->dtype == DGX_F64)
-    lift_drag_kernel<double><<<grid, 128, 0, ctx->stream>>>(P, d_faces, n_faces, (const double *)u->d, (const double *)p->d, partial, result);
+    lift_drag_kernel<double><<<grid, 128, 0, ctx->stream>>>(P, d_faces, n_faces, (const double *)u->d, (const double *)p->d, d_X, partial, result);
   else
-    lift_drag_kernel<float><<<grid, 128, 0, ctx->stream>>>(P, d_faces, n_faces, (const float *)u->d, (const float *)p->d, partial, result);
+    lift_drag_kernel<float><<<grid, 128, 0, ctx->stream>>>(P, d_faces, n_faces, (const float *)u->d, (const float *)p->d, d_X, partial, result);
   count_launch();
   DGX_CUDA_CHECK(cudaGetLastError());
   if (!mf->replicated) {   // Utilities::MPI::sum, NS.cc:2698-2699
@@ -248,13 +342,15 @@ int dgx_output_patch_data(const dgx_vec *u_n, const dgx_vec *pres_n, const dgx_v
   for (int s = 0; s < 2; ++s)
     for (int i = 0; i < P.nv; ++i) P.gv[s][i] = sv.g[s][i];
   for (int d = 0; d < MAX_DIM; ++d) P.ih[d] = d < dim ? 1.0 / mf->h[d] : 1.0;
+  const double *d_X = nullptr;
+  if (int rc = cell_vertex_table(mf, &d_X)) return rc;
   double *d_out = nullptr;
   DGX_CUDA_CHECK(cudaMalloc(&d_out, (size_t)total * sizeof(double)));
   const int grid = (int)std::max<long long>(1, std::min<long long>((mf->n_owned * NV + 127) / 128, 148 * 8));
   if (u_n->dtype == DGX_F64)
-    patch_kernel<double><<<grid, 128, 0, ctx->stream>>>(P, mf->n_owned, (const double *)u_n->d, (const double *)pres_n->d, (const double *)u_n_minus_1->d, d_out);
+    patch_kernel<double><<<grid, 128, 0, ctx->stream>>>(P, mf->n_owned, (const double *)u_n->d, (const double *)pres_n->d, (const double *)u_n_minus_1->d, d_X, d_out);
   else
-    patch_kernel<float><<<grid, 128, 0, ctx->stream>>>(P, mf->n_owned, (const float *)u_n->d, (const float *)pres_n->d, (const float *)u_n_minus_1->d, d_out);
+    patch_kernel<float><<<grid, 128, 0, ctx->stream>>>(P, mf->n_owned, (const float *)u_n->d, (const float *)pres_n->d, (const float *)u_n_minus_1->d, d_X, d_out);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, d_out, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
@@ -321,12 +417,14 @@ int dgx_output_results(const dgx_vec *u_n, const dgx_vec *pres_n, const dgx_vec 
   const int dim = mf->dim, NV = 1 << dim, nf = dgx_output_n_fields(dim);
   std::vector<double> data((size_t)mf->n_owned * NV * nf), pts((size_t)mf->n_owned * NV * dim);
   if (int rc = dgx_output_patch_data(u_n, pres_n, u_n_minus_1, data.data(), (long long)data.size())) return rc;
-  for (long long c = 0; c < mf->n_owned; ++c) {
-    int cc[MAX_DIM] = {0, 0, 0};
-    m.coords_of(mf->level, mf->first_cell + c, cc);
-    for (int v = 0; v < NV; ++v)
-      for (int d = 0; d < dim; ++d) pts[((size_t)c * NV + v) * dim + d] = m.lo[d] + (cc[d] + ((v >> d) & 1)) * mf->h[d];
-  }
+  if (mf->general) pts = mf->h_cellX;   // filled by dgx_output_patch_data above
+  else
+    for (long long c = 0; c < mf->n_owned; ++c) {
+      int cc[MAX_DIM] = {0, 0, 0};
+      m.coords_of(mf->level, mf->first_cell + c, cc);
+      for (int v = 0; v < NV; ++v)
+        for (int d = 0; d < dim; ++d) pts[((size_t)c * NV + v) * dim + d] = m.lo[d] + (cc[d] + ((v >> d) & 1)) * mf->h[d];
+    }
   const bool parallel = ctx->nranks > 1 && !mf->replicated;
   if (mf->replicated && ctx->rank != 0) return DGX_OK;   // every rank holds the same cells: rank 0 writes
   std::string base(path), piece = base;

@@ -266,6 +266,7 @@ int dgx_mf_destroy(dgx_mf *mf) {
   dgx::p2p_destroy(mf);
   for (auto &kv : mf->bfaces) if (kv.second.d) cudaFree(kv.second.d);
   dgx::general_metric_destroy(mf);
+  if (mf->d_cellX) cudaFree(mf->d_cellX);
   for (auto &p : mf->peers) if (p.d_send_cells) cudaFree(p.d_send_cells);
   delete mf;
   return DGX_OK;

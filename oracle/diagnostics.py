@@ -98,3 +98,81 @@ def patch_points(mesh: CartesianMesh):
         for d in range(mesh.dim):
             out[:, v, d] = org[:, d] + ((v >> d) & 1) * mesh.h[d]
     return out
+
+
+# ---- the same two functions on a MappingQ1 (non-Cartesian) mesh: dense point evaluation with physical gradients ----------------
+def _dense_tables(degree, pts_per_dir):
+    """B[q, i], dBref[q, i, e] for a tensor grid of reference points (pts_per_dir[d] = 1-D points of direction d), x fastest"""
+    from .general import _tensor_tables
+    nodes = gauss_lobatto_nodes(degree + 1)
+    tabs = [tuple(np.asarray(a, np.float64) for a in lagrange_eval(nodes, np.asarray(p, dtype=np.longdouble))) for p in pts_per_dir]
+    return _tensor_tables(tabs)
+
+
+def lift_and_drag_general(gmesh, degree_v: int, degree_p: int, u, p, Re: float, boundary_id: int = 4):
+    """compute_lift_and_drag (NS.cc:2642-2708) with FEFaceValues on MappingQ1 cells: normal_vector, JxW and the velocity gradients
+    J^-T grad_xi u at the points of QGauss<dim-1>(degree_p + 2)"""
+    from .dg1d import gauss_legendre
+    from .general import _points, q1_jacobian
+    dim = gmesh.dim
+    nq = degree_p + 2
+    xq, wq = (np.asarray(a, np.float64) for a in gauss_legendre(nq))
+    X = gmesh.cell_vertices()
+    U = np.asarray(u, np.float64).reshape(gmesh.n_cells, dim, -1)
+    P = np.asarray(p, np.float64).reshape(gmesh.n_cells, -1)
+    drag = lift = 0.0
+    for f in range(2 * dim):
+        d, s = f // 2, f % 2
+        cells = np.nonzero(gmesh.nbr[:, f] == -1 - boundary_id)[0]
+        if len(cells) == 0:
+            continue
+        per_dir = [np.array([float(s)]) if e == d else xq for e in range(dim)]
+        Bv, dBv = _dense_tables(degree_v, per_dir)
+        Bp, _ = _dense_tables(degree_p, per_dir)
+        pts = _points(per_dir)
+        wf = np.ones(1)
+        for e in range(dim):
+            if e != d:
+                wf = np.kron(wq, wf)
+        invJ, det = q1_jacobian(X[cells], pts)
+        gxi = invJ[:, :, d, :]
+        norm = np.linalg.norm(gxi, axis=-1)
+        n_out = (2 * s - 1) * gxi / norm[..., None]
+        JxW = det * norm * wf
+        grad = np.einsum("qie,cqek,cmi->cqmk", dBv, invJ, U[cells])      # d u_m / d x_k
+        pres = P[cells] @ Bp.T
+        stress = grad / Re
+        for m in range(dim):
+            stress[:, :, m, m] -= pres
+        forces = np.einsum("cqmk,cqk,cq->cm", stress, -n_out, JxW)        # NS.cc:2679-2688
+        drag += float(forces[:, 0].sum())
+        lift += float(forces[:, 1].sum())
+    return lift, drag
+
+
+def patch_data_general(gmesh, degree_v: int, degree_p: int, u_n, pres_n, u_n_minus_1):
+    """output_results' patch data on MappingQ1 cells: values at the cell vertices, vorticity from J^-T grad_xi u there"""
+    from .general import _points, q1_jacobian
+    dim = gmesh.dim
+    per_dir = [np.array([0.0, 1.0])] * dim
+    Bv, dBv = _dense_tables(degree_v, per_dir)
+    Bp, _ = _dense_tables(degree_p, per_dir)
+    pts = _points(per_dir)                                               # vertex v = bits (x fastest): deal.II vertex order
+    X = gmesh.cell_vertices()
+    invJ, _ = q1_jacobian(X, pts)
+    U = np.asarray(u_n, np.float64).reshape(gmesh.n_cells, dim, -1)
+    Uo = np.asarray(u_n_minus_1, np.float64).reshape(gmesh.n_cells, dim, -1)
+    P = np.asarray(pres_n, np.float64).reshape(gmesh.n_cells, -1)
+    nvort = 1 if dim == 2 else 3
+    out = np.zeros((gmesh.n_cells, 1 << dim, 2 * dim + 1 + nvort))
+    out[:, :, 0:dim] = np.einsum("qi,cmi->cqm", Bv, U)
+    out[:, :, dim] = P @ Bp.T
+    out[:, :, dim + 1:2 * dim + 1] = np.einsum("qi,cmi->cqm", Bv, Uo)
+    grad = np.einsum("qie,cqek,cmi->cqmk", dBv, invJ, U)
+    if dim == 2:
+        out[:, :, 2 * dim + 1] = grad[:, :, 1, 0] - grad[:, :, 0, 1]
+    else:
+        out[:, :, 2 * dim + 1] = grad[:, :, 2, 1] - grad[:, :, 1, 2]
+        out[:, :, 2 * dim + 2] = grad[:, :, 0, 2] - grad[:, :, 2, 0]
+        out[:, :, 2 * dim + 3] = grad[:, :, 1, 0] - grad[:, :, 0, 1]
+    return out

@@ -69,6 +69,21 @@ def _points(tabs_x):
     return np.stack([g.reshape(-1) for g in grids[::-1]], axis=-1)
 
 
+def q1_jacobian(X, pts):
+    """inverse Jacobian invJ[c, q, e, k] = d xi_e / d x_k and det J [c, q] of the multilinear cells with vertices X[c, 2^dim, dim]
+    at the reference points pts[q, dim]"""
+    dim = X.shape[-1]
+    J = np.zeros((X.shape[0], len(pts), dim, dim))                       # J[c, q, k, e] = d x_k / d xi_e
+    for v in range(1 << dim):
+        for e in range(dim):
+            dN = np.ones(len(pts))
+            for d in range(dim):
+                b = (v >> d) & 1
+                dN = dN * ((1.0 if b else -1.0) if d == e else (pts[:, d] if b else 1.0 - pts[:, d]))
+            J[:, :, :, e] += X[:, v, None, :] * dN[None, :, None]
+    return np.linalg.inv(J), np.linalg.det(J)
+
+
 class PressureOperatorGeneral:
     def __init__(self, gmesh: GeneralMesh, degree: int, dt: float, dtype=np.float64):
         self.gm, self.degree, self.dim = gmesh, degree, gmesh.dim
@@ -113,17 +128,7 @@ class PressureOperatorGeneral:
 
     # geometry ------------------------------------------------------------------------------------
     def _jac(self, pts):
-        """inverse Jacobian invJ[c, q, e, k] = d xi_e / d x_k and det J [c, q] of the multilinear map at reference points pts[q, dim]"""
-        dim = self.dim
-        J = np.zeros((self.gm.n_cells, len(pts), dim, dim))              # J[c, q, k, e] = d x_k / d xi_e
-        for v in range(1 << dim):
-            for e in range(dim):
-                dN = np.ones(len(pts))
-                for d in range(dim):
-                    b = (v >> d) & 1
-                    dN = dN * ((1.0 if b else -1.0) if d == e else (pts[:, d] if b else 1.0 - pts[:, d]))
-                J[:, :, :, e] += self.X[:, v, None, :] * dN[None, :, None]
-        return np.linalg.inv(J), np.linalg.det(J)
+        return q1_jacobian(self.X, pts)
 
     # operator ------------------------------------------------------------------------------------
     def set_dt(self, dt):

@@ -99,3 +99,36 @@ def test_vtu_writer_round_trip(dgx, tmp_path):
     assert np.array_equal(arr["v_old"][:, :2], flat[:, 3:5]) and np.array_equal(arr["vorticity"], flat[:, 5])
     assert np.array_equal(arr["connectivity"].reshape(-1, 4)[1], [4, 5, 7, 6]) and np.all(arr["types"] == 9)
     assert np.array_equal(arr["offsets"], 4 * np.arange(1, om.n_cells + 1))
+
+
+def annulus(r0, r1):
+    """(r, theta) in [0, 1]^2 -> ring around the origin: a structured O-grid around a cylinder, periodic in theta (direction 1)"""
+    def fn(X):
+        x = np.array(X, dtype=np.float64)
+        r, th = r0 + (r1 - r0) * x[..., 0], 2 * np.pi * x[..., 1]      # (r, theta) counter-clockwise: det J = 2 pi r (r1 - r0) > 0
+        out = x.copy()
+        out[..., 0], out[..., 1] = r * np.cos(th), r * np.sin(th)
+        return out
+    return fn
+
+
+def test_general_diagnostics_reduce_to_cartesian_and_obey_the_divergence_theorem():
+    from oracle.diagnostics import lift_and_drag_general, patch_data_general
+    from oracle.general import GeneralMesh
+    Re = 7.0
+    om = CartesianMesh(2, [2, 1], 2, [0, 0], [2, 1], [False, False], [0, 1, 4, 3])
+    u, p = fields_2d(om)
+    gm = GeneralMesh(om, lambda X: X)
+    a, b = lift_and_drag_general(gm, 2, 1, u, p, Re), lift_and_drag(om, 2, 1, u, p, Re)
+    assert abs(a[0] - b[0]) < 1e-13 and abs(a[1] - b[1]) < 1e-13
+    assert np.max(np.abs(patch_data_general(gm, 2, 1, u, p, u) - patch_data(om, 2, 1, u, p, u))) < 1e-12
+    # cylinder of radius 0.5 as the inner boundary (id 4) of an O-grid with 16 cells around: with u = 0 and p = x the force is
+    # oint p n dS = (area of the 16-gon, 0) by the divergence theorem (the reference's normal points INTO the fluid domain's hole)
+    ring = CartesianMesh(2, [1, 1], 4, [0, 0], [1, 1], [False, True], [4, 1, 2, 3])
+    g = GeneralMesh(ring, annulus(0.5, 2.0))
+    nodes = np.asarray(gauss_lobatto_nodes(2), dtype=np.float64)
+    X = g.cell_vertices()                                                # Q1 pressure dofs sit at the vertices
+    px = X[:, :, 0].reshape(-1)
+    lift, drag = lift_and_drag_general(g, 2, 1, np.zeros(ring.n_cells * 2 * 9), px, Re)
+    area = 0.5 * 16 * 0.25 * np.sin(2 * np.pi / 16)
+    assert abs(drag + area) < 1e-12 and abs(lift) < 1e-12                # forces = (-p I)(-n_out) = p n_out, n_out = -e_r (into the cylinder)

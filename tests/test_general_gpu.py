@@ -133,3 +133,65 @@ def test_mg_cg_on_a_deformed_mesh(dgx, gpu_ctx, dim, nref, degree):
     assert abs(its - oits) <= 1, (its, oits)
     assert rel_l2(vx.to_host(), x) < 1e-4
     assert np.linalg.norm(osolver.op.vmult(vx.to_host()) - rhs) <= 1.5 * tol
+
+
+def test_o_grid_around_a_cylinder(dgx, gpu_ctx, tmp_path):
+    """A structured O-grid around a cylinder (periodic in the angular direction, geometry periodic up to a ROTATION): the pressure
+    operator with the cylinder as a no-flux boundary (id 4) and a Dirichlet outer boundary (id 1), the lift / drag integrals over
+    the cylinder (NS.cc:2642-2708, boundary id 4 as in the reference) and the output data on the curved mesh."""
+    from oracle.diagnostics import lift_and_drag_general, patch_data_general
+    from test_diagnostics_cpu import annulus, read_vtu
+    dim, cells0, nref, periodic, bids = 2, [1, 1], 4, [False, True], [4, 1, 2, 3]
+    gm, om = meshes(dgx, dim, cells0, nref, periodic, bids, annulus(0.5, 2.0))
+    mf = dgx.MatrixFree(gpu_ctx, gm)
+    for degree in (1, 2, 3):
+        op = dgx.NavierStokesProjectionOperator(mf, dgx.OP_PRESSURE, degree, 100.0, 5e-3)
+        oop = PressureOperatorGeneral(om, degree, 5e-3)
+        u = np.random.default_rng(degree).standard_normal(oop.n_dofs)
+        src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+        src.from_host(u)
+        op.vmult(dst, src)
+        assert rel_l2(dst.to_host(), oop.vmult(u)) < 1e-12
+    rng = np.random.default_rng(11)
+    dp, Re = 1, 20.0
+    nv, npn = om.n_cells * 2 * (dp + 2) ** 2, om.n_cells * (dp + 1) ** 2
+    u, uo, p = rng.standard_normal(nv), rng.standard_normal(nv), rng.standard_normal(npn)
+    vu, vuo, vp = mf.initialize_dof_vector(dp + 1, 2), mf.initialize_dof_vector(dp + 1, 2), mf.initialize_dof_vector(dp, 1)
+    vu.from_host(u); vuo.from_host(uo); vp.from_host(p)
+    lift, drag = dgx.compute_lift_and_drag(vu, vp, Re)
+    rl, rd = lift_and_drag_general(om, dp + 1, dp, u, p, Re)
+    assert abs(lift - rl) < 1e-11 * max(1.0, abs(rl)) and abs(drag - rd) < 1e-11 * max(1.0, abs(rd))
+    out = dgx.output_patch_data(vu, vp, vuo)
+    ref = patch_data_general(om, dp + 1, dp, u, p, uo)
+    assert np.max(np.abs(out - ref)) < 1e-10 * np.max(np.abs(ref))
+    # divergence theorem: u = 0, p = x  =>  |drag| = area of the 16-gon that is the cylinder on this mesh, lift = 0
+    X = om.cell_vertices()
+    vp.from_host(X[:, :, 0].reshape(-1)); vu.set(0.0)
+    lift, drag = dgx.compute_lift_and_drag(vu, vp, Re)
+    assert abs(drag + 0.5 * 16 * 0.25 * np.sin(2 * np.pi / 16)) < 1e-12 and abs(lift) < 1e-12
+    path = str(tmp_path / "ring.vtu")
+    dgx.output_results(vu, vp, vuo, path)
+    npnt, ncell, arr = read_vtu(path)
+    assert ncell == om.n_cells and np.allclose(arr["points"][:, :2], X.reshape(-1, 2), atol=0) and np.allclose(arr["p"], X[:, :, 0].reshape(-1), atol=0)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_diagnostics_on_a_deformed_mesh(dgx, gpu_ctx, dim):
+    from oracle.diagnostics import lift_and_drag_general, patch_data_general
+    bids = [4, 1, 4, 3] if dim == 2 else [0, 4, 2, 3, 4, 5]
+    gm, om = meshes(dgx, dim, [2, 1, 1][:dim], 1, [False] * dim, bids, wavy(0.04))
+    rng = np.random.default_rng(3)
+    for dtype in (dgx.F64, dgx.F32):
+        mf = dgx.MatrixFree(gpu_ctx, gm, dtype=dtype)
+        for dp in (1, 2):
+            nv, npn = om.n_cells * dim * (dp + 2) ** dim, om.n_cells * (dp + 1) ** dim
+            u, uo, p = rng.standard_normal(nv), rng.standard_normal(nv), rng.standard_normal(npn)
+            if dtype == dgx.F32:
+                u, uo, p = (a.astype(np.float32).astype(np.float64) for a in (u, uo, p))
+            vu, vuo, vp = mf.initialize_dof_vector(dp + 1, dim), mf.initialize_dof_vector(dp + 1, dim), mf.initialize_dof_vector(dp, 1)
+            vu.from_host(u); vuo.from_host(uo); vp.from_host(p)
+            lift, drag = dgx.compute_lift_and_drag(vu, vp, 9.0)
+            rl, rd = lift_and_drag_general(om, dp + 1, dp, u, p, 9.0)
+            assert abs(lift - rl) < 1e-11 * max(1.0, abs(rl)) and abs(drag - rd) < 1e-11 * max(1.0, abs(rd)), (dtype, dp)
+            ref = patch_data_general(om, dp + 1, dp, u, p, uo)
+            assert np.max(np.abs(dgx.output_patch_data(vu, vp, vuo) - ref)) < 1e-10 * np.max(np.abs(ref))
