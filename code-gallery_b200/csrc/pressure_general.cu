@@ -259,21 +259,23 @@ pressure_general_kernel(const __grid_constant__ GenParams<T, n> P, const int *__
       }
     }
     __syncthreads();
-    if (active) {
+    if (active) {   // both sides of the line in one read-modify-write of the result
+      T Fval[2], Fnor[2];
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
-        T Fval = SF(c, s, 7)[l];
+        T v = SF(c, s, 7)[l];
         const T *F0 = SF(c, s, 5), *F1 = SF(c, s, 6);
 #pragma unroll
-        for (int a = 0; a < n; ++a) Fval += P.Dh[a * n + t0] * F0[a + n * t1];
+        for (int a = 0; a < n; ++a) v += P.Dh[a * n + t0] * F0[a + n * t1];
         if (dim == 3) {
 #pragma unroll
-          for (int b = 0; b < n; ++b) Fval += P.Dh[b * n + t1] * F1[t0 + n * b];
+          for (int b = 0; b < n; ++b) v += P.Dh[b * n + t1] * F1[t0 + n * b];
         }
-        const T Fnor = SF(c, s, 4)[l];
-#pragma unroll
-        for (int q = 0; q < n; ++q) sr[c * ND + base + stride * q] += P.fh[s][q] * Fval + P.gh[s][q] * Fnor;
+        Fval[s] = v; Fnor[s] = SF(c, s, 4)[l];
       }
+#pragma unroll
+      for (int q = 0; q < n; ++q)
+        sr[c * ND + base + stride * q] += P.fh[0][q] * Fval[0] + P.gh[0][q] * Fnor[0] + P.fh[1][q] * Fval[1] + P.gh[1][q] * Fnor[1];
     }
     __syncthreads();
   }
