@@ -247,6 +247,31 @@ def general_mapping_report(dgx, ctx, hbm_gbs, refine=6, steps=10):
         op.vmult(dst, src)
         res.append(dst.to_host())
     out["identity_vs_cartesian_rel_l2"] = float(np.linalg.norm(res[1] - res[0]) / np.linalg.norm(res[0]))
+    # projection_step's solver (NS.cc:2486-2546) with every multigrid level a MappingQ1 mesh: fp64 CG, fp32 V-cycle on the metric kernel
+    r, deg = 5, 3
+    mesh = dgx.Mesh(3, [1, 1, 1], r, [0, 0, 0], [1, 1, 1], [True] * 3)
+    mesh.transform(wavy, [0, 0, 0], [1, 1, 1], [1, 1, 1])
+    mf = dgx.MatrixFree(ctx, mesh)
+    op = dgx.NavierStokesProjectionOperator(mf, dgx.OP_PRESSURE, deg, 100.0, 5e-3)
+    mg = dgx.Multigrid(ctx, mesh, deg, 100.0, 5e-3)
+    x, b = op.initialize_dof_vector(), op.initialize_dof_vector()
+    n = b.locally_owned_size()
+    g = np.sin(np.arange(n) * 3e-3) + 0.1 * np.random.default_rng(1).standard_normal(n)
+    g -= g.mean()
+    b.from_host(g)
+    tol = 1e-8 * float(np.linalg.norm(g))
+    its, times = None, []
+    for _ in range(4):
+        x.set(0.0)
+        ctx.synchronize()
+        ctx.timer_start()
+        mg.setup(tol, 10000)
+        its, _res = dgx.solve_cg(op, x, b, mg, 10000, tol)
+        times.append(round(ctx.timer_stop(), 2))
+    out["mg_cg"] = {"workload": f"pressure MG-CG, Q{deg}, {1 << r}^3 deformed cells, {n} DoFs, {mg.n_levels()} MappingQ1 levels, tol 1e-8*||rhs||",
+                    "cg_iterations": its, "ms_per_solve_first": times[0], "ms_per_solve": times[-1],
+                    "note": "first solve: level diagonals probed with n^dim operator applications per level (as NS.cc:2018-2060) + eigenvalue estimates; "
+                            "later solves with the same (stage, dt): cached diagonals / estimates, single-CTA coarse CG, V-cycle replayed as a CUDA graph"}
     return out
 
 

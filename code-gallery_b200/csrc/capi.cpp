@@ -286,6 +286,8 @@ int dgx_op_destroy(dgx_op *op) {
     if (v) { v->borrowed = false; dgx_vec_destroy(v); }
   for (dgx_vec *v : {op->u_extr, op->inv_diag, op->h_src, op->h_dst, op->work[0], op->work[1], op->work[2], op->work[3]})
     if (v) { v->borrowed = false; dgx_vec_destroy(v); }
+  for (auto &dc : op->gen_diag_cache)
+    if (dc.v) { dc.v->borrowed = false; dgx_vec_destroy(dc.v); }
   for (cudaEvent_t e : op->hp_in) cudaEventDestroy(e);
   for (cudaEvent_t e : op->hp_done) cudaEventDestroy(e);
   if (op->hp_s_in) cudaStreamDestroy(op->hp_s_in);
@@ -408,6 +410,25 @@ int dgx_op_precondition_Jacobi(dgx_op *op, dgx_vec *dst, const dgx_vec *src, dou
   int rc = dgx_vec_equ(dst, omega, src);
   if (rc) return rc;
   return dgx_vec_scale_by(dst, op->inv_diag);
+}
+
+int dgx_op_el(dgx_op *op, long long i, double *value) {
+  DGX_REQUIRE(op && value, "null argument");
+  DGX_REQUIRE(op->inv_diag, "compute_diagonal() has not been called");
+  DGX_REQUIRE(i >= 0 && i < op->inv_diag->n_owned, "row is not locally owned");
+  cudaStream_t st = op->mf->ctx->stream;
+  double d = 0;
+  if (op->inv_diag->dtype == DGX_F64) {
+    DGX_CUDA_CHECK(cudaMemcpyAsync(&d, (const double *)op->inv_diag->d + i, sizeof(double), cudaMemcpyDeviceToHost, st));
+    DGX_CUDA_CHECK(cudaStreamSynchronize(st));
+  } else {
+    float f = 0;
+    DGX_CUDA_CHECK(cudaMemcpyAsync(&f, (const float *)op->inv_diag->d + i, sizeof(float), cudaMemcpyDeviceToHost, st));
+    DGX_CUDA_CHECK(cudaStreamSynchronize(st));
+    d = f;
+  }
+  *value = 1.0 / d;
+  return DGX_OK;
 }
 
 int dgx_mf_host_pipeline_plan(const dgx_mf *mf, long long bytes_per_cell, int chunk_log2, int capacity, long long *up_begin, long long *up_end,

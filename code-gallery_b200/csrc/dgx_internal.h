@@ -183,6 +183,10 @@ struct dgx_op {
   int hp_lg = 0;                                // log2(cells per chunk); 0 = not decided yet, -1 = pipeline not used
   std::vector<cudaEvent_t> hp_in, hp_done;
   cudaStream_t hp_s_in = nullptr, hp_s_out = nullptr;
+  // probed inverse diagonals of a non-Cartesian level per (TR_BDF2 stage, dt): the geometry does not change between time steps, so
+  // the n^dim probing applications of compute_diagonal run once per pair (pressure_general.cu)
+  struct DiagCache { int stage; double dt; dgx_vec *v; };
+  std::vector<DiagCache> gen_diag_cache;
   dgx_vec *work[4] = {nullptr, nullptr, nullptr, nullptr};   // Krylov work vectors, allocated on first use and kept
   std::vector<dgx_vec *> pool;                                // further work vectors (GMRES basis, diagonal probes), kept
 };
@@ -203,6 +207,8 @@ int pressure_apply_fused(dgx_op *op, dgx_vec *dst, dgx_vec *x, const FusedUpdate
 // pressure operator on a level with vertex positions (MappingQ1 metric at every quadrature point); bfac scales the boundary penalty
 int pressure_general_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const FusedUpdate *fu, double bfac);
 int pressure_general_diagonal(dgx_op *op, dgx_vec *diag_inv);
+int pressure_general_coarse_cg(dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_vec *r, dgx_vec *p, dgx_vec *v, const double *d_tol, int max_it, int *d_info,
+                               double *d_res, int *d_count, int log_cap);
 void general_metric_destroy(dgx_mf *mf);
 long long general_metric_bytes(dgx_mf *mf, int n);
 // i-th pooled work vector of the operator's space (created on first use, lives as long as the operator)

@@ -21,10 +21,12 @@
 // Kernel: cell-centric, one thread per line, Gauss-point collocation basis (values at quadrature points are the coefficients,
 // gradients a 1-D collocation derivative), everything between the first load and the last store in shared memory.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "pressure_op.cuh"
+#include "reduce.cuh"
 
 namespace dgx {
 namespace {
@@ -59,17 +61,18 @@ __device__ __forceinline__ void gline(int d, int l, int &base, int &stride) {
   }
 }
 
+// one batch of CPB cells: dst[cells] (+)= A src.  Shared by the operator kernel (one batch per block) and the single-CTA coarse-grid CG
+// kernel (loops over the batches of a tiny level).  Block-wide phases; every thread of the block must call it.
 template <int dim, int n, typename T>
-__global__ void __launch_bounds__(gen_cpb<dim, n, T>() * ipow(n, dim - 1))
-pressure_general_kernel(const __grid_constant__ GenParams<T, n> P, const int *__restrict__ nbr, int n_owned, const T *__restrict__ cellG,
-                        const T *__restrict__ faceA, const T *__restrict__ src, T *__restrict__ dst, int add, const __grid_constant__ Epilogue<T> E) {
+__device__ __forceinline__ void general_cell_batch(const GenParams<T, n> &P, const int *__restrict__ nbr, int n_owned, const T *__restrict__ cellG,
+                                                   const T *__restrict__ faceA, const T *src, T *dst, int add, const Epilogue<T> &E, int cell0, T *su, T *sr,
+                                                   T *st_all, T *sf) {
   constexpr int NL = ipow(n, dim - 1), ND = NL * n, CPB = gen_cpb<dim, n, T>(), NT = CPB * NL;
   constexpr int NS = dim * (dim + 1) / 2, NFD = 2 * dim + 1, NFA = 8;
-  __shared__ T su[CPB * ND];            // u in the Gauss-point basis
-  __shared__ T sr[CPB * ND];            // result
-  __shared__ T st[dim][CPB * ND];       // reference gradient, then the flux Gs grad_xi u
-  __shared__ T sf[CPB * 2 * NFA * NL];  // face fields of the current direction: [cell][side][field][tangential point]
-  const int tid = threadIdx.x, cell0 = blockIdx.x * CPB, nblk = min(CPB, n_owned - cell0);
+  T *st[dim];
+#pragma unroll
+  for (int e = 0; e < dim; ++e) st[e] = st_all + e * CPB * ND;
+  const int tid = threadIdx.x, nblk = min(CPB, n_owned - cell0);
   const int c = tid / NL, l = tid - c * NL;
   const bool active = c < nblk;
   const int cell = cell0 + c;
@@ -312,6 +315,88 @@ pressure_general_kernel(const __grid_constant__ GenParams<T, n> P, const int *__
   }
 }
 
+template <int dim, int n, typename T>
+__global__ void __launch_bounds__(gen_cpb<dim, n, T>() * ipow(n, dim - 1))
+pressure_general_kernel(const __grid_constant__ GenParams<T, n> P, const int *__restrict__ nbr, int n_owned, const T *__restrict__ cellG,
+                        const T *__restrict__ faceA, const T *__restrict__ src, T *__restrict__ dst, int add, const __grid_constant__ Epilogue<T> E) {
+  constexpr int NL = ipow(n, dim - 1), ND = NL * n, CPB = gen_cpb<dim, n, T>();
+  __shared__ T su[CPB * ND];            // u in the Gauss-point basis
+  __shared__ T sr[CPB * ND];            // result
+  __shared__ T st[dim * CPB * ND];      // reference gradient, then the flux Gs grad_xi u
+  __shared__ T sf[CPB * 2 * 8 * NL];    // face fields of the current direction: [cell][side][field][tangential point]
+  general_cell_batch<dim, n, T>(P, nbr, n_owned, cellG, faceA, src, dst, add, E, blockIdx.x * CPB, su, sr, st, sf);
+}
+
+// MGCoarseGridIterativeSolver<SolverCG, PreconditionIdentity> (NS.cc:2519-2529) for a metric level of a few cells, entirely inside ONE
+// CTA: same algebra as pressure_coarse_cg_kernel (pressure_op.cu) / cg_core (solvers.cu) with x0 = 0; the device-side log makes the
+// V-cycle capturable as a CUDA graph on MappingQ1 hierarchies too.
+template <int dim, int n, typename T>
+__global__ void __launch_bounds__(gen_cpb<dim, n, T>() * ipow(n, dim - 1))
+pressure_general_coarse_cg_kernel(const __grid_constant__ GenParams<T, n> P, const int *nbr, int n_cells, const T *cellG, const T *faceA, const T *b, T *x,
+                                  T *r, T *p, T *v, const double *tol_ptr, int max_it, int *info, double *res_out, int *log_count, int log_cap) {
+  const double tol = *tol_ptr;
+  constexpr int NL = ipow(n, dim - 1), ND = NL * n, CPB = gen_cpb<dim, n, T>(), NT = CPB * NL;
+  __shared__ T su[CPB * ND];
+  __shared__ T sr[CPB * ND];
+  __shared__ T st[dim * CPB * ND];
+  __shared__ T sf[CPB * 2 * 8 * NL];
+  __shared__ double red[32];
+  __shared__ double bc;
+  const int tid = threadIdx.x, N = n_cells * ND;
+  const Epilogue<T> E;
+  auto block_sum = [&](double val) -> double {
+    val = warp_sum_existing(val);   // NT is not a multiple of 32 for most degrees
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = val;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0;
+      for (int w = 0; w < (NT + 31) / 32; ++w) s += red[w];
+      bc = s;
+    }
+    __syncthreads();
+    return bc;
+  };
+  double acc = 0;
+  for (int i = tid; i < N; i += NT) { const T bi = b[i]; r[i] = bi; x[i] = 0; acc += (double)bi * (double)bi; }
+  double rr = block_sum(acc), res = sqrt(rr), prev_rr = 0;
+  int it = 0;
+  bool conv = res <= tol;
+  while (!conv && it < max_it && isfinite(res)) {
+    ++it;
+    if (it > 1) {
+      const T beta = (T)(rr / prev_rr);
+      for (int i = tid; i < N; i += NT) p[i] = beta * p[i] + r[i];
+    } else {
+      for (int i = tid; i < N; i += NT) p[i] = r[i];
+    }
+    __syncthreads();
+    for (int c0 = 0; c0 < n_cells; c0 += CPB) {
+      general_cell_batch<dim, n, T>(P, nbr, n_cells, cellG, faceA, p, v, 0, E, c0, su, sr, st, sf);
+      __syncthreads();
+    }
+    acc = 0;
+    for (int i = tid; i < N; i += NT) acc += (double)p[i] * (double)v[i];
+    const double pv = block_sum(acc);
+    const T alpha = (T)(rr / pv);
+    acc = 0;
+    for (int i = tid; i < N; i += NT) {
+      x[i] += alpha * p[i];
+      const T ri = r[i] - alpha * v[i];
+      r[i] = ri;
+      acc += (double)ri * (double)ri;
+    }
+    prev_rr = rr;
+    rr = block_sum(acc);
+    res = sqrt(rr);
+    conv = res <= tol;
+  }
+  if (tid == 0) {   // append to the device-side log: (iterations, converged), residual
+    const int slot = atomicAdd(log_count, 1) % log_cap;
+    info[2 * slot] = it; info[2 * slot + 1] = conv ? 1 : 0; res_out[slot] = res;
+  }
+}
+
 // ---- metric tables (host, double) ------------------------------------------------------------------------------------------
 struct CellGeom {
   int dim;
@@ -366,7 +451,7 @@ bool build_metric(const dgx_mf *mf, int n, std::vector<double> &cellG, std::vect
   cellG.assign((size_t)mf->n_owned * (NS + 1) * ND, 0.0);
   faceA.assign((size_t)mf->n_owned * 2 * dim * NFD * NL, 0.0);
   bool ok = true;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) reduction(&& : ok)
   for (long long c = 0; c < mf->n_owned; ++c) {
     int cc[MAX_DIM] = {0, 0, 0};
     m.coords_of(level, mf->first_cell + c, cc);
@@ -453,7 +538,12 @@ int get_metric(dgx_mf *mf, int n, dgx_mf::GeneralMetric **out) {
     DGX_CUDA_CHECK(cudaSetDevice(mf->ctx->device));
     int rc = mf->dtype == DGX_F64 ? upload<double>(cellG, &gm.cellG) : upload<float>(cellG, &gm.cellG);
     if (!rc) rc = mf->dtype == DGX_F64 ? upload<double>(faceA, &gm.faceA) : upload<float>(faceA, &gm.faceA);
-    if (rc) return rc;
+    if (rc) {   // e.g. out of memory: the tables of a large level are 100+ bytes per dof
+      if (gm.cellG) cudaFree(gm.cellG);
+      if (gm.faceA) cudaFree(gm.faceA);
+      cudaGetLastError();
+      return rc;
+    }
     gm.bytes = (cellG.size() + faceA.size()) * (mf->dtype == DGX_F64 ? 8 : 4);
     it = mf->gmetric.emplace(n, gm).first;
   }
@@ -468,14 +558,8 @@ int launch_general(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const
   if (n_owned == 0) return DGX_OK;
   dgx_mf::GeneralMetric *gm = nullptr;
   if (int rc = get_metric(mf, n, &gm)) return rc;
-  const Shape1D &s = get_shape(n - 1, n);
   GenParams<T, n> P;
-  for (int i = 0; i < n * n; ++i) { P.S[i] = (T)s.S[i]; P.Dh[i] = (T)s.Dhat[i]; }
-  for (int sd = 0; sd < 2; ++sd)
-    for (int i = 0; i < n; ++i) { P.fh[sd][i] = (T)s.fhat[sd][i]; P.gh[sd][i] = (T)s.ghat[sd][i]; P.gN[sd][i] = (T)s.g[sd][i]; }
-  P.kappa = (T)pressure_kappa(op);
-  P.theta = (T)1.0;   // theta_p, NS.cc:291
-  P.bfac = (T)bfac;
+  fill_gen_params<T, n>(P, op, bfac);
   Epilogue<T> E;
   if (fu) {
     E.on = 1;
@@ -502,6 +586,47 @@ int general_by_degree(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, co
     case 5: return launch_general<dim, 6, T>(op, dst, src, add, fu, bfac);
     case 6: return launch_general<dim, 7, T>(op, dst, src, add, fu, bfac);
     default: set_error("pressure operator on a general mesh: degree must be in 1..6"); return DGX_ERR_UNSUPPORTED;
+  }
+}
+
+template <typename T, int n>
+void fill_gen_params(GenParams<T, n> &P, const dgx_op *op, double bfac) {
+  const Shape1D &s = get_shape(n - 1, n);
+  for (int i = 0; i < n * n; ++i) { P.S[i] = (T)s.S[i]; P.Dh[i] = (T)s.Dhat[i]; }
+  for (int sd = 0; sd < 2; ++sd)
+    for (int i = 0; i < n; ++i) { P.fh[sd][i] = (T)s.fhat[sd][i]; P.gh[sd][i] = (T)s.ghat[sd][i]; P.gN[sd][i] = (T)s.g[sd][i]; }
+  P.kappa = (T)pressure_kappa(op);
+  P.theta = (T)1.0;   // theta_p, NS.cc:291
+  P.bfac = (T)bfac;
+}
+
+template <int dim, int n, typename T>
+int launch_general_coarse(dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_vec *r, dgx_vec *p, dgx_vec *v, const double *d_tol, int max_it, int *d_info, double *d_res,
+                          int *d_count, int log_cap) {
+  dgx_mf *mf = op->mf;
+  dgx_mf::GeneralMetric *gm = nullptr;
+  if (int rc = get_metric(mf, n, &gm)) return rc;
+  GenParams<T, n> P;
+  fill_gen_params<T, n>(P, op, 1.0);
+  constexpr int NT = gen_cpb<dim, n, T>() * ipow(n, dim - 1);
+  pressure_general_coarse_cg_kernel<dim, n, T><<<1, NT, 0, mf->ctx->stream>>>(P, mf->d_nbr, (int)mf->n_owned, (const T *)gm->cellG, (const T *)gm->faceA, (const T *)b->d,
+                                                                              (T *)x->d, (T *)r->d, (T *)p->d, (T *)v->d, d_tol, max_it, d_info, d_res, d_count, log_cap);
+  count_launch();
+  DGX_CUDA_CHECK(cudaGetLastError());
+  return DGX_OK;
+}
+
+template <int dim, typename T>
+int general_coarse_by_degree(dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_vec *r, dgx_vec *p, dgx_vec *v, const double *d_tol, int max_it, int *d_info, double *d_res,
+                             int *d_count, int log_cap) {
+  switch (op->degree) {
+    case 1: return launch_general_coarse<dim, 2, T>(op, x, b, r, p, v, d_tol, max_it, d_info, d_res, d_count, log_cap);
+    case 2: return launch_general_coarse<dim, 3, T>(op, x, b, r, p, v, d_tol, max_it, d_info, d_res, d_count, log_cap);
+    case 3: return launch_general_coarse<dim, 4, T>(op, x, b, r, p, v, d_tol, max_it, d_info, d_res, d_count, log_cap);
+    case 4: return launch_general_coarse<dim, 5, T>(op, x, b, r, p, v, d_tol, max_it, d_info, d_res, d_count, log_cap);
+    case 5: return launch_general_coarse<dim, 6, T>(op, x, b, r, p, v, d_tol, max_it, d_info, d_res, d_count, log_cap);
+    case 6: return launch_general_coarse<dim, 7, T>(op, x, b, r, p, v, d_tol, max_it, d_info, d_res, d_count, log_cap);
+    default: return DGX_ERR_UNSUPPORTED;
   }
 }
 
@@ -548,8 +673,39 @@ static int general_diag(dgx_op *op, dgx_vec *out) {
   return rc;
 }
 
+// The probed diagonal depends on (TR_BDF2 stage, dt) only (through 1/coeff): it is kept per pair, so a time loop with a fixed dt
+// pays the n^dim probing applications once per stage and level (DGX_NO_DIAG_CACHE: probe on every call like the reference).
 int pressure_general_diagonal(dgx_op *op, dgx_vec *out) {
-  return op->mf->dtype == DGX_F64 ? general_diag<double>(op, out) : general_diag<float>(op, out);
+  static const bool no_cache = getenv("DGX_NO_DIAG_CACHE") != nullptr;
+  if (!no_cache)
+    for (auto &dc : op->gen_diag_cache)
+      if (dc.stage == op->stage && dc.dt == op->dt) return dgx_vec_copy(out, dc.v);
+  int rc = op->mf->dtype == DGX_F64 ? general_diag<double>(op, out) : general_diag<float>(op, out);
+  if (rc || no_cache) return rc;
+  if (op->gen_diag_cache.size() >= 4) {   // keep the table short: a changing dt (last step of a run) evicts the oldest pair
+    dgx_vec *old = op->gen_diag_cache.front().v;
+    old->borrowed = false;
+    dgx_vec_destroy(old);
+    op->gen_diag_cache.erase(op->gen_diag_cache.begin());
+  }
+  dgx_vec *keep = nullptr;
+  rc = dgx_vec_create(op->mf, op->degree, op->ncomp, &keep);
+  if (rc) return rc;
+  keep->borrowed = true;
+  rc = dgx_vec_copy(keep, out);
+  if (rc) { keep->borrowed = false; dgx_vec_destroy(keep); return rc; }
+  op->gen_diag_cache.push_back({op->stage, op->dt, keep});
+  return DGX_OK;
+}
+
+// single-CTA coarse solve on a metric level (same conditions as pressure_coarse_cg checks for Cartesian levels)
+int pressure_general_coarse_cg(dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_vec *r, dgx_vec *p, dgx_vec *v, const double *d_tol, int max_it, int *d_info, double *d_res,
+                               int *d_count, int log_cap) {
+  dgx_mf *mf = op->mf;
+  if (mf->dim == 2) return mf->dtype == DGX_F64 ? general_coarse_by_degree<2, double>(op, x, b, r, p, v, d_tol, max_it, d_info, d_res, d_count, log_cap)
+                                                 : general_coarse_by_degree<2, float>(op, x, b, r, p, v, d_tol, max_it, d_info, d_res, d_count, log_cap);
+  return mf->dtype == DGX_F64 ? general_coarse_by_degree<3, double>(op, x, b, r, p, v, d_tol, max_it, d_info, d_res, d_count, log_cap)
+                              : general_coarse_by_degree<3, float>(op, x, b, r, p, v, d_tol, max_it, d_info, d_res, d_count, log_cap);
 }
 
 void general_metric_destroy(dgx_mf *mf) {

@@ -408,7 +408,8 @@ int coarse_by_degree(int degree, dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_v
 // (caller falls back to cg_core)
 int pressure_coarse_cg(dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_vec *r, dgx_vec *p, dgx_vec *v, const double *d_tol, int max_it, int *d_info, double *d_res, int *d_count, int log_cap) {
   dgx_mf *mf = op->mf;
-  if (op->kind != DGX_OP_PRESSURE || (mf->ctx->nranks != 1 && !mf->replicated) || mf->n_ghost != 0 || mf->n_owned < 1 || mf->n_owned > 64 || mf->general) return DGX_ERR_UNSUPPORTED;
+  if (op->kind != DGX_OP_PRESSURE || (mf->ctx->nranks != 1 && !mf->replicated) || mf->n_ghost != 0 || mf->n_owned < 1 || mf->n_owned > 64) return DGX_ERR_UNSUPPORTED;
+  if (mf->general) return pressure_general_coarse_cg(op, x, b, r, p, v, d_tol, max_it, d_info, d_res, d_count, log_cap);
   const int degree = op->degree;
   if (mf->dim == 2) return mf->dtype == DGX_F64 ? coarse_by_degree<2, double>(degree, op, x, b, r, p, v, d_tol, max_it, d_info, d_res, d_count, log_cap)
                                                  : coarse_by_degree<2, float>(degree, op, x, b, r, p, v, d_tol, max_it, d_info, d_res, d_count, log_cap);

@@ -371,6 +371,19 @@ class NavierStokesProjectionOperator:
         _check(lib.dgx_op_get_matrix_diagonal_inverse(self.h, C.byref(h)))
         return Vector(self.mf, self.degree, self.ncomp, _handle=h)
 
+    def el(self, i, j=None):
+        """Base::el(i, i): diagonal entry of locally owned row i"""
+        assert j is None or j == i, "only the diagonal is available (MatrixFreeOperators::Base::el)"
+        v = c_dbl()
+        _check(lib.dgx_op_el(self.h, c_ll(i), C.byref(v)))
+        return v.value
+
+    def n(self):
+        return self.m()
+
+    def get_matrix_free(self):
+        return self.mf
+
     def precondition_Jacobi(self, dst, src, omega=1.0):
         _check(lib.dgx_op_precondition_Jacobi(self.h, dst.h, src.h, c_dbl(omega)))
 

@@ -170,6 +170,8 @@ int dgx_op_mass_inverse(dgx_op *op, dgx_vec *dst, dgx_vec *src);
 int dgx_op_compute_diagonal(dgx_op *op);                  /* NS.cc:2018-2060 (stores the INVERSE) */
 int dgx_op_get_matrix_diagonal_inverse(dgx_op *op, dgx_vec **out); /* borrowed handle, NS.cc:2515 */
 int dgx_op_precondition_Jacobi(dgx_op *op, dgx_vec *dst, const dgx_vec *src, double omega);
+/* Base::el(i, i): the diagonal entry of locally owned row i (= 1 / inverse diagonal; needs compute_diagonal first) */
+int dgx_op_el(dgx_op *op, long long i, double *value);
 /* right-hand-side linear forms (zero_dst_vector = true); every source gets update_ghost_values first (NS.cc:789-790, 916-917) */
 int dgx_op_vmult_rhs_velocity(dgx_op *op, dgx_vec *dst, dgx_vec *const *srcs, int n_srcs);   /* NS.cc:788; srcs as NS.cc:2439 / 2444 */
 int dgx_op_vmult_rhs_pressure(dgx_op *op, dgx_vec *dst, dgx_vec *const *srcs, int n_srcs);   /* NS.cc:915; srcs = {u_star, pres_old} */

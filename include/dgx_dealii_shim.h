@@ -198,6 +198,12 @@ public:
   void Tvmult(Vec &dst, const Vec &src) const { check(dgx_op_Tvmult(h, dst.h, src.h)); }
   void Tvmult_add(Vec &dst, const Vec &src) const { check(dgx_op_Tvmult_add(h, dst.h, src.h)); }
   std::size_t m() const { return (std::size_t)dgx_op_m(h); }                                           // NS.cc:2512
+  std::size_t n() const { return m(); }
+  Number el(std::size_t row, std::size_t col) const {                                                  // Base::el: diagonal entries only
+    if (row != col) throw ExcDGX("el(i, j): only the diagonal is available (MatrixFreeOperators::Base::el)");
+    double v; check(dgx_op_el(h, (long long)row, &v)); return (Number)v;
+  }
+  const MatrixFree<dim, Number> *get_matrix_free() const { return mf_; }
   void compute_diagonal() { check(dgx_op_compute_diagonal(h)); }                                       // NS.cc:2018
   void precondition_Jacobi(Vec &dst, const Vec &src, double omega) const { check(dgx_op_precondition_Jacobi(h, dst.h, src.h, omega)); }
   void vmult_rhs_velocity(Vec &dst, const std::vector<Vec *> &src) const {                             // NS.cc:788
@@ -257,6 +263,11 @@ public:
   void compute_diagonal() { check(dgx_op_compute_diagonal(h)); }                                       // NS.cc:2514
   dgx_vec *get_matrix_diagonal_inverse() const { dgx_vec *d = nullptr; check(dgx_op_get_matrix_diagonal_inverse(h, &d)); return d; }   // NS.cc:2515
   std::size_t m() const { return (std::size_t)dgx_op_m(h); }                                           // NS.cc:2512
+  std::size_t n() const { return m(); }
+  float el(std::size_t row, std::size_t col) const {                                                   // Base::el: diagonal entries only
+    if (row != col) throw ExcDGX("el(i, j): only the diagonal is available (MatrixFreeOperators::Base::el)");
+    double v; check(dgx_op_el(h, (long long)row, &v)); return (float)v;
+  }
   int level() const { return level_; }
   dgx_op *h = nullptr;
 

@@ -75,6 +75,22 @@ def test_inverse_diagonal_matches_reference_probing(dgx, gpu_ctx, case, np_dtype
         assert rel_l2(d, dref) < TOL[np_dtype], degree
 
 
+def test_el_returns_the_diagonal_entry(dgx, gpu_ctx):
+    """MatrixFreeOperators::Base::el(i, i) = 1 / inverse diagonal entry; m() == n()"""
+    gm, om = make_meshes(dgx, 2, [2, 1], 1, [False, False])
+    mf = dgx.MatrixFree(gpu_ctx, gm)
+    op = dgx.NavierStokesProjectionOperator(mf, dgx.OP_PRESSURE, 2, 100.0, 5e-3)
+    with pytest.raises(dgx.DgxError):
+        op.el(0)
+    op.compute_diagonal()
+    dinv = PressureOperator(om, 2, 5e-3).compute_diagonal()
+    for i in (0, 7, op.m() - 1):
+        assert abs(op.el(i, i) - 1.0 / dinv[i]) < 1e-12 / abs(dinv[i])
+    assert op.n() == op.m() and op.get_matrix_free() is mf
+    with pytest.raises(dgx.DgxError):
+        op.el(op.m())
+
+
 def test_mass_operator(dgx, gpu_ctx):
     for dim, cells0, nref in [(2, [2, 1], 2), (3, [1, 1, 2], 1)]:
         gm, om = make_meshes(dgx, dim, cells0, nref, [False] * dim)
