@@ -383,6 +383,18 @@ int dgx_op_mass_inverse(dgx_op *op, dgx_vec *dst, dgx_vec *src) {
   return mass_inverse_apply(op, dst, src);
 }
 
+int dgx_mf_general_metric_tables(const dgx_mf *mf, int degree, double *cell_tables, long long cell_capacity, double *face_tables, long long face_capacity,
+                                 long long *n_cell_values, long long *n_face_values) {
+  DGX_REQUIRE(mf && degree >= 1 && degree <= 6, "arguments");
+  std::vector<double> cellG, faceA;
+  if (int rc = general_metric_host_tables(mf, degree + 1, cellG, faceA)) return rc;
+  if (n_cell_values) *n_cell_values = (long long)cellG.size();
+  if (n_face_values) *n_face_values = (long long)faceA.size();
+  if (cell_tables) { DGX_REQUIRE(cell_capacity >= (long long)cellG.size(), "cell table buffer too small"); std::copy(cellG.begin(), cellG.end(), cell_tables); }
+  if (face_tables) { DGX_REQUIRE(face_capacity >= (long long)faceA.size(), "face table buffer too small"); std::copy(faceA.begin(), faceA.end(), face_tables); }
+  return DGX_OK;
+}
+
 long long dgx_mf_general_metric_bytes(dgx_mf *mf, int degree) { return mf ? general_metric_bytes(mf, degree + 1) : 0; }
 
 int dgx_op_compute_diagonal(dgx_op *op) {

@@ -708,6 +708,13 @@ int pressure_general_coarse_cg(dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_vec
                               : general_coarse_by_degree<3, float>(op, x, b, r, p, v, d_tol, max_it, d_info, d_res, d_count, log_cap);
 }
 
+// host tables of a metric level (introspection / tests; pure host logic, works without a device): sizes first, then the data
+int general_metric_host_tables(const dgx_mf *mf, int n, std::vector<double> &cellG, std::vector<double> &faceA) {
+  if (!mf->general) { set_error("not a non-Cartesian level"); return DGX_ERR_INVALID; }
+  if (!build_metric(mf, n, cellG, faceA)) { set_error("general mesh: a cell has a non-positive Jacobian determinant"); return DGX_ERR_INVALID; }
+  return DGX_OK;
+}
+
 void general_metric_destroy(dgx_mf *mf) {
   for (auto &kv : mf->gmetric) {
     if (kv.second.cellG) cudaFree(kv.second.cellG);

@@ -201,6 +201,15 @@ class MatrixFree:
     def initialize_dof_vector(self, degree, ncomp=1):
         return Vector(self, degree, ncomp)
 
+    def general_metric_tables(self, degree):
+        """host copy (fp64) of the metric tables of a non-Cartesian level: (cell[c, ns + 1, n^dim], face[c, 2 dim, 2 dim + 1, n^(dim-1)])"""
+        nc, nf = c_ll(), c_ll()
+        _check(lib.dgx_mf_general_metric_tables(self.h, c_int(degree), None, c_ll(0), None, c_ll(0), C.byref(nc), C.byref(nf)))
+        cell, face = np.empty(nc.value), np.empty(nf.value)
+        _check(lib.dgx_mf_general_metric_tables(self.h, c_int(degree), cell.ctypes.data_as(c_vp), nc, face.ctypes.data_as(c_vp), nf, None, None))
+        n, dim, cells = degree + 1, self.dim, self.n_owned_cells()
+        return cell.reshape(cells, dim * (dim + 1) // 2 + 1, n ** dim), face.reshape(cells, 2 * dim, 2 * dim + 1, n ** (dim - 1))
+
     def general_metric_bytes(self, degree):
         """bytes of per-quadrature-point metric data a degree-`degree` operator streams per application on a non-Cartesian level"""
         return int(lib.dgx_mf_general_metric_bytes(self.h, c_int(degree)))

@@ -106,6 +106,12 @@ int dgx_mf_ghost_cells(const dgx_mf *mf, long long *out);
 /* bytes of metric data in HBM (J^-1 J^-T JxW per cell point; J^-1 n JxW of both sides and the penalty per face point) that a
  * degree-`degree` operator on a non-Cartesian level streams per application; 0 before its first application / on Cartesian levels */
 long long dgx_mf_general_metric_bytes(dgx_mf *mf, int degree);
+/* the same tables in double precision on the host (introspection / tests; pure host logic, no device needed), n = degree + 1:
+ *   cell_tables[cell][dim (dim+1)/2 + 1][n^dim]: (J^-1 J^-T)_{ee'} JxW in the order 00, 11, (22,) 01, (02, 12), then JxW
+ *   face_tables[cell][2 dim faces][2 dim + 1][n^(dim-1)]: (J_own^-1 n)_e JxW_f, (J_nbr^-1 n)_e JxW_f, sigma JxW_f   (n = own outward normal)
+ * NULL pointers only query the sizes. */
+int dgx_mf_general_metric_tables(const dgx_mf *mf, int degree, double *cell_tables, long long cell_capacity, double *face_tables, long long face_capacity,
+                                 long long *n_cell_values, long long *n_face_values);
 /* ghost-exchange plan (Utilities::MPI::Partitioner import / export lists): peers in ascending rank order */
 int dgx_mf_n_peers(const dgx_mf *mf);
 int dgx_mf_peer_info(const dgx_mf *mf, int i, int *rank, long long *n_send, long long *recv_first, long long *recv_count);

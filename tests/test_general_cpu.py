@@ -79,3 +79,40 @@ def test_symmetric_and_reproduces_linear_fields_on_a_deformed_mesh(dim):
         interior = np.all(cm.nbr >= 0, axis=1)
         assert interior.sum() == 4
         assert np.max(np.abs(r[interior] - mass[interior])) < 1e-11 * np.max(np.abs(r))
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_metric_tables_of_the_library_match_the_oracle_geometry(dgx, dim):
+    """MatrixFree::reinit on a MappingQ1 level is host logic (csrc/pressure_general.cu::build_metric): its tables -- J^-1 J^-T JxW per cell
+    point, J^-1 n JxW_f of both sides and the penalty per face point -- against the oracle's independently computed Jacobians."""
+    periodic, bids = ([False, True], [1, 0, 2, 3]) if dim == 2 else ([True, False, False], [0, 1, 1, 3, 4, 1])
+    cells0, nref, lo, hi = [2, 1, 1][:dim], 1, [0.0] * dim, [1.0] * dim
+    cm = CartesianMesh(dim, cells0, nref, lo, hi, periodic, bids)
+    om = GeneralMesh(cm, wavy(0.03))
+    gm = dgx.Mesh(dim, cells0, nref, lo, hi, periodic, bids)
+    gm.transform(wavy(0.03), lo, hi, cells0)
+    ctx = dgx.Context(0)                                  # host-only context when there is no device
+    mf = dgx.MatrixFree(ctx, gm)
+    degree = 2
+    cell, face = mf.general_metric_tables(degree)
+    op = PressureOperatorGeneral(om, degree, 5e-3)
+    G = np.einsum("cqek,cqfk,cq->cqef", op.invJ, op.invJ, op.JxW)
+    pairs = [(0, 0), (1, 1), (0, 1)] if dim == 2 else [(0, 0), (1, 1), (2, 2), (0, 1), (0, 2), (1, 2)]
+    for k, (e, f) in enumerate(pairs):
+        assert np.allclose(cell[:, k], G[:, :, e, f], rtol=1e-12, atol=1e-14)
+    assert np.allclose(cell[:, len(pairs)], op.JxW, rtol=1e-13)
+    for fno in range(2 * dim):
+        d, s = fno // 2, fno % 2
+        fe = op.face[(d, s)]
+        nb = cm.nbr[:, fno]
+        used = (nb >= 0) | (nb == -2)
+        own = np.einsum("cqek,cqk,cq->cqe", fe["invJ"], fe["normal"], fe["JxW"])
+        assert np.allclose(face[used, fno, 0:dim], np.moveaxis(own, 2, 1)[used], rtol=1e-12, atol=1e-14)
+        assert np.all(face[~used, fno] == 0)
+        fo = op.face[(d, 1 - s)]
+        inner = nb >= 0
+        nbr_side = np.einsum("cqek,cqk,cq->cqe", fo["invJ"][nb[inner]], fe["normal"][inner], fe["JxW"][inner])
+        assert np.allclose(face[inner, fno, dim:2 * dim], np.moveaxis(nbr_side, 2, 1), rtol=1e-12, atol=1e-14)
+        sigma = np.where(inner, 0.5 * (fe["norm"][:, 0] + fo["norm"][np.maximum(nb, 0), 0]), fe["norm"][:, 0]) * op.C_p
+        assert np.allclose(face[used, fno, 2 * dim], (sigma[:, None] * fe["JxW"])[used], rtol=1e-12)
+    ctx.close()

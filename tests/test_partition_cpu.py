@@ -58,6 +58,24 @@ def _worker(rank, world, port, q):
                         continue
                     rf, rc = expect[0]
                     assert len(sent) == 1 and np.array_equal(sent[0], mine["ghosts"][rf:rf + rc])
+        # metric tables of a MappingQ1 level (host logic of MatrixFree::reinit on non-Cartesian cells): a rank's tables are its slice of
+        # the single-rank tables, bit for bit -- also for faces whose neighbour cell lives on the other rank (its Jacobian enters A_nbr, sigma)
+        def wavy(X):
+            x = np.array(X, dtype=np.float64)
+            out = x.copy()
+            out[..., 0] = x[..., 0] + 0.03 * np.sin(2 * np.pi * x[..., 1])
+            out[..., 1] = x[..., 1] + 0.03 * np.sin(2 * np.pi * x[..., 2])
+            out[..., 2] = x[..., 2] + 0.03 * np.sin(2 * np.pi * x[..., 0])
+            return out
+        solo = dgx.Context(0)
+        mesh = dgx.Mesh(3, [1, 1, 1], 2, [0.0] * 3, [1.0] * 3, [True, False, True], [0, 1, 1, 1, 4, 5])
+        mesh.transform(wavy, [0.0] * 3, [1.0] * 3, [1, 1, 1])
+        for level in (1, 2):
+            mfm, mfs = dgx.MatrixFree(ctx, mesh, level), dgx.MatrixFree(solo, mesh, level)
+            cm, fm = mfm.general_metric_tables(2)
+            cs, fs = mfs.general_metric_tables(2)
+            lo, n = mfm.first_owned_cell(), mfm.n_owned_cells()
+            assert n > 0 and np.array_equal(cm, cs[lo:lo + n]) and np.array_equal(fm, fs[lo:lo + n])
         q.put((rank, "ok"))
     except Exception as exc:  # noqa: BLE001
         q.put((rank, repr(exc)))
