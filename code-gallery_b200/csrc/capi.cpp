@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <omp.h>
 
 #include "dgx_internal.h"
 
@@ -123,7 +124,8 @@ static int host_plan_chunk_log2(const dgx_mf *mf, size_t cell_bytes) {
 static bool host_pipeline_applies(dgx_op *op) {
   dgx_mf *mf = op->mf;
   static const bool off = getenv("DGX_NO_HOST_PIPELINE") != nullptr;
-  if (off || op->kind != DGX_OP_PRESSURE || mf->ctx->nranks != 1 || mf->general) return false;
+  static const bool multi_off = getenv("DGX_NO_HOST_PIPELINE_MULTI") != nullptr;
+  if (off || op->kind != DGX_OP_PRESSURE || mf->general || mf->replicated || (mf->ctx->nranks != 1 && multi_off)) return false;
   if (op->hp_lg == 0) op->hp_lg = host_plan_chunk_log2(mf, (size_t)op->h_src->dofs_per_cell * op->h_src->elem());
   return op->hp_lg > 0;
 }
@@ -138,12 +140,49 @@ static int vmult_host_pipelined(dgx_op *op, void *dst_host, const void *src_host
     for (cudaEvent_t &e : op->hp_done) DGX_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     DGX_CUDA_CHECK(cudaStreamCreateWithFlags(&op->hp_s_in, cudaStreamNonBlocking));
     DGX_CUDA_CHECK(cudaStreamCreateWithFlags(&op->hp_s_out, cudaStreamNonBlocking));
+    if (ctx->nranks > 1 && !mf->peers.empty()) {
+      std::vector<int> all;
+      for (const auto &p : mf->peers) all.insert(all.end(), p.send_cells.begin(), p.send_cells.end());
+      std::sort(all.begin(), all.end());
+      all.erase(std::unique(all.begin(), all.end()), all.end());
+      op->hp_bcells = all;
+      const size_t cb = (size_t)op->h_src->dofs_per_cell * op->h_src->elem();
+      if (!all.empty()) {
+        DGX_CUDA_CHECK(cudaMalloc(&op->hp_d_bcells, all.size() * sizeof(int)));
+        DGX_CUDA_CHECK(cudaMemcpy(op->hp_d_bcells, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice));
+        DGX_CUDA_CHECK(cudaMallocHost(&op->hp_stage_h, all.size() * cb));
+        DGX_CUDA_CHECK(cudaMalloc(&op->hp_stage_d, all.size() * cb));
+      }
+      DGX_CUDA_CHECK(cudaEventCreateWithFlags(&op->hp_ev_ghosts, cudaEventDisableTiming));
+    }
   }
   const size_t cell_bytes = (size_t)op->h_src->dofs_per_cell * op->h_src->elem();
   cudaStream_t st = ctx->stream;
-  // uploads start once earlier work of the context's stream is done (it may still read the staging vectors)
-  DGX_CUDA_CHECK(cudaEventRecord(ctx->ev_src_ready, st));
-  DGX_CUDA_CHECK(cudaStreamWaitEvent(op->hp_s_in, ctx->ev_src_ready, 0));
+  if (ctx->nranks > 1 && !mf->peers.empty()) {
+    // rank-boundary cells first: host gather (all cores) -> one upload -> scatter into the vector -> ghost import over NVLink.  The
+    // bulk upload below rewrites these cells with the same values; it starts when the import has read them.
+    const long long nb = (long long)op->hp_bcells.size();
+    const int *cells = op->hp_bcells.data();
+    char *stage = (char *)op->hp_stage_h;
+    const char *srcb = (const char *)src_host;
+    // torchrun exports OMP_NUM_THREADS=1: size the team from the cores this rank may run on instead
+    const int nthreads = std::max(1, std::min(8, omp_get_num_procs() / std::max(1, std::min(ctx->nranks, 8)) * 2));
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+    for (long long i = 0; i < nb; ++i) std::memcpy(stage + (size_t)i * cell_bytes, srcb + (size_t)cells[i] * cell_bytes, cell_bytes);
+    if (nb) {
+      DGX_CUDA_CHECK(cudaMemcpyAsync(op->hp_stage_d, op->hp_stage_h, (size_t)nb * cell_bytes, cudaMemcpyHostToDevice, st));
+      int rc = scatter_cells(op->h_src, op->hp_stage_d, op->hp_d_bcells, nb, st);
+      if (rc) return rc;
+    }
+    int rc = ghost_exchange(op->h_src);
+    if (rc) return rc;
+    DGX_CUDA_CHECK(cudaEventRecord(op->hp_ev_ghosts, st));
+    DGX_CUDA_CHECK(cudaStreamWaitEvent(op->hp_s_in, op->hp_ev_ghosts, 0));
+  } else {
+    // uploads start once earlier work of the context's stream is done (it may still read the staging vectors)
+    DGX_CUDA_CHECK(cudaEventRecord(ctx->ev_src_ready, st));
+    DGX_CUDA_CHECK(cudaStreamWaitEvent(op->hp_s_in, ctx->ev_src_ready, 0));
+  }
   for (size_t k = 0; k < op->hp_up.size(); ++k) {
     const size_t off = (size_t)op->hp_up[k].b * cell_bytes, len = (size_t)(op->hp_up[k].e - op->hp_up[k].b) * cell_bytes;
     DGX_CUDA_CHECK(cudaMemcpyAsync((char *)op->h_src->d + off, (const char *)src_host + off, len, cudaMemcpyHostToDevice, op->hp_s_in));
@@ -286,6 +325,10 @@ int dgx_op_destroy(dgx_op *op) {
     if (v) { v->borrowed = false; dgx_vec_destroy(v); }
   for (dgx_vec *v : {op->u_extr, op->inv_diag, op->h_src, op->h_dst, op->work[0], op->work[1], op->work[2], op->work[3]})
     if (v) { v->borrowed = false; dgx_vec_destroy(v); }
+  if (op->hp_d_bcells) cudaFree(op->hp_d_bcells);
+  if (op->hp_stage_d) cudaFree(op->hp_stage_d);
+  if (op->hp_stage_h) cudaFreeHost(op->hp_stage_h);
+  if (op->hp_ev_ghosts) cudaEventDestroy(op->hp_ev_ghosts);
   for (auto &dc : op->gen_diag_cache)
     if (dc.v) { dc.v->borrowed = false; dgx_vec_destroy(dc.v); }
   for (cudaEvent_t e : op->hp_in) cudaEventDestroy(e);
@@ -448,7 +491,7 @@ int dgx_mf_host_pipeline_plan(const dgx_mf *mf, long long bytes_per_cell, int ch
   DGX_REQUIRE(mf && n_up && n_grp && bytes_per_cell > 0, "null argument");
   const int lg = chunk_log2 > 0 ? chunk_log2 : host_plan_chunk_log2(mf, (size_t)bytes_per_cell);
   *n_up = 0; *n_grp = 0;
-  if (lg <= 0 || mf->ctx->nranks != 1) return DGX_OK;   // the call is not pipelined
+  if (lg <= 0 || mf->general || mf->replicated) return DGX_OK;   // the call is not pipelined
   std::vector<dgx_op::HostSeg> up, grp;
   build_host_plan(mf, lg, up, grp);
   *n_up = (int)up.size(); *n_grp = (int)grp.size();

@@ -183,6 +183,12 @@ struct dgx_op {
   int hp_lg = 0;                                // log2(cells per chunk); 0 = not decided yet, -1 = pipeline not used
   std::vector<cudaEvent_t> hp_in, hp_done;
   cudaStream_t hp_s_in = nullptr, hp_s_out = nullptr;
+  // several ranks: the cells other ranks need (union of the send lists) go first -- gathered on the host into a pinned staging buffer,
+  // uploaded in one copy, scattered into the vector and exchanged -- so that the pipeline below never waits for a neighbour rank
+  std::vector<int> hp_bcells;
+  int *hp_d_bcells = nullptr;
+  void *hp_stage_h = nullptr, *hp_stage_d = nullptr;
+  cudaEvent_t hp_ev_ghosts = nullptr;
   // probed inverse diagonals of a non-Cartesian level per (TR_BDF2 stage, dt): the geometry does not change between time steps, so
   // the n^dim probing applications of compute_diagonal run once per pair (pressure_general.cu)
   struct DiagCache { int stage; double dt; dgx_vec *v; };
@@ -223,6 +229,7 @@ int mass_cg_front(dgx_op *op, dgx_vec *p, const dgx_vec *r, double beta, bool fi
 int velocity_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add);
 int velocity_diagonal(dgx_op *op, dgx_vec *diag_inv);
 int ghost_exchange(dgx_vec *v);
+int scatter_cells(dgx_vec *v, const void *d_staged, const int *d_cells, long long ncells, cudaStream_t stream);
 // Ghost cells of an import that is still in flight (p2p.cu, asynchronous mode): the consumer kernel waits for the neighbours'
 // sequence numbers itself and reads the ghost cells straight from the mailbox slot.  base == nullptr: ghosts are in the vector tail.
 struct GhostSrc {

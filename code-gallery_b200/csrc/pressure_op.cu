@@ -433,7 +433,7 @@ int pressure_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add) {
 
 int pressure_apply_range(dgx_op *op, dgx_vec *dst, const dgx_vec *src, long long cell_begin, long long cell_end, cudaStream_t stream) {
   dgx_mf *mf = op->mf;
-  if (op->kind != DGX_OP_PRESSURE || mf->ctx->nranks != 1 || mf->general) return DGX_ERR_UNSUPPORTED;
+  if (op->kind != DGX_OP_PRESSURE || mf->general) return DGX_ERR_UNSUPPORTED;   // several ranks: the caller has imported the ghosts
   CellRange r;
   r.begin = cell_begin; r.end = cell_end; r.stream = stream;
   if (mf->dim == 2) return mf->dtype == DGX_F64 ? generic_by_degree<2, double>(op->degree, op, dst, src, false, nullptr, &r)

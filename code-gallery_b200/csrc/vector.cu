@@ -98,6 +98,17 @@ __global__ void pack_cells_kernel(T *__restrict__ out, const T *__restrict__ v, 
   }
 }
 
+// inverse of pack_cells_kernel: v[cells[c]] = in[c] (whole cells)
+template <typename T>
+__global__ void scatter_cells_kernel(T *__restrict__ v, const T *__restrict__ in, const int *__restrict__ cells, long long ncells, int dpc) {
+  const long long total = ncells * dpc;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long c = i / dpc;
+    int k = (int)(i - c * dpc);
+    v[(long long)cells[c] * dpc + k] = in[i];
+  }
+}
+
 constexpr int kMaxMulti = 32;
 template <typename T> struct PtrTable { const T *v[kMaxMulti]; double h[kMaxMulti]; };
 
@@ -247,6 +258,18 @@ static int ghost_exchange_on(dgx_vec *v, cudaStream_t stream) {
 
 
 int ghost_exchange(dgx_vec *v) { return ghost_exchange_on(v, v->mf->ctx->stream); }
+
+// v[cells[c]] = staged[c] for whole cells, on `stream` (the multi-rank host entry point uploads the rank-boundary cells first)
+int scatter_cells(dgx_vec *v, const void *d_staged, const int *d_cells, long long ncells, cudaStream_t stream) {
+  if (ncells == 0) return DGX_OK;
+  const int dpc = (int)v->dofs_per_cell;
+  const int grid = grid_for(ncells * dpc);
+  if (v->dtype == DGX_F64) scatter_cells_kernel<double><<<grid, kThreads, 0, stream>>>((double *)v->d, (const double *)d_staged, d_cells, ncells, dpc);
+  else scatter_cells_kernel<float><<<grid, kThreads, 0, stream>>>((float *)v->d, (const float *)d_staged, d_cells, ncells, dpc);
+  count_launch();
+  DGX_CUDA_CHECK(cudaGetLastError());
+  return DGX_OK;
+}
 
 int ghost_exchange_start(dgx_vec *v) {
   dgx_ctx *ctx = v->mf->ctx;

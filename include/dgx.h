@@ -189,7 +189,8 @@ int dgx_op_vmult_host(dgx_op *op, void *dst_host, const void *src_host, long lon
 /* schedule of the pipelined form of dgx_op_vmult_host for vectors with bytes_per_cell bytes per cell (introspection / tests; pure
  * host logic): upload segments (cells [up_begin, up_end), in upload order) and compute groups (cells [grp_begin, grp_end), in
  * compute order, each computable once upload segment grp_need is in).  chunk_log2 = 0: automatic brick size.  *n_up = 0 means the
- * call is not pipelined (several ranks, or fewer than 16 bricks).  Arrays may be NULL; at most `capacity` entries are written. */
+ * call is not pipelined (fewer than 16 bricks, non-Cartesian or replicated level).  With several ranks the cells other ranks need are
+ * gathered on the host, uploaded and exchanged first; the schedule of the owned cells is the same.  Arrays may be NULL; at most `capacity` entries are written. */
 int dgx_mf_host_pipeline_plan(const dgx_mf *mf, long long bytes_per_cell, int chunk_log2, int capacity, long long *up_begin, long long *up_end,
                               long long *grp_begin, long long *grp_end, int *grp_need, int *n_up, int *n_grp);
 

@@ -68,6 +68,33 @@ for name, cells0, nref, periodic, kind, degree in [
         dist.all_reduce(e[:2])
         errs.append({"dtype": "f64" if dt == dgx.F64 else "f32", "rel_l2": float(torch.sqrt(e[0] / e[1])), "dot_abs_err": float(e[2])})
     report[name] = errs
+# host entry point across ranks (dgx_op_vmult_host: rank-boundary cells first, ghost import, then the upload / compute / download pipeline)
+os.environ["DGX_HOST_CHUNK_LOG2"] = "5"      # 32-cell bricks so that these small meshes are pipelined
+for name, cells0, nref, periodic, degree in [("host entry Q4 periodic cube", [1, 1, 1], 4, [True] * 3, 4),
+                                             ("host entry Q2 box with boundaries", [2, 1, 1], 3, [False] * 3, 2)]:
+    mesh = dgx.Mesh(3, cells0, nref, [0, 0, 0], [float(c) for c in cells0], periodic)
+    mfd, mfs = dgx.MatrixFree(ctx, mesh), dgx.MatrixFree(solo, mesh)
+    opd, ops = (dgx.NavierStokesProjectionOperator(m, dgx.OP_PRESSURE, degree, 100.0, 5e-3) for m in (mfd, mfs))
+    dpc = (degree + 1) ** 3
+    g = np.random.default_rng(3).standard_normal(mesh.n_cells() * dpc)
+    lo, n = mfd.first_owned_cell() * dpc, mfd.n_owned_cells() * dpc
+    ups, grps = mfd.host_pipeline_plan(dpc * 8)
+    xs, ys = ops.initialize_dof_vector(), ops.initialize_dof_vector()
+    xs.from_host(g)
+    ops.set_variant(1)
+    ops.vmult(ys, xs)
+    ref = ys.to_host()[lo:lo + n]
+    hin, hout = np.ascontiguousarray(g[lo:lo + n]), np.zeros(n)
+    worst = 0.0
+    for rep in range(3):
+        hout[:] = 0
+        opd.vmult_host(hout, hin)
+        worst = max(worst, float(np.sum((hout - ref) ** 2)))
+    e = torch.tensor([worst, float(np.sum(ref ** 2))], dtype=torch.float64, device="cuda")
+    dist.all_reduce(e)
+    report[name] = [{"dtype": "f64", "rel_l2": float(torch.sqrt(e[0] / e[1])), "pipelined_groups": int(len(grps))}]
+os.environ.pop("DGX_HOST_CHUNK_LOG2", None)
+
 # lift / drag face integrals (compute_lift_and_drag, NS.cc:2642-2708) summed over the ranks == the single-GPU value
 mesh = dgx.Mesh(3, [2, 1, 1], 2, [0, 0, 0], [2.0, 1.0, 1.0], [False] * 3)   # boundary id 4 = the lower z face
 rng = np.random.default_rng(5)
