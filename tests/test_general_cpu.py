@@ -1,6 +1,8 @@
 """CPU pins of the oracle's MappingQ1 pressure operator (oracle/general.py, following NS.cc:1230-1326 with deal.II's general-mapping
 semantics): it must reduce to the Cartesian restatement (itself pinned by the exact-rational element matrices), be invariant under
 rigid motions, stay symmetric on a deformed mesh and reproduce linear fields."""
+import os
+
 import numpy as np
 import pytest
 
@@ -116,3 +118,28 @@ def test_metric_tables_of_the_library_match_the_oracle_geometry(dgx, dim):
         sigma = np.where(inner, 0.5 * (fe["norm"][:, 0] + fo["norm"][np.maximum(nb, 0), 0]), fe["norm"][:, 0]) * op.C_p
         assert np.allclose(face[used, fno, 2 * dim], (sigma[:, None] * fe["JxW"])[used], rtol=1e-12)
     ctx.close()
+
+
+SHEARED = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "exact_sheared.npz"))
+
+
+def sheared_meshes():
+    hx, hy, s = float(SHEARED["hx"]), float(SHEARED["hy"]), float(SHEARED["shear"])
+    args = (2, [2, 1], 0, [0.0, 0.0], [2 * hx, hy], [False, False])          # colorized ids: 1 = the upper x face
+    shear = lambda X: np.stack([X[..., 0] + s * X[..., 1], X[..., 1]], axis=-1)
+    return args, shear
+
+
+@pytest.mark.parametrize("p", [1, 2])
+def test_oracle_equals_exact_forms_on_sheared_cells(p):
+    """tests/golden/exact_sheared.npz: the 2-cell operator on parallelograms as exact rational integrals of the weak forms
+    (tests/golden/make_exact_sheared.py: no oracle code, no quadrature, no metric tables)"""
+    args, shear = sheared_meshes()
+    for stage in (1, 2):
+        op = PressureOperatorGeneral(GeneralMesh(CartesianMesh(*args), shear), p, float(SHEARED["dt"]))
+        op.set_TR_BDF2_stage(stage)
+        ref = SHEARED[f"pressure_q{p}_stage{stage}"]
+        A = np.stack([op.vmult(e) for e in np.eye(ref.shape[0])], axis=1)
+        assert np.abs(A - ref).max() <= 1e-12 * np.abs(ref).max(), (p, stage)
+    K = SHEARED[f"pressure_q{p}_K"]
+    assert np.abs(K - K.T).max() < 1e-13 * np.abs(K).max()

@@ -195,3 +195,26 @@ def test_diagnostics_on_a_deformed_mesh(dgx, gpu_ctx, dim):
             assert abs(lift - rl) < 1e-11 * max(1.0, abs(rl)) and abs(drag - rd) < 1e-11 * max(1.0, abs(rd)), (dtype, dp)
             ref = patch_data_general(om, dp + 1, dp, u, p, uo)
             assert np.max(np.abs(dgx.output_patch_data(vu, vp, vuo) - ref)) < 1e-10 * np.max(np.abs(ref))
+
+
+@pytest.mark.parametrize("p", [1, 2])
+def test_metric_kernel_equals_exact_forms_on_sheared_cells(dgx, gpu_ctx, p):
+    """the CUDA metric kernel against tests/golden/exact_sheared.npz (exact rational integrals of the weak forms on 2 parallelograms,
+    derived without oracle code): no oracle in this test"""
+    from test_general_cpu import SHEARED, sheared_meshes
+    args, shear = sheared_meshes()
+    gm = dgx.Mesh(*args)
+    gm.transform(shear, args[3], args[4], args[1])
+    mf = dgx.MatrixFree(gpu_ctx, gm)
+    op = dgx.NavierStokesProjectionOperator(mf, dgx.OP_PRESSURE, p, 100.0, float(SHEARED["dt"]))
+    src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+    for stage in (1, 2):
+        op.set_TR_BDF2_stage(stage)
+        ref = SHEARED[f"pressure_q{p}_stage{stage}"]
+        A = np.empty_like(ref)
+        for j in range(ref.shape[0]):
+            e = np.zeros(ref.shape[0]); e[j] = 1.0
+            src.from_host(e)
+            op.vmult(dst, src)
+            A[:, j] = dst.to_host()
+        assert np.abs(A - ref).max() <= 1e-12 * np.abs(ref).max(), (p, stage)
