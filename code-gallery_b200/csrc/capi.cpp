@@ -400,8 +400,8 @@ static int apply(dgx_op *op, dgx_vec *dst, dgx_vec *src, bool add) {
     rc = pressure_apply_fast_async(op, dst, src, add);
     if (rc != DGX_ERR_UNSUPPORTED) return rc;
   }
-  if (op->mf->general && op->kind != DGX_OP_PRESSURE) {
-    set_error("only the pressure operator (NS_stage 2) supports non-Cartesian levels");
+  if (op->mf->general && op->kind == DGX_OP_VELOCITY) {
+    set_error("the velocity operator (NS_stage 1) does not support non-Cartesian levels yet");
     return DGX_ERR_UNSUPPORTED;
   }
   if (op->kind != DGX_OP_MASS) { rc = ghost_exchange(src); if (rc) return rc; }

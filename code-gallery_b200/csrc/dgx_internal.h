@@ -215,6 +215,7 @@ int pressure_general_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool ad
 int pressure_general_diagonal(dgx_op *op, dgx_vec *diag_inv);
 int pressure_general_coarse_cg(dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_vec *r, dgx_vec *p, dgx_vec *v, const double *d_tol, int max_it, int *d_info,
                                double *d_res, int *d_count, int log_cap);
+int mass_general_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, bool inverse);
 void general_metric_destroy(dgx_mf *mf);
 int general_metric_host_tables(const dgx_mf *mf, int n, std::vector<double> &cellG, std::vector<double> &faceA);
 long long general_metric_bytes(dgx_mf *mf, int n);

@@ -219,7 +219,7 @@ int mass_cg_front_by_degree(dgx_op *op, dgx_vec *p, const dgx_vec *r, double bet
 // p = r + beta p (p = r when first), v = M p, *pv = p . v in one kernel; DGX_ERR_UNSUPPORTED: caller takes the unfused route
 int mass_cg_front(dgx_op *op, dgx_vec *p, const dgx_vec *r, double beta, bool first, dgx_vec *v, double *pv) {
   dgx_mf *mf = op->mf;
-  if (op->kind != DGX_OP_MASS || p->dtype != r->dtype || p->dtype != v->dtype) return DGX_ERR_UNSUPPORTED;
+  if (op->kind != DGX_OP_MASS || p->dtype != r->dtype || p->dtype != v->dtype || mf->general) return DGX_ERR_UNSUPPORTED;
   if (mf->dim == 2) return mf->dtype == DGX_F64 ? mass_cg_front_by_degree<2, double>(op, p, r, beta, first, v, pv) : mass_cg_front_by_degree<2, float>(op, p, r, beta, first, v, pv);
   return mf->dtype == DGX_F64 ? mass_cg_front_by_degree<3, double>(op, p, r, beta, first, v, pv) : mass_cg_front_by_degree<3, float>(op, p, r, beta, first, v, pv);
 }
@@ -232,6 +232,7 @@ int mass_inverse_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src) { return ma
 
 int mass_apply_any(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, bool inverse) {
   dgx_mf *mf = op->mf;
+  if (mf->general) return mass_general_apply(op, dst, src, add, inverse);
   if (mf->dim == 2) return mf->dtype == DGX_F64 ? mass_by_degree<2, double>(op->degree, op, dst, src, add, inverse) : mass_by_degree<2, float>(op->degree, op, dst, src, add, inverse);
   return mf->dtype == DGX_F64 ? mass_by_degree<3, double>(op->degree, op, dst, src, add, inverse) : mass_by_degree<3, float>(op->degree, op, dst, src, add, inverse);
 }

@@ -698,6 +698,124 @@ int pressure_general_diagonal(dgx_op *op, dgx_vec *out) {
   return DGX_OK;
 }
 
+// ---- DG mass operator on MappingQ1 cells (NS_stage 3, assemble_cell_term_projection_grad_p NS.cc:1373-1390) ------------------------
+// Per component M_cell = S^T diag(JxW) S with S = nodal -> Gauss points (n_q = n) and JxW the last row of the cell table; its exact
+// inverse S^-1 diag(1 / JxW) S^-T is the same kernel with other 1-D matrices (opt-in replacement of project_grad's CG, as on
+// Cartesian cells).  Algorithmic bytes: src + dst + 1 value per point.
+namespace {
+template <typename T, int n>
+struct MassGenParams {
+  T A1[n * n];   // first sweeps:  out[q] = sum_i A1[q][i] in[i]
+  T A2[n * n];   // second sweeps: out[i] = sum_q A2[i][q] in[q]
+};
+
+template <int dim, int n, typename T>
+__global__ void __launch_bounds__(gen_cpb<dim, n, T>() * ipow(n, dim - 1))
+mass_general_kernel(const __grid_constant__ MassGenParams<T, n> P, long long n_items, int ncomp, const T *__restrict__ cellG, int invert, const T *__restrict__ src,
+                    T *__restrict__ dst, int add) {
+  constexpr int NL = ipow(n, dim - 1), ND = NL * n, CPB = gen_cpb<dim, n, T>(), NT = CPB * NL, NS = dim * (dim + 1) / 2;
+  __shared__ T sa[CPB * ND];
+  const int tid = threadIdx.x;
+  const long long item0 = (long long)blockIdx.x * CPB;     // item = (cell, component): n^dim contiguous values
+  const int nblk = (int)min((long long)CPB, n_items - item0);
+  for (int idx = tid; idx < nblk * ND; idx += NT) sa[idx] = src[(size_t)item0 * ND + idx];
+  __syncthreads();
+  const int c = tid / NL, l = tid - c * NL;
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+    for (int d = 0; d < dim; ++d) {
+      if (c < nblk) {
+        int base, stride;
+        gline<dim, n>(d, l, base, stride);
+        T u[n];
+#pragma unroll
+        for (int i = 0; i < n; ++i) u[i] = sa[c * ND + base + stride * i];
+#pragma unroll
+        for (int q = 0; q < n; ++q) {
+          T acc = 0;
+#pragma unroll
+          for (int i = 0; i < n; ++i) acc += (pass == 0 ? P.A1[q * n + i] : P.A2[q * n + i]) * u[i];
+          sa[c * ND + base + stride * q] = acc;
+        }
+      }
+      __syncthreads();
+    }
+    if (pass == 0) {
+      for (int idx = tid; idx < nblk * ND; idx += NT) {
+        const long long item = item0 + idx / ND;
+        const T jxw = cellG[(size_t)(item / ncomp) * (NS + 1) * ND + (size_t)NS * ND + (idx % ND)];
+        sa[idx] = invert ? sa[idx] / jxw : sa[idx] * jxw;
+      }
+      __syncthreads();
+    }
+  }
+  for (int idx = tid; idx < nblk * ND; idx += NT) {
+    const size_t o = (size_t)item0 * ND + idx;
+    dst[o] = add ? dst[o] + sa[idx] : sa[idx];
+  }
+}
+
+template <int dim, int n, typename T>
+int launch_mass_general(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, bool inverse) {
+  dgx_mf *mf = op->mf;
+  const long long items = mf->n_owned * op->ncomp;
+  if (items == 0) return DGX_OK;
+  dgx_mf::GeneralMetric *gm = nullptr;
+  if (int rc = get_metric(mf, n, &gm)) return rc;
+  const Shape1D &s = get_shape(n - 1, n);
+  MassGenParams<T, n> P;
+  if (!inverse) {
+    for (int q = 0; q < n; ++q)
+      for (int i = 0; i < n; ++i) { P.A1[q * n + i] = (T)s.S[q * n + i]; P.A2[i * n + q] = (T)s.S[q * n + i]; }
+  } else {   // S^-1 by Gauss-Jordan with partial pivoting (n <= 7)
+    long double A[MAX_N * MAX_N], B[MAX_N * MAX_N];
+    for (int i = 0; i < n * n; ++i) { A[i] = s.S[i]; B[i] = 0; }
+    for (int i = 0; i < n; ++i) B[i * n + i] = 1;
+    for (int col = 0; col < n; ++col) {
+      int piv = col;
+      for (int r = col + 1; r < n; ++r) if (fabsl(A[r * n + col]) > fabsl(A[piv * n + col])) piv = r;
+      for (int k = 0; k < n; ++k) { std::swap(A[col * n + k], A[piv * n + k]); std::swap(B[col * n + k], B[piv * n + k]); }
+      const long double d = 1 / A[col * n + col];
+      for (int k = 0; k < n; ++k) { A[col * n + k] *= d; B[col * n + k] *= d; }
+      for (int r = 0; r < n; ++r) {
+        if (r == col) continue;
+        const long double f = A[r * n + col];
+        for (int k = 0; k < n; ++k) { A[r * n + k] -= f * A[col * n + k]; B[r * n + k] -= f * B[col * n + k]; }
+      }
+    }
+    // B = S^-1 with B[i][q]; first sweeps apply S^-T: out[q] = sum_i B[i][q] in[i]; second sweeps S^-1: out[i] = sum_q B[i][q] in[q]
+    for (int q = 0; q < n; ++q)
+      for (int i = 0; i < n; ++i) { P.A1[q * n + i] = (T)B[i * n + q]; P.A2[i * n + q] = (T)B[i * n + q]; }
+  }
+  constexpr int CPB = gen_cpb<dim, n, T>(), NT = CPB * ipow(n, dim - 1);
+  mass_general_kernel<dim, n, T><<<(int)((items + CPB - 1) / CPB), NT, 0, mf->ctx->stream>>>(P, items, op->ncomp, (const T *)gm->cellG, inverse ? 1 : 0,
+                                                                                            (const T *)src->d, (T *)dst->d, add ? 1 : 0);
+  count_launch();
+  DGX_CUDA_CHECK(cudaGetLastError());
+  return DGX_OK;
+}
+
+template <int dim, typename T>
+int mass_general_by_degree(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, bool inverse) {
+  switch (op->degree) {
+    case 1: return launch_mass_general<dim, 2, T>(op, dst, src, add, inverse);
+    case 2: return launch_mass_general<dim, 3, T>(op, dst, src, add, inverse);
+    case 3: return launch_mass_general<dim, 4, T>(op, dst, src, add, inverse);
+    case 4: return launch_mass_general<dim, 5, T>(op, dst, src, add, inverse);
+    case 5: return launch_mass_general<dim, 6, T>(op, dst, src, add, inverse);
+    case 6: return launch_mass_general<dim, 7, T>(op, dst, src, add, inverse);
+    default: set_error("mass operator on a general mesh: degree must be in 1..6"); return DGX_ERR_UNSUPPORTED;
+  }
+}
+}  // namespace
+
+int mass_general_apply(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, bool inverse) {
+  dgx_mf *mf = op->mf;
+  if (mf->dim == 2) return mf->dtype == DGX_F64 ? mass_general_by_degree<2, double>(op, dst, src, add, inverse) : mass_general_by_degree<2, float>(op, dst, src, add, inverse);
+  return mf->dtype == DGX_F64 ? mass_general_by_degree<3, double>(op, dst, src, add, inverse) : mass_general_by_degree<3, float>(op, dst, src, add, inverse);
+}
+
 // single-CTA coarse solve on a metric level (same conditions as pressure_coarse_cg checks for Cartesian levels)
 int pressure_general_coarse_cg(dgx_op *op, dgx_vec *x, const dgx_vec *b, dgx_vec *r, dgx_vec *p, dgx_vec *v, const double *d_tol, int max_it, int *d_info, double *d_res,
                                int *d_count, int log_cap) {

@@ -839,6 +839,7 @@ extern "C" {
 int dgx_op_vmult_rhs_velocity(dgx_op *op, dgx_vec *dst, dgx_vec *const *srcs, int n_srcs) {
   DGX_REQUIRE(op && dst && srcs, "null argument");
   DGX_REQUIRE(op->kind == DGX_OP_VELOCITY, "vmult_rhs_velocity needs the velocity operator (NS_stage 1)");
+  if (op->mf->general) { set_error("right-hand-side forms do not support non-Cartesian levels yet"); return DGX_ERR_UNSUPPORTED; }
   DGX_REQUIRE(n_srcs == (op->stage == 1 ? 3 : 4), "stage 1 takes {u_n, u_extr, p_n}, stage 2 {u_n, u_n_gamma, p, u_extr}");
   DGX_REQUIRE(op->mf->dtype == DGX_F64, "rhs forms are fp64");
   for (int i = 0; i < n_srcs; ++i) {
@@ -856,6 +857,7 @@ int dgx_op_vmult_rhs_velocity(dgx_op *op, dgx_vec *dst, dgx_vec *const *srcs, in
 int dgx_op_vmult_rhs_pressure(dgx_op *op, dgx_vec *dst, dgx_vec *const *srcs, int n_srcs) {
   DGX_REQUIRE(op && dst && srcs && n_srcs == 2, "vmult_rhs_pressure takes {u_star, pres_old}");
   DGX_REQUIRE(op->kind == DGX_OP_PRESSURE, "vmult_rhs_pressure needs the pressure operator (NS_stage 2)");
+  if (op->mf->general) { set_error("right-hand-side forms do not support non-Cartesian levels yet"); return DGX_ERR_UNSUPPORTED; }
   DGX_REQUIRE(op->mf->dtype == DGX_F64, "rhs forms are fp64");
   DGX_REQUIRE(srcs[0] && srcs[1] && srcs[0]->mf == op->mf && srcs[1]->mf == op->mf, "source vector of a different MatrixFree");
   DGX_REQUIRE(srcs[0]->degree == op->degree + 1 && srcs[0]->ncomp == op->mf->dim, "u_star must be the velocity space (degree_p + 1)");
@@ -868,6 +870,7 @@ int dgx_op_vmult_rhs_pressure(dgx_op *op, dgx_vec *dst, dgx_vec *const *srcs, in
 int dgx_op_vmult_grad_p_projection(dgx_op *op, dgx_vec *dst, const dgx_vec *src) {
   DGX_REQUIRE(op && dst && src, "null argument");
   DGX_REQUIRE(op->kind == DGX_OP_MASS || op->kind == DGX_OP_VELOCITY, "vmult_grad_p_projection needs an operator on the velocity space");
+  if (op->mf->general) { set_error("right-hand-side forms do not support non-Cartesian levels yet"); return DGX_ERR_UNSUPPORTED; }
   DGX_REQUIRE(op->mf->dtype == DGX_F64 && src->mf == op->mf && dst->mf == op->mf, "vectors of a different MatrixFree");
   DGX_REQUIRE(src->degree == op->degree - 1 && src->ncomp == 1 && dst->degree == op->degree && dst->ncomp == op->ncomp, "vector spaces");
   return op->mf->dim == 2 ? rhs_grad_p_dim<2>(op->mf, op->degree, dst, src) : rhs_grad_p_dim<3>(op->mf, op->degree, dst, src);

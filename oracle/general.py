@@ -204,3 +204,34 @@ class PressureOperatorGeneral:
             diag[:, i] = self.vmult(probe.reshape(-1), 2.0).reshape(self.gm.n_cells, self.ND)[:, i]
         self.inverse_diagonal = (1.0 / diag).reshape(-1).astype(self.dtype)
         return self.inverse_diagonal
+
+
+class MassOperatorGeneral:
+    """NS_stage 3 (assemble_cell_term_projection_grad_p, NS.cc:1373-1390) on MappingQ1 cells: per component
+    M_ij = sum_q phi_i(x_q) phi_j(x_q) JxW_q with the velocity quadrature QGauss(degree_v + 1); dense"""
+
+    def __init__(self, gmesh: GeneralMesh, degree_v: int, ncomp=None, dtype=np.float64):
+        self.gm, self.degree, self.dim = gmesh, degree_v, gmesh.dim
+        self.ncomp = gmesh.dim if ncomp is None else ncomp
+        self.dtype = np.dtype(dtype).type
+        n = degree_v + 1
+        self.ND = n ** self.dim
+        self.n_dofs = gmesh.n_cells * self.ncomp * self.ND
+        nodes = gauss_lobatto_nodes(n)
+        xq, wq = gauss_legendre(n)
+        tq = tuple(np.asarray(a, np.float64) for a in lagrange_eval(nodes, xq))
+        self.B, _ = _tensor_tables([tq] * self.dim)
+        w = np.ones(1)
+        for _d in range(self.dim):
+            w = np.kron(np.asarray(wq, np.float64), w)
+        _inv, det = q1_jacobian(gmesh.cell_vertices(), _points([np.asarray(xq, np.float64)] * self.dim))
+        self.JxW = det * w
+        self.M = np.einsum("qi,qj,cq->cij", self.B, self.B, self.JxW)
+
+    def vmult(self, src):
+        u = np.asarray(src, dtype=np.float64).reshape(self.gm.n_cells, self.ncomp, self.ND)
+        return np.einsum("cij,cmj->cmi", self.M, u).reshape(-1).astype(self.dtype)
+
+    def inverse(self, src):
+        u = np.asarray(src, dtype=np.float64).reshape(self.gm.n_cells, self.ncomp, self.ND)
+        return np.stack([np.linalg.solve(self.M[c], u[c].T).T for c in range(self.gm.n_cells)]).reshape(-1).astype(self.dtype)

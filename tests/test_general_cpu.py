@@ -143,3 +143,20 @@ def test_oracle_equals_exact_forms_on_sheared_cells(p):
         assert np.abs(A - ref).max() <= 1e-12 * np.abs(ref).max(), (p, stage)
     K = SHEARED[f"pressure_q{p}_K"]
     assert np.abs(K - K.T).max() < 1e-13 * np.abs(K).max()
+
+
+def test_general_mass_operator_pins():
+    """identity map == the Cartesian mass operator; 1^T M 1 = area of the deformed mesh (det J of a bilinear cell is linear: exact)"""
+    from oracle.general import MassOperatorGeneral
+    from oracle.operators import MassOperator
+    cm = CartesianMesh(2, [2, 1], 1, [0.0, 0.0], [1.0, 1.5], [False, False])
+    ref, gen = MassOperator(cm, 2), MassOperatorGeneral(GeneralMesh(cm, lambda X: X), 2)
+    u = rng_vec(ref.n_dofs, 1)
+    assert np.linalg.norm(gen.vmult(u) - ref.vmult(u)) < 1e-13 * np.linalg.norm(ref.vmult(u))
+    gm = GeneralMesh(cm, wavy(0.05))
+    op = MassOperatorGeneral(gm, 2, ncomp=1)
+    X = gm.cell_vertices()[:, [0, 1, 3, 2]]                               # counter-clockwise
+    area = 0.5 * np.abs(np.sum(X[:, :, 0] * np.roll(X[:, :, 1], -1, axis=1) - np.roll(X[:, :, 0], -1, axis=1) * X[:, :, 1], axis=1)).sum()
+    one = np.ones(op.n_dofs)
+    assert abs(one @ op.vmult(one) - area) < 1e-13 * area
+    assert np.linalg.norm(op.inverse(op.vmult(u[:op.n_dofs])) - u[:op.n_dofs]) < 1e-12 * np.linalg.norm(u[:op.n_dofs])
