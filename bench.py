@@ -233,6 +233,7 @@ def general_mapping_report(dgx, ctx, hbm_gbs, refine=6, steps=10):
         bpd = 2 * es + mf.general_metric_bytes(degree) / n
         out["entries"].append({"dtype": name, "dofs": n, "ms": round(ms, 4), "gdofs": round(n / ms * 1e-6, 2), "algorithmic_bytes_per_dof": round(bpd, 1),
                                "GBs": round(bpd * n / ms * 1e-6, 1), "hbm_frac": round(bpd * n / ms * 1e-6 / hbm_gbs, 3), "kernel": "pressure_general_kernel"})
+        mf.release_general_metric()      # 4 GB of tables (fp64) that the rest of the run does not need
         del src, dst, op, mf, mesh
     r = 4
     res = []

@@ -438,6 +438,15 @@ int dgx_mf_general_metric_tables(const dgx_mf *mf, int degree, double *cell_tabl
   return DGX_OK;
 }
 
+int dgx_mf_release_general_metric(dgx_mf *mf) {
+  DGX_REQUIRE(mf, "null argument");
+  if (mf->ctx && mf->ctx->stream) DGX_CUDA_CHECK(cudaStreamSynchronize(mf->ctx->stream));   // kernels in flight may still read the tables
+  general_metric_destroy(mf);
+  if (mf->d_cellX) { cudaFree(mf->d_cellX); mf->d_cellX = nullptr; }
+  mf->h_cellX.clear(); mf->h_cellX.shrink_to_fit();
+  return DGX_OK;
+}
+
 long long dgx_mf_general_metric_bytes(dgx_mf *mf, int degree) { return mf ? general_metric_bytes(mf, degree + 1) : 0; }
 
 int dgx_op_compute_diagonal(dgx_op *op) {

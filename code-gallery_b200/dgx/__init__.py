@@ -210,6 +210,10 @@ class MatrixFree:
         n, dim, cells = degree + 1, self.dim, self.n_owned_cells()
         return cell.reshape(cells, dim * (dim + 1) // 2 + 1, n ** dim), face.reshape(cells, 2 * dim, 2 * dim + 1, n ** (dim - 1))
 
+    def release_general_metric(self):
+        """free the metric tables of a non-Cartesian level (rebuilt by the next operator application)"""
+        _check(lib.dgx_mf_release_general_metric(self.h))
+
     def general_metric_bytes(self, degree):
         """bytes of per-quadrature-point metric data a degree-`degree` operator streams per application on a non-Cartesian level"""
         return int(lib.dgx_mf_general_metric_bytes(self.h, c_int(degree)))

@@ -106,6 +106,8 @@ int dgx_mf_ghost_cells(const dgx_mf *mf, long long *out);
 /* bytes of metric data in HBM (J^-1 J^-T JxW per cell point; J^-1 n JxW of both sides and the penalty per face point) that a
  * degree-`degree` operator on a non-Cartesian level streams per application; 0 before its first application / on Cartesian levels */
 long long dgx_mf_general_metric_bytes(dgx_mf *mf, int degree);
+/* frees the metric tables of a non-Cartesian level (100+ bytes per dof); they are rebuilt by the next operator application */
+int dgx_mf_release_general_metric(dgx_mf *mf);
 /* the same tables in double precision on the host (introspection / tests; pure host logic, no device needed), n = degree + 1:
  *   cell_tables[cell][dim (dim+1)/2 + 1][n^dim]: (J^-1 J^-T)_{ee'} JxW in the order 00, 11, (22,) 01, (02, 12), then JxW
  *   face_tables[cell][2 dim faces][2 dim + 1][n^(dim-1)]: (J_own^-1 n)_e JxW_f, (J_nbr^-1 n)_e JxW_f, sigma JxW_f   (n = own outward normal)

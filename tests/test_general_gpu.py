@@ -246,3 +246,18 @@ def test_mass_operator_on_a_deformed_mesh(dgx, gpu_ctx, dim):
     with pytest.raises(dgx.DgxError):   # the right-hand-side forms are Cartesian-only so far: loud error, never a silent wrong answer
         pop = mf.initialize_dof_vector(1, 1)
         op.vmult_grad_p_projection(dst, pop)
+
+
+def test_metric_tables_can_be_released_and_are_rebuilt(dgx, gpu_ctx):
+    gm, om = meshes(dgx, 2, [2, 1], 2, [False, True], None, wavy(0.03))
+    mf = dgx.MatrixFree(gpu_ctx, gm)
+    op = dgx.NavierStokesProjectionOperator(mf, dgx.OP_PRESSURE, 2, 100.0, 5e-3)
+    src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+    src.from_host(np.random.default_rng(0).standard_normal(src.locally_owned_size()))
+    op.vmult(dst, src)
+    first = dst.to_host()
+    assert mf.general_metric_bytes(2) > 0
+    mf.release_general_metric()
+    assert mf.general_metric_bytes(2) == 0
+    op.vmult(dst, src)
+    assert np.array_equal(dst.to_host(), first) and mf.general_metric_bytes(2) > 0
