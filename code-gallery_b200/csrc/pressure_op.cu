@@ -9,6 +9,7 @@
 // uses the Kronecker-factored form documented in pressure_op.cuh.  The blocked fast path for large
 // 3-D meshes lives in pressure_fast.cu.
 #include <cstdlib>
+#include <cstring>
 
 #include "pressure_op.cuh"
 #include "reduce.cuh"
@@ -178,6 +179,121 @@ pressure_generic_kernel(const __grid_constant__ PresParams<T, n> P, const int *_
   pressure_cell_batch<dim, n, T>(P, nbr, n_owned, src, dst, add, cell_begin + blockIdx.x * CPB, su, sa, E, cell_end);
 }
 
+// Q1 (n = 2): a cell has 2^dim dofs (64 B in 3-D fp64), so the line-per-thread decomposition of the generic kernel leaves 4 threads per
+// cell shuffling 8 values through shared memory.  Here ONE THREAD owns a cell: its dofs and the accumulator live in registers, same
+// algebra and tables as pressure_cell_batch, no barrier but one.  A warp reading "my cell" with per-thread 16-byte loads touches 16
+// cache lines per instruction (64 B stride between lanes: the first version was bound by L1 tag look-ups, 75 % l1tex with 5 % LSU
+// issue), so the block's 128 consecutive cells are fetched with lane-contiguous 16-byte loads into a padded shared-memory copy, from
+// which every thread takes its own cell AND those neighbour cells that lie inside the block (most of them: consecutive cells of the
+// hierarchical order form a compact brick); only neighbours outside the block are read from global memory.
+template <int dim, typename T>
+__global__ void __launch_bounds__(128, 6)
+pressure_q1_kernel(const __grid_constant__ PresParams<T, 2> P, const int *__restrict__ nbr, int n_owned, const T *__restrict__ src, T *__restrict__ dst,
+                   int add, const __grid_constant__ Epilogue<T> E, int cell_begin, int cell_end) {
+  constexpr int ND = 1 << dim, VPC = ND * (int)sizeof(T) / 16, RW = VPC + 1;   // 16-byte vectors per cell; row stride (one vector of padding)
+  __shared__ int4 sm4[128 * RW];
+  const int bcell0 = cell_begin + blockIdx.x * 128, ncb = min(128, cell_end - bcell0);
+  {
+    const int4 *g = reinterpret_cast<const int4 *>(src + (size_t)bcell0 * ND);
+    for (int v = threadIdx.x; v < ncb * VPC; v += 128) sm4[(v / VPC) * RW + (v % VPC)] = __ldg(g + v);
+  }
+  __syncthreads();
+  const int cell = bcell0 + threadIdx.x;
+  if (cell >= cell_end) return;
+  auto cell_from_smem = [&](int row, T (&out)[ND]) {
+#pragma unroll
+    for (int k = 0; k < VPC; ++k) {
+      const int4 t = sm4[row * RW + k];
+      T tmp[16 / sizeof(T)];
+      memcpy(tmp, &t, 16);
+#pragma unroll
+      for (int j = 0; j < (int)(16 / sizeof(T)); ++j) out[k * (16 / sizeof(T)) + j] = tmp[j];
+    }
+  };
+  T u[ND], acc[ND];
+  cell_from_smem(threadIdx.x, u);
+#pragma unroll
+  for (int i = 0; i < ND; ++i) acc[i] = P.kappa * u[i];
+  // neighbour indices of all faces first (independent loads), then one neighbour cell at a time: 8 values of neighbour data live
+  int nbs[2 * dim];
+#pragma unroll
+  for (int f = 0; f < 2 * dim; ++f) nbs[f] = nbr[(size_t)f * n_owned + cell];
+#pragma unroll
+  for (int d = 0; d < dim; ++d) {
+    const int st = 1 << d;
+#pragma unroll
+    for (int i0 = 0; i0 < ND; ++i0) {
+      if (i0 & st) continue;             // lines along d: (i0, i0 + st) with bit d of i0 clear
+      const int i1 = i0 + st;
+      acc[i0] += P.Kt[d][0] * u[i0] + P.Kt[d][1] * u[i1];
+      acc[i1] += P.Kt[d][2] * u[i0] + P.Kt[d][3] * u[i1];
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int nb = nbs[2 * d + s];
+      if (!(nb >= 0 || nb == -2)) continue;
+      T xn[ND];
+      if (nb >= 0) {
+        const int row = nb - bcell0;
+        if (row >= 0 && row < ncb) cell_from_smem(row, xn);
+        else load_row<T, ND>(src + (size_t)nb * ND, xn);
+      }
+#pragma unroll
+      for (int i0 = 0; i0 < ND; ++i0) {
+        if (i0 & st) continue;
+        const int i1 = i0 + st;
+        const T u0 = u[i0], u1 = u[i1];
+        const T V = s ? u1 : u0;
+        const T G = P.g[s][0] * u0 + P.g[s][1] * u1;
+        T FV, FG;
+        if (nb >= 0) {
+          const T x0 = xn[i0], x1 = xn[i1];
+          const T Gn = P.gn[s][0] * x0 + P.gn[s][1] * x1;
+          const T Vn = s ? x0 : x1;    // the neighbour's value on the shared face
+          FV = T(-0.5) * (G + Gn) + P.C * (V - Vn);
+          FG = T(-0.5) * (V - Vn);
+        } else {                       // boundary_id == 1: weak Dirichlet (NS.cc:1308-1322)
+          FV = -G + P.C * V;
+          FG = -V;
+        }
+        acc[i0] += P.a[d][s][0] * FV + P.b[d][s][0] * FG;
+        acc[i1] += P.a[d][s][1] * FV + P.b[d][s][1] * FG;
+      }
+    }
+  }
+  // mass: (h_x M) (x) (h_y M) (x) (h_z M)
+#pragma unroll
+  for (int d = 0; d < dim; ++d) {
+    const int st = 1 << d;
+#pragma unroll
+    for (int i0 = 0; i0 < ND; ++i0) {
+      if (i0 & st) continue;
+      const int i1 = i0 + st;
+      const T a0 = acc[i0], a1 = acc[i1];
+      acc[i0] = P.Mh[d][0] * a0 + P.Mh[d][1] * a1;
+      acc[i1] = P.Mh[d][2] * a0 + P.Mh[d][3] * a1;
+    }
+  }
+  const size_t o = (size_t)cell * ND;
+  if (E.on) {
+    T rhs[ND], dd[ND], xo[ND];
+    load_row<T, ND>(E.rhs + o, rhs);
+    if (E.d) load_row<T, ND>(E.d + o, dd);
+    if (E.xold) load_row<T, ND>(E.xold + o, xo);
+#pragma unroll
+    for (int i = 0; i < ND; ++i) {
+      T v = E.c * (rhs[i] - acc[i]);
+      if (E.d) v *= dd[i];
+      v += E.a * u[i];
+      if (E.xold) v += E.b * xo[i];
+      acc[i] = v;
+    }
+    store_row<T, ND>(dst + o, acc, 0);
+  } else {
+    store_row<T, ND>(dst + o, acc, add);
+  }
+}
+
 // MGCoarseGridIterativeSolver<SolverCG, PreconditionIdentity> (NS.cc:2519-2529) for a level of a few cells, entirely inside
 // ONE CTA: no launch and no host round trip per iteration.  Same algebra as cg_core (solvers.cu) with x0 = 0.
 // info[0] = iterations, info[1] = 1 if converged; res[0] = final residual norm.
@@ -312,6 +428,15 @@ int launch_generic(dgx_op *op, dgx_vec *dst, const dgx_vec *src, bool add, const
     E.d = fu->d ? (const T *)fu->d->d : nullptr;
     E.rhs = (const T *)fu->rhs->d;
     E.a = (T)fu->a; E.b = (T)fu->b; E.c = (T)fu->c;
+  }
+  static const bool q1_off = getenv("DGX_NO_Q1_KERNEL") != nullptr;
+  if constexpr (n == 2) {
+    if (!q1_off) {
+      pressure_q1_kernel<dim, T><<<(ce - cb + 127) / 128, 128, 0, stream>>>(P, mf->d_nbr, n_owned, (const T *)src->d, (T *)dst->d, add ? 1 : 0, E, cb, ce);
+      count_launch();
+      DGX_CUDA_CHECK(cudaGetLastError());
+      return DGX_OK;
+    }
   }
   pressure_generic_kernel<dim, n, T><<<grid, NT, 0, stream>>>(P, mf->d_nbr, n_owned, (const T *)src->d, (T *)dst->d, add ? 1 : 0, E, cb, ce);
   count_launch();
