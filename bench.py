@@ -195,7 +195,7 @@ def degree_sweep_report(dgx, ctx, hbm_gbs, steps=5):
             gb = 2 * nb * n / (ms * 1e-3) / 1e9
             out.append({"degree": p, "dtype": name, "cells": f"{2 ** refine[p]}^3", "dofs": n, "ms": round(ms, 4),
                         "gdofs": round(n / (ms * 1e-3) / 1e9, 2), "hbm_frac": round(gb / hbm_gbs, 3),
-                        "kernel": "marching" if 2 <= p <= 4 else "generic"})
+                        "kernel": "marching" if 2 <= p <= 4 else ("q1 (one thread per cell)" if p == 1 else "generic")})
             del src, dst, op, mf
     return out
 
