@@ -31,6 +31,8 @@ for name, cells0, nref, periodic, kind, degree in [
         ("pressure Q4 periodic slab (marching kernel)", [world, 1, 1], 3, [True] * 3, dgx.OP_PRESSURE, 4),
         ("pressure Q3 periodic cube (Morton chunks)", [1, 1, 1], 3, [True] * 3, dgx.OP_PRESSURE, 3),
         ("pressure Q2 box with boundaries", [2, 1, 1], 2, [False] * 3, dgx.OP_PRESSURE, 2),
+        ("pressure Q1 periodic cube (one-thread-per-cell kernel)", [1, 1, 1], 4, [True] * 3, dgx.OP_PRESSURE, 1),
+        ("pressure Q1 box with boundaries (one-thread-per-cell kernel)", [2, 1, 1], 3, [False] * 3, dgx.OP_PRESSURE, 1),
         ("pressure Q3 deformed periodic cube (metric kernel)", [1, 1, 1], 2, [True] * 3, dgx.OP_PRESSURE, 3),
         ("pressure Q2 deformed box with boundaries (metric kernel)", [2, 1, 1], 2, [False, True, False], dgx.OP_PRESSURE, 2),
         ("velocity Q3 periodic cube", [1, 1, 1], 2, [True] * 3, dgx.OP_VELOCITY, 3)]:
