@@ -58,6 +58,27 @@ def _worker(rank, world, port, q):
                         continue
                     rf, rc = expect[0]
                     assert len(sent) == 1 and np.array_equal(sent[0], mine["ghosts"][rf:rf + rc])
+        # host entry point on several ranks: every rank's upload / compute schedule of its OWNED cells is valid on its own (the cells
+        # other ranks need are staged and exchanged before the schedule starts, so only owned neighbours constrain it)
+        mesh = dgx.Mesh(3, [1, 1, 1], 5, [0.0] * 3, [1.0] * 3, [True] * 3)
+        mf = dgx.MatrixFree(ctx, mesh)
+        nc = mf.n_owned_cells()
+        ups, grps = mf.host_pipeline_plan(1000, 8)
+        assert len(ups) >= 16 and len(grps) >= 8
+        for segs in (ups, grps):
+            order = np.argsort(segs[:, 0])
+            assert segs[order[0], 0] == 0 and segs[order[-1], 1] == nc and np.array_equal(segs[order[1:], 0], segs[order[:-1], 1])
+        seg_of = np.empty(nc, dtype=np.int64)
+        for k, (b, e) in enumerate(ups):
+            seg_of[b:e] = k
+        nbr = mf.local_neighbors()
+        for b, e, need in grps:
+            nb = nbr[:, b:e]
+            nb = nb[(nb >= 0) & (nb < nc)]
+            assert seg_of[b:e].max() <= need and seg_of[nb].max() <= need
+        sent = np.unique(np.concatenate([cells for _r, cells, _rf, _rc in mf.peers()]))
+        ghost_nb = np.unique(np.nonzero((nbr >= nc).any(axis=0))[0])
+        assert np.array_equal(sent, ghost_nb)     # the staged cells are exactly the owned cells with a neighbour on another rank
         # metric tables of a MappingQ1 level (host logic of MatrixFree::reinit on non-Cartesian cells): a rank's tables are its slice of
         # the single-rank tables, bit for bit -- also for faces whose neighbour cell lives on the other rank (its Jacobian enters A_nbr, sigma)
         def wavy(X):
