@@ -117,8 +117,66 @@ def solver_cases():
     return out
 
 
+# MappingQ1 (non-Cartesian) levels: name -> (dim, cells0, nref, periodic, boundary_ids, deformation amplitude | "ring")
+GENERAL_MESHES = {
+    "wavy2d": (2, [2, 1], 2, [False, True], [1, 4, 2, 3], 0.03),
+    "wavy3d": (3, [2, 1, 1], 1, [False, True, False], [1, 1, 2, 3, 4, 5], 0.03),
+    "ring": (2, [1, 1], 3, [False, True], [4, 1, 2, 3], "ring"),
+}
+
+
+def general_map(kind):
+    """the vertex maps of the fixtures (the GPU test applies the same function through Mesh.transform)"""
+    if kind == "ring":      # O-grid around a cylinder of radius 0.5, periodic in the angle
+        def ring(X):
+            x = np.array(X, dtype=np.float64)
+            r, th = 0.5 + 1.5 * x[..., 0], 2 * np.pi * x[..., 1]
+            out = x.copy()
+            out[..., 0], out[..., 1] = r * np.cos(th), r * np.sin(th)
+            return out
+        return ring
+
+    def wavy(X):
+        x = np.array(X, dtype=np.float64)
+        out = x.copy()
+        out[..., 0] = x[..., 0] + kind * np.sin(2 * np.pi * x[..., 1]) * (1 + 0.5 * np.cos(2 * np.pi * x[..., 0]))
+        out[..., 1] = x[..., 1] + kind * np.sin(2 * np.pi * x[..., 0])
+        if x.shape[-1] == 3:
+            out[..., 1] += 0.5 * kind * np.sin(2 * np.pi * x[..., 2])
+            out[..., 2] = x[..., 2] + kind * np.sin(2 * np.pi * (x[..., 0] + x[..., 1]))
+        return out
+    return wavy
+
+
+def general_cases():
+    """pressure operator + probed diagonal, mass operator, lift / drag and output data on MappingQ1 meshes (oracle/general.py,
+    oracle/diagnostics.py)"""
+    from oracle.diagnostics import lift_and_drag_general, patch_data_general
+    from oracle.general import GeneralMesh, MassOperatorGeneral, PressureOperatorGeneral
+    out = {}
+    for mname, (dim, cells0, nref, periodic, bids, kind) in GENERAL_MESHES.items():
+        gm = GeneralMesh(CartesianMesh(dim, cells0, nref, [0.0] * dim, [1.0] * dim, periodic, bids), general_map(kind))
+        for p in (1, 2):
+            for stage in (1, 2):
+                op = PressureOperatorGeneral(gm, p, 5e-3)
+                op.set_TR_BDF2_stage(stage)
+                u = rand(op.n_dofs, 300 + p)
+                key = f"{mname}_Q{p}_s{stage}"
+                out[key + "_u"], out[key + "_Au"] = u, op.vmult(u)
+                if stage == 1:
+                    out[key + "_invdiag"] = op.compute_diagonal()
+            mass = MassOperatorGeneral(gm, p + 1)
+            v = rand(mass.n_dofs, 310 + p)
+            vo, pr = rand(mass.n_dofs, 320 + p), rand(gm.n_cells * (p + 1) ** dim, 330 + p)
+            key = f"{mname}_Q{p}"
+            out[key + "_v"], out[key + "_Mv"], out[key + "_vold"], out[key + "_p"] = v, mass.vmult(v), vo, pr
+            out[key + "_liftdrag"] = np.array(lift_and_drag_general(gm, p + 1, p, v, pr, 50.0, 4))
+            out[key + "_patches"] = patch_data_general(gm, p + 1, p, v, pr, vo)
+    return out
+
+
 def build():
-    return {"pressure": pressure_cases(), "velocity": velocity_cases(), "rhs": rhs_cases(), "solvers": solver_cases()}
+    return {"pressure": pressure_cases(), "velocity": velocity_cases(), "rhs": rhs_cases(), "solvers": solver_cases(), "general": general_cases()}
 
 
 if __name__ == "__main__":

@@ -17,10 +17,11 @@ def _load_generator():
     return mod
 
 
-@pytest.mark.parametrize("name", ["pressure", "velocity", "rhs", "solvers"])
+@pytest.mark.parametrize("name", ["pressure", "velocity", "rhs", "solvers", "general"])
 def test_oracle_reproduces_golden(name):
     gen = _load_generator()
-    fresh = {"pressure": gen.pressure_cases, "velocity": gen.velocity_cases, "rhs": gen.rhs_cases, "solvers": gen.solver_cases}[name]()
+    fresh = {"pressure": gen.pressure_cases, "velocity": gen.velocity_cases, "rhs": gen.rhs_cases, "solvers": gen.solver_cases,
+             "general": gen.general_cases}[name]()
     stored = np.load(os.path.join(HERE, "golden", name + ".npz"))
     assert sorted(stored.files) == sorted(fresh.keys())
     for key in stored.files:
