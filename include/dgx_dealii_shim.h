@@ -78,14 +78,47 @@ public:
     check(dgx_mesh_create_cartesian(dim, c0, n_global_refinements, lo, hi, mask, boundary_ids, &h));
     n_refine = n_global_refinements;
     for (int d = 0; d < dim; ++d) cell_size[d] = (p2[d] - p1[d]) / (repetitions[d] * (1 << n_global_refinements));
-    for (int d = 0; d < dim; ++d) origin[d] = p1[d];
+    for (int d = 0; d < dim; ++d) { origin[d] = p1[d]; extent[d] = p2[d] - p1[d]; }
   }
   unsigned int n_global_levels() const { return (unsigned)dgx_mesh_n_levels(h); }                    // NS.cc:2351
   long long n_global_active_cells() const { return dgx_mesh_n_cells(h, n_refine); }
   dgx_mesh *h = nullptr;
   int n_refine = 0;
-  std::array<double, dim> cell_size{}, origin{};
+  std::array<double, dim> cell_size{}, origin{}, extent{};
 };
+
+// GridTools::transform(f, triangulation): every vertex of every level of the hierarchy is moved to f(vertex); MatrixFree objects
+// created afterwards treat the cells as MappingQ1 images of the unit cell (NS.cc:2329 reinit(MappingQ1, ...)): the pressure and mass
+// operators, lift / drag and output then use the metric at every quadrature point.  f: std::array<double, dim> -> std::array<double, dim>.
+namespace GridTools {
+template <int dim, typename F>
+void transform(F &&f, Triangulation<dim> &tria) {
+  for (int level = 0; level <= tria.n_refine; ++level) {
+    int nv[3] = {1, 1, 1};
+    double h[3] = {1, 1, 1};
+    // cells per direction on this level = coarse repetitions << level: recover them from the finest cell size
+    for (int d = 0; d < dim; ++d) {
+      const double extent = tria.extent[d];
+      const long long fine = std::llround(extent / tria.cell_size[d]);
+      const long long here = fine >> (tria.n_refine - level);
+      nv[d] = (int)here + 1;
+      h[d] = extent / (double)here;
+    }
+    std::vector<double> coords((std::size_t)nv[0] * nv[1] * nv[2] * dim);
+    std::size_t k = 0;
+    for (int iz = 0; iz < nv[2]; ++iz)
+      for (int iy = 0; iy < nv[1]; ++iy)
+        for (int ix = 0; ix < nv[0]; ++ix) {
+          const int idx[3] = {ix, iy, iz};
+          std::array<double, dim> X;
+          for (int d = 0; d < dim; ++d) X[d] = tria.origin[d] + idx[d] * h[d];
+          const std::array<double, dim> x = f(X);
+          for (int d = 0; d < dim; ++d) coords[k++] = x[d];
+        }
+    check(dgx_mesh_set_vertices(tria.h, level, coords.data(), (long long)coords.size()));
+  }
+}
+}  // namespace GridTools
 
 // MatrixFree<dim, Number>::reinit (NS.cc:2329 fine / double)
 template <int dim, typename Number = double>

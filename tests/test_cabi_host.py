@@ -110,6 +110,43 @@ def test_dealii_shim_header_and_driver_build(dgx):
         assert r.returncode == 1 and "no CUDA device" in r.stderr
 
 
+def test_shim_gridtools_transform_builds_metric_tables(dgx, tmp_path):
+    """GridTools::transform of the C++ shim -> dgx_mesh_set_vertices for every level -> MatrixFree carries MappingQ1 metric tables: a
+    small C++ program (plain g++ against libdgx.so, host-only context) shears a 2 x 1 mesh and prints two table entries with closed forms"""
+    import subprocess
+    src = r'''
+#include <cstdio>
+#include "dgx_dealii_shim.h"
+using namespace dgxshim;
+int main() {
+  Context ctx(0);
+  Triangulation<2> tria;
+  tria.subdivided_hyper_rectangle({2, 1}, {0.0, 0.0}, {1.0, 1.0 / 3.0}, {false, false}, 1);
+  GridTools::transform<2>([](const std::array<double, 2> &X) { return std::array<double, 2>{X[0] + 0.75 * X[1], X[1]}; }, tria);
+  if (!dgx_mesh_is_general(tria.h, 0) || !dgx_mesh_is_general(tria.h, 1)) return 2;
+  MatrixFree<2> mf(ctx, tria);
+  long long nc = 0, nf = 0;
+  check(dgx_mf_general_metric_tables(mf.h, 1, nullptr, 0, nullptr, 0, &nc, &nf));
+  std::vector<double> cell(nc), face(nf);
+  check(dgx_mf_general_metric_tables(mf.h, 1, cell.data(), nc, face.data(), nf, nullptr, nullptr));
+  // cell 0, first quadrature point: JxW = det J w = hx hy / 4; G_00 = (1 + s^2) / hx^2 JxW
+  std::printf("%lld %lld %.17g %.17g\n", nc, nf, cell[3 * 4], cell[0]);
+  return 0;
+}
+'''
+    exe = str(tmp_path / "shim_transform")
+    libdir = os.path.dirname(dgx.LIB_PATH)
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), "-x", "c++", "-", "-L", libdir, "-ldgx",
+                        "-Wl,-rpath," + libdir, "-Wl,--allow-shlib-undefined", "-o", exe], input=src, text=True, capture_output=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    nc, nf, jxw, g00 = r.stdout.split()
+    hx, hy = 0.25, 1.0 / 6.0                     # 4 x 2 cells on the finest level
+    assert int(nc) == 8 * 4 * 4 and int(nf) == 8 * 4 * 5 * 2
+    assert abs(float(jxw) - hx * hy / 4) < 1e-15 and abs(float(g00) - (1 + 0.75 ** 2) / hx ** 2 * hx * hy / 4) < 1e-13
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the CPU arm the driver runs beside the CUDA arm) prints one JSON line with the contract's
     keys; it times the oracle's C port on a bounded sample and needs no GPU."""
