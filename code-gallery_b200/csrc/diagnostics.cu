@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -209,6 +210,71 @@ __global__ void __launch_bounds__(128) patch_kernel(const __grid_constant__ Patc
   }
 }
 
+struct IndicatorTables {
+  double S[kMaxNq * MAX_N], D[kMaxNq * MAX_N];   // velocity basis and derivative at the cell quadrature points: [q][i]
+  double xq[kMaxNq], w[kMaxNq];
+  double h[MAX_DIM];
+  int n, nq, dim;
+};
+
+// refine_mesh's indicator (NS.cc:2727-2752): one warp per cell, lanes over the quadrature points of QGauss<dim>(nq);
+// out[cell] = diameter^2 * sum_q (d u_1 / d x_0 - d u_0 / d x_1)^2 JxW   (the reference takes this component in 3-D too)
+template <typename T>
+__global__ void __launch_bounds__(128) vorticity_indicator_kernel(const __grid_constant__ IndicatorTables P, long long n_cells, const T *__restrict__ u,
+                                                                  const double *__restrict__ cellX, float *__restrict__ out) {
+  const int dim = P.dim, n = P.n, nq = P.nq, lane = threadIdx.x & 31;
+  const long long cell = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (cell >= n_cells) return;
+  int nd = 1, nqt = 1;
+  for (int d = 0; d < dim; ++d) { nd *= n; nqt *= nq; }
+  double acc = 0.0;
+  for (int q = lane; q < nqt; q += 32) {
+    int qi[3] = {q % nq, (q / nq) % nq, dim == 3 ? q / (nq * nq) : 0};
+    double gref[2][3] = {{0, 0, 0}, {0, 0, 0}};   // reference gradients of the components 0 and 1
+    for (int c = 0; c < 2; ++c) {
+      const T *uc = u + ((size_t)cell * dim + c) * nd;
+      for (int k = 0; k < (dim == 3 ? n : 1); ++k)
+        for (int j = 0; j < n; ++j)
+          for (int i = 0; i < n; ++i) {
+            const double v = (double)uc[i + n * (j + n * k)];
+            const double sx = P.S[qi[0] * n + i], sy = P.S[qi[1] * n + j], sz = dim == 3 ? P.S[qi[2] * n + k] : 1.0;
+            gref[c][0] += P.D[qi[0] * n + i] * sy * sz * v;
+            gref[c][1] += sx * P.D[qi[1] * n + j] * sz * v;
+            if (dim == 3) gref[c][2] += sx * sy * P.D[qi[2] * n + k] * v;
+          }
+    }
+    double w = P.w[qi[0]] * P.w[qi[1]] * (dim == 3 ? P.w[qi[2]] : 1.0), d10, d01, JxW;
+    if (cellX == nullptr) {
+      d10 = gref[1][0] / P.h[0]; d01 = gref[0][1] / P.h[1];
+      JxW = w * P.h[0] * P.h[1] * (dim == 3 ? P.h[2] : 1.0);
+    } else {
+      double xi[3] = {P.xq[qi[0]], P.xq[qi[1]], dim == 3 ? P.xq[qi[2]] : 0.0}, inv[3][3];
+      const double det = q1_jacobian(dim, cellX + (size_t)cell * (1 << dim) * dim, xi, inv);
+      d10 = 0; d01 = 0;
+      for (int e = 0; e < dim; ++e) { d10 += gref[1][e] * inv[e][0]; d01 += gref[0][e] * inv[e][1]; }
+      JxW = det * w;
+    }
+    const double vort = d10 - d01;
+    acc += vort * vort * JxW;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    double diam2 = 0;
+    if (cellX == nullptr) {
+      for (int d = 0; d < dim; ++d) diam2 += P.h[d] * P.h[d];
+    } else {   // TriaAccessor::diameter(): the longest diagonal of the quadrilateral / hexahedron
+      const double *X = cellX + (size_t)cell * (1 << dim) * dim;
+      const int NV = 1 << dim;
+      for (int v = 0; v < NV / 2; ++v) {
+        double s2 = 0;
+        for (int d = 0; d < dim; ++d) { const double t = X[v * dim + d] - X[(NV - 1 - v) * dim + d]; s2 += t * t; }
+        diam2 = fmax(diam2, s2);
+      }
+    }
+    out[cell] = (float)(diam2 * acc);
+  }
+}
+
 int check_pair(const dgx_vec *u, const dgx_vec *p) {
   DGX_REQUIRE(u && p, "null argument");
   DGX_REQUIRE(u->mf == p->mf, "velocity and pressure must live on the same MatrixFree");
@@ -317,6 +383,64 @@ int dgx_compute_lift_and_drag(const dgx_vec *u, const dgx_vec *p, double Re, int
   DGX_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   *drag = ctx->h_scratch[0];
   *lift = ctx->h_scratch[1];
+  return DGX_OK;
+}
+
+int dgx_estimate_vorticity_indicator(const dgx_vec *u, int n_q_points_1d, float *out_host, long long capacity) {
+  DGX_REQUIRE(u && out_host, "null argument");
+  dgx_mf *mf = u->mf;
+  dgx_ctx *ctx = mf->ctx;
+  DGX_REQUIRE(ctx->d_scratch, "no device");
+  DGX_REQUIRE(u->ncomp == mf->dim && u->degree >= 1 && u->degree + 1 <= MAX_N, "velocity vector (dim components) expected");
+  DGX_REQUIRE(n_q_points_1d >= 1 && n_q_points_1d <= kMaxNq, "number of quadrature points");
+  DGX_REQUIRE(capacity >= mf->n_owned, "output buffer too small");
+  if (mf->n_owned == 0) return DGX_OK;
+  DGX_CUDA_CHECK(cudaSetDevice(ctx->device));
+  IndicatorTables P;
+  std::memset(&P, 0, sizeof(P));
+  const Shape1D &sv = get_shape(u->degree, n_q_points_1d);
+  P.n = u->degree + 1; P.nq = n_q_points_1d; P.dim = mf->dim;
+  for (int q = 0; q < P.nq; ++q) {
+    for (int i = 0; i < P.n; ++i) { P.S[q * P.n + i] = sv.S[q * P.n + i]; P.D[q * P.n + i] = sv.D[q * P.n + i]; }
+    P.xq[q] = sv.xq[q]; P.w[q] = sv.wq[q];
+  }
+  for (int d = 0; d < MAX_DIM; ++d) P.h[d] = d < mf->dim ? mf->h[d] : 1.0;
+  const double *d_X = nullptr;
+  if (int rc = cell_vertex_table(mf, &d_X)) return rc;
+  float *d_out = nullptr;
+  DGX_CUDA_CHECK(cudaMalloc(&d_out, (size_t)mf->n_owned * sizeof(float)));
+  const int grid = (int)((mf->n_owned + 3) / 4);
+  if (u->dtype == DGX_F64) vorticity_indicator_kernel<double><<<grid, 128, 0, ctx->stream>>>(P, mf->n_owned, (const double *)u->d, d_X, d_out);
+  else vorticity_indicator_kernel<float><<<grid, 128, 0, ctx->stream>>>(P, mf->n_owned, (const float *)u->d, d_X, d_out);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, d_out, (size_t)mf->n_owned * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_out);
+  if (e != cudaSuccess) { set_error(std::string("vorticity indicator: ") + cudaGetErrorString(e)); return DGX_ERR_CUDA; }
+  return DGX_OK;
+}
+
+// GridRefinement::refine_and_coarsen_fixed_number (NS.cc:2771) on one rank: the top_fraction * N cells with the largest indicators are
+// flagged for refinement (value >= the threshold, as GridRefinement::refine), the bottom_fraction * N with the smallest for coarsening
+// (value <= the threshold, as GridRefinement::coarsen); a cell never gets both.  Pure host logic.
+int dgx_refine_and_coarsen_fixed_number(const float *indicators, long long n, double top_fraction, double bottom_fraction, signed char *flags) {
+  DGX_REQUIRE(indicators && flags && n >= 0, "null argument");
+  DGX_REQUIRE(top_fraction >= 0 && bottom_fraction >= 0 && top_fraction + bottom_fraction <= 1.0, "fractions");
+  for (long long i = 0; i < n; ++i) flags[i] = 0;
+  if (n == 0) return DGX_OK;
+  const long long n_refine = (long long)(top_fraction * (double)n), n_coarsen = (long long)(bottom_fraction * (double)n);
+  std::vector<float> tmp(indicators, indicators + n);
+  if (n_refine > 0) {
+    std::nth_element(tmp.begin(), tmp.begin() + (n_refine - 1), tmp.end(), std::greater<float>());
+    const float thr = tmp[n_refine - 1];
+    for (long long i = 0; i < n; ++i) if (indicators[i] >= thr) flags[i] = 1;
+  }
+  if (n_coarsen > 0) {
+    std::nth_element(tmp.begin(), tmp.begin() + (n_coarsen - 1), tmp.end());
+    const float thr = tmp[n_coarsen - 1];
+    for (long long i = 0; i < n; ++i) if (indicators[i] <= thr && flags[i] == 0) flags[i] = -1;
+  }
   return DGX_OK;
 }
 

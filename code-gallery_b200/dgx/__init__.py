@@ -544,6 +544,23 @@ def compute_lift_and_drag(u: Vector, p: Vector, Re, boundary_id=4):
     return lift.value, drag.value
 
 
+def estimate_vorticity_indicator(u: Vector, n_q_points_1d=None):
+    """refine_mesh's cell-wise indicator (NS.cc:2727-2752): diameter^2 int (d u_1/d x_0 - d u_0/d x_1)^2, float32 per owned cell"""
+    nq = u.degree + 1 if n_q_points_1d is None else n_q_points_1d          # degree_p + 2 = degree_v + 1
+    out = np.empty(u.mf.n_owned_cells(), dtype=np.float32)
+    _check(lib.dgx_estimate_vorticity_indicator(u.h, c_int(nq), out.ctypes.data_as(c_vp), c_ll(out.size)))
+    return out
+
+
+def refine_and_coarsen_fixed_number(indicators, top_fraction=0.01, bottom_fraction=0.3):
+    """GridRefinement::refine_and_coarsen_fixed_number (NS.cc:2771; one rank): +1 refine / -1 coarsen / 0 per cell"""
+    ind = np.ascontiguousarray(indicators, dtype=np.float32)
+    flags = np.zeros(ind.size, dtype=np.int8)
+    _check(lib.dgx_refine_and_coarsen_fixed_number(ind.ctypes.data_as(c_vp), c_ll(ind.size), c_dbl(top_fraction), c_dbl(bottom_fraction),
+                                                   flags.ctypes.data_as(c_vp)))
+    return flags
+
+
 def output_patch_data(u_n: Vector, pres_n: Vector, u_n_minus_1: Vector):
     """what DataOut::build_patches(MappingQ1, 1) collects in output_results (NS.cc:2608-2630):
     [owned cells, 2^dim vertices, fields] with fields = v (dim), p, v_old (dim), vorticity (1 in 2-D, 3 in 3-D)"""

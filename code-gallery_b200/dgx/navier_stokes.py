@@ -8,7 +8,7 @@ from __future__ import annotations
 import os
 
 from . import (GAMMA, OP_MASS, OP_PRESSURE, OP_VELOCITY, MatrixFree, Multigrid, NavierStokesProjectionOperator, compute_lift_and_drag,
-               interpolate_velocity, output_results, solve_cg, solve_gmres)
+               estimate_vorticity_indicator, interpolate_velocity, output_results, refine_and_coarsen_fixed_number, solve_cg, solve_gmres)
 
 
 class NavierStokesProjection:
@@ -126,6 +126,12 @@ class NavierStokesProjection:
         path = os.path.join(saving_dir, f"solution-{step:05d}.vtu")
         output_results(self.u_n, self.pres_n, self.u_n_minus_1, path)
         return path
+
+    def refinement_flags(self, top_fraction=0.01, bottom_fraction=0.3):                    # NS.cc:2727-2771
+        """first half of refine_mesh: the vorticity indicator of u_n per cell (device) and the refine / coarsen flags
+        refine_and_coarsen_fixed_number would set (+1 / -1 / 0).  Executing them needs hanging-node faces: not built yet."""
+        eta = estimate_vorticity_indicator(self.u_n, self.degree_p + 2)
+        return eta, refine_and_coarsen_fixed_number(eta, top_fraction, bottom_fraction)
 
     def run(self, T, output_interval=0, saving_dir=".", verbose=False, boundary_id=4):
         """NavierStokesProjection::run (NS.cc:2928-3010) without mesh refinement: returns the (lift, drag) history"""

@@ -241,6 +241,14 @@ int dgx_solve_gmres(dgx_op *A, dgx_vec *x, dgx_vec *b, int precond_kind, void *p
  * reference: 4) of (1/Re grad u - p I) (-n) JxW at the points of QGauss<dim-1>(degree_p + 2); drag = component 0, lift = component 1,
  * summed over all ranks (Utilities::MPI::sum).  u, p: vectors of one MatrixFree. */
 int dgx_compute_lift_and_drag(const dgx_vec *u, const dgx_vec *p, double Re, int boundary_id, double *lift, double *drag);
+/* refine_mesh's cell-wise error indicator (NS.cc:2727-2752), evaluated on the device: out_host[owned cell] = diameter(K)^2 *
+ * int_K (d u_1 / d x_0 - d u_0 / d x_1)^2 dx with QGauss<dim>(n_q_points_1d) (the reference: degree_p + 2; it takes this vorticity
+ * component in 3-D as well), float like Vector<float> estimated_error_per_cell; Cartesian and MappingQ1 levels */
+int dgx_estimate_vorticity_indicator(const dgx_vec *u, int n_q_points_1d, float *out_host, long long capacity);
+/* GridRefinement::refine_and_coarsen_fixed_number (NS.cc:2771) on one rank, pure host logic: flags[i] = +1 (refine) for the
+ * top_fraction * n cells with the largest indicators, -1 (coarsen) for the bottom_fraction * n smallest, else 0.  The refinement
+ * itself (hanging-node faces, SolutionTransfer) is not part of this library yet: the flags are what refine_mesh would execute. */
+int dgx_refine_and_coarsen_fixed_number(const float *indicators, long long n, double top_fraction, double bottom_fraction, signed char *flags);
 /* fields per patch point of output_results: v (dim), p, v_old (dim), vorticity (1 in 2-D, 3 in 3-D) */
 int dgx_output_n_fields(int dim);
 /* the data DataOut::build_patches(MappingQ1, 1) collects for output_results (NS.cc:2608-2630): one patch per owned cell, its 2^dim

@@ -176,3 +176,40 @@ def patch_data_general(gmesh, degree_v: int, degree_p: int, u_n, pres_n, u_n_min
         out[:, :, 2 * dim + 2] = grad[:, :, 0, 2] - grad[:, :, 2, 0]
         out[:, :, 2 * dim + 3] = grad[:, :, 1, 0] - grad[:, :, 0, 1]
     return out
+
+
+def vorticity_indicator(gmesh_or_mesh, degree_v: int, u, nq=None):
+    """refine_mesh's indicator (NS.cc:2727-2752): eta_K = diameter(K)^2 sum_q (d u_1/d x_0 - d u_0/d x_1)^2 JxW with QGauss<dim>(nq),
+    nq = degree_p + 2 = degree_v + 1; dense point evaluation with physical gradients.  Accepts a CartesianMesh or a GeneralMesh."""
+    from .dg1d import gauss_legendre
+    from .general import GeneralMesh, _points, q1_jacobian
+    gm = gmesh_or_mesh if isinstance(gmesh_or_mesh, GeneralMesh) else GeneralMesh(gmesh_or_mesh, lambda X: X)
+    dim = gm.dim
+    nq = degree_v + 1 if nq is None else nq
+    xq, wq = (np.asarray(a, np.float64) for a in gauss_legendre(nq))
+    _B, dB = _dense_tables(degree_v, [xq] * dim)
+    w = np.ones(1)
+    for _d in range(dim):
+        w = np.kron(wq, w)
+    X = gm.cell_vertices()
+    invJ, det = q1_jacobian(X, _points([xq] * dim))
+    U = np.asarray(u, np.float64).reshape(gm.n_cells, dim, -1)
+    grad = np.einsum("qie,cqek,cmi->cqmk", dB, invJ, U)                  # d u_m / d x_k
+    vort = grad[:, :, 1, 0] - grad[:, :, 0, 1]                           # NS.cc:2745
+    NV = 1 << dim
+    diam2 = np.max(np.stack([np.sum((X[:, v] - X[:, NV - 1 - v]) ** 2, axis=-1) for v in range(NV // 2)]), axis=0)
+    return (diam2 * np.einsum("cq,cq->c", vort * vort, det * w)).astype(np.float32)
+
+
+def refine_and_coarsen_fixed_number(indicators, top_fraction=0.01, bottom_fraction=0.3):
+    """GridRefinement::refine_and_coarsen_fixed_number, serial semantics: refine the int(top_fraction N) largest (>= threshold),
+    coarsen the int(bottom_fraction N) smallest (<= threshold)"""
+    ind = np.asarray(indicators, dtype=np.float32)
+    flags = np.zeros(ind.size, dtype=np.int8)
+    nr, ncs = int(top_fraction * ind.size), int(bottom_fraction * ind.size)
+    srt = np.sort(ind)
+    if nr > 0:
+        flags[ind >= srt[-nr]] = 1
+    if ncs > 0:
+        flags[(ind <= srt[ncs - 1]) & (flags == 0)] = -1
+    return flags

@@ -132,3 +132,54 @@ def test_general_diagnostics_reduce_to_cartesian_and_obey_the_divergence_theorem
     lift, drag = lift_and_drag_general(g, 2, 1, np.zeros(ring.n_cells * 2 * 9), px, Re)
     area = 0.5 * 16 * 0.25 * np.sin(2 * np.pi / 16)
     assert abs(drag + area) < 1e-12 and abs(lift) < 1e-12                # forces = (-p I)(-n_out) = p n_out, n_out = -e_r (into the cylinder)
+
+
+def mapped_dof_points(gm, degree):
+    """physical support points of a scalar FE_DGQ(degree) field on a MappingQ1 mesh: [cell, (k,) j, i, dim]"""
+    nodes = np.asarray(gauss_lobatto_nodes(degree + 1), dtype=np.float64)
+    X, dim = gm.cell_vertices(), gm.dim
+    grids = np.meshgrid(*([nodes] * dim), indexing="ij")              # axes slowest..fastest
+    xi = [grids[dim - 1 - d] for d in range(dim)]                      # xi[d] = reference coordinate d at every dof
+    pts = 0
+    for v in range(1 << dim):
+        N = 1.0
+        for d in range(dim):
+            N = N * (xi[d] if (v >> d) & 1 else 1.0 - xi[d])
+        pts = pts + N[None, ..., None] * X[:, v].reshape((gm.n_cells,) + (1,) * dim + (dim,))
+    return pts
+
+
+def rigid_rotation(gm, degree, c):
+    pts = mapped_dof_points(gm, degree)
+    comps = [-c * pts[..., 1], c * pts[..., 0]] + ([0.3 * pts[..., 0]] if gm.dim == 3 else [])
+    return np.stack(comps, axis=1).reshape(-1)
+
+
+def test_vorticity_indicator_and_refinement_flags(dgx):
+    """refine_mesh's indicator (NS.cc:2727-2752) for the rigid rotation u = c (-y, x): vorticity 2 c, eta_K = diameter^2 4 c^2 |K| on
+    Cartesian and deformed cells; refine_and_coarsen_fixed_number of the library (host logic) == the oracle's, ties included"""
+    from oracle.diagnostics import refine_and_coarsen_fixed_number, vorticity_indicator
+    from oracle.general import GeneralMesh
+    from test_general_cpu import wavy
+    c = 0.7
+    cm = CartesianMesh(2, [2, 1], 2, [0, 0], [2, 1], [False, False])
+    eta = vorticity_indicator(cm, 2, rigid_rotation(GeneralMesh(cm, lambda X: X), 2, c))
+    assert np.allclose(eta, (cm.h[0] ** 2 + cm.h[1] ** 2) * 4 * c * c * cm.h[0] * cm.h[1], rtol=1e-6)
+    for dim in (2, 3):
+        cmd = CartesianMesh(dim, [2, 1, 1][:dim], 1, [0.0] * dim, [1.0] * dim, [False] * dim)
+        gm = GeneralMesh(cmd, wavy(0.05))
+        eta = vorticity_indicator(gm, 2, rigid_rotation(gm, 2, c))
+        X = gm.cell_vertices()
+        NV = 1 << dim
+        diam2 = np.max(np.stack([np.sum((X[:, v] - X[:, NV - 1 - v]) ** 2, axis=-1) for v in range(NV // 2)]), axis=0)
+        from oracle.general import MassOperatorGeneral
+        vol = MassOperatorGeneral(gm, 1, ncomp=1).M.sum(axis=(1, 2))
+        assert np.allclose(eta, diam2 * 4 * c * c * vol, rtol=1e-5)
+    rng = np.random.default_rng(0)
+    ind = rng.random(1000).astype(np.float32)
+    ind[10:20] = ind[5]                                            # ties
+    import ctypes as C
+    for top, bottom in ((0.01, 0.3), (0.2, 0.2), (0.0, 0.5), (0.5, 0.0)):
+        flags = dgx.refine_and_coarsen_fixed_number(ind, top, bottom)
+        assert np.array_equal(flags, refine_and_coarsen_fixed_number(ind, top, bottom))
+        assert (flags == 1).sum() >= int(top * 1000) and (flags == -1).sum() >= min(int(bottom * 1000), 1000 - (flags == 1).sum()) - 10

@@ -96,3 +96,37 @@ def test_run_loop_reports_forces_and_writes_output(dgx, gpu_ctx, tmp_path):
     files = sorted(p.name for p in tmp_path.iterdir())
     assert files == ["solution-00001.vtu", "solution-00002.vtu", "solution-00003.vtu"]
     assert read_vtu(str(tmp_path / files[2]))[1] == om.n_cells
+
+
+def test_vorticity_indicator_matches_oracle(dgx, gpu_ctx):
+    """refine_mesh's cell-wise indicator (NS.cc:2727-2752) on the device: Cartesian 2-D / 3-D, deformed cells, the O-grid; float32 results"""
+    from oracle.diagnostics import vorticity_indicator
+    from oracle.general import GeneralMesh
+    from oracle.mesh import CartesianMesh
+    from test_diagnostics_cpu import annulus, rigid_rotation
+    from test_general_cpu import wavy
+    rng = np.random.default_rng(8)
+    for dim, cells0, nref, periodic, fn in ((2, [2, 1], 2, [False, True], None), (3, [1, 1, 1], 2, [True] * 3, None),
+                                            (2, [2, 1], 1, [False, False], wavy(0.04)), (3, [2, 1, 1], 1, [False] * 3, wavy(0.04)),
+                                            (2, [1, 1], 3, [False, True], annulus(0.5, 2.0))):
+        lo, hi = [0.0] * dim, [1.0] * dim
+        cm = CartesianMesh(dim, cells0, nref, lo, hi, periodic)
+        gm = dgx.Mesh(dim, cells0, nref, lo, hi, periodic)
+        if fn is not None:
+            gm.transform(fn, lo, hi, cells0)
+        om = GeneralMesh(cm, fn) if fn is not None else cm
+        mf = dgx.MatrixFree(gpu_ctx, gm)
+        for dv in (2, 3):
+            u = rng.standard_normal(cm.n_cells * dim * (dv + 1) ** dim)
+            v = mf.initialize_dof_vector(dv, dim)
+            v.from_host(u)
+            eta = dgx.estimate_vorticity_indicator(v)
+            ref = vorticity_indicator(om, dv, u)
+            assert eta.dtype == np.float32 and np.allclose(eta, ref, rtol=2e-6), (dim, dv, fn is not None)
+    # closed form: rigid rotation on the O-grid, vorticity 2 c everywhere
+    g = GeneralMesh(cm, annulus(0.5, 2.0))
+    v = mf.initialize_dof_vector(2, 2)
+    v.from_host(rigid_rotation(g, 2, 0.7))
+    eta = dgx.estimate_vorticity_indicator(v)
+    flags = dgx.refine_and_coarsen_fixed_number(eta, 0.1, 0.3)
+    assert (flags == 1).sum() >= 6 and (flags == -1).sum() >= 19 and np.all(eta[flags == 1].min() >= eta[flags == -1].max())
