@@ -118,16 +118,20 @@ struct TransferParams {
 // one block per parent cell; thread = (child, line).  PROLONG: fine[child] += P parent;  else coarse += P^T fine[child]
 template <int dim, int n, typename T, bool PROLONG>
 __global__ void __launch_bounds__((1 << dim) * ipow(n, dim - 1))
-transfer_kernel(const __grid_constant__ TransferParams<T, n> P, long long n_parents, T *__restrict__ dst, const T *__restrict__ src) {
+transfer_kernel(const __grid_constant__ TransferParams<T, n> P, long long n_parents, int ncomp, T *__restrict__ dst, const T *__restrict__ src) {
   constexpr int NC = 1 << dim, NL = ipow(n, dim - 1), ND = NL * n, NT = NC * NL;
   __shared__ T buf[NC][ND];
   __shared__ T par[ND];
-  const long long parent = blockIdx.x;
+  // one block per (parent cell, component): cells are component-blocked, [cell][comp][n^dim]
+  const long long parent = blockIdx.x / ncomp;
+  const int comp = (int)(blockIdx.x - parent * ncomp);
+  const size_t coarse_off = ((size_t)parent * ncomp + comp) * ND;
+  auto fine_off = [&](int child) { return (((size_t)parent * NC + child) * ncomp + comp) * ND; };
   const int tid = threadIdx.x, c = tid / NL, l = tid % NL;
   if (PROLONG) {
-    for (int i = tid; i < ND; i += NT) par[i] = src[parent * ND + i];
+    for (int i = tid; i < ND; i += NT) par[i] = src[coarse_off + i];
   } else {
-    for (int i = tid; i < NC * ND; i += NT) buf[i / ND][i % ND] = src[parent * NC * ND + i];
+    for (int i = tid; i < NC * ND; i += NT) buf[i / ND][i % ND] = src[fine_off(i / ND) + i % ND];
   }
   __syncthreads();
   if (PROLONG)
@@ -154,41 +158,41 @@ transfer_kernel(const __grid_constant__ TransferParams<T, n> P, long long n_pare
     __syncthreads();
   }
   if (PROLONG) {
-    for (int i = tid; i < NC * ND; i += NT) dst[parent * NC * ND + i] += buf[i / ND][i % ND];
+    for (int i = tid; i < NC * ND; i += NT) dst[fine_off(i / ND) + i % ND] += buf[i / ND][i % ND];
   } else {
     for (int i = tid; i < ND; i += NT) {
       T s = 0;
 #pragma unroll
       for (int cc = 0; cc < NC; ++cc) s += buf[cc][i];
-      dst[parent * ND + i] += s;
+      dst[coarse_off + i] += s;
     }
   }
 }
 
 template <int dim, int n, typename T>
-int launch_transfer(dgx_ctx *ctx, bool prolong, long long n_parents, void *dst, const void *src) {
+int launch_transfer(dgx_ctx *ctx, bool prolong, long long n_parents, int ncomp, void *dst, const void *src) {
   const Shape1D &s = get_shape(n - 1, n);
   TransferParams<T, n> P;
   for (int c = 0; c < 2; ++c)
     for (int i = 0; i < n * n; ++i) P.P[c][i] = (T)s.P[c][i];
   constexpr int NT = (1 << dim) * ipow(n, dim - 1);
   if (n_parents == 0) return DGX_OK;
-  if (prolong) transfer_kernel<dim, n, T, true><<<(unsigned)n_parents, NT, 0, ctx->stream>>>(P, n_parents, (T *)dst, (const T *)src);
-  else transfer_kernel<dim, n, T, false><<<(unsigned)n_parents, NT, 0, ctx->stream>>>(P, n_parents, (T *)dst, (const T *)src);
+  if (prolong) transfer_kernel<dim, n, T, true><<<(unsigned)(n_parents * ncomp), NT, 0, ctx->stream>>>(P, n_parents, ncomp, (T *)dst, (const T *)src);
+  else transfer_kernel<dim, n, T, false><<<(unsigned)(n_parents * ncomp), NT, 0, ctx->stream>>>(P, n_parents, ncomp, (T *)dst, (const T *)src);
   count_launch();
   DGX_CUDA_CHECK(cudaGetLastError());
   return DGX_OK;
 }
 
 template <int dim, typename T>
-int transfer_by_degree(int degree, dgx_ctx *ctx, bool prolong, long long np, void *dst, const void *src) {
+int transfer_by_degree(int degree, dgx_ctx *ctx, bool prolong, long long np, int ncomp, void *dst, const void *src) {
   switch (degree) {
-    case 1: return launch_transfer<dim, 2, T>(ctx, prolong, np, dst, src);
-    case 2: return launch_transfer<dim, 3, T>(ctx, prolong, np, dst, src);
-    case 3: return launch_transfer<dim, 4, T>(ctx, prolong, np, dst, src);
-    case 4: return launch_transfer<dim, 5, T>(ctx, prolong, np, dst, src);
-    case 5: return launch_transfer<dim, 6, T>(ctx, prolong, np, dst, src);
-    case 6: return launch_transfer<dim, 7, T>(ctx, prolong, np, dst, src);
+    case 1: return launch_transfer<dim, 2, T>(ctx, prolong, np, ncomp, dst, src);
+    case 2: return launch_transfer<dim, 3, T>(ctx, prolong, np, ncomp, dst, src);
+    case 3: return launch_transfer<dim, 4, T>(ctx, prolong, np, ncomp, dst, src);
+    case 4: return launch_transfer<dim, 5, T>(ctx, prolong, np, ncomp, dst, src);
+    case 5: return launch_transfer<dim, 6, T>(ctx, prolong, np, ncomp, dst, src);
+    case 6: return launch_transfer<dim, 7, T>(ctx, prolong, np, ncomp, dst, src);
     default: set_error("transfer: degree must be in 1..6"); return DGX_ERR_UNSUPPORTED;
   }
 }
@@ -197,7 +201,8 @@ int transfer(bool prolong, dgx_vec *dst, const dgx_vec *src) {
   DGX_REQUIRE(dst && src, "null argument");
   const dgx_vec *fine = prolong ? dst : src, *coarse = prolong ? src : dst;
   DGX_REQUIRE(fine->mf->level == coarse->mf->level + 1 && fine->mf->mesh == coarse->mf->mesh, "vectors must live on consecutive levels of one mesh");
-  DGX_REQUIRE(fine->degree == coarse->degree && fine->ncomp == 1 && coarse->ncomp == 1 && fine->dtype == coarse->dtype, "transfer: scalar spaces of equal degree and number type");
+  DGX_REQUIRE(fine->degree == coarse->degree && fine->ncomp == coarse->ncomp && fine->dtype == coarse->dtype, "transfer: spaces of equal degree, components and number type");
+  const int ncomp = fine->ncomp;
   const int dim = fine->mf->dim, nc = 1 << dim;
   // the parents of this rank's fine cells: the coarse cells [par_first, par_first + np) in global numbering
   if (fine->mf->first_cell % nc != 0 || fine->mf->n_owned % nc != 0) {
@@ -217,10 +222,10 @@ int transfer(bool prolong, dgx_vec *dst, const dgx_vec *src) {
   void *dptr = prolong ? dst->d : (char *)dst->d + (size_t)coarse_off * es;
   const void *sptr = prolong ? (const char *)src->d + (size_t)coarse_off * es : src->d;
   int rc;
-  if (dim == 2) rc = fine->dtype == DGX_F64 ? transfer_by_degree<2, double>(fine->degree, ctx, prolong, np, dptr, sptr)
-                                            : transfer_by_degree<2, float>(fine->degree, ctx, prolong, np, dptr, sptr);
-  else rc = fine->dtype == DGX_F64 ? transfer_by_degree<3, double>(fine->degree, ctx, prolong, np, dptr, sptr)
-                                   : transfer_by_degree<3, float>(fine->degree, ctx, prolong, np, dptr, sptr);
+  if (dim == 2) rc = fine->dtype == DGX_F64 ? transfer_by_degree<2, double>(fine->degree, ctx, prolong, np, ncomp, dptr, sptr)
+                                            : transfer_by_degree<2, float>(fine->degree, ctx, prolong, np, ncomp, dptr, sptr);
+  else rc = fine->dtype == DGX_F64 ? transfer_by_degree<3, double>(fine->degree, ctx, prolong, np, ncomp, dptr, sptr)
+                                   : transfer_by_degree<3, float>(fine->degree, ctx, prolong, np, ncomp, dptr, sptr);
   if (rc || prolong || !gather) return rc;
   // restriction into a replicated level: every rank has filled the piece of its own parents; one all-gather completes the
   // vector on all ranks (equal pieces: the fine level is cut into equal chunks).  Nothing is sent on the way up.
@@ -368,6 +373,14 @@ extern "C" {
 // ---- MGTransferMatrixFree ----------------------------------------------------------------------------
 int dgx_transfer_prolongate_and_add(dgx_vec *dst_fine, const dgx_vec *src_coarse) { return transfer(true, dst_fine, src_coarse); }
 int dgx_transfer_restrict_and_add(dgx_vec *dst_coarse, const dgx_vec *src_fine) { return transfer(false, dst_coarse, src_fine); }
+
+// SolutionTransfer::interpolate after a global refinement (refine_mesh, NS.cc:2781-2822, restricted to the case where every cell is
+// refined): a DG field on the children of a cell is the embedding of the parent's polynomial -- exact, component by component.
+int dgx_solution_transfer_refine(dgx_vec *dst_fine, const dgx_vec *src_coarse) {
+  DGX_REQUIRE(dst_fine && src_coarse, "null argument");
+  RC(dgx_vec_set(dst_fine, 0.0));
+  return transfer(true, dst_fine, src_coarse);
+}
 
 // ---- PreconditionChebyshev ----------------------------------------------------------------------------
 int dgx_cheb_create(dgx_op *op, int degree, double smoothing_range, int eig_cg_n_iterations, dgx_cheb **out) {

@@ -438,6 +438,11 @@ def transfer_restrict_and_add(dst_coarse: Vector, src_fine: Vector):
     _check(lib.dgx_transfer_restrict_and_add(dst_coarse.h, src_fine.h))
 
 
+def solution_transfer_refine(dst_fine: Vector, src_coarse: Vector):
+    """SolutionTransfer::interpolate after refine_global (the all-cells-refined case of refine_mesh, NS.cc:2781-2822)"""
+    _check(lib.dgx_solution_transfer_refine(dst_fine.h, src_coarse.h))
+
+
 class PreconditionChebyshev:
     """PreconditionChebyshev<Op, Vector> with the operator's inverse diagonal (NS.cc:2493-2516)."""
 

@@ -200,6 +200,10 @@ int dgx_mf_host_pipeline_plan(const dgx_mf *mf, long long bytes_per_cell, int ch
 /* dst_fine += P src_coarse ; dst_coarse += P^T src_fine (vectors on consecutive levels of one mesh) */
 int dgx_transfer_prolongate_and_add(dgx_vec *dst_fine, const dgx_vec *src_coarse);
 int dgx_transfer_restrict_and_add(dgx_vec *dst_coarse, const dgx_vec *src_fine);
+/* (scalar or vector-valued spaces: cells are component-blocked)
+ * SolutionTransfer::interpolate for the globally refined case of refine_mesh (NS.cc:2781-2822): dst_fine = embedding of src_coarse into
+ * the children of every cell (exact for DG), vectors on consecutive levels of one mesh, any number of components */
+int dgx_solution_transfer_refine(dgx_vec *dst_fine, const dgx_vec *src_coarse);
 
 /* ---- PreconditionChebyshev<LevelOp, Vector<float>> with the inverse diagonal inside (NS.cc:2493-2516) ------- */
 int dgx_cheb_create(dgx_op *op, int degree, double smoothing_range, int eig_cg_n_iterations, dgx_cheb **out);

@@ -187,3 +187,39 @@ def test_mg_cg_pressure_solve(dgx, gpu_ctx, dim, cells0, nref, degree):
         vx.set(0.0)
         its2, _ = dgx.solve_cg(op, vx, vb, mg, 10000, tol)
         assert its2 == its and np.array_equal(vx.to_host(), x1)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_solution_transfer_after_global_refinement(dgx, gpu_ctx, dim):
+    """SolutionTransfer::interpolate for the all-cells-refined case of refine_mesh (NS.cc:2781-2822): the embedding of a DG field into
+    the children is exact, so a polynomial velocity field (degree <= p per variable) interpolated on level L and transferred equals its
+    interpolation on level L + 1; vector-valued spaces are component-blocked per cell."""
+    from oracle.dg1d import gauss_lobatto_nodes
+    from oracle.mesh import CartesianMesh
+    args = (dim, [2, 1, 1][:dim], 2, [0.0] * dim, [1.0, 1.5, 0.75][:dim], [False] * dim)
+    gm = dgx.Mesh(*args)
+    fine, coarse = dgx.MatrixFree(gpu_ctx, gm, 2), dgx.MatrixFree(gpu_ctx, gm, 1)
+    for degree, ncomp in ((2, dim), (1, 1), (3, dim)):
+        nodes = np.asarray(gauss_lobatto_nodes(degree + 1), dtype=np.float64)
+
+        def field(level):
+            om = CartesianMesh(args[0], args[1], level, args[3], args[4], args[5])
+            pts = om.dof_points(nodes)
+            x = [pts[..., d] for d in range(dim)]
+            comps = [(1 + c) * x[0] ** degree - x[1] ** (degree - 1) * (x[dim - 1] + 0.5 * c) + 0.25 * c for c in range(ncomp)]   # degree <= p per variable
+            return np.stack(comps, axis=1).reshape(-1)
+        vc, vf = coarse.initialize_dof_vector(degree, ncomp), fine.initialize_dof_vector(degree, ncomp)
+        vc.from_host(field(1))
+        vf.set(7.0)                                   # overwritten, not accumulated into
+        dgx.solution_transfer_refine(vf, vc)
+        ref = field(2)
+        assert np.max(np.abs(vf.to_host() - ref)) < 1e-13 * max(1.0, np.max(np.abs(ref))), (degree, ncomp)
+        # restriction is the transpose, also for vector-valued spaces: <P c, f> = <c, P^T f>
+        rng = np.random.default_rng(degree)
+        c_h, f_h = rng.standard_normal(vc.locally_owned_size()), rng.standard_normal(vf.locally_owned_size())
+        vc.from_host(c_h); vf.set(0.0)
+        dgx.transfer_prolongate_and_add(vf, vc)
+        lhs = float(vf.to_host() @ f_h)
+        vf.from_host(f_h); vc.set(0.0)
+        dgx.transfer_restrict_and_add(vc, vf)
+        assert abs(lhs - float(vc.to_host() @ c_h)) < 1e-11 * abs(lhs)
