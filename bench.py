@@ -8,11 +8,13 @@ FE_DGQ(4), periodic, fp64 (262,144,000 DoFs, 2.1 GB per vector => inputs exceed 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--refine R] [--degree P] [--impl reference]
 
 Prints ONE JSON line (rank 0).  `value` = DoFs processed per second with src/dst resident in HBM;
-`e2e` = the same through dgx_op_vmult_host (pinned host buffers, H2D + vmult + D2H timed; on one rank the three legs
-  of a call are pipelined brick by brick, see DESIGN.md "Host entry point");
+`e2e` = the same through dgx_op_vmult_host (pinned host buffers, H2D + vmult + D2H timed; the three legs of a call are
+  pipelined brick by brick on any number of ranks, see DESIGN.md "Host entry point");
 `roofline` = algorithmic bytes (16 B/DoF) / kernel time vs MEASURED_PEAKS.json;
 `cpu_baseline` = the reference algorithm as deal.II executes it (SIMD over cells, even-odd, compile-time degree), restated in C
   (oracle/cpu_simd.c), timed on all host cores on the SAME 128^3 workload (3 applications).
+Extra keys outside the timed region: `mg_solve` (MG-CG pressure solve), `trbdf2_step`, `degree_sweep` (Q1..Q8 x fp64/fp32),
+`general_mapping` (pressure operator and MG-CG on MappingQ1 cells), `marching_vs_generic_rel_l2`, `multi_gpu_parity` (N > 1).
 `--impl reference` times that CPU implementation alone on the arm's config (rank 0 only, all host threads).
 """
 import argparse
