@@ -93,6 +93,9 @@ def test_run_loop_reports_forces_and_writes_output(dgx, gpu_ctx, tmp_path):
     lift, drag = forces[-1]
     rl, rd = lift_and_drag(om, 2, 1, ns.u_n.to_host(), ns.pres_n.to_host(), 100.0, 0)
     assert abs(lift - rl) < 1e-11 * max(1.0, abs(rl)) and abs(drag - rd) < 1e-11 * max(1.0, abs(rd)) and max(abs(rl), abs(rd)) > 1e-6
+    eta, flags = ns.refinement_flags(0.1, 0.3)          # first half of refine_mesh on the current u_n
+    assert eta.shape == (om.n_cells,) and np.all(eta >= 0) and (flags == 1).sum() >= 3 and (flags == -1).sum() >= 9
+    assert np.allclose(eta, __import__("oracle.diagnostics", fromlist=["x"]).vorticity_indicator(om, 2, ns.u_n.to_host()), rtol=2e-6)
     files = sorted(p.name for p in tmp_path.iterdir())
     assert files == ["solution-00001.vtu", "solution-00002.vtu", "solution-00003.vtu"]
     assert read_vtu(str(tmp_path / files[2]))[1] == om.n_cells
