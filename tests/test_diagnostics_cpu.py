@@ -183,3 +183,19 @@ def test_vorticity_indicator_and_refinement_flags(dgx):
         flags = dgx.refine_and_coarsen_fixed_number(ind, top, bottom)
         assert np.array_equal(flags, refine_and_coarsen_fixed_number(ind, top, bottom))
         assert (flags == 1).sum() >= int(top * 1000) and (flags == -1).sum() >= min(int(bottom * 1000), 1000 - (flags == 1).sum()) - 10
+
+
+def test_vtu_writer_round_trip_3d(dgx, tmp_path):
+    om = CartesianMesh(3, [1, 2, 1], 0, [0, 0, 0], [1, 2, 1], [False] * 3)
+    u, p = fields_3d(om)
+    data = patch_data(om, 2, 1, u, p, 3 * u)
+    pts = patch_points(om)
+    path = str(tmp_path / "piece3d.vtu")
+    dgx.lib.dgx_write_vtu_piece.argtypes = [C.c_char_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]
+    assert dgx.lib.dgx_write_vtu_piece(path.encode(), 3, om.n_cells, np.ascontiguousarray(pts).ctypes.data, np.ascontiguousarray(data).ctypes.data) == 0
+    npnt, ncell, arr = read_vtu(path)
+    flat = data.reshape(-1, data.shape[-1])
+    assert npnt == om.n_cells * 8 and ncell == om.n_cells and np.all(arr["types"] == 12)
+    assert np.array_equal(arr["points"], pts.reshape(-1, 3)) and np.array_equal(arr["v"], flat[:, 0:3]) and np.array_equal(arr["p"], flat[:, 3])
+    assert np.array_equal(arr["v_old"], flat[:, 4:7]) and np.array_equal(arr["vorticity"], flat[:, 7:10])
+    assert np.array_equal(arr["connectivity"].reshape(-1, 8)[1], 8 + np.array([0, 1, 3, 2, 4, 5, 7, 6]))
